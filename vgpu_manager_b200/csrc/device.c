@@ -1,0 +1,484 @@
+/*
+ * device.c - per-GPU device runtime: loads the embedded sm_100a image into the tenant's
+ * context through the *real* driver table (never through our own hooks), owns the private
+ * streams, the pinned host blocks and the HBM-resident limiter / slab state, and exposes the
+ * direct C-ABI entry points declared in include/vgpu_b200.h.
+ *
+ * No reference counterpart: the reference has no device code.
+ */
+#include "vgpu_internal.h"
+
+#include <errno.h>
+#include <sched.h>
+#include <time.h>
+
+#include "../../include/vgpu_b200.h"
+
+extern const unsigned char vgpu_kernels_image[]; /* generated from kernels.cu (bin2c) */
+extern const unsigned long long vgpu_kernels_image_size;
+
+static vgpu_dev_rt g_rt[VGPU_MAX_DEVICES];
+static pthread_mutex_t g_rt_mu = PTHREAD_MUTEX_INITIALIZER;
+static volatile pid_t g_rt_pid;
+
+#define CU_TRY(call, what)                                                             \
+  do {                                                                                 \
+    CUresult _r = (call);                                                              \
+    if (_r != CUDA_SUCCESS) {                                                          \
+      VLOG(VL_ERROR, "device runtime: %s failed: %d (%s)", what, _r, vgpu_cu_err(_r)); \
+      goto fail;                                                                       \
+    }                                                                                  \
+  } while (0)
+
+static int pinned_block(size_t bytes, void **host, CUdeviceptr *dev) {
+  if (!R.cuMemHostAlloc || !R.cuMemHostGetDevicePointer_v2) return -1;
+  if (R.cuMemHostAlloc(host, bytes, VCU_MEMHOSTALLOC_PORTABLE | VCU_MEMHOSTALLOC_DEVICEMAP)) return -1;
+  memset(*host, 0, bytes);
+  if (R.cuMemHostGetDevicePointer_v2(dev, *host, 0)) return -1;
+  return 0;
+}
+
+CUresult vgpu_rt_launch(vgpu_dev_rt *rt, CUfunction f, unsigned grid, unsigned block, unsigned smem,
+                        CUstream s, void **params) {
+  (void)rt;
+  return R.cuLaunchKernel(f, grid, 1, 1, block, 1, 1, smem, s, params, NULL);
+}
+
+/* bytes NVML attributes to this process on `nvdev` (calibration of our own footprint only) */
+static uint64_t own_process_bytes(nvmlDevice_t nvdev) {
+  if (!nvdev || !R.nvmlDeviceGetComputeRunningProcesses) return 0;
+  static __thread vgpu_proc_t procs[VGPU_MAX_PIDS];
+  unsigned int n = VGPU_MAX_PIDS;
+  if (R.nvmlDeviceGetComputeRunningProcesses(nvdev, &n, procs) != NVML_SUCCESS) return 0;
+  uint32_t me = (uint32_t)getpid();
+  for (unsigned int i = 0; i < n; i++)
+    if (procs[i].pid == me) return procs[i].used_bytes;
+  /* pid namespace: our host pid is unknown; with a single process on the device it is us */
+  return n == 1 ? procs[0].used_bytes : 0;
+}
+
+static int spin_seq(volatile uint32_t *word, uint32_t want, CUstream s) {
+  /* the kernel publishes its sequence number with a system-scope release; polling the pinned
+   * word is ~2x cheaper than cuStreamSynchronize for a ~5 us kernel */
+  for (int i = 0; i < 2000000; i++) {
+    if (*word == want) return 0;
+    if ((i & 1023) == 1023) {
+      CUresult q = R.cuStreamQuery ? R.cuStreamQuery(s) : CUDA_SUCCESS;
+      if (q != CUDA_SUCCESS && q != CUDA_ERROR_NOT_READY) return -1;
+      sched_yield();
+    }
+    __builtin_ia32_pause();
+  }
+  if (R.cuStreamSynchronize(s) != CUDA_SUCCESS) return -1;
+  return *word == want ? 0 : -1;
+}
+
+static void write_limiter_config(vgpu_dev_rt *rt, vgpu_lim_dev_t *init) {
+  const vgpu_cfg_dev_t *c = (rt->host_index >= 0 && G_cfg) ? &G_cfg->devices[rt->host_index] : NULL;
+  memset(init, 0, sizeof *init);
+  init->sm_num = rt->sm_num;
+  init->max_thread_per_sm = rt->max_thread_per_sm;
+  init->total_cores = rt->total_cores;
+  init->pre_sys_process_num = 1;
+  if (c) {
+    init->hard_core = c->hard_core;
+    init->soft_core = c->soft_core;
+    init->core_limit = c->core_limit;
+    init->hard_limit = c->hard_limit;
+    init->up_limit = c->hard_core;
+  }
+  for (unsigned i = 0; i < VGPU_MAX_SMS * 4; i++) init->probe_idle[i] = 0xffffffffu;
+}
+
+static vgpu_dev_rt *bring_up(vgpu_dev_rt *rt, int slot, int host_index, CUdevice dev) {
+  CUcontext ctx = NULL;
+  if (!R.cuCtxGetCurrent || R.cuCtxGetCurrent(&ctx) != CUDA_SUCCESS || !ctx) return NULL;
+  if (!R.cuModuleLoadData || !R.cuLaunchKernel || !R.cuMemAlloc_v2) {
+    VLOG(VL_ERROR, "device runtime: driver lacks module/launch entry points");
+    rt->ready = -1;
+    return NULL;
+  }
+  memset(rt, 0, sizeof *rt);
+  pthread_mutex_init(&rt->q_mu, NULL);
+  rt->host_index = host_index;
+  rt->cuda_dev = dev;
+  rt->ctx = ctx;
+
+  nvmlDevice_t nvdev = vgpu_nvml_handle_of_host(host_index);
+  int lock_fd = host_index >= 0 ? vgpu_lock_gpu(host_index) : -1;
+  uint64_t before = own_process_bytes(nvdev);
+
+  R.cuDeviceGetAttribute(&rt->sm_num, VCU_ATTR_SM_COUNT, dev);
+  R.cuDeviceGetAttribute(&rt->max_thread_per_sm, VCU_ATTR_MAX_THREADS_PER_SM, dev);
+  rt->total_cores = (int64_t)rt->max_thread_per_sm * (int64_t)rt->sm_num * 32; /* cuda_hook.c:534 */
+  int m64 = 0;
+  R.cuDeviceGetAttribute(&m64, 122 /* CAN_USE_64_BIT_STREAM_MEM_OPS */, dev);
+  rt->memops64 = m64 && R.cuStreamWaitValue64_v2 && R.cuStreamWriteValue64_v2;
+
+  CU_TRY(R.cuModuleLoadData(&rt->mod, vgpu_kernels_image), "cuModuleLoadData(sm_100a image)");
+  CU_TRY(R.cuModuleGetFunction(&rt->k_clear, rt->mod, VGPU_K_CLEAR), VGPU_K_CLEAR);
+  CU_TRY(R.cuModuleGetFunction(&rt->k_spill, rt->mod, VGPU_K_SPILL), VGPU_K_SPILL);
+  CU_TRY(R.cuModuleGetFunction(&rt->k_copy_generic, rt->mod, "vgpu_copy_generic_kernel"), "generic copy");
+  CU_TRY(R.cuModuleGetFunction(&rt->k_quota, rt->mod, VGPU_K_QUOTA), VGPU_K_QUOTA);
+  CU_TRY(R.cuModuleGetFunction(&rt->k_slab_insert, rt->mod, VGPU_K_SLAB_INSERT), VGPU_K_SLAB_INSERT);
+  CU_TRY(R.cuModuleGetFunction(&rt->k_slab_remove, rt->mod, VGPU_K_SLAB_REMOVE), VGPU_K_SLAB_REMOVE);
+  CU_TRY(R.cuModuleGetFunction(&rt->k_controller, rt->mod, VGPU_K_CONTROLLER), VGPU_K_CONTROLLER);
+  CU_TRY(R.cuModuleGetFunction(&rt->k_sampler, rt->mod, VGPU_K_SAMPLER), VGPU_K_SAMPLER);
+  CU_TRY(R.cuModuleGetFunction(&rt->k_gate, rt->mod, VGPU_K_GATE), VGPU_K_GATE);
+  if (R.cuFuncSetAttribute) /* CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES = 8 */
+    CU_TRY(R.cuFuncSetAttribute(rt->k_spill, 8, VGPU_SPILL_SMEM_BYTES), "spill smem opt-in");
+
+  int lo = 0, hi = 0;
+  if (R.cuCtxGetStreamPriorityRange) R.cuCtxGetStreamPriorityRange(&lo, &hi);
+  if (R.cuStreamCreateWithPriority) {
+    CU_TRY(R.cuStreamCreateWithPriority(&rt->q_stream, VCU_STREAM_NON_BLOCKING, hi), "quota stream");
+    CU_TRY(R.cuStreamCreateWithPriority(&rt->s_stream, VCU_STREAM_NON_BLOCKING, hi), "sampler stream");
+  } else {
+    CU_TRY(R.cuStreamCreate(&rt->q_stream, VCU_STREAM_NON_BLOCKING), "quota stream");
+    CU_TRY(R.cuStreamCreate(&rt->s_stream, VCU_STREAM_NON_BLOCKING), "sampler stream");
+  }
+
+  if (pinned_block(sizeof(vgpu_quota_req_t), (void **)&rt->q_req, &rt->q_req_d) ||
+      pinned_block(sizeof(vgpu_quota_res_t), (void **)&rt->q_res, &rt->q_res_d) ||
+      pinned_block(sizeof(vgpu_slab_res_t), (void **)&rt->slab_res, &rt->slab_res_d) ||
+      pinned_block(sizeof(vgpu_lim_host_t), (void **)&rt->lim_h, &rt->lim_h_d)) {
+    VLOG(VL_ERROR, "device runtime: pinned host blocks unavailable");
+    goto fail;
+  }
+  rt->lim_h->ext_user_override = -1;
+  rt->lim_h->ext_sys_process_num = 1;
+  {
+    const char *src = getenv("VGPU_B200_UTIL_SOURCE"); /* queue (default) | sm | max */
+    rt->lim_h->util_source = (src && !strcmp(src, "sm")) ? 1 : (src && !strcmp(src, "max")) ? 2 : 0;
+  }
+
+  /* one HBM allocation: limiter state followed by the UVA slab */
+  size_t lim_bytes = (sizeof(vgpu_lim_dev_t) + 255) & ~(size_t)255;
+  size_t hbm_bytes = lim_bytes + sizeof(vgpu_slab_slot_t) * VGPU_SLAB_SLOTS;
+  CU_TRY(R.cuMemAlloc_v2(&rt->lim_d, hbm_bytes), "HBM state");
+  rt->slab_d = rt->lim_d + lim_bytes;
+  CU_TRY(R.cuMemsetD8_v2(rt->lim_d, 0, hbm_bytes), "HBM state clear");
+  {
+    vgpu_lim_dev_t *init = (vgpu_lim_dev_t *)malloc(sizeof *init);
+    if (!init) goto fail;
+    write_limiter_config(rt, init);
+    CUresult r = R.cuMemcpyHtoD_v2(rt->lim_d, init, sizeof *init);
+    free(init);
+    CU_TRY(r, "HBM state init");
+  }
+
+  /* force lazy module loading to materialise every kernel now, so that the footprint we
+   * measure below is final: null-work launches */
+  {
+    unsigned long long zero = 0;
+    CUdeviceptr nullp = rt->slab_d;
+    void *p_clear[] = {&nullp, &zero};
+    void *p_copy[] = {&nullp, &nullp, &zero};
+    CU_TRY(vgpu_rt_launch(rt, rt->k_clear, 1, 256, 0, rt->q_stream, p_clear), "warm clear");
+    CU_TRY(vgpu_rt_launch(rt, rt->k_spill, 1, 32, VGPU_SPILL_SMEM_BYTES, rt->q_stream, p_copy), "warm spill");
+    CU_TRY(vgpu_rt_launch(rt, rt->k_copy_generic, 1, 256, 0, rt->q_stream, p_copy), "warm copy");
+    rt->q_req->seq = ++rt->seq;
+    void *p_quota[] = {&rt->q_req_d, &rt->q_res_d};
+    CU_TRY(vgpu_rt_launch(rt, rt->k_quota, 1, 1024, 0, rt->q_stream, p_quota), "warm quota");
+    uint32_t sq = ++rt->seq;
+    unsigned long long key = 2, bytes = 0;
+    void *p_ins[] = {&rt->slab_d, &key, &bytes, &rt->slab_res_d, &sq};
+    void *p_rem[] = {&rt->slab_d, &key, &rt->slab_res_d, &sq};
+    CU_TRY(vgpu_rt_launch(rt, rt->k_slab_insert, 1, 32, 0, rt->q_stream, p_ins), "warm slab insert");
+    CU_TRY(vgpu_rt_launch(rt, rt->k_slab_remove, 1, 32, 0, rt->q_stream, p_rem), "warm slab remove");
+    vgpu_ctrl_in_t in = {0, 0, 0, 1};
+    void *p_ctl[] = {&rt->lim_d, &rt->lim_h_d, &in};
+    CU_TRY(vgpu_rt_launch(rt, rt->k_controller, 1, 32, 0, rt->q_stream, p_ctl), "warm controller");
+    uint32_t w = 0, iv = 1, per = 0x7fffffff, ep = 0;
+    void *p_smp[] = {&rt->lim_d, &rt->lim_h_d, &w, &iv, &per, &ep};
+    CU_TRY(vgpu_rt_launch(rt, rt->k_sampler, 1, 128, 0, rt->q_stream, p_smp), "warm sampler");
+    long long tk = 0;
+    uint32_t to = 1;
+    void *p_gate[] = {&rt->lim_d, &tk, &to};
+    CU_TRY(vgpu_rt_launch(rt, rt->k_gate, 1, 1, 0, rt->q_stream, p_gate), "warm gate");
+    CU_TRY(R.cuStreamSynchronize(rt->q_stream), "warm-up sync");
+    /* the warm-up controller/sampler steps touched the state: re-initialise it */
+    CU_TRY(R.cuMemsetD8_v2(rt->lim_d, 0, lim_bytes), "HBM state re-clear");
+    vgpu_lim_dev_t *init = (vgpu_lim_dev_t *)malloc(sizeof *init);
+    if (!init) goto fail;
+    write_limiter_config(rt, init);
+    CUresult r = R.cuMemcpyHtoD_v2(rt->lim_d, init, sizeof *init);
+    free(init);
+    CU_TRY(r, "HBM state init");
+    memset((void *)rt->lim_h, 0, offsetof(vgpu_lim_host_t, user_current));
+    rt->lim_h->ext_user_override = -1;
+    rt->lim_h->ext_sys_process_num = 1;
+    const char *src = getenv("VGPU_B200_UTIL_SOURCE");
+    rt->lim_h->util_source = (src && !strcmp(src, "sm")) ? 1 : (src && !strcmp(src, "max")) ? 2 : 0;
+  }
+
+  uint64_t after = own_process_bytes(nvdev);
+  rt->self_bytes = after > before ? after - before : 0;
+  vgpu_unlock_gpu(lock_fd);
+  __sync_synchronize();
+  rt->ready = 1;
+  VLOG(VL_INFO, "device runtime up: slot %d host %d sms %d own footprint %" PRIu64 " bytes memops64 %d",
+       slot, host_index, rt->sm_num, rt->self_bytes, rt->memops64);
+  return rt;
+fail:
+  vgpu_unlock_gpu(lock_fd);
+  rt->ready = -1;
+  VLOG(VL_ERROR, "device runtime bring-up failed on cuda device %d: the sm_100a enforcement "
+                 "kernels are unavailable (no CPU fallback exists)", dev);
+  return NULL;
+}
+
+vgpu_dev_rt *vgpu_rt_get(int host_index, CUdevice dev) {
+  int slot = host_index >= 0 ? host_index : (dev >= 0 && dev < VGPU_MAX_DEVICES ? dev : 0);
+  pid_t me = getpid();
+  vgpu_dev_rt *rt = &g_rt[slot];
+  if (likely(g_rt_pid == me && rt->ready == 1)) return rt;
+  pthread_mutex_lock(&g_rt_mu);
+  if (g_rt_pid != me) { /* fork: device state does not survive, start over */
+    memset(g_rt, 0, sizeof g_rt);
+    g_rt_pid = me;
+  }
+  vgpu_dev_rt *out = NULL;
+  if (rt->ready == 1) out = rt;
+  else if (rt->ready == 0) out = bring_up(rt, slot, host_index, dev);
+  pthread_mutex_unlock(&g_rt_mu);
+  return out;
+}
+
+vgpu_dev_rt *vgpu_rt_peek(int host_index) {
+  if (host_index < 0 || host_index >= VGPU_MAX_DEVICES) return NULL;
+  vgpu_dev_rt *rt = &g_rt[host_index];
+  return (g_rt_pid == getpid() && rt->ready == 1) ? rt : NULL;
+}
+
+/* ------------------------------------------------------------------ kernel drivers used by the hooks */
+int vgpu_rt_quota(vgpu_dev_rt *rt, vgpu_quota_res_t *out) {
+  /* caller filled rt->q_req (except seq) and holds rt->q_mu */
+  uint32_t seq = ++rt->seq;
+  rt->q_req->seq = seq;
+  rt->q_req->self_bytes = rt->self_bytes;
+  __sync_synchronize();
+  void *params[] = {&rt->q_req_d, &rt->q_res_d};
+  CUresult r = vgpu_rt_launch(rt, rt->k_quota, 1, 1024, 0, rt->q_stream, params);
+  if (r != CUDA_SUCCESS) {
+    VLOG(VL_ERROR, "quota kernel launch failed: %d (%s)", r, vgpu_cu_err(r));
+    return -1;
+  }
+  if (spin_seq(&rt->q_res->seq_done, seq, rt->q_stream)) {
+    VLOG(VL_ERROR, "quota kernel did not complete");
+    return -1;
+  }
+  *out = *rt->q_res;
+  vgpu_metric_add(rt->host_index, VM_QUOTA_KERNELS, 1);
+  return 0;
+}
+
+int vgpu_rt_slab_insert(vgpu_dev_rt *rt, CUdeviceptr dptr, uint64_t bytes) {
+  pthread_mutex_lock(&rt->q_mu);
+  uint32_t seq = ++rt->seq;
+  unsigned long long k = dptr, b = bytes;
+  void *params[] = {&rt->slab_d, &k, &b, &rt->slab_res_d, &seq};
+  int rc = -1;
+  if (vgpu_rt_launch(rt, rt->k_slab_insert, 1, 32, 0, rt->q_stream, params) == CUDA_SUCCESS &&
+      spin_seq(&rt->slab_res->seq_done, seq, rt->q_stream) == 0 && rt->slab_res->slot != 0xffffffffu) {
+    __sync_fetch_and_add(&rt->uva_live, 1);
+    rc = 0;
+  }
+  pthread_mutex_unlock(&rt->q_mu);
+  return rc;
+}
+
+int vgpu_rt_slab_remove(vgpu_dev_rt *rt, CUdeviceptr dptr, uint64_t *bytes) {
+  if (rt->uva_live <= 0) return 1; /* nothing recorded: not a UVA allocation */
+  pthread_mutex_lock(&rt->q_mu);
+  uint32_t seq = ++rt->seq;
+  unsigned long long k = dptr;
+  void *params[] = {&rt->slab_d, &k, &rt->slab_res_d, &seq};
+  int rc = -1;
+  if (vgpu_rt_launch(rt, rt->k_slab_remove, 1, 32, 0, rt->q_stream, params) == CUDA_SUCCESS &&
+      spin_seq(&rt->slab_res->seq_done, seq, rt->q_stream) == 0) {
+    if (rt->slab_res->slot != 0xffffffffu) {
+      *bytes = rt->slab_res->bytes;
+      __sync_fetch_and_sub(&rt->uva_live, 1);
+      rc = 0;
+    } else {
+      rc = 1;
+    }
+  }
+  pthread_mutex_unlock(&rt->q_mu);
+  return rc;
+}
+
+static unsigned copy_grid(vgpu_dev_rt *rt, unsigned long long work_items, unsigned per_sm) {
+  unsigned long long g = (unsigned long long)(rt->sm_num > 0 ? rt->sm_num : 148) * per_sm;
+  if (work_items < g) g = work_items ? work_items : 1;
+  return (unsigned)g;
+}
+
+CUresult vgpu_rt_clear(vgpu_dev_rt *rt, CUdeviceptr dst, size_t bytes, CUstream s) {
+  unsigned long long n = bytes;
+  void *params[] = {&dst, &n};
+  unsigned long long tiles = (n / 16 + 2047) / 2048; /* 256 threads x 8 x 16 B per tile */
+  return vgpu_rt_launch(rt, rt->k_clear, copy_grid(rt, tiles, 16), 256, 0, s, params);
+}
+
+CUresult vgpu_rt_spill(vgpu_dev_rt *rt, CUdeviceptr dst, CUdeviceptr src, size_t bytes, CUstream s) {
+  unsigned long long n = bytes;
+  void *params[] = {&dst, &src, &n};
+  if (((dst ^ src) & 15) != 0) /* TMA bulk copies need 16-byte congruent endpoints */
+    return vgpu_rt_launch(rt, rt->k_copy_generic, copy_grid(rt, (n + 4095) / 4096, 8), 256, 0, s, params);
+  unsigned long long chunks = (n + VGPU_SPILL_CHUNK - 1) / VGPU_SPILL_CHUNK;
+  return vgpu_rt_launch(rt, rt->k_spill, copy_grid(rt, chunks, VGPU_SPILL_CTAS_PER_SM), 32,
+                        VGPU_SPILL_SMEM_BYTES, s, params);
+}
+
+/* ------------------------------------------------------------------ direct C-ABI (include/vgpu_b200.h) */
+static vgpu_dev_rt *attached(void) {
+  vgpu_boot();
+  CUdevice dev;
+  if (!R.cuCtxGetDevice || R.cuCtxGetDevice(&dev) != CUDA_SUCCESS) return NULL;
+  vgpu_map_devices();
+  return vgpu_rt_get(vgpu_host_index_of_cuda(dev), dev);
+}
+
+VGPU_EXPORT int vgpu_b200_attach(void) { return attached() ? 0 : -1; }
+
+VGPU_EXPORT int vgpu_b200_clear(unsigned long long dst, size_t bytes, void *stream) {
+  vgpu_dev_rt *rt = attached();
+  if (!rt) return -1;
+  return vgpu_rt_clear(rt, dst, bytes, (CUstream)stream);
+}
+
+VGPU_EXPORT int vgpu_b200_spill_copy(unsigned long long dst, unsigned long long src, size_t bytes,
+                                     void *stream) {
+  vgpu_dev_rt *rt = attached();
+  if (!rt) return -1;
+  return vgpu_rt_spill(rt, dst, src, bytes, (CUstream)stream);
+}
+
+VGPU_EXPORT int vgpu_b200_quota_eval(const void *req_, void *res_) {
+  const vgpu_quota_req_t *req = (const vgpu_quota_req_t *)req_;
+  vgpu_quota_res_t *res = (vgpu_quota_res_t *)res_;
+  vgpu_dev_rt *rt = attached();
+  if (!rt || !req || !res) return -1;
+  pthread_mutex_lock(&rt->q_mu);
+  memcpy(rt->q_req, req, sizeof *req);
+  uint64_t keep = rt->self_bytes;
+  rt->self_bytes = req->self_bytes; /* the caller's request is evaluated verbatim */
+  int rc = vgpu_rt_quota(rt, res);
+  rt->self_bytes = keep;
+  pthread_mutex_unlock(&rt->q_mu);
+  return rc;
+}
+
+VGPU_EXPORT int vgpu_b200_slab_insert(unsigned long long dptr, unsigned long long bytes) {
+  vgpu_dev_rt *rt = attached();
+  return rt ? vgpu_rt_slab_insert(rt, dptr, bytes) : -1;
+}
+
+VGPU_EXPORT int vgpu_b200_slab_remove(unsigned long long dptr, unsigned long long *bytes) {
+  vgpu_dev_rt *rt = attached();
+  uint64_t b = 0;
+  int rc = rt ? vgpu_rt_slab_remove(rt, dptr, &b) : -1;
+  if (bytes) *bytes = b;
+  return rc;
+}
+
+static int read_lim(vgpu_dev_rt *rt, vgpu_b200_limiter_state_t *out) {
+  vgpu_lim_dev_t *d = (vgpu_lim_dev_t *)malloc(sizeof *d);
+  if (!d) return -1;
+  int rc = R.cuMemcpyDtoH_v2(d, rt->lim_d, sizeof *d) == CUDA_SUCCESS ? 0 : -1;
+  if (rc == 0 && out) {
+    out->granted = d->granted;
+    out->consumed = rt->lim_h->consumed;
+    out->bucket = d->bucket_last;
+    out->share = d->share;
+    out->up_limit = d->up_limit;
+    out->sys_free = d->sys_free;
+    out->avg_sys_free = d->avg_sys_free;
+    out->ctr_i = d->ctr_i;
+    out->pre_sys_process_num = d->pre_sys_process_num;
+    out->valid = d->valid;
+    out->user_current = d->last_user_current;
+    out->sys_current = d->last_sys_current;
+    out->sm_active_pct = d->last_sm_active_pct;
+    out->queue_busy_pct = d->last_queue_busy_pct;
+    out->steps = d->steps;
+  }
+  free(d);
+  return rc;
+}
+
+VGPU_EXPORT int vgpu_b200_limiter_reset(int sm_num, int max_thread_per_sm, int hard_core,
+                                        int soft_core, int core_limit, int hard_limit) {
+  vgpu_dev_rt *rt = attached();
+  if (!rt) return -1;
+  vgpu_lim_dev_t *init = (vgpu_lim_dev_t *)malloc(sizeof *init);
+  if (!init) return -1;
+  write_limiter_config(rt, init);
+  if (sm_num > 0) {
+    init->sm_num = sm_num;
+    init->max_thread_per_sm = max_thread_per_sm;
+    init->total_cores = (int64_t)max_thread_per_sm * (int64_t)sm_num * 32;
+  }
+  init->hard_core = hard_core;
+  init->soft_core = soft_core;
+  init->core_limit = core_limit;
+  init->hard_limit = hard_limit;
+  init->up_limit = hard_core;
+  R.cuStreamSynchronize(rt->s_stream);
+  int rc = R.cuMemcpyHtoD_v2(rt->lim_d, init, sizeof *init) == CUDA_SUCCESS ? 0 : -1;
+  free(init);
+  rt->lim_h->consumed = 0;
+  rt->lim_h->granted_mirror = 0;
+  return rc;
+}
+
+VGPU_EXPORT int vgpu_b200_limiter_step(int user_current, int sys_current, int valid,
+                                       int sys_process_num, vgpu_b200_limiter_state_t *out) {
+  vgpu_dev_rt *rt = attached();
+  if (!rt) return -1;
+  vgpu_ctrl_in_t in = {user_current, sys_current, valid, sys_process_num};
+  void *params[] = {&rt->lim_d, &rt->lim_h_d, &in};
+  if (vgpu_rt_launch(rt, rt->k_controller, 1, 32, 0, rt->q_stream, params) != CUDA_SUCCESS) return -1;
+  if (R.cuStreamSynchronize(rt->q_stream) != CUDA_SUCCESS) return -1;
+  return read_lim(rt, out);
+}
+
+VGPU_EXPORT int vgpu_b200_limiter_consume(long long tokens) {
+  vgpu_dev_rt *rt = attached();
+  if (!rt) return -1;
+  __sync_fetch_and_add(&rt->lim_h->consumed, tokens);
+  return 0;
+}
+
+VGPU_EXPORT int vgpu_b200_limiter_state(vgpu_b200_limiter_state_t *out) {
+  vgpu_dev_rt *rt = attached();
+  return rt ? read_lim(rt, out) : -1;
+}
+
+VGPU_EXPORT int vgpu_b200_sampler_run(unsigned window_us, unsigned interval_us, unsigned period_ticks,
+                                      int user_override, vgpu_b200_limiter_state_t *out) {
+  vgpu_dev_rt *rt = attached();
+  if (!rt) return -1;
+  static uint32_t epoch = 1u << 20;
+  rt->lim_h->ext_user_override = user_override;
+  uint32_t ep = ++epoch;
+  void *params[] = {&rt->lim_d, &rt->lim_h_d, &window_us, &interval_us, &period_ticks, &ep};
+  unsigned grid = rt->sm_num > 0 ? (unsigned)rt->sm_num : 148u;
+  if (vgpu_rt_launch(rt, rt->k_sampler, grid, 128, 0, rt->s_stream, params) != CUDA_SUCCESS) return -1;
+  if (R.cuStreamSynchronize(rt->s_stream) != CUDA_SUCCESS) return -1;
+  vgpu_metric_add(rt->host_index, VM_SAMPLER_LAUNCHES, 1);
+  return read_lim(rt, out);
+}
+
+VGPU_EXPORT unsigned long long vgpu_b200_self_bytes(void) {
+  vgpu_dev_rt *rt = attached();
+  return rt ? rt->self_bytes : 0;
+}
+
+VGPU_EXPORT unsigned long long vgpu_b200_metric(int host_index, int which) {
+  return vgpu_metric_get(host_index, which);
+}
+
+VGPU_EXPORT const char *vgpu_b200_version(void) { return "vgpu-manager_b200 0.1 (sm_100a)"; }

@@ -1,0 +1,59 @@
+/*
+ * hooktab.c - the intercepted symbol surface as a name -> entry-point table.
+ *
+ * This is the drop-in boundary of SURVEY.md 8(b): the 37 CUDA names of reference
+ * library/src/cuda_hook.c:243-281 and the 7 NVML names of library/src/nvml_hook.c:20-28, plus
+ * cuCtxSynchronize (needed so a resident sampler kernel never delays a tenant's device
+ * synchronisation) and nvmlDeviceGetUtilizationRates (named by BASELINE.json; pure forward in
+ * the reference, library/src/nvml_originals.c:698-702).
+ * The entry points are only address-taken here, hence the untyped declarations.
+ */
+#include <stddef.h>
+#include <stdio.h>
+#include <string.h>
+
+#define HOOK_DECL(n) extern void n(void);
+#define VGPU_CUDA_HOOKS(X)                                                                    \
+  X(cuDriverGetVersion) X(cuInit) X(cuGetProcAddress) X(cuGetProcAddress_v2)                  \
+  X(cuMemAllocManaged) X(cuMemAlloc_v2) X(cuMemAlloc) X(cuMemAllocPitch_v2) X(cuMemAllocPitch) \
+  X(cuArrayCreate_v2) X(cuArrayCreate) X(cuArray3DCreate_v2) X(cuArray3DCreate)               \
+  X(cuMipmappedArrayCreate) X(cuDeviceTotalMem_v2) X(cuDeviceTotalMem) X(cuMemGetInfo_v2)     \
+  X(cuMemGetInfo) X(cuLaunchKernel_ptsz) X(cuLaunchKernel) X(cuLaunchKernelEx_ptsz)           \
+  X(cuLaunchKernelEx) X(cuLaunch) X(cuLaunchCooperativeKernel_ptsz) X(cuLaunchCooperativeKernel) \
+  X(cuLaunchGrid) X(cuLaunchGridAsync) X(cuFuncSetBlockShape) X(cuMemAllocAsync)              \
+  X(cuMemAllocAsync_ptsz) X(cuMemCreate) X(cuMemAllocFromPoolAsync)                           \
+  X(cuMemAllocFromPoolAsync_ptsz) X(cuMemFree_v2) X(cuMemFree) X(cuMemFreeAsync)              \
+  X(cuMemFreeAsync_ptsz) X(cuCtxSynchronize)
+#define VGPU_NVML_HOOKS(X)                                                                    \
+  X(nvmlInit) X(nvmlInit_v2) X(nvmlInitWithFlags) X(nvmlDeviceGetMemoryInfo)                  \
+  X(nvmlDeviceGetMemoryInfo_v2) X(nvmlDeviceSetComputeMode) X(nvmlDeviceGetPersistenceMode)   \
+  X(nvmlDeviceGetUtilizationRates)
+VGPU_CUDA_HOOKS(HOOK_DECL)
+VGPU_NVML_HOOKS(HOOK_DECL)
+
+typedef struct { const char *name; void *fn; } hook_ent;
+#define HOOK_ENT(n) {#n, (void *)n},
+static const hook_ent g_cuda_hooks[] = {VGPU_CUDA_HOOKS(HOOK_ENT)};
+static const hook_ent g_nvml_hooks[] = {VGPU_NVML_HOOKS(HOOK_ENT)};
+
+static void *find_hook(const hook_ent *t, size_t n, const char *name) {
+  for (size_t i = 0; i < n; i++)
+    if (!strcmp(t[i].name, name)) return t[i].fn;
+  return NULL;
+}
+
+void *vgpu_lookup_cuda_hook(const char *name, int want_ptsz) {
+  size_t n = sizeof g_cuda_hooks / sizeof g_cuda_hooks[0];
+  if (want_ptsz) {
+    char alt[96];
+    snprintf(alt, sizeof alt, "%s_ptsz", name);
+    void *f = find_hook(g_cuda_hooks, n, alt);
+    if (f) return f;
+  }
+  return find_hook(g_cuda_hooks, n, name);
+}
+
+void *vgpu_lookup_nvml_hook(const char *name) {
+  return find_hook(g_nvml_hooks, sizeof g_nvml_hooks / sizeof g_nvml_hooks[0], name);
+}
+

@@ -1,0 +1,168 @@
+/*
+ * kernel_abi.h - parameter blocks shared by the host shim (C), the sm_100a kernels (CUDA) and
+ * the CPU-only fake GPU used by the plumbing tests (tests/stub).  Plain C, fixed-width types,
+ * no padding surprises (static asserts below).
+ */
+#ifndef VGPU_KERNEL_ABI_H
+#define VGPU_KERNEL_ABI_H
+
+#include <stdint.h>
+#include "../../include/vgpu_contract.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* kernel entry names inside the embedded sm_100a image */
+#define VGPU_K_CLEAR "vgpu_clear_kernel"
+#define VGPU_K_SPILL "vgpu_spill_copy_kernel"
+#define VGPU_K_QUOTA "vgpu_quota_kernel"
+#define VGPU_K_SLAB_INSERT "vgpu_slab_insert_kernel"
+#define VGPU_K_SLAB_REMOVE "vgpu_slab_remove_kernel"
+#define VGPU_K_CONTROLLER "vgpu_controller_kernel"
+#define VGPU_K_SAMPLER "vgpu_sampler_kernel"
+#define VGPU_K_GATE "vgpu_gate_kernel"
+
+/* ---------------------------------------------------------------- spill copy geometry */
+#define VGPU_SPILL_CHUNK 16384u      /* bytes per TMA bulk copy                      */
+#define VGPU_SPILL_STAGES 6u         /* shared-memory ring depth per CTA             */
+#define VGPU_SPILL_SMEM_BYTES (VGPU_SPILL_CHUNK * VGPU_SPILL_STAGES)
+#define VGPU_SPILL_CTAS_PER_SM 2u    /* 2 x 96 KiB of staging per SM                 */
+
+/* ---------------------------------------------------------------- memory quota */
+
+#define VGPU_FLAG_PRIMARY 1u /* pid passes the compatibility mode's own container test */
+#define VGPU_FLAG_LOCAL 2u   /* pid passes the open-kernel "local container pid" test   */
+
+enum { VGPU_Q_ALLOC = 0, VGPU_Q_NVML_INFO = 1, VGPU_Q_CU_INFO = 2 };
+enum { VGPU_PATH_GPU = 0, VGPU_PATH_UVA = 1, VGPU_PATH_OOM = 2 };
+
+/* request block: pinned, device-mapped host memory, one per GPU; written by the host under the
+ * per-GPU file lock, read by the kernel with coalesced 128-bit loads */
+typedef struct {
+  uint32_t seq;          /* echoed into the result when the kernel is done           */
+  uint32_t kind;         /* VGPU_Q_*                                                 */
+  uint32_t mode;         /* compatibility mode                                       */
+  uint32_t allow_uva;
+  uint32_t memory_oversold;
+  uint32_t real_ok;      /* CU_INFO: driver's cuMemGetInfo succeeded                 */
+  uint32_t n_compute;
+  uint32_t n_graphics;
+  uint32_t n_vmem;       /* ledger records of this GPU (0 when vmem_node is off)     */
+  uint32_t _pad;
+  uint64_t total_memory;
+  uint64_t real_memory;
+  uint64_t request;
+  uint64_t real_total;   /* CU_INFO: driver total                                    */
+  uint64_t self_bytes;   /* this library's own device footprint, removed from `used` */
+  uint32_t self_pid;
+  uint32_t _pad2;
+  vgpu_proc_t compute[VGPU_MAX_PIDS];
+  vgpu_proc_t graphics[VGPU_MAX_PIDS];
+  vgpu_vmem_rec_t vmem[VGPU_MAX_PIDS];
+  uint8_t cflags[VGPU_MAX_PIDS];
+  uint8_t gflags[VGPU_MAX_PIDS];
+} vgpu_quota_req_t;
+
+typedef struct {
+  uint64_t used;     /* container's physical bytes (NVML view)              */
+  uint64_t vmem;     /* ledger sum                                          */
+  uint64_t total;    /* reported total                                      */
+  uint64_t out_used; /* reported used                                       */
+  uint64_t out_free; /* reported free                                       */
+  uint32_t path;     /* VGPU_PATH_*                                         */
+  uint32_t seq_done; /* written last (release, system scope)                */
+} vgpu_quota_res_t;
+
+/* ---------------------------------------------------------------- UVA slab ledger */
+
+#define VGPU_SLAB_SLOTS 16384u /* power of two; 16 B each = 256 KiB of HBM */
+typedef struct {
+  uint64_t dptr; /* 0 = free, 1 = tombstone */
+  uint64_t bytes;
+} vgpu_slab_slot_t;
+
+typedef struct {
+  uint64_t bytes;    /* remove: size of the record found (0 if none)        */
+  uint32_t slot;     /* slot index used / found, 0xffffffff if none         */
+  uint32_t seq_done;
+} vgpu_slab_res_t;
+
+/* ---------------------------------------------------------------- limiter */
+
+#define VGPU_STREAM_SLOTS 64u
+#define VGPU_TICKET_RING 1024u /* per stream slot; power of two */
+#define VGPU_MAX_SMS 256u
+
+/* device-resident (HBM) limiter state, one per GPU */
+typedef struct {
+  /* token bucket: tokens = granted - consumed (consumed lives in the host block) */
+  int64_t granted;
+  int64_t bucket_last;
+  /* controller statics == reference cuda_hook.c:369-378 */
+  int64_t share;
+  int32_t sys_free;
+  int32_t avg_sys_free;
+  int32_t ctr_i;
+  int32_t pre_sys_process_num;
+  int32_t up_limit;
+  int32_t valid;
+  /* configuration */
+  int32_t hard_core, soft_core, core_limit, hard_limit;
+  int32_t sm_num, max_thread_per_sm;
+  int64_t total_cores;
+  /* sampler accumulators for the current control period */
+  unsigned long long busy_samples;
+  unsigned long long total_samples;
+  unsigned long long probe_cycles;      /* sum over SM sub-partitions of measured probe cycles */
+  unsigned long long probe_idle_cycles; /* sum of the calibrated idle cost of those probes      */
+  unsigned long long probe_count;
+  uint32_t cta_done;                    /* ticket for "last CTA runs the controller"            */
+  uint32_t period_tick;                 /* sampler launches since the last control step         */
+  uint32_t quit_dev;                    /* set by CTA 0 when the host asked the sampler to leave */
+  uint32_t _pad_q;
+  uint32_t probe_idle[VGPU_MAX_SMS * 4];/* per SM sub-partition calibrated idle probe cycles    */
+  uint32_t sm_epoch[VGPU_MAX_SMS];      /* last sampler launch (epoch) that ran on this %smid   */
+  /* last results, for metrics and tests */
+  int32_t last_user_current;
+  int32_t last_sys_current;
+  int32_t last_sm_active_pct;
+  int32_t last_queue_busy_pct;
+  unsigned long long steps;
+} vgpu_lim_dev_t;
+
+/* pinned, device-mapped, portable host block: what the launch hook touches */
+typedef struct {
+  volatile long long consumed;        /* host-owned, fetch_add by the hook                     */
+  volatile long long granted_mirror;  /* device-written copy of granted                        */
+  volatile uint32_t quit;             /* host asks a running sampler to leave early            */
+  volatile uint32_t util_source;      /* 0 queue-busy, 1 sm-active, 2 max of both              */
+  volatile int32_t ext_sys_current;   /* other tenants' util (host-provided, balance mode)     */
+  volatile int32_t ext_sys_process_num;
+  volatile int32_t ext_user_override; /* >=0: test hook, use this as user_current              */
+  volatile int32_t _pad;
+  volatile unsigned long long launched[VGPU_STREAM_SLOTS]; /* per-slot launch sequence (host)   */
+  /* per-slot completion markers, written by cuStreamWriteValue64 right after each launch */
+  volatile unsigned long long done[VGPU_STREAM_SLOTS];
+  /* ticket (= `consumed` before the launch) of launch `seq` of slot s at [s][seq % RING] */
+  volatile long long ticket[VGPU_STREAM_SLOTS][VGPU_TICKET_RING];
+  /* mirrors for the host (metrics / tests) */
+  volatile int32_t user_current, sys_current, sm_active_pct, queue_busy_pct;
+  volatile long long share_mirror, bucket_mirror;
+  volatile int32_t up_limit_mirror;
+  volatile int32_t _pad3;
+  volatile unsigned long long steps;
+} vgpu_lim_host_t;
+
+/* one explicit controller step (also the unit the parity tests drive) */
+typedef struct {
+  int32_t user_current;
+  int32_t sys_current;
+  int32_t valid;
+  int32_t sys_process_num;
+} vgpu_ctrl_in_t;
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,675 @@
+/*
+ * kernels.cu - the sm_100a device side of the interception library.
+ *
+ *   vgpu_clear_kernel        128-bit vectorised clear (scrub of spilled / recycled pages)
+ *   vgpu_spill_copy_kernel   HBM -> HBM/UVM page staging with TMA bulk copies
+ *                            (cp.async.bulk global->shared->global, mbarrier pipeline)
+ *   vgpu_copy_generic_kernel fallback for mutually misaligned buffers
+ *   vgpu_quota_kernel        memory-cap bookkeeping: process-list fold, ledger sum, quota check,
+ *                            GPU/UVA/OOM decision and the numbers nvml/cuMemGetInfo report
+ *   vgpu_slab_*_kernel       device-resident slab of UVA allocation records (free-slot scan)
+ *   vgpu_controller_kernel   one step of the compute-share controller (token refill)
+ *   vgpu_sampler_kernel      per-SM sampler: %smid/%clock64 probe deltas + stream-queue busy
+ *                            sampling, warp-reduced into the HBM token bucket; the last CTA of
+ *                            the last tick of a period runs the controller
+ *   vgpu_gate_kernel         device-side gate (fallback when 64-bit stream mem-ops are missing)
+ *
+ * None of this exists in the reference: both of its enforcement paths are host C
+ * (library/src/cuda_hook.c:292-471 and :93-136,735-920; library/src/loader.c:1824-1922).  The
+ * arithmetic restated on the device follows those lines exactly and is checked bit-for-bit
+ * against oracle/ (tests/test_gpu_*.py).
+ *
+ * Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -fatbin
+ */
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "kernel_abi.h"
+
+#define DEVINL __device__ __forceinline__
+
+/* ======================================================================= small PTX helpers */
+DEVINL uint64_t globaltimer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+DEVINL uint32_t smid() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%smid;" : "=r"(r));
+  return r;
+}
+DEVINL uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+DEVINL void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+DEVINL void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+DEVINL void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+/* TMA bulk (non-tensor) copy global -> shared, completion on an mbarrier (SASS: UBLKCP) */
+DEVINL void bulk_g2s(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+/* TMA bulk copy shared -> global, tracked by bulk async-groups */
+DEVINL void bulk_s2g(void *gdst, const void *smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst),
+               "r"(smem_u32(smem_src)), "r"(bytes)
+               : "memory");
+}
+DEVINL void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+DEVINL void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+DEVINL void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+/* ======================================================================= clear
+ * N bytes written, nothing read: algorithmic traffic = N.  Each thread issues UNROLL
+ * independent st.global.v4 (128-bit) per iteration; the grid is a multiple of the SM count. */
+#define CLEAR_THREADS 256
+#define CLEAR_UNROLL 8
+extern "C" __global__ void __launch_bounds__(CLEAR_THREADS)
+    vgpu_clear_kernel(uint8_t *dst, unsigned long long bytes) {
+  /* head: bytes up to the first 16-byte boundary; tail: bytes after the last one */
+  unsigned long long mis = (16 - ((unsigned long long)dst & 15)) & 15;
+  if (mis > bytes) mis = bytes;
+  unsigned long long body = (bytes - mis) & ~15ull;
+  unsigned long long tail = bytes - mis - body;
+  if (blockIdx.x == 0) {
+    if (threadIdx.x < mis) dst[threadIdx.x] = 0;
+    if (threadIdx.x < tail) dst[mis + body + threadIdx.x] = 0;
+  }
+  uint4 *v = reinterpret_cast<uint4 *>(dst + mis);
+  const unsigned long long nvec = body >> 4;
+  const uint4 z = make_uint4(0, 0, 0, 0);
+  const unsigned long long tile = (unsigned long long)CLEAR_THREADS * CLEAR_UNROLL;
+  for (unsigned long long base = (unsigned long long)blockIdx.x * tile; base < nvec;
+       base += (unsigned long long)gridDim.x * tile) {
+#pragma unroll
+    for (int u = 0; u < CLEAR_UNROLL; u++) {
+      unsigned long long i = base + (unsigned long long)u * CLEAR_THREADS + threadIdx.x;
+      if (i < nvec) __stcs(&v[i], z); /* st.global.cs.v4: streaming, evict-first */
+    }
+  }
+}
+
+/* ======================================================================= spill copy (TMA)
+ * N bytes moved: algorithmic traffic = 2N (N read + N written).
+ * One elected thread per CTA drives a SPILL_STAGES-deep ring of SPILL_CHUNK-byte shared-memory
+ * buffers: bulk load chunk i+STAGES-1 while chunk i is being stored.  No generic-proxy access to
+ * the staging buffers ever happens, so no proxy fence is needed between the load's mbarrier
+ * completion and the bulk store that reads the same buffer.
+ * Precondition: dst and src are congruent mod 16 (the host wrapper checks). */
+#define SPILL_CHUNK VGPU_SPILL_CHUNK
+#define SPILL_STAGES VGPU_SPILL_STAGES
+#define SPILL_THREADS 32
+extern "C" __global__ void __launch_bounds__(SPILL_THREADS)
+    vgpu_spill_copy_kernel(uint8_t *dst, const uint8_t *src, unsigned long long bytes) {
+  extern __shared__ __align__(128) uint8_t stage_mem[];
+  __shared__ __align__(8) uint64_t full[SPILL_STAGES];
+
+  unsigned long long mis = (16 - ((unsigned long long)dst & 15)) & 15;
+  if (mis > bytes) mis = bytes;
+  unsigned long long body = (bytes - mis) & ~15ull;
+  unsigned long long tail = bytes - mis - body;
+  if (blockIdx.x == 0) { /* ragged ends, at most 15 + 15 bytes */
+    if (threadIdx.x < mis) dst[threadIdx.x] = src[threadIdx.x];
+    if (threadIdx.x < tail) dst[mis + body + threadIdx.x] = src[mis + body + threadIdx.x];
+  }
+  if (threadIdx.x != 0) return;
+
+  const uint8_t *s = src + mis;
+  uint8_t *d = dst + mis;
+  const unsigned long long nchunks = (body + SPILL_CHUNK - 1) / SPILL_CHUNK;
+  /* chunks owned by this CTA: blockIdx.x, blockIdx.x + gridDim.x, ... */
+  if (blockIdx.x >= nchunks) return;
+  const unsigned long long mine = (nchunks - 1 - blockIdx.x) / gridDim.x + 1;
+
+  for (int i = 0; i < SPILL_STAGES; i++) mbar_init(&full[i], 1);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+
+  auto chunk_off = [&](unsigned long long k) { return (blockIdx.x + k * gridDim.x) * (unsigned long long)SPILL_CHUNK; };
+  auto chunk_len = [&](unsigned long long k) -> uint32_t {
+    unsigned long long off = chunk_off(k);
+    unsigned long long rem = body - off;
+    return (uint32_t)(rem < SPILL_CHUNK ? rem : SPILL_CHUNK);
+  };
+  auto issue_load = [&](unsigned long long k) {
+    int st = (int)(k % SPILL_STAGES);
+    uint32_t len = chunk_len(k);
+    mbar_expect_tx(&full[st], len);
+    bulk_g2s(stage_mem + (size_t)st * SPILL_CHUNK, s + chunk_off(k), len, &full[st]);
+  };
+
+  /* prologue: STAGES-1 loads in flight */
+  unsigned long long issued = 0;
+  for (; issued < mine && issued < SPILL_STAGES - 1; issued++) issue_load(issued);
+
+  for (unsigned long long k = 0; k < mine; k++) {
+    int st = (int)(k % SPILL_STAGES);
+    uint32_t parity = (uint32_t)((k / SPILL_STAGES) & 1);
+    mbar_wait(&full[st], parity);
+    bulk_s2g(d + chunk_off(k), stage_mem + (size_t)st * SPILL_CHUNK, chunk_len(k));
+    bulk_commit();
+    if (issued < mine) {
+      /* the buffer to refill is the one chunk k-1 was stored from; allow only the store just
+       * committed to still be reading shared memory */
+      bulk_wait_read<1>();
+      issue_load(issued);
+      issued++;
+    }
+  }
+  bulk_wait_all();
+}
+
+/* fallback when src and dst disagree mod 16: plain grid-stride copy, widest common word */
+extern "C" __global__ void __launch_bounds__(256)
+    vgpu_copy_generic_kernel(uint8_t *dst, const uint8_t *src, unsigned long long bytes) {
+  unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  if ((((unsigned long long)dst | (unsigned long long)src) & 3) == 0) {
+    unsigned long long n4 = bytes >> 2;
+    for (unsigned long long k = i; k < n4; k += stride)
+      reinterpret_cast<uint32_t *>(dst)[k] = reinterpret_cast<const uint32_t *>(src)[k];
+    for (unsigned long long k = (n4 << 2) + i; k < bytes; k += stride) dst[k] = src[k];
+  } else {
+    for (unsigned long long k = i; k < bytes; k += stride) dst[k] = src[k];
+  }
+}
+
+/* ======================================================================= block reductions */
+DEVINL unsigned long long warp_sum_u64(unsigned long long v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  return v;
+}
+DEVINL unsigned int warp_min_u32(unsigned int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = min(v, __shfl_down_sync(0xffffffffu, v, o));
+  return v;
+}
+/* all threads of a 1024-thread CTA call; result valid in every thread */
+DEVINL unsigned long long block_sum_u64(unsigned long long v, unsigned long long *scratch) {
+  v = warp_sum_u64(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
+  __syncthreads();
+  unsigned long long r = 0;
+  if (threadIdx.x < 32) {
+    r = (threadIdx.x < (blockDim.x >> 5)) ? scratch[threadIdx.x] : 0;
+    r = warp_sum_u64(r);
+    if (threadIdx.x == 0) scratch[32] = r;
+  }
+  __syncthreads();
+  return scratch[32];
+}
+DEVINL unsigned int block_min_u32(unsigned int v, unsigned int *scratch) {
+  v = warp_min_u32(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    unsigned int r = (threadIdx.x < (blockDim.x >> 5)) ? scratch[threadIdx.x] : 0xffffffffu;
+    r = warp_min_u32(r);
+    if (threadIdx.x == 0) scratch[32] = r;
+  }
+  __syncthreads();
+  return scratch[32];
+}
+
+/* ======================================================================= memory quota
+ * One CTA of 1024 threads: thread i owns compute record i, graphics record i and ledger
+ * record i (each list is capped at 1024 by the contract).  The request block lives in pinned
+ * host memory; every record is fetched with one 128-bit load. */
+
+/* membership ladder shared by memory and utilisation folds (cuda_hook.c:740-803) */
+enum { SEL_PRIMARY_OPEN = 0, SEL_OPEN_ONLY = 1, SEL_HOST = 2, SEL_BAD = 3 };
+DEVINL int mode_select(uint32_t mode, int *open_mode) {
+  *open_mode = (mode & VGPU_MODE_OPEN_KERNEL) == VGPU_MODE_OPEN_KERNEL;
+  if ((mode & VGPU_MODE_CLIENT) == VGPU_MODE_CLIENT) return SEL_PRIMARY_OPEN;
+  if ((mode & VGPU_MODE_CGROUPV2) == VGPU_MODE_CGROUPV2) return SEL_PRIMARY_OPEN;
+  if ((mode & VGPU_MODE_CGROUPV1) == VGPU_MODE_CGROUPV1) return SEL_PRIMARY_OPEN;
+  if (*open_mode) return SEL_OPEN_ONLY;
+  if (mode == VGPU_MODE_HOST) return SEL_HOST;
+  return SEL_BAD;
+}
+
+/* Sum of `bytes` over the records the reference's sequential latch would accept.
+ * The latch (matchX / matchOpenKernel) makes the *first* record that passes either test pick
+ * the regime for the whole list: primary regime sums every primary pid, open-kernel regime
+ * sums every local pid.  `live` masks records removed by the graphics/compute dedup. */
+DEVINL unsigned long long fold_list(int sel, int open_mode, bool live, uint32_t flags,
+                                    unsigned long long bytes, unsigned long long *s64,
+                                    unsigned int *s32) {
+  const bool prim = live && (flags & VGPU_FLAG_PRIMARY);
+  const bool loc = live && open_mode && (flags & VGPU_FLAG_LOCAL);
+  bool take;
+  if (sel == SEL_HOST) {
+    take = live;
+  } else if (sel == SEL_OPEN_ONLY) {
+    take = live && (flags & VGPU_FLAG_LOCAL);
+  } else if (sel == SEL_PRIMARY_OPEN) {
+    unsigned int first = block_min_u32((prim || loc) ? threadIdx.x : 0xffffffffu, s32);
+    /* the regime is primary iff the first matching record is a primary one */
+    __shared__ int regime_primary;
+    if (threadIdx.x == first) regime_primary = prim ? 1 : 0;
+    __syncthreads();
+    take = (first != 0xffffffffu) && (regime_primary ? prim : loc);
+  } else {
+    take = false;
+  }
+  return block_sum_u64(take ? bytes : 0ull, s64);
+}
+
+extern "C" __global__ void __launch_bounds__(1024)
+    vgpu_quota_kernel(const vgpu_quota_req_t *__restrict__ req, vgpu_quota_res_t *res) {
+  __shared__ unsigned long long s64[33];
+  __shared__ unsigned int s32[33];
+  __shared__ uint32_t cpid[VGPU_MAX_PIDS];
+
+  const uint32_t t = threadIdx.x;
+  const uint32_t nc = min(req->n_compute, (uint32_t)VGPU_MAX_PIDS);
+  const uint32_t ng = min(req->n_graphics, (uint32_t)VGPU_MAX_PIDS);
+  const uint32_t nv = min(req->n_vmem, (uint32_t)VGPU_MAX_PIDS);
+  int open_mode;
+  const int sel = mode_select(req->mode, &open_mode);
+
+  /* compute list */
+  uint4 c = make_uint4(0, 0, 0, 0);
+  if (t < nc) c = *reinterpret_cast<const uint4 *>(&req->compute[t]);
+  cpid[t] = (t < nc) ? c.x : 0xffffffffu;
+  unsigned long long cbytes = ((unsigned long long)c.w << 32) | c.z;
+  uint32_t cf = (t < nc) ? req->cflags[t] : 0;
+  __syncthreads();
+  unsigned long long used = fold_list(sel, open_mode, t < nc, cf, cbytes, s64, s32);
+
+  /* graphics list minus pids already present in the compute list (cuda_hook.c:868-887) */
+  uint4 g = make_uint4(0, 0, 0, 0);
+  if (t < ng) g = *reinterpret_cast<const uint4 *>(&req->graphics[t]);
+  bool glive = t < ng;
+  if (glive) {
+    for (uint32_t j = 0; j < nc; j++)
+      if (cpid[j] == g.x) { glive = false; break; }
+  }
+  unsigned long long gbytes = ((unsigned long long)g.w << 32) | g.z;
+  uint32_t gf = (t < ng) ? req->gflags[t] : 0;
+  used += fold_list(sel, open_mode, glive, gf, gbytes, s64, s32);
+
+  /* UVA ledger sum (loader.c:1909-1922) */
+  unsigned long long v = 0;
+  if (t < nv) {
+    uint4 r = *reinterpret_cast<const uint4 *>(&req->vmem[t]);
+    v = ((unsigned long long)r.w << 32) | r.z;
+  }
+  unsigned long long vmem = block_sum_u64(v, s64);
+
+  if (t == 0) {
+    /* the library's own device footprint is not part of the tenant's usage */
+    unsigned long long self = req->self_bytes;
+    used = used >= self ? used - self : 0;
+
+    const unsigned long long total = req->total_memory;
+    unsigned long long o_total = total, o_used = 0, o_free = 0;
+    uint32_t path = VGPU_PATH_GPU;
+    if (req->kind == VGPU_Q_ALLOC) {
+      /* cuda_hook.c:105-115, size_t arithmetic wraps exactly like the host's */
+      if ((used + vmem + req->request) > total) path = VGPU_PATH_OOM;
+      else if (req->allow_uva && req->memory_oversold && (used + req->request) > req->real_memory)
+        path = VGPU_PATH_UVA;
+    } else if (req->kind == VGPU_Q_NVML_INFO) {
+      /* nvml_hook.c:58-63 */
+      unsigned long long tu = used + vmem;
+      o_used = tu >= total ? total : tu;
+      o_free = o_total - o_used;
+    } else {
+      /* cuda_hook.c:1741-1787 */
+      unsigned long long actual = total;
+      if (!req->memory_oversold && req->real_ok && req->real_total > 0 && req->real_total < total)
+        actual = req->real_total;
+      o_total = actual;
+      o_free = (used + vmem) >= actual ? 0 : (actual - used - vmem);
+      o_used = o_total - o_free;
+    }
+    res->used = used;
+    res->vmem = vmem;
+    res->total = o_total;
+    res->out_used = o_used;
+    res->out_free = o_free;
+    res->path = path;
+    __threadfence_system();
+    *reinterpret_cast<volatile uint32_t *>(&res->seq_done) = req->seq;
+    __threadfence_system();
+  }
+}
+
+/* ======================================================================= UVA slab
+ * Open-addressing table of {dptr, bytes} in HBM.  One warp: lane l inspects slot
+ * (h + step*32 + l) so each probe step is one coalesced 512-byte read; __ballot_sync is the
+ * free-list / match scan.  Callers serialise (host mutex), so plain stores suffice. */
+DEVINL uint32_t slab_hash(unsigned long long p) {
+  return (uint32_t)((p >> 9) * 0x9E3779B97F4A7C15ull >> 40) & (VGPU_SLAB_SLOTS - 1);
+}
+
+extern "C" __global__ void __launch_bounds__(32)
+    vgpu_slab_insert_kernel(vgpu_slab_slot_t *slab, unsigned long long dptr, unsigned long long bytes,
+                            vgpu_slab_res_t *res, uint32_t seq) {
+  const uint32_t lane = threadIdx.x;
+  uint32_t h = slab_hash(dptr), found = 0xffffffffu;
+  for (uint32_t step = 0; step < VGPU_SLAB_SLOTS / 32; step++) {
+    uint32_t idx = (h + step * 32 + lane) & (VGPU_SLAB_SLOTS - 1);
+    unsigned long long k = slab[idx].dptr;
+    uint32_t freem = __ballot_sync(0xffffffffu, k <= 1ull);
+    if (freem) {
+      uint32_t win = __ffs(freem) - 1;
+      found = (h + step * 32 + win) & (VGPU_SLAB_SLOTS - 1);
+      if (lane == win) {
+        slab[idx].bytes = bytes;
+        slab[idx].dptr = dptr;
+      }
+      break;
+    }
+  }
+  if (lane == 0) {
+    res->bytes = bytes;
+    res->slot = found;
+    __threadfence_system();
+    *reinterpret_cast<volatile uint32_t *>(&res->seq_done) = seq;
+    __threadfence_system();
+  }
+}
+
+extern "C" __global__ void __launch_bounds__(32)
+    vgpu_slab_remove_kernel(vgpu_slab_slot_t *slab, unsigned long long dptr, vgpu_slab_res_t *res,
+                            uint32_t seq) {
+  const uint32_t lane = threadIdx.x;
+  uint32_t h = slab_hash(dptr), found = 0xffffffffu;
+  unsigned long long bytes = 0;
+  for (uint32_t step = 0; step < VGPU_SLAB_SLOTS / 32; step++) {
+    uint32_t idx = (h + step * 32 + lane) & (VGPU_SLAB_SLOTS - 1);
+    unsigned long long k = slab[idx].dptr;
+    uint32_t hit = __ballot_sync(0xffffffffu, k == dptr);
+    uint32_t empty = __ballot_sync(0xffffffffu, k == 0ull);
+    /* a hit only counts if no never-used slot precedes it in probe order */
+    uint32_t before_empty = empty ? ((1u << (__ffs(empty) - 1)) - 1u) : 0xffffffffu;
+    hit &= before_empty;
+    if (hit) {
+      uint32_t win = __ffs(hit) - 1;
+      found = (h + step * 32 + win) & (VGPU_SLAB_SLOTS - 1);
+      bytes = __shfl_sync(0xffffffffu, slab[idx].bytes, win);
+      if (lane == win) {
+        slab[idx].dptr = 1ull; /* tombstone keeps later probe chains intact */
+        slab[idx].bytes = 0;
+      }
+      break;
+    }
+    if (empty) break;
+  }
+  if (lane == 0) {
+    res->bytes = bytes;
+    res->slot = found;
+    __threadfence_system();
+    *reinterpret_cast<volatile uint32_t *>(&res->seq_done) = seq;
+    __threadfence_system();
+  }
+}
+
+/* ======================================================================= controller
+ * Exactly the reference's delta / change_token / watcher body (cuda_hook.c:292-367, :413-466),
+ * with the bucket expressed as granted - consumed so that the host hook (sole writer of
+ * `consumed`) and the device (sole writer of `granted`) never need a cross-PCIe atomic. */
+DEVINL long long ctl_delta(const vgpu_lim_dev_t *D, int up_limit, int user_current, long long share) {
+  long long sm = D->sm_num, thr = D->max_thread_per_sm;
+  int diff = abs(up_limit - user_current);
+  if (diff < 5) diff = 5;
+  long long inc = sm * sm * thr * (long long)diff / 2560;
+  if (__fdiv_rn((float)diff, (float)up_limit) > 0.5f) inc = inc * diff * 2 / (up_limit + 1);
+  if (inc < 0 || inc > 2147483647ll) inc = 10;
+  if (user_current <= up_limit) share = (share + inc) > D->total_cores ? D->total_cores : (share + inc);
+  else share = (share - inc) < 0 ? 0 : (share - inc);
+  return share;
+}
+
+DEVINL void ctl_step(vgpu_lim_dev_t *D, vgpu_lim_host_t *H, int user_current, int sys_current,
+                     int valid_now, int sys_process_num) {
+  if (valid_now) D->valid = 1; /* sticky, like top_result->valid */
+  D->last_user_current = user_current;
+  D->last_sys_current = sys_current;
+  long long consumed = *reinterpret_cast<volatile long long *>(&H->consumed);
+  long long bucket = D->granted - consumed;
+  bool touched = false;
+  if (D->core_limit && D->valid) {
+    D->sys_free = 100 - sys_current;
+    if (D->hard_limit) {
+      if (sys_process_num == 1 && user_current < D->up_limit / 10) {
+        bucket = ctl_delta(D, D->hard_core, user_current, D->share); /* jitter guard: direct write */
+        touched = true;
+      } else {
+        D->share = ctl_delta(D, D->hard_core, user_current, D->share);
+      }
+    } else {
+      if (D->pre_sys_process_num != sys_process_num) {
+        if (D->pre_sys_process_num < sys_process_num) {
+          D->share = (long long)D->max_thread_per_sm;
+          D->up_limit = D->hard_core;
+          D->ctr_i = 0;
+          D->avg_sys_free = 0;
+        }
+        D->pre_sys_process_num = sys_process_num;
+      }
+      if (sys_process_num == 1) {
+        D->up_limit = D->soft_core;
+        D->share = ctl_delta(D, D->up_limit, user_current, D->share);
+      } else {
+        D->ctr_i++;
+        D->avg_sys_free += D->sys_free;
+        if (D->ctr_i % 30 == 0) {
+          if (D->avg_sys_free * 2 / 30 > 5) {
+            int cand = D->up_limit + D->hard_core / 10;
+            D->up_limit = cand > D->soft_core ? D->soft_core : cand;
+          }
+          D->ctr_i = 0;
+        }
+        D->avg_sys_free = (D->ctr_i % 15 == 0) ? 0 : D->avg_sys_free;
+        D->share = ctl_delta(D, D->up_limit, user_current, D->share);
+      }
+    }
+    if (!touched) {
+      long long after = bucket + D->share; /* change_token */
+      if (after > D->total_cores) after = D->total_cores;
+      else if (after < 0) after = 0;
+      bucket = after;
+    }
+    D->granted = bucket + consumed;
+  }
+  D->bucket_last = bucket;
+  D->steps++;
+  /* publish to the host-visible block */
+  H->granted_mirror = D->granted;
+  H->bucket_mirror = bucket;
+  H->share_mirror = D->share;
+  H->up_limit_mirror = D->up_limit;
+  H->user_current = user_current;
+  H->sys_current = sys_current;
+  H->sm_active_pct = D->last_sm_active_pct;
+  H->queue_busy_pct = D->last_queue_busy_pct;
+  __threadfence_system();
+  H->steps = D->steps;
+}
+
+extern "C" __global__ void vgpu_controller_kernel(vgpu_lim_dev_t *D, vgpu_lim_host_t *H,
+                                                  vgpu_ctrl_in_t in) {
+  if (threadIdx.x == 0 && blockIdx.x == 0)
+    ctl_step(D, H, in.user_current, in.sys_current, in.valid, in.sys_process_num);
+}
+
+/* ======================================================================= sampler
+ * grid = one CTA per SM (as scheduled), 4 warps = one per SM sub-partition.
+ *
+ *  (a) SM probe: each warp times a fixed issue-bound instruction burst with %clock64.  Its
+ *      calibrated idle cost over the measured cost is the share of issue slots it got; the
+ *      complement is what co-resident tenant warps took on that %smid sub-partition.  SMs on
+ *      which no sampler CTA could be placed during the window count as fully busy.
+ *  (b) queue-busy: warp 0 of CTA 0 reads the per-stream launch/done sequence numbers the launch
+ *      hook maintains and asks, per stream, "is the oldest unfinished launch admitted by the
+ *      bucket?" - i.e. is tenant work executing right now.  Its time average is the quantity
+ *      NVML calls SM utilisation (fraction of time a kernel was resident).
+ *
+ * Everything is accumulated in registers, warp-reduced, and added to the HBM block once per
+ * warp per launch.  The last CTA to retire bumps the tick; every `period_ticks` ticks it turns
+ * the accumulators into user_current and runs ctl_step (refilling the token bucket). */
+#define SAMPLER_THREADS 128
+DEVINL uint32_t probe_burst() {
+  uint32_t a0 = threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, b0 = a0 ^ 5, b1 = a0 ^ 6,
+           b2 = a0 ^ 7, b3 = a0 ^ 9;
+  const uint32_t m = 2654435761u, c = 40503u;
+  long long t0 = clock64();
+#pragma unroll 1
+  for (int k = 0; k < 48; k++) {
+    asm volatile(
+        "mad.lo.u32 %0, %0, %8, %9;\n"
+        "xor.b32 %4, %4, %9;\n"
+        "mad.lo.u32 %1, %1, %8, %9;\n"
+        "add.u32 %5, %5, %8;\n"
+        "mad.lo.u32 %2, %2, %8, %9;\n"
+        "xor.b32 %6, %6, %8;\n"
+        "mad.lo.u32 %3, %3, %8, %9;\n"
+        "add.u32 %7, %7, %9;\n"
+        : "+r"(a0), "+r"(a1), "+r"(a2), "+r"(a3), "+r"(b0), "+r"(b1), "+r"(b2), "+r"(b3)
+        : "r"(m), "r"(c));
+  }
+  long long t1 = clock64();
+  uint32_t sink = a0 ^ a1 ^ a2 ^ a3 ^ b0 ^ b1 ^ b2 ^ b3;
+  if (sink == 0x12345u) asm volatile("trap;"); /* keeps the burst alive; never true in practice */
+  return (uint32_t)(t1 - t0);
+}
+
+extern "C" __global__ void __launch_bounds__(SAMPLER_THREADS)
+    vgpu_sampler_kernel(vgpu_lim_dev_t *D, vgpu_lim_host_t *H, uint32_t window_us,
+                        uint32_t interval_us, uint32_t period_ticks, uint32_t epoch) {
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t sm = smid();
+  const uint32_t pslot = (sm < VGPU_MAX_SMS ? sm : VGPU_MAX_SMS - 1) * 4 + warp;
+  const uint64_t t_start = globaltimer_ns();
+  const uint64_t window_ns = (uint64_t)window_us * 1000ull;
+  const bool queue_warp = (blockIdx.x == 0 && warp == 0);
+
+  uint32_t idle = D->probe_idle[pslot];
+  unsigned long long probe_sum = 0, idle_sum = 0, nprobe = 0, busy = 0, total = 0;
+  volatile uint32_t *quit_dev = &D->quit_dev;
+
+  for (uint32_t it = 0; it < 100000u; it++) {
+    /* (a) SM probe */
+    uint32_t cyc = probe_burst();
+    cyc = __shfl_sync(0xffffffffu, cyc, 0);
+    if (cyc < idle) idle = cyc;
+    probe_sum += cyc;
+    idle_sum += idle;
+    nprobe++;
+
+    /* (b) queue-busy */
+    if (queue_warp) {
+      bool running = false;
+      long long granted = *reinterpret_cast<volatile long long *>(&D->granted);
+#pragma unroll
+      for (uint32_t s = lane; s < VGPU_STREAM_SLOTS; s += 32) {
+        unsigned long long l = H->launched[s];
+        unsigned long long d = H->done[s];
+        if (l > d) {
+          long long tk = H->ticket[s][(d + 1) & (VGPU_TICKET_RING - 1)];
+          if (granted - tk >= 0) running = true;
+        }
+      }
+      bool any = __any_sync(0xffffffffu, running);
+      total++;
+      busy += any ? 1 : 0;
+      if (lane == 0 && H->quit) *quit_dev = 1;
+    }
+    if (*quit_dev) break;
+    if (globaltimer_ns() - t_start >= window_ns) break;
+    __nanosleep(interval_us * 1000u);
+  }
+
+  if (lane == 0) {
+    atomicAdd(&D->probe_cycles, probe_sum);
+    atomicAdd(&D->probe_idle_cycles, idle_sum);
+    atomicAdd(&D->probe_count, nprobe);
+    atomicMin(&D->probe_idle[pslot], idle); /* host initialises the table to 0xffffffff */
+    if (warp == 0) D->sm_epoch[sm < VGPU_MAX_SMS ? sm : VGPU_MAX_SMS - 1] = epoch;
+    if (queue_warp) {
+      atomicAdd(&D->busy_samples, busy);
+      atomicAdd(&D->total_samples, total);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  __threadfence();
+  if (atomicAdd(&D->cta_done, 1u) != gridDim.x - 1) return;
+
+  /* ---- last CTA of this launch ---- */
+  D->cta_done = 0;
+  *quit_dev = 0;
+  /* coverage: SMs that hosted a sampler CTA at least once this period */
+  uint32_t tick = ++D->period_tick;
+  if (tick < period_ticks) return;
+  D->period_tick = 0;
+  __threadfence();
+
+  unsigned long long pc = D->probe_cycles, pi = D->probe_idle_cycles;
+  unsigned long long bs = D->busy_samples, ts = D->total_samples;
+  int nsm = D->sm_num > 0 ? D->sm_num : (int)gridDim.x;
+  int covered = 0;
+  for (int i = 0; i < nsm && i < (int)VGPU_MAX_SMS; i++) covered += ((epoch - D->sm_epoch[i]) < period_ticks) ? 1 : 0;
+  int active = pc ? (int)(100 - (pi * 100ull) / pc) : 0;
+  if (active < 0) active = 0;
+  if (covered < nsm) active = (active * covered + 100 * (nsm - covered)) / nsm;
+  int qbusy = ts ? (int)((bs * 100ull) / ts) : 0;
+  D->last_sm_active_pct = active;
+  D->last_queue_busy_pct = qbusy;
+  D->probe_cycles = D->probe_idle_cycles = D->probe_count = 0;
+  D->busy_samples = D->total_samples = 0;
+
+  int user;
+  uint32_t srcsel = H->util_source;
+  if (srcsel == 1) user = active;
+  else if (srcsel == 2) user = active > qbusy ? active : qbusy;
+  else user = qbusy;
+  int ov = H->ext_user_override;
+  if (ov >= 0) user = ov;
+  int others = H->ext_sys_current;
+  int sys = user + (others > 0 ? others : 0);
+  int nproc = H->ext_sys_process_num;
+  if (nproc <= 0) nproc = 1;
+  ctl_step(D, H, user, sys, (ts > 0 || ov >= 0) ? 1 : 0, nproc);
+}
+
+/* ======================================================================= gate
+ * Device-side admission for contexts without 64-bit stream mem-ops: one thread spins (with
+ * nanosleep back-off) until the bucket has granted this launch's ticket.  Fails open after
+ * `timeout_ms` so a dead refill path can never wedge the tenant's stream. */
+extern "C" __global__ void vgpu_gate_kernel(const long long *granted, long long ticket,
+                                            uint32_t timeout_ms) {
+  const uint64_t t0 = globaltimer_ns();
+  while (*reinterpret_cast<const volatile long long *>(granted) - ticket < 0) {
+    if (globaltimer_ns() - t0 > (uint64_t)timeout_ms * 1000000ull) break;
+    __nanosleep(2000);
+  }
+}

@@ -1,0 +1,313 @@
+/*
+ * limiter.c - compute-share limiter: launch hooks, the host side of the token bucket and the
+ * tick thread that keeps the on-device sampler/controller running.
+ *
+ * Reference behaviour being replaced (library/src/cuda_hook.c):
+ *   rate_limiter :308-330   a launch proceeds iff the bucket is >= 0, then pays
+ *                           gridX*gridY*gridZ tokens; otherwise the CPU thread sleeps in 10 ms
+ *                           steps until the watcher refills the bucket.
+ *   utilization_watcher :380-471 + get_used_gpu_utilization :1044-1159   one CPU thread per <=4
+ *                           devices polls NVML every ~80 ms and recomputes the refill share.
+ *
+ * B200 design:
+ *   bucket   = granted - consumed.  `consumed` is host-owned (pinned page, one fetch_add per
+ *              launch); `granted` is device-owned (HBM word + host-visible mirror), written only
+ *              by the controller that runs at the tail of the sampler kernel.  The hook reads
+ *              the mirror with a single 8-byte load.
+ *   gate     = when the bucket is empty the launch is NOT delayed on the CPU: a
+ *              cuStreamWaitValue64(granted >= ticket) is enqueued in front of it, so the stream
+ *              itself waits on the HBM word and the host thread keeps going.  (Contexts without
+ *              64-bit stream mem-ops use vgpu_gate_kernel, a one-thread device spin.)
+ *   markers  = after each launch a cuStreamWriteValue64 bumps the stream's `done` sequence;
+ *              the sampler compares it with `launched` to measure how long tenant work is
+ *              actually resident (the NVML notion of utilisation) without NVML.
+ *   tick     = one light thread per process launches vgpu_sampler_kernel every 10 ms
+ *              (TIME_TICK) on a private non-blocking stream; every 8th launch the kernel's last
+ *              CTA runs the controller (the reference's ~80 ms control period).
+ */
+#include "vgpu_internal.h"
+
+#include <errno.h>
+#include <sched.h>
+#include <time.h>
+
+extern vgpu_dev_rt *vgpu_rt_get(int host_index, CUdevice dev);
+
+/* ------------------------------------------------------------------ stream slots */
+typedef struct {
+  volatile uintptr_t key; /* CUstream | ptsz bit; 0 = empty */
+} slot_key_t;
+static slot_key_t g_slots[VGPU_MAX_DEVICES][VGPU_STREAM_SLOTS];
+
+static inline uint32_t slot_of(int host_index, CUstream s, int ptsz) {
+  uintptr_t key = ((uintptr_t)s << 1) | (uintptr_t)(ptsz & 1) | ((uintptr_t)1 << 63);
+  uint32_t h = (uint32_t)((key >> 4) * 0x9E3779B97F4A7C15ull >> 58); /* 6 bits */
+  slot_key_t *tab = g_slots[host_index];
+  for (uint32_t i = 0; i < VGPU_STREAM_SLOTS - 1; i++) {
+    uint32_t idx = (h + i) % (VGPU_STREAM_SLOTS - 1);
+    uintptr_t k = tab[idx].key;
+    if (k == key) return idx;
+    if (k == 0 && __sync_bool_compare_and_swap(&tab[idx].key, 0, key)) return idx;
+    if (tab[idx].key == key) return idx;
+  }
+  return VGPU_STREAM_SLOTS - 1; /* overflow slot, shared */
+}
+
+/* ------------------------------------------------------------------ tick thread */
+static pthread_once_t g_tick_once = PTHREAD_ONCE_INIT;
+static volatile pid_t g_tick_pid;
+static volatile int g_tick_devices[VGPU_MAX_DEVICES]; /* host indexes with a live runtime + core limit */
+static uint32_t g_window_us = 8000, g_interval_us = 100, g_period_ticks = 8, g_tick_ms = 10;
+static volatile int g_capture_depth;
+
+static uint32_t env_u32(const char *name, uint32_t dflt) {
+  const char *s = getenv(name);
+  return (s && *s) ? (uint32_t)strtoul(s, NULL, 10) : dflt;
+}
+
+static void refresh_process_count(vgpu_dev_rt *rt) {
+  /* sys_process_num feeds the jitter guard and the balance policy (cuda_hook.c:424,:431-449);
+   * it changes on process start/exit, so one cheap list query per second is plenty */
+  nvmlDevice_t nv = vgpu_nvml_handle_of_host(rt->host_index);
+  if (!nv || !R.nvmlDeviceGetComputeRunningProcesses) return;
+  static vgpu_proc_t procs[VGPU_MAX_PIDS];
+  unsigned int n = VGPU_MAX_PIDS;
+  if (R.nvmlDeviceGetComputeRunningProcesses(nv, &n, procs) == NVML_SUCCESS)
+    rt->lim_h->ext_sys_process_num = n ? (int)n : 1;
+  if (!G_cfg->devices[rt->host_index].hard_limit && R.nvmlDeviceGetUtilizationRates) {
+    /* balance policy needs the whole GPU's load; other tenants are invisible from inside
+     * this context, so take the device-level figure and let the kernel subtract ours */
+    vnv_utilization_t u;
+    if (R.nvmlDeviceGetUtilizationRates(nv, &u) == NVML_SUCCESS) {
+      int others = (int)u.gpu - rt->lim_h->user_current;
+      rt->lim_h->ext_sys_current = others > 0 ? others : 0;
+    }
+  }
+}
+
+static void *tick_main(void *arg) {
+  (void)arg;
+  struct timespec nap = {0, (long)g_tick_ms * 1000000L};
+  uint32_t epoch = 0;
+  int fails = 0;
+  for (;;) {
+    nanosleep(&nap, NULL);
+    if (g_tick_pid != getpid()) return NULL;
+    epoch++;
+    for (int h = 0; h < VGPU_MAX_DEVICES; h++) {
+      if (!g_tick_devices[h]) continue;
+      vgpu_dev_rt *rt = vgpu_rt_peek(h);
+      if (!rt) continue;
+      if (R.cuCtxPushCurrent_v2(rt->ctx) != CUDA_SUCCESS) continue;
+      CUresult q = R.cuStreamQuery(rt->s_stream);
+      if (q == CUDA_SUCCESS) {
+        rt->lim_h->quit = 0;
+        if ((epoch % 100) == 1) refresh_process_count(rt);
+        uint32_t ep = epoch;
+        void *params[] = {&rt->lim_d, &rt->lim_h_d, &g_window_us, &g_interval_us, &g_period_ticks, &ep};
+        unsigned grid = rt->sm_num > 0 ? (unsigned)rt->sm_num : 148u;
+        CUresult r = R.cuLaunchKernel(rt->k_sampler, grid, 1, 1, 128, 1, 1, 0, rt->s_stream, params, NULL);
+        if (r == CUDA_SUCCESS) {
+          fails = 0;
+          vgpu_metric_add(h, VM_SAMPLER_LAUNCHES, 1);
+        } else if (++fails == 100) {
+          /* fail open: never leave tenant streams parked on a bucket nobody refills */
+          VLOG(VL_ERROR, "sampler launch keeps failing (%d: %s); opening the gate", r, vgpu_cu_err(r));
+          long long open_val = (long long)1 << 60;
+          R.cuMemcpyHtoD_v2(rt->lim_d, &open_val, sizeof open_val);
+          rt->lim_h->granted_mirror = open_val;
+        }
+      }
+      CUcontext dummy;
+      R.cuCtxPopCurrent_v2(&dummy);
+    }
+  }
+}
+
+static void tick_start(void) {
+  g_window_us = env_u32("VGPU_B200_SAMPLER_WINDOW_US", 8000);
+  g_interval_us = env_u32("VGPU_B200_SAMPLER_INTERVAL_US", 100);
+  g_period_ticks = env_u32("VGPU_B200_PERIOD_TICKS", 8);
+  g_tick_ms = env_u32("VGPU_B200_TICK_MS", 10);
+  if (!g_period_ticks) g_period_ticks = 1;
+  if (!g_tick_ms) g_tick_ms = 1;
+  g_tick_pid = getpid();
+  pthread_t tid;
+  if (pthread_create(&tid, NULL, tick_main, NULL) == 0) {
+    pthread_setname_np(tid, "vgpu_b200_tick");
+    pthread_detach(tid);
+  }
+}
+
+void vgpu_limiter_start(void) {
+  /* reference: initialization() spawns watch_util_bt_N threads at the first successful cuInit
+   * (cuda_hook.c:566-577).  Here the thread is created lazily by the first limited launch,
+   * because the sampler needs the tenant's context; this entry point only re-arms after fork
+   * (the reference does not - SURVEY.md Appendix B.13). */
+  if (g_tick_pid && g_tick_pid != getpid()) {
+    memset((void *)g_tick_devices, 0, sizeof g_tick_devices);
+    memset(g_slots, 0, sizeof g_slots);
+    g_tick_once = (pthread_once_t)PTHREAD_ONCE_INIT;
+    g_tick_pid = 0;
+  }
+}
+
+void vgpu_limiter_quiesce(vgpu_dev_rt *rt) {
+  if (rt && rt->lim_h && g_tick_devices[rt->host_index >= 0 ? rt->host_index : 0]) rt->lim_h->quit = 1;
+}
+
+/* ------------------------------------------------------------------ admission */
+typedef struct {
+  vgpu_dev_rt *rt;
+  uint32_t slot;
+  unsigned long long seq;
+  int ptsz;
+} admit_t;
+
+/* returns 0 when the launch should simply be forwarded */
+static inline int admit(admit_t *a, unsigned gx, unsigned gy, unsigned gz, CUstream s, int ptsz) {
+  CUdevice dev;
+  if (unlikely(R.cuCtxGetDevice(&dev) != CUDA_SUCCESS)) return -1;
+  int h = vgpu_host_index_of_cuda(dev);
+  if (h < 0 || !G_cfg->devices[h].core_limit) return 0;
+  vgpu_dev_rt *rt = vgpu_rt_get(h, dev);
+  if (unlikely(!rt)) return 0; /* bring-up failed: logged there; launches stay un-throttled */
+  if (unlikely(!g_tick_devices[h])) {
+    g_tick_devices[h] = 1;
+    pthread_once(&g_tick_once, tick_start);
+  }
+  vgpu_lim_host_t *H = rt->lim_h;
+  /* the reference multiplies the three unsigned dims in 32 bits and passes the result as int */
+  long long cost = (long long)(int)(gx * gy * gz);
+  long long ticket = __sync_fetch_and_add(&H->consumed, cost);
+  a->rt = rt;
+  a->ptsz = ptsz;
+  a->slot = slot_of(h, s, ptsz);
+  int capturing = 0;
+  if (unlikely(g_capture_depth > 0) && R.cuStreamIsCapturing) R.cuStreamIsCapturing(s, &capturing);
+  if (capturing) { /* graph capture: tokens are paid at capture time, like the reference */
+    a->rt = NULL;
+    return 1;
+  }
+  /* bounded run-ahead: the ticket ring holds VGPU_TICKET_RING outstanding launches per stream */
+  unsigned long long seq = H->launched[a->slot] + 1;
+  while (unlikely(seq - H->done[a->slot] >= VGPU_TICKET_RING - 2)) sched_yield();
+  H->ticket[a->slot][seq & (VGPU_TICKET_RING - 1)] = ticket;
+  __sync_synchronize();
+  H->launched[a->slot] = seq;
+  a->seq = seq;
+  if (H->granted_mirror - ticket < 0) {
+    /* bucket empty: park the *stream* on the HBM word, not the CPU thread */
+    vgpu_metric_add(h, VM_RATE_GATED, 1);
+    if (likely(rt->memops64)) {
+      CUresult (*wait)(CUstream, CUdeviceptr, cuuint64_t, unsigned) =
+          (ptsz && R.cuStreamWaitValue64_v2_ptsz) ? R.cuStreamWaitValue64_v2_ptsz : R.cuStreamWaitValue64_v2;
+      wait(s, rt->lim_d + offsetof(vgpu_lim_dev_t, granted), (cuuint64_t)ticket, VCU_WAIT_GEQ);
+    } else {
+      CUdeviceptr gp = rt->lim_d + offsetof(vgpu_lim_dev_t, granted);
+      uint32_t timeout_ms = 2000;
+      void *params[] = {&gp, &ticket, &timeout_ms};
+      (ptsz && R.cuLaunchKernel_ptsz ? R.cuLaunchKernel_ptsz : R.cuLaunchKernel)(
+          rt->k_gate, 1, 1, 1, 1, 1, 1, 0, s, params, NULL);
+    }
+  } else {
+    vgpu_metric_add(h, VM_RATE_FAST, 1);
+  }
+  return 1;
+}
+
+static inline void mark_done(const admit_t *a, CUstream s) {
+  if (!a->rt) return;
+  vgpu_dev_rt *rt = a->rt;
+  CUdeviceptr addr = rt->lim_h_d + offsetof(vgpu_lim_host_t, done) + (CUdeviceptr)a->slot * sizeof(unsigned long long);
+  if (likely(rt->memops64)) {
+    CUresult (*wr)(CUstream, CUdeviceptr, cuuint64_t, unsigned) =
+        (a->ptsz && R.cuStreamWriteValue64_v2_ptsz) ? R.cuStreamWriteValue64_v2_ptsz : R.cuStreamWriteValue64_v2;
+    wr(s, addr, (cuuint64_t)a->seq, 0);
+  } else {
+    rt->lim_h->done[a->slot] = a->seq; /* no completion signal available: treat as instantaneous */
+  }
+}
+
+#define LIMITED_LAUNCH(gx, gy, gz, stream, ptsz, CALL)          \
+  do {                                                          \
+    admit_t a_ = {0};                                           \
+    int st_ = admit(&a_, (gx), (gy), (gz), (stream), (ptsz));   \
+    if (st_ < 0) return CUDA_ERROR_INVALID_CONTEXT;             \
+    CUresult r_ = (CALL);                                       \
+    if (st_ > 0) mark_done(&a_, (stream));                      \
+    return r_;                                                  \
+  } while (0)
+
+VGPU_EXPORT CUresult cuLaunchKernel(CUfunction f, unsigned gx, unsigned gy, unsigned gz, unsigned bx,
+                                    unsigned by, unsigned bz, unsigned smem, CUstream s, void **params,
+                                    void **extra) {
+  if (unlikely(!R.cuLaunchKernel)) return CUDA_ERROR_NOT_FOUND;
+  LIMITED_LAUNCH(gx, gy, gz, s, 0, R.cuLaunchKernel(f, gx, gy, gz, bx, by, bz, smem, s, params, extra));
+}
+
+VGPU_EXPORT CUresult cuLaunchKernel_ptsz(CUfunction f, unsigned gx, unsigned gy, unsigned gz, unsigned bx,
+                                         unsigned by, unsigned bz, unsigned smem, CUstream s,
+                                         void **params, void **extra) {
+  if (unlikely(!R.cuLaunchKernel_ptsz)) return CUDA_ERROR_NOT_FOUND;
+  LIMITED_LAUNCH(gx, gy, gz, s, 1, R.cuLaunchKernel_ptsz(f, gx, gy, gz, bx, by, bz, smem, s, params, extra));
+}
+
+VGPU_EXPORT CUresult cuLaunchKernelEx(const vcu_launch_config_t *c, CUfunction f, void **params, void **extra) {
+  if (unlikely(!R.cuLaunchKernelEx)) return CUDA_ERROR_NOT_FOUND;
+  LIMITED_LAUNCH(c->gridDimX, c->gridDimY, c->gridDimZ, c->hStream, 0, R.cuLaunchKernelEx(c, f, params, extra));
+}
+
+VGPU_EXPORT CUresult cuLaunchKernelEx_ptsz(const vcu_launch_config_t *c, CUfunction f, void **params,
+                                           void **extra) {
+  if (unlikely(!R.cuLaunchKernelEx_ptsz)) return CUDA_ERROR_NOT_FOUND;
+  LIMITED_LAUNCH(c->gridDimX, c->gridDimY, c->gridDimZ, c->hStream, 1,
+                 R.cuLaunchKernelEx_ptsz(c, f, params, extra));
+}
+
+VGPU_EXPORT CUresult cuLaunchCooperativeKernel(CUfunction f, unsigned gx, unsigned gy, unsigned gz,
+                                               unsigned bx, unsigned by, unsigned bz, unsigned smem,
+                                               CUstream s, void **params) {
+  if (unlikely(!R.cuLaunchCooperativeKernel)) return CUDA_ERROR_NOT_FOUND;
+  LIMITED_LAUNCH(gx, gy, gz, s, 0, R.cuLaunchCooperativeKernel(f, gx, gy, gz, bx, by, bz, smem, s, params));
+}
+
+VGPU_EXPORT CUresult cuLaunchCooperativeKernel_ptsz(CUfunction f, unsigned gx, unsigned gy, unsigned gz,
+                                                    unsigned bx, unsigned by, unsigned bz, unsigned smem,
+                                                    CUstream s, void **params) {
+  if (unlikely(!R.cuLaunchCooperativeKernel_ptsz)) return CUDA_ERROR_NOT_FOUND;
+  LIMITED_LAUNCH(gx, gy, gz, s, 1,
+                 R.cuLaunchCooperativeKernel_ptsz(f, gx, gy, gz, bx, by, bz, smem, s, params));
+}
+
+/* legacy launch API: the grid comes from the call, the block shape from cuFuncSetBlockShape
+ * (cuda_hook.c:1883-2002); only the grid size is charged */
+VGPU_EXPORT CUresult cuLaunch(CUfunction f) {
+  if (unlikely(!R.cuLaunch)) return CUDA_ERROR_NOT_FOUND;
+  LIMITED_LAUNCH(1, 1, 1, NULL, 0, R.cuLaunch(f));
+}
+VGPU_EXPORT CUresult cuLaunchGrid(CUfunction f, int w, int h) {
+  if (unlikely(!R.cuLaunchGrid)) return CUDA_ERROR_NOT_FOUND;
+  LIMITED_LAUNCH((unsigned)(w * h), 1, 1, NULL, 0, R.cuLaunchGrid(f, w, h));
+}
+VGPU_EXPORT CUresult cuLaunchGridAsync(CUfunction f, int w, int h, CUstream s) {
+  if (unlikely(!R.cuLaunchGridAsync)) return CUDA_ERROR_NOT_FOUND;
+  LIMITED_LAUNCH((unsigned)(w * h), 1, 1, s, 0, R.cuLaunchGridAsync(f, w, h, s));
+}
+VGPU_EXPORT CUresult cuFuncSetBlockShape(CUfunction f, int x, int y, int z) {
+  CUdevice dev; /* the reference only caches the shape for logging; the driver call needs a ctx */
+  if (!R.cuCtxGetDevice || R.cuCtxGetDevice(&dev) != CUDA_SUCCESS) return CUDA_ERROR_INVALID_CONTEXT;
+  return R.cuFuncSetBlockShape ? R.cuFuncSetBlockShape(f, x, y, z) : CUDA_ERROR_NOT_FOUND;
+}
+
+/* B200 addition: a device-wide synchronise must not wait out the sampler's residency window */
+VGPU_EXPORT CUresult cuCtxSynchronize(void) {
+  vgpu_boot();
+  if (unlikely(!R.cuCtxSynchronize)) return CUDA_ERROR_NOT_FOUND;
+  CUdevice dev;
+  if (R.cuCtxGetDevice && R.cuCtxGetDevice(&dev) == CUDA_SUCCESS) {
+    vgpu_dev_rt *rt = vgpu_rt_peek(vgpu_host_index_of_cuda(dev));
+    if (rt) vgpu_limiter_quiesce(rt);
+  }
+  return R.cuCtxSynchronize();
+}

@@ -1,0 +1,567 @@
+/*
+ * memgate.c - memory-cap / oversubscription hooks.
+ *
+ * What stays on the host: calling NVML for the per-process lists (the driver is the only
+ * source), the container-membership file reads, the cross-process locks and the calls into
+ * the real allocator.  What moved to the device: the fold of those lists into the container's
+ * `used`, the ledger sum, the quota check, the GPU/UVA/OOM decision and the reported
+ * total/used/free numbers (vgpu_quota_kernel), plus the record table of UVA allocations
+ * (vgpu_slab_*_kernel).  If the device runtime cannot be brought up the hooks fail loudly
+ * (CUDA_ERROR_NOT_SUPPORTED / NVML_ERROR_NOT_SUPPORTED): there is no CPU decision path.
+ *
+ * Behavioural contract (reference library/src/cuda_hook.c):
+ *   prepare_memory_allocation :93-116      load_limited_memory_view :118-136
+ *   get_used_gpu_memory       :807-920     allocation hooks        :1316-1697, :2004-2050
+ *   cuDeviceTotalMem/MemGetInfo :1699-1808 free hooks              :2052-2109
+ * and library/src/loader.c:1824-1922 (UVA ledger), library/src/nvml_hook.c:47-126.
+ */
+#include "vgpu_internal.h"
+
+/* ------------------------------------------------------------------ limited memory view */
+typedef struct {
+  int host_index;
+  int lock_fd;
+  int limited;      /* the device has a memory cap and the view was computed */
+  int failed;       /* the device runtime is unavailable                     */
+  vgpu_dev_rt *rt;
+  vgpu_quota_res_t res;
+} memview_t;
+
+static uint32_t fetch_list(nvmlDevice_t nv, int graphics, vgpu_proc_t *out, nvmlReturn_t *rc) {
+  unsigned int n = VGPU_MAX_PIDS;
+  nvmlReturn_t r;
+  nvmlReturn_t (*v1)(nvmlDevice_t, unsigned int *, vgpu_proc_t *) =
+      graphics ? R.nvmlDeviceGetGraphicsRunningProcesses : R.nvmlDeviceGetComputeRunningProcesses;
+  nvmlReturn_t (*v3)(nvmlDevice_t, unsigned int *, vgpu_proc_v2_t *) =
+      graphics ? R.nvmlDeviceGetGraphicsRunningProcesses_v3 : R.nvmlDeviceGetComputeRunningProcesses_v3;
+  if (v1) {
+    r = v1(nv, &n, out); /* unversioned symbol == 16-byte v1 records (nvml-subset.h:81-88) */
+  } else if (v3) {
+    /* the reference would hand its 16-byte array to the 24-byte ABI here; convert instead */
+    static __thread vgpu_proc_v2_t wide[VGPU_MAX_PIDS];
+    r = v3(nv, &n, wide);
+    if (r == NVML_SUCCESS)
+      for (unsigned int i = 0; i < n; i++) {
+        out[i].pid = wide[i].pid;
+        out[i]._pad = 0;
+        out[i].used_bytes = wide[i].used_bytes;
+      }
+  } else {
+    r = NVML_ERROR_FUNCTION_NOT_FOUND;
+  }
+  *rc = r;
+  return r == NVML_SUCCESS ? n : 0;
+}
+
+/* Fill the request block with everything the kernel needs to restate get_used_gpu_memory +
+ * get_used_gpu_virt_memory.  Caller holds rt->q_mu and the per-GPU file lock. */
+static void stage_request(vgpu_dev_rt *rt, int host_index, nvmlDevice_t nv) {
+  vgpu_quota_req_t *q = rt->q_req;
+  const vgpu_cfg_dev_t *c = &G_cfg->devices[host_index];
+  q->mode = (uint32_t)G_cfg->compatibility_mode;
+  q->memory_oversold = (uint32_t)c->memory_oversold;
+  q->total_memory = c->total_memory;
+  q->real_memory = c->real_memory;
+  q->self_pid = (uint32_t)getpid();
+  q->n_compute = q->n_graphics = q->n_vmem = 0;
+
+  nvmlReturn_t rc;
+  uint32_t nc = fetch_list(nv, 0, q->compute, &rc);
+  if (rc != NVML_SUCCESS) {
+    /* compute list unavailable => used = 0 and the graphics list is not consulted (:825-830) */
+    VLOG(VL_ERROR, "nvmlDeviceGetComputeRunningProcesses call failed, return: %d, str: %s", rc,
+         vgpu_nv_err(rc));
+  } else {
+    q->n_compute = nc;
+    uint32_t ng = fetch_list(nv, 1, q->graphics, &rc);
+    if (rc != NVML_SUCCESS) {
+      VLOG(VL_ERROR, "nvmlDeviceGetGraphicsRunningProcesses call failed, return: %d, str: %s", rc,
+           vgpu_nv_err(rc));
+      ng = 0;
+    }
+    q->n_graphics = ng;
+    if (G_cfg->compatibility_mode != VGPU_MODE_HOST) {
+      static __thread uint32_t pids[VGPU_MAX_PIDS];
+      for (uint32_t i = 0; i < nc; i++) pids[i] = q->compute[i].pid;
+      vgpu_pid_flags(pids, nc, q->cflags);
+      for (uint32_t i = 0; i < ng; i++) pids[i] = q->graphics[i].pid;
+      vgpu_pid_flags(pids, ng, q->gflags);
+    }
+  }
+  if (G_cfg->vmem_node && G_vmem) {
+    int fd = vgpu_vmem_lock(host_index, 0);
+    if (fd >= 0) {
+      const vgpu_vmem_dev_t *d = &G_vmem->devices[host_index];
+      uint32_t n = d->processes_size > VGPU_MAX_PIDS ? VGPU_MAX_PIDS : d->processes_size;
+      memcpy(q->vmem, d->processes, (size_t)n * sizeof(vgpu_vmem_rec_t));
+      q->n_vmem = n;
+      vgpu_vmem_unlock(fd, host_index);
+    }
+  }
+}
+
+extern int vgpu_rt_quota(vgpu_dev_rt *rt, vgpu_quota_res_t *out);
+extern int vgpu_rt_slab_insert(vgpu_dev_rt *rt, CUdeviceptr dptr, uint64_t bytes);
+extern int vgpu_rt_slab_remove(vgpu_dev_rt *rt, CUdeviceptr dptr, uint64_t *bytes);
+
+/* Run the quota kernel for (kind, request).  On return the per-GPU lock is still held
+ * (mv->lock_fd) exactly like load_limited_memory_view leaves it. */
+static void memview(memview_t *mv, CUdevice dev, int host_index, nvmlDevice_t nv, uint32_t kind,
+                    uint64_t request, int allow_uva, int real_ok, uint64_t real_total) {
+  memset(mv, 0, sizeof *mv);
+  mv->lock_fd = -1;
+  mv->host_index = host_index;
+  if (host_index < 0 || !G_cfg->devices[host_index].memory_limit) return;
+  vgpu_dev_rt *rt = vgpu_rt_get(host_index, dev);
+  if (!rt) {
+    mv->failed = 1;
+    return;
+  }
+  mv->rt = rt;
+  mv->lock_fd = vgpu_lock_gpu(host_index);
+  if (!nv) nv = vgpu_nvml_handle_of_host(host_index);
+  pthread_mutex_lock(&rt->q_mu);
+  vgpu_quota_req_t *q = rt->q_req;
+  if (nv) {
+    stage_request(rt, host_index, nv);
+  } else {
+    VLOG(VL_ERROR, "cuda device %d cannot find the corresponding nvml devices", dev);
+    q->n_compute = q->n_graphics = 0;
+    stage_request(rt, host_index, NULL);
+  }
+  q->kind = kind;
+  q->request = request;
+  q->allow_uva = (uint32_t)allow_uva;
+  q->real_ok = (uint32_t)real_ok;
+  q->real_total = real_total;
+  if (vgpu_rt_quota(rt, &mv->res)) mv->failed = 1;
+  else mv->limited = 1;
+  pthread_mutex_unlock(&rt->q_mu);
+}
+
+/* ------------------------------------------------------------------ UVA ledger (host file + device slab) */
+static void ledger_add(vgpu_dev_rt *rt, CUdeviceptr dptr, uint64_t bytes, int host_index) {
+  if (rt && vgpu_rt_slab_insert(rt, dptr, bytes))
+    VLOG(VL_ERROR, "failed to record virt memory node (slab full)");
+  if (host_index < 0 || host_index >= VGPU_MAX_DEVICES || !G_vmem) return;
+  int fd = vgpu_vmem_lock(host_index, 1);
+  if (fd < 0) return;
+  vgpu_vmem_dev_t *d = &G_vmem->devices[host_index];
+  int me = getpid();
+  uint32_t n = d->processes_size, i;
+  for (i = 0; i < n; i++)
+    if (d->processes[i].pid == me) {
+      d->processes[i].used += bytes;
+      break;
+    }
+  if (i == n) {
+    if (n >= VGPU_MAX_PIDS) {
+      VLOG(VL_ERROR, "host device %d virtual memory process list is full", host_index);
+    } else {
+      d->processes[n].pid = me;
+      d->processes[n].used = bytes;
+      d->processes_size = n + 1;
+    }
+  }
+  vgpu_vmem_unlock(fd, host_index);
+}
+
+static void ledger_sub(CUdevice dev, CUdeviceptr dptr) {
+  int host_index = vgpu_host_index_of_cuda(dev);
+  int slot = host_index >= 0 ? host_index : dev;
+  vgpu_dev_rt *rt = vgpu_rt_peek(slot);
+  if (!rt) return; /* nothing was ever recorded by this process on this device */
+  uint64_t bytes = 0;
+  if (vgpu_rt_slab_remove(rt, dptr, &bytes) != 0) return;
+  if (host_index < 0 || host_index >= VGPU_MAX_DEVICES || !G_vmem) return;
+  int fd = vgpu_vmem_lock(host_index, 1);
+  if (fd < 0) return;
+  vgpu_vmem_dev_t *d = &G_vmem->devices[host_index];
+  int me = getpid();
+  for (uint32_t i = 0; i < d->processes_size; i++)
+    if (d->processes[i].pid == me) {
+      d->processes[i].used = d->processes[i].used >= bytes ? d->processes[i].used - bytes : 0;
+      break;
+    }
+  vgpu_vmem_unlock(fd, host_index);
+}
+
+/* ------------------------------------------------------------------ allocation front half */
+typedef struct {
+  CUresult early;   /* != SUCCESS: return this without touching the driver */
+  int path;         /* VGPU_PATH_* */
+  memview_t mv;
+  CUdevice dev;
+} gate_t;
+
+static void gate_open(gate_t *g, uint64_t request, int allow_uva, const vcu_mem_alloc_prop_t *prop) {
+  memset(g, 0, sizeof *g);
+  g->mv.lock_fd = -1;
+  g->mv.host_index = -1;
+  g->path = VGPU_PATH_GPU;
+  CUresult r = R.cuCtxGetDevice ? R.cuCtxGetDevice(&g->dev) : CUDA_ERROR_NOT_FOUND;
+  if (r != CUDA_SUCCESS) {
+    if (prop && prop->location.type == 1) g->dev = prop->location.id; /* cuMemCreate w/o ctx (:1678) */
+    else { g->early = r; return; }
+  }
+  int host_index = vgpu_host_index_of_cuda(g->dev);
+  memview(&g->mv, g->dev, host_index, NULL, VGPU_Q_ALLOC, request, allow_uva, 0, 0);
+  if (g->mv.failed) {
+    g->early = CUDA_ERROR_NOT_SUPPORTED;
+    return;
+  }
+  if (g->mv.limited) g->path = (int)g->mv.res.path;
+  if (g->path == VGPU_PATH_OOM) {
+    vgpu_metric_add(host_index, VM_OOM_LIMIT, 1);
+    g->early = CUDA_ERROR_OUT_OF_MEMORY;
+  }
+}
+
+static inline void gate_close(gate_t *g) { vgpu_unlock_gpu(g->mv.lock_fd); }
+
+static int oversold(const gate_t *g) {
+  return g->mv.host_index >= 0 && G_cfg->devices[g->mv.host_index].memory_oversold;
+}
+
+/* GPU path failed with driver OOM on an oversold device => retry through UVA (:1372-1386) */
+static CUresult to_uva(gate_t *g, CUdeviceptr *dptr, size_t bytes) {
+  CUresult r = R.cuMemAllocManaged ? R.cuMemAllocManaged(dptr, bytes, VCU_MEM_ATTACH_GLOBAL)
+                                   : CUDA_ERROR_NOT_FOUND;
+  VLOG(VL_VERBOSE, "cuMemAllocManaged to allocate unified memory (oversold), size: %zu, ret: %d", bytes, r);
+  if (r == CUDA_SUCCESS) {
+    vgpu_dev_rt *rt = g->mv.rt ? g->mv.rt : vgpu_rt_get(g->mv.host_index, g->dev);
+    ledger_add(rt, *dptr, bytes, g->mv.host_index);
+  }
+  return r;
+}
+
+#define DRIVER_OOM_RETRY(g, r)                                               \
+  ((r) == CUDA_ERROR_OUT_OF_MEMORY && oversold(g) &&                         \
+   (vgpu_metric_add((g)->mv.host_index, VM_OOM_DRIVER, 1),                   \
+    vgpu_metric_add((g)->mv.host_index, VM_UVA_FALLBACK, 1), 1))
+
+VGPU_EXPORT CUresult cuMemAllocManaged(CUdeviceptr *dptr, size_t bytes, unsigned int flags) {
+  gate_t g;
+  gate_open(&g, bytes, 1, NULL);
+  CUresult r = g.early;
+  if (r == CUDA_SUCCESS) {
+    if (g.path == VGPU_PATH_UVA) flags = VCU_MEM_ATTACH_GLOBAL;
+    r = R.cuMemAllocManaged ? R.cuMemAllocManaged(dptr, bytes, flags) : CUDA_ERROR_NOT_FOUND;
+    /* every GLOBAL-attached managed allocation is ledgered, requested or rerouted (:1336) */
+    if (r == CUDA_SUCCESS && flags == VCU_MEM_ATTACH_GLOBAL) {
+      vgpu_dev_rt *rt = g.mv.rt ? g.mv.rt : vgpu_rt_get(g.mv.host_index, g.dev);
+      ledger_add(rt, *dptr, bytes, g.mv.host_index);
+    }
+  }
+  gate_close(&g);
+  return r;
+}
+
+static CUresult alloc_linear(CUdeviceptr *dptr, size_t bytes) {
+  gate_t g;
+  gate_open(&g, bytes, 1, NULL);
+  CUresult r = g.early;
+  if (r == CUDA_SUCCESS) {
+    if (g.path == VGPU_PATH_UVA) {
+      r = to_uva(&g, dptr, bytes);
+    } else {
+      r = R.cuMemAlloc_v2 ? R.cuMemAlloc_v2(dptr, bytes)
+          : R.cuMemAlloc  ? R.cuMemAlloc(dptr, bytes)
+                          : CUDA_ERROR_NOT_FOUND;
+      if (DRIVER_OOM_RETRY(&g, r)) r = to_uva(&g, dptr, bytes);
+    }
+  }
+  gate_close(&g);
+  return r;
+}
+VGPU_EXPORT CUresult cuMemAlloc_v2(CUdeviceptr *dptr, size_t bytes) { return alloc_linear(dptr, bytes); }
+VGPU_EXPORT CUresult cuMemAlloc(CUdeviceptr *dptr, size_t bytes) { return alloc_linear(dptr, bytes); }
+
+static CUresult alloc_pitch(CUdeviceptr *dptr, size_t *pitch, size_t width, size_t height, unsigned elem) {
+  /* request = guessed pitch x height (:1411-1412) */
+  size_t guess = (((width - 1) / elem) + 1) * elem;
+  size_t request = guess * height;
+  gate_t g;
+  gate_open(&g, request, 1, NULL);
+  CUresult r = g.early;
+  if (r == CUDA_SUCCESS) {
+    int uva = g.path == VGPU_PATH_UVA;
+    if (!uva) {
+      r = R.cuMemAllocPitch_v2 ? R.cuMemAllocPitch_v2(dptr, pitch, width, height, elem)
+          : R.cuMemAllocPitch  ? R.cuMemAllocPitch(dptr, pitch, width, height, elem)
+                               : CUDA_ERROR_NOT_FOUND;
+      uva = DRIVER_OOM_RETRY(&g, r);
+    }
+    if (uva) {
+      r = to_uva(&g, dptr, request);
+      if (r == CUDA_SUCCESS) *pitch = guess;
+    }
+  }
+  gate_close(&g);
+  return r;
+}
+VGPU_EXPORT CUresult cuMemAllocPitch_v2(CUdeviceptr *d, size_t *p, size_t w, size_t h, unsigned e) {
+  return alloc_pitch(d, p, w, h, e);
+}
+VGPU_EXPORT CUresult cuMemAllocPitch(CUdeviceptr *d, size_t *p, size_t w, size_t h, unsigned e) {
+  return alloc_pitch(d, p, w, h, e);
+}
+
+static CUresult alloc_async(CUdeviceptr *dptr, size_t bytes, CUstream s, int ptsz) {
+  gate_t g;
+  gate_open(&g, bytes, 1, NULL);
+  CUresult r = g.early;
+  if (r == CUDA_SUCCESS) {
+    if (g.path == VGPU_PATH_UVA) {
+      r = to_uva(&g, dptr, bytes);
+    } else {
+      CUresult (*fn)(CUdeviceptr *, size_t, CUstream) = ptsz ? R.cuMemAllocAsync_ptsz : R.cuMemAllocAsync;
+      r = fn ? fn(dptr, bytes, s) : CUDA_ERROR_NOT_FOUND;
+      if (DRIVER_OOM_RETRY(&g, r)) r = to_uva(&g, dptr, bytes);
+    }
+  }
+  gate_close(&g);
+  return r;
+}
+VGPU_EXPORT CUresult cuMemAllocAsync(CUdeviceptr *d, size_t n, CUstream s) { return alloc_async(d, n, s, 0); }
+VGPU_EXPORT CUresult cuMemAllocAsync_ptsz(CUdeviceptr *d, size_t n, CUstream s) { return alloc_async(d, n, s, 1); }
+
+/* the cap applies but these can never spill (allow_uva = 0, Appendix B.15) */
+static CUresult alloc_pool(CUdeviceptr *dptr, size_t bytes, CUmemoryPool pool, CUstream s, int ptsz) {
+  gate_t g;
+  gate_open(&g, bytes, 0, NULL);
+  CUresult r = g.early;
+  if (r == CUDA_SUCCESS) {
+    CUresult (*fn)(CUdeviceptr *, size_t, CUmemoryPool, CUstream) =
+        ptsz ? R.cuMemAllocFromPoolAsync_ptsz : R.cuMemAllocFromPoolAsync;
+    r = fn ? fn(dptr, bytes, pool, s) : CUDA_ERROR_NOT_FOUND;
+  }
+  gate_close(&g);
+  return r;
+}
+VGPU_EXPORT CUresult cuMemAllocFromPoolAsync(CUdeviceptr *d, size_t n, CUmemoryPool p, CUstream s) {
+  return alloc_pool(d, n, p, s, 0);
+}
+VGPU_EXPORT CUresult cuMemAllocFromPoolAsync_ptsz(CUdeviceptr *d, size_t n, CUmemoryPool p, CUstream s) {
+  return alloc_pool(d, n, p, s, 1);
+}
+
+VGPU_EXPORT CUresult cuMemCreate(CUmemGenericAllocationHandle *h, size_t size,
+                                 const vcu_mem_alloc_prop_t *prop, unsigned long long flags) {
+  gate_t g;
+  gate_open(&g, size, 0, prop);
+  CUresult r = g.early;
+  if (r == CUDA_SUCCESS) r = R.cuMemCreate ? R.cuMemCreate(h, size, prop, flags) : CUDA_ERROR_NOT_FOUND;
+  gate_close(&g);
+  return r;
+}
+
+/* array requests are sized in *bits* per channel - a reference quirk we keep (:1546-1569) */
+static size_t array_unit(int format) {
+  switch (format) {
+  case 0x01: case 0x08: return 8;
+  case 0x02: case 0x09: case 0x10: return 16;
+  default: return 32;
+  }
+}
+
+static CUresult array2d(CUarray *h, const vcu_array_desc_t *d) {
+  gate_t g;
+  gate_open(&g, array_unit(d->Format) * d->NumChannels * d->Height * d->Width, 0, NULL);
+  CUresult r = g.early;
+  if (r == CUDA_SUCCESS)
+    r = R.cuArrayCreate_v2 ? R.cuArrayCreate_v2(h, d) : R.cuArrayCreate ? R.cuArrayCreate(h, d) : CUDA_ERROR_NOT_FOUND;
+  gate_close(&g);
+  return r;
+}
+VGPU_EXPORT CUresult cuArrayCreate_v2(CUarray *h, const vcu_array_desc_t *d) { return array2d(h, d); }
+VGPU_EXPORT CUresult cuArrayCreate(CUarray *h, const vcu_array_desc_t *d) { return array2d(h, d); }
+
+static size_t array3d_request(const vcu_array3d_desc_t *d) {
+  return array_unit(d->Format) * d->NumChannels * d->Height * d->Width * d->Depth;
+}
+static CUresult array3d(CUarray *h, const vcu_array3d_desc_t *d) {
+  gate_t g;
+  gate_open(&g, array3d_request(d), 0, NULL);
+  CUresult r = g.early;
+  if (r == CUDA_SUCCESS)
+    r = R.cuArray3DCreate_v2 ? R.cuArray3DCreate_v2(h, d)
+        : R.cuArray3DCreate  ? R.cuArray3DCreate(h, d)
+                             : CUDA_ERROR_NOT_FOUND;
+  gate_close(&g);
+  return r;
+}
+VGPU_EXPORT CUresult cuArray3DCreate_v2(CUarray *h, const vcu_array3d_desc_t *d) { return array3d(h, d); }
+VGPU_EXPORT CUresult cuArray3DCreate(CUarray *h, const vcu_array3d_desc_t *d) { return array3d(h, d); }
+
+VGPU_EXPORT CUresult cuMipmappedArrayCreate(CUmipmappedArray *h, const vcu_array3d_desc_t *d,
+                                            unsigned int levels) {
+  gate_t g;
+  gate_open(&g, array3d_request(d), 0, NULL);
+  CUresult r = g.early;
+  if (r == CUDA_SUCCESS)
+    r = R.cuMipmappedArrayCreate ? R.cuMipmappedArrayCreate(h, d, levels) : CUDA_ERROR_NOT_FOUND;
+  gate_close(&g);
+  return r;
+}
+
+/* ------------------------------------------------------------------ free */
+static CUresult free_sync(CUdeviceptr dptr) {
+  CUdevice dev;
+  CUresult r = R.cuCtxGetDevice ? R.cuCtxGetDevice(&dev) : CUDA_ERROR_NOT_FOUND;
+  if (r != CUDA_SUCCESS) return r;
+  /* cuMemFree synchronises the device: do not let a resident sampler stretch that */
+  vgpu_dev_rt *rt = vgpu_rt_peek(vgpu_host_index_of_cuda(dev));
+  if (rt) vgpu_limiter_quiesce(rt);
+  r = R.cuMemFree_v2 ? R.cuMemFree_v2(dptr) : R.cuMemFree ? R.cuMemFree(dptr) : CUDA_ERROR_NOT_FOUND;
+  if (r == CUDA_SUCCESS) ledger_sub(dev, dptr);
+  return r;
+}
+VGPU_EXPORT CUresult cuMemFree_v2(CUdeviceptr p) { return free_sync(p); }
+VGPU_EXPORT CUresult cuMemFree(CUdeviceptr p) { return free_sync(p); }
+
+static CUresult free_async(CUdeviceptr dptr, CUstream s, int ptsz) {
+  CUdevice dev;
+  CUresult r = R.cuCtxGetDevice ? R.cuCtxGetDevice(&dev) : CUDA_ERROR_NOT_FOUND;
+  if (r != CUDA_SUCCESS) return r;
+  CUresult (*fn)(CUdeviceptr, CUstream) = ptsz ? R.cuMemFreeAsync_ptsz : R.cuMemFreeAsync;
+  r = fn ? fn(dptr, s) : CUDA_ERROR_NOT_FOUND;
+  if (r == CUDA_SUCCESS) ledger_sub(dev, dptr);
+  return r;
+}
+VGPU_EXPORT CUresult cuMemFreeAsync(CUdeviceptr p, CUstream s) { return free_async(p, s, 0); }
+VGPU_EXPORT CUresult cuMemFreeAsync_ptsz(CUdeviceptr p, CUstream s) { return free_async(p, s, 1); }
+
+/* ------------------------------------------------------------------ reported sizes */
+static CUresult total_mem(size_t *bytes, CUdevice dev) {
+  int h = vgpu_host_index_of_cuda(dev);
+  if (h >= 0 && G_cfg->devices[h].memory_limit) {
+    *bytes = G_cfg->devices[h].total_memory;
+    return CUDA_SUCCESS;
+  }
+  return R.cuDeviceTotalMem_v2 ? R.cuDeviceTotalMem_v2(bytes, dev)
+         : R.cuDeviceTotalMem  ? R.cuDeviceTotalMem(bytes, dev)
+                               : CUDA_ERROR_NOT_FOUND;
+}
+VGPU_EXPORT CUresult cuDeviceTotalMem_v2(size_t *b, CUdevice d) { return total_mem(b, d); }
+VGPU_EXPORT CUresult cuDeviceTotalMem(size_t *b, CUdevice d) { return total_mem(b, d); }
+
+static CUresult real_meminfo(size_t *fr, size_t *tot) {
+  return R.cuMemGetInfo_v2 ? R.cuMemGetInfo_v2(fr, tot) : R.cuMemGetInfo ? R.cuMemGetInfo(fr, tot) : CUDA_ERROR_NOT_FOUND;
+}
+
+static CUresult mem_info(size_t *free_out, size_t *total_out) {
+  CUdevice dev;
+  CUresult r = R.cuCtxGetDevice ? R.cuCtxGetDevice(&dev) : CUDA_ERROR_NOT_FOUND;
+  if (r != CUDA_SUCCESS) return r;
+  int h = vgpu_host_index_of_cuda(dev);
+  if (h < 0 || !G_cfg->devices[h].memory_limit) return real_meminfo(free_out, total_out);
+  memview_t mv;
+  /* the reference takes the lock and measures first, then (not oversold) asks the driver for
+   * its real total to clamp against (:1739-1782); the clamp itself happens in the kernel, so
+   * the driver query has to precede the launch */
+  size_t rfree = 0, rtotal = 0;
+  int real_ok = 0;
+  if (!G_cfg->devices[h].memory_oversold) real_ok = real_meminfo(&rfree, &rtotal) == CUDA_SUCCESS;
+  memview(&mv, dev, h, NULL, VGPU_Q_CU_INFO, 0, 0, real_ok, rtotal);
+  if (mv.failed) {
+    r = CUDA_ERROR_NOT_SUPPORTED;
+  } else {
+    *total_out = mv.res.total;
+    *free_out = mv.res.out_free;
+    r = CUDA_SUCCESS;
+  }
+  vgpu_unlock_gpu(mv.lock_fd);
+  return r;
+}
+VGPU_EXPORT CUresult cuMemGetInfo_v2(size_t *f, size_t *t) { return mem_info(f, t); }
+VGPU_EXPORT CUresult cuMemGetInfo(size_t *f, size_t *t) { return mem_info(f, t); }
+
+/* ------------------------------------------------------------------ NVML hooks */
+static vgpu_dev_rt *rt_for_nvml(int host_index, CUdevice *dev_out) {
+  /* an NVML-only client (nvidia-smi) has no CUDA context: the kernels then cannot run */
+  vgpu_dev_rt *rt = vgpu_rt_peek(host_index);
+  if (rt) {
+    *dev_out = rt->cuda_dev;
+    return rt;
+  }
+  CUdevice dev;
+  if (R.cuCtxGetDevice && R.cuCtxGetDevice(&dev) == CUDA_SUCCESS && vgpu_host_index_of_cuda(dev) == host_index) {
+    *dev_out = dev;
+    return vgpu_rt_get(host_index, dev);
+  }
+  return NULL;
+}
+
+static nvmlReturn_t nvml_view(nvmlDevice_t device, int host_index, vgpu_quota_res_t *out) {
+  CUdevice dev = 0;
+  vgpu_dev_rt *rt = rt_for_nvml(host_index, &dev);
+  if (!rt) {
+    VLOG(VL_ERROR, "nvmlDeviceGetMemoryInfo: no CUDA context on host device %d, the quota kernel "
+                   "cannot run (no CPU fallback)", host_index);
+    return NVML_ERROR_NOT_SUPPORTED;
+  }
+  memview_t mv;
+  CUcontext prev = NULL;
+  int pushed = 0;
+  if (R.cuCtxGetCurrent && R.cuCtxGetCurrent(&prev) == CUDA_SUCCESS && prev != rt->ctx &&
+      R.cuCtxPushCurrent_v2 && R.cuCtxPushCurrent_v2(rt->ctx) == CUDA_SUCCESS)
+    pushed = 1;
+  memview(&mv, dev, host_index, device, VGPU_Q_NVML_INFO, 0, 0, 0, 0);
+  if (pushed) R.cuCtxPopCurrent_v2(&prev);
+  vgpu_unlock_gpu(mv.lock_fd);
+  if (mv.failed || !mv.limited) return NVML_ERROR_NOT_SUPPORTED;
+  *out = mv.res;
+  return NVML_SUCCESS;
+}
+
+VGPU_EXPORT nvmlReturn_t nvmlDeviceGetMemoryInfo(nvmlDevice_t device, vnv_memory_t *memory) {
+  vgpu_boot();
+  int h = vgpu_host_index_of_nvml(device);
+  if (h >= 0 && G_cfg->devices[h].memory_limit) {
+    vgpu_quota_res_t res;
+    nvmlReturn_t r = nvml_view(device, h, &res);
+    if (r != NVML_SUCCESS) return r;
+    memory->total = res.total;
+    memory->used = res.out_used;
+    memory->free = res.out_free;
+    return NVML_SUCCESS;
+  }
+  return R.nvmlDeviceGetMemoryInfo ? R.nvmlDeviceGetMemoryInfo(device, memory) : NVML_ERROR_FUNCTION_NOT_FOUND;
+}
+
+VGPU_EXPORT nvmlReturn_t nvmlDeviceGetMemoryInfo_v2(nvmlDevice_t device, vnv_memory_v2_t *memory) {
+  vgpu_boot();
+  nvmlReturn_t r = R.nvmlDeviceGetMemoryInfo_v2 ? R.nvmlDeviceGetMemoryInfo_v2(device, memory)
+                                                : NVML_ERROR_FUNCTION_NOT_FOUND;
+  if (r != NVML_SUCCESS) return r;
+  int h = vgpu_host_index_of_nvml(device);
+  if (h >= 0 && G_cfg->devices[h].memory_limit) {
+    vgpu_quota_res_t res;
+    r = nvml_view(device, h, &res);
+    if (r != NVML_SUCCESS) return r;
+    memory->total = res.total; /* version / reserved stay the driver's (nvml_hook.c:89-98) */
+    memory->used = res.out_used;
+    memory->free = res.out_free;
+  }
+  return NVML_SUCCESS;
+}
+
+VGPU_EXPORT nvmlReturn_t nvmlDeviceSetComputeMode(nvmlDevice_t device, int mode) {
+  vgpu_boot();
+  int h = vgpu_host_index_of_nvml(device);
+  if (h >= 0 && (G_cfg->devices[h].memory_limit || G_cfg->devices[h].core_limit)) return NVML_ERROR_NOT_SUPPORTED;
+  return R.nvmlDeviceSetComputeMode ? R.nvmlDeviceSetComputeMode(device, mode) : NVML_ERROR_FUNCTION_NOT_FOUND;
+}
+
+VGPU_EXPORT nvmlReturn_t nvmlDeviceGetPersistenceMode(nvmlDevice_t device, int *mode) {
+  (void)device;
+  *mode = 0; /* NVML_FEATURE_DISABLED, unconditionally (nvml_hook.c:121-126) */
+  return NVML_SUCCESS;
+}
+
+VGPU_EXPORT nvmlReturn_t nvmlDeviceGetUtilizationRates(nvmlDevice_t device, vnv_utilization_t *u) {
+  vgpu_boot(); /* pure forward, like the reference (nvml_originals.c:698-702) */
+  return R.nvmlDeviceGetUtilizationRates ? R.nvmlDeviceGetUtilizationRates(device, u)
+                                         : NVML_ERROR_FUNCTION_NOT_FOUND;
+}

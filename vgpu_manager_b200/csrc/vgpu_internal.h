@@ -1,0 +1,308 @@
+/*
+ * vgpu_internal.h - private declarations of the B200 interception library.
+ *
+ * The host side is plain C over the CUDA driver / NVML C ABIs.  We deliberately do not include
+ * <cuda.h>/<nvml.h>: their versioning macros (#define cuMemAlloc cuMemAlloc_v2 ...) collide
+ * with the very symbols this library must export.  Only the handful of types the hooked entry
+ * points touch are restated here (vcu_ / vnv_ prefix); tests/test_abi_layout.c static-asserts
+ * them against the real CUDA 12.9 headers.
+ */
+#ifndef VGPU_INTERNAL_H
+#define VGPU_INTERNAL_H
+
+#include <inttypes.h>
+#include <pthread.h>
+#include <stddef.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <unistd.h>
+
+#include "../../include/vgpu_contract.h"
+#include "kernel_abi.h"
+
+/* ------------------------------------------------------------------ driver ABI subset */
+typedef int CUresult;
+typedef int CUdevice;
+typedef unsigned long long CUdeviceptr;
+typedef unsigned long long cuuint64_t;
+typedef void *CUcontext, *CUstream, *CUfunction, *CUmodule, *CUarray, *CUmipmappedArray,
+    *CUmemoryPool, *CUevent;
+typedef unsigned long long CUmemGenericAllocationHandle;
+typedef struct { char bytes[16]; } CUuuid;
+
+enum {
+  CUDA_SUCCESS = 0,
+  CUDA_ERROR_INVALID_VALUE = 1,
+  CUDA_ERROR_OUT_OF_MEMORY = 2,
+  CUDA_ERROR_NOT_INITIALIZED = 3,
+  CUDA_ERROR_INVALID_CONTEXT = 201,
+  CUDA_ERROR_NOT_FOUND = 500,
+  CUDA_ERROR_NOT_READY = 600,
+  CUDA_ERROR_NOT_SUPPORTED = 801,
+};
+
+typedef struct {
+  size_t Width, Height;
+  int Format;
+  unsigned int NumChannels;
+} vcu_array_desc_t; /* CUDA_ARRAY_DESCRIPTOR_v2 */
+
+typedef struct {
+  size_t Width, Height, Depth;
+  int Format;
+  unsigned int NumChannels, Flags;
+} vcu_array3d_desc_t; /* CUDA_ARRAY3D_DESCRIPTOR_v2 */
+
+typedef struct {
+  int type; /* CUmemAllocationType */
+  int requestedHandleTypes;
+  struct { int type; int id; } location; /* CUmemLocation; type 1 == DEVICE */
+  void *win32HandleMetaData;
+  struct { unsigned char compressionType, gpuDirectRDMACapable; unsigned short usage; unsigned char reserved[4]; } allocFlags;
+} vcu_mem_alloc_prop_t; /* CUmemAllocationProp_v1 */
+
+typedef struct {
+  unsigned int gridDimX, gridDimY, gridDimZ, blockDimX, blockDimY, blockDimZ, sharedMemBytes;
+  CUstream hStream;
+  void *attrs;
+  unsigned int numAttrs;
+} vcu_launch_config_t; /* CUlaunchConfig */
+
+#define VCU_MEM_ATTACH_GLOBAL 0x1u
+#define VCU_STREAM_NON_BLOCKING 0x1u
+#define VCU_MEMHOSTALLOC_PORTABLE 0x1u
+#define VCU_MEMHOSTALLOC_DEVICEMAP 0x2u
+#define VCU_ATTR_SM_COUNT 16
+#define VCU_ATTR_MAX_THREADS_PER_SM 39
+#define VCU_GET_PROC_PTDS (1ull << 1)
+#define VCU_WAIT_GEQ 0x0u
+
+/* ------------------------------------------------------------------ NVML ABI subset */
+typedef int nvmlReturn_t;
+typedef void *nvmlDevice_t;
+enum {
+  NVML_SUCCESS = 0,
+  NVML_ERROR_NOT_SUPPORTED = 3,
+  NVML_ERROR_NOT_FOUND = 6,
+  NVML_ERROR_FUNCTION_NOT_FOUND = 13,
+};
+typedef struct { unsigned long long total, free, used; } vnv_memory_t;
+typedef struct { unsigned int version; unsigned long long total, reserved, free, used; } vnv_memory_v2_t;
+typedef struct { unsigned int gpu, memory; } vnv_utilization_t;
+
+/* ------------------------------------------------------------------ logging
+ * Same line format as the reference (hook.h:316-327); FATAL exits the process. */
+enum { VL_FATAL = 0, VL_ERROR, VL_WARNING, VL_INFO, VL_VERBOSE, VL_DETAIL };
+int vgpu_log_level(void);
+void vgpu_log_emit(int level, const char *file, int line, const char *fmt, ...)
+    __attribute__((format(printf, 4, 5)));
+#define VLOG(level, ...)                                                        \
+  do {                                                                          \
+    if ((level) <= vgpu_log_level()) vgpu_log_emit((level), __FILE__, __LINE__, __VA_ARGS__); \
+    if ((level) == VL_FATAL) exit(1);                                           \
+  } while (0)
+
+#define VGPU_EXPORT __attribute__((visibility("default")))
+#define likely(x) __builtin_expect(!!(x), 1)
+#define unlikely(x) __builtin_expect(!!(x), 0)
+
+/* ------------------------------------------------------------------ real entry points
+ * X(name, return type, (args)) - resolved from libcuda.so.<ver> / libnvidia-ml.so.<ver>. */
+#define VGPU_REAL_CUDA(X)                                                                       \
+  X(cuInit, CUresult, (unsigned int))                                                           \
+  X(cuDriverGetVersion, CUresult, (int *))                                                      \
+  X(cuGetProcAddress, CUresult, (const char *, void **, int, cuuint64_t))                       \
+  X(cuGetProcAddress_v2, CUresult, (const char *, void **, int, cuuint64_t, void *))            \
+  X(cuGetErrorString, CUresult, (CUresult, const char **))                                      \
+  X(cuDeviceGetCount, CUresult, (int *))                                                        \
+  X(cuDeviceGet, CUresult, (CUdevice *, int))                                                   \
+  X(cuDeviceGetAttribute, CUresult, (int *, int, CUdevice))                                     \
+  X(cuDeviceGetUuid, CUresult, (CUuuid *, CUdevice))                                            \
+  X(cuDeviceGetUuid_v2, CUresult, (CUuuid *, CUdevice))                                         \
+  X(cuDeviceTotalMem, CUresult, (size_t *, CUdevice))                                           \
+  X(cuDeviceTotalMem_v2, CUresult, (size_t *, CUdevice))                                        \
+  X(cuCtxGetDevice, CUresult, (CUdevice *))                                                     \
+  X(cuCtxGetCurrent, CUresult, (CUcontext *))                                                   \
+  X(cuCtxSetCurrent, CUresult, (CUcontext))                                                     \
+  X(cuCtxPushCurrent_v2, CUresult, (CUcontext))                                                 \
+  X(cuCtxPopCurrent_v2, CUresult, (CUcontext *))                                                \
+  X(cuCtxSynchronize, CUresult, (void))                                                         \
+  X(cuMemAlloc, CUresult, (CUdeviceptr *, size_t))                                              \
+  X(cuMemAlloc_v2, CUresult, (CUdeviceptr *, size_t))                                           \
+  X(cuMemAllocManaged, CUresult, (CUdeviceptr *, size_t, unsigned int))                         \
+  X(cuMemAllocPitch, CUresult, (CUdeviceptr *, size_t *, size_t, size_t, unsigned int))         \
+  X(cuMemAllocPitch_v2, CUresult, (CUdeviceptr *, size_t *, size_t, size_t, unsigned int))      \
+  X(cuMemAllocAsync, CUresult, (CUdeviceptr *, size_t, CUstream))                               \
+  X(cuMemAllocAsync_ptsz, CUresult, (CUdeviceptr *, size_t, CUstream))                          \
+  X(cuMemAllocFromPoolAsync, CUresult, (CUdeviceptr *, size_t, CUmemoryPool, CUstream))         \
+  X(cuMemAllocFromPoolAsync_ptsz, CUresult, (CUdeviceptr *, size_t, CUmemoryPool, CUstream))    \
+  X(cuMemCreate, CUresult,                                                                      \
+    (CUmemGenericAllocationHandle *, size_t, const vcu_mem_alloc_prop_t *, unsigned long long)) \
+  X(cuArrayCreate, CUresult, (CUarray *, const vcu_array_desc_t *))                             \
+  X(cuArrayCreate_v2, CUresult, (CUarray *, const vcu_array_desc_t *))                          \
+  X(cuArray3DCreate, CUresult, (CUarray *, const vcu_array3d_desc_t *))                         \
+  X(cuArray3DCreate_v2, CUresult, (CUarray *, const vcu_array3d_desc_t *))                      \
+  X(cuMipmappedArrayCreate, CUresult,                                                           \
+    (CUmipmappedArray *, const vcu_array3d_desc_t *, unsigned int))                             \
+  X(cuMemFree, CUresult, (CUdeviceptr))                                                         \
+  X(cuMemFree_v2, CUresult, (CUdeviceptr))                                                      \
+  X(cuMemFreeAsync, CUresult, (CUdeviceptr, CUstream))                                          \
+  X(cuMemFreeAsync_ptsz, CUresult, (CUdeviceptr, CUstream))                                     \
+  X(cuMemGetInfo, CUresult, (size_t *, size_t *))                                               \
+  X(cuMemGetInfo_v2, CUresult, (size_t *, size_t *))                                            \
+  X(cuMemHostAlloc, CUresult, (void **, size_t, unsigned int))                                  \
+  X(cuMemFreeHost, CUresult, (void *))                                                          \
+  X(cuMemHostGetDevicePointer_v2, CUresult, (CUdeviceptr *, void *, unsigned int))              \
+  X(cuMemsetD8_v2, CUresult, (CUdeviceptr, unsigned char, size_t))                              \
+  X(cuMemcpyDtoH_v2, CUresult, (void *, CUdeviceptr, size_t))                                   \
+  X(cuMemcpyHtoD_v2, CUresult, (CUdeviceptr, const void *, size_t))                             \
+  X(cuModuleLoadData, CUresult, (CUmodule *, const void *))                                     \
+  X(cuModuleGetFunction, CUresult, (CUfunction *, CUmodule, const char *))                      \
+  X(cuModuleUnload, CUresult, (CUmodule))                                                       \
+  X(cuFuncSetAttribute, CUresult, (CUfunction, int, int))                                       \
+  X(cuStreamCreate, CUresult, (CUstream *, unsigned int))                                       \
+  X(cuStreamCreateWithPriority, CUresult, (CUstream *, unsigned int, int))                      \
+  X(cuCtxGetStreamPriorityRange, CUresult, (int *, int *))                                      \
+  X(cuStreamSynchronize, CUresult, (CUstream))                                                  \
+  X(cuStreamQuery, CUresult, (CUstream))                                                        \
+  X(cuStreamIsCapturing, CUresult, (CUstream, int *))                                           \
+  X(cuStreamWaitValue64_v2, CUresult, (CUstream, CUdeviceptr, cuuint64_t, unsigned int))        \
+  X(cuStreamWaitValue64_v2_ptsz, CUresult, (CUstream, CUdeviceptr, cuuint64_t, unsigned int))   \
+  X(cuStreamWriteValue64_v2, CUresult, (CUstream, CUdeviceptr, cuuint64_t, unsigned int))       \
+  X(cuStreamWriteValue64_v2_ptsz, CUresult, (CUstream, CUdeviceptr, cuuint64_t, unsigned int))  \
+  X(cuLaunchKernel, CUresult,                                                                   \
+    (CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, CUstream, \
+     void **, void **))                                                                         \
+  X(cuLaunchKernel_ptsz, CUresult,                                                              \
+    (CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, CUstream, \
+     void **, void **))                                                                         \
+  X(cuLaunchKernelEx, CUresult, (const vcu_launch_config_t *, CUfunction, void **, void **))    \
+  X(cuLaunchKernelEx_ptsz, CUresult, (const vcu_launch_config_t *, CUfunction, void **, void **)) \
+  X(cuLaunchCooperativeKernel, CUresult,                                                        \
+    (CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, CUstream, \
+     void **))                                                                                  \
+  X(cuLaunchCooperativeKernel_ptsz, CUresult,                                                   \
+    (CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, CUstream, \
+     void **))                                                                                  \
+  X(cuLaunch, CUresult, (CUfunction))                                                           \
+  X(cuLaunchGrid, CUresult, (CUfunction, int, int))                                             \
+  X(cuLaunchGridAsync, CUresult, (CUfunction, int, int, CUstream))                              \
+  X(cuFuncSetBlockShape, CUresult, (CUfunction, int, int, int))
+
+#define VGPU_REAL_NVML(X)                                                                       \
+  X(nvmlInit, nvmlReturn_t, (void))                                                             \
+  X(nvmlInit_v2, nvmlReturn_t, (void))                                                          \
+  X(nvmlInitWithFlags, nvmlReturn_t, (unsigned int))                                            \
+  X(nvmlErrorString, const char *, (nvmlReturn_t))                                              \
+  X(nvmlDeviceGetCount, nvmlReturn_t, (unsigned int *))                                         \
+  X(nvmlDeviceGetCount_v2, nvmlReturn_t, (unsigned int *))                                      \
+  X(nvmlDeviceGetHandleByIndex, nvmlReturn_t, (unsigned int, nvmlDevice_t *))                   \
+  X(nvmlDeviceGetHandleByIndex_v2, nvmlReturn_t, (unsigned int, nvmlDevice_t *))                \
+  X(nvmlDeviceGetIndex, nvmlReturn_t, (nvmlDevice_t, unsigned int *))                           \
+  X(nvmlDeviceGetUUID, nvmlReturn_t, (nvmlDevice_t, char *, unsigned int))                      \
+  X(nvmlDeviceGetComputeRunningProcesses, nvmlReturn_t, (nvmlDevice_t, unsigned int *, vgpu_proc_t *)) \
+  X(nvmlDeviceGetGraphicsRunningProcesses, nvmlReturn_t, (nvmlDevice_t, unsigned int *, vgpu_proc_t *)) \
+  X(nvmlDeviceGetComputeRunningProcesses_v3, nvmlReturn_t, (nvmlDevice_t, unsigned int *, vgpu_proc_v2_t *)) \
+  X(nvmlDeviceGetGraphicsRunningProcesses_v3, nvmlReturn_t, (nvmlDevice_t, unsigned int *, vgpu_proc_v2_t *)) \
+  X(nvmlDeviceGetProcessUtilization, nvmlReturn_t,                                              \
+    (nvmlDevice_t, vgpu_util_sample_t *, unsigned int *, unsigned long long))                   \
+  X(nvmlDeviceGetUtilizationRates, nvmlReturn_t, (nvmlDevice_t, vnv_utilization_t *))           \
+  X(nvmlDeviceGetMemoryInfo, nvmlReturn_t, (nvmlDevice_t, vnv_memory_t *))                      \
+  X(nvmlDeviceGetMemoryInfo_v2, nvmlReturn_t, (nvmlDevice_t, vnv_memory_v2_t *))                \
+  X(nvmlDeviceSetComputeMode, nvmlReturn_t, (nvmlDevice_t, int))                                \
+  X(nvmlDeviceGetPersistenceMode, nvmlReturn_t, (nvmlDevice_t, int *))
+
+typedef struct {
+#define X(name, ret, args) ret(*name) args;
+  VGPU_REAL_CUDA(X)
+  VGPU_REAL_NVML(X)
+#undef X
+} vgpu_real_t;
+
+extern vgpu_real_t R; /* real entry points; NULL when the driver lacks the symbol */
+typedef void *(*vgpu_dlsym_fn)(void *, const char *);
+extern vgpu_dlsym_fn vgpu_real_dlsym;
+
+/* ------------------------------------------------------------------ global state */
+extern vgpu_cfg_t *G_cfg;       /* mmap'ed (RO) or env-built vgpu.config */
+extern vgpu_smutil_t *G_smutil; /* optional external watcher file        */
+extern vgpu_vmem_t *G_vmem;     /* shared UVA ledger file (RW)           */
+
+/* Optional development/test sandbox: VGPU_B200_SANDBOX=/dir prefixes every contract path
+ * (never set in production; the control plane knows nothing about it). */
+const char *vgpu_path(const char *abs, char *buf, size_t cap);
+#define VP(p) vgpu_path((p), (char[512]){0}, 512)
+
+/* boot.c */
+void vgpu_boot(void);             /* == reference load_necessary_data (loader.c:2166) */
+void vgpu_map_devices(void);      /* == reference init_devices_mapping (loader.c:2178) */
+const char *vgpu_cu_err(CUresult r);
+const char *vgpu_nv_err(nvmlReturn_t r);
+void *vgpu_lookup_cuda_hook(const char *name, int want_ptsz);
+void *vgpu_lookup_nvml_hook(const char *name);
+
+/* config.c */
+int vgpu_host_index_of_cuda(CUdevice dev);
+int vgpu_nvml_index_of_cuda(CUdevice dev);
+int vgpu_host_index_of_nvml(nvmlDevice_t dev);
+nvmlDevice_t vgpu_nvml_handle_of_host(int host_index);
+int vgpu_lock_gpu(int host_index);
+void vgpu_unlock_gpu(int fd);
+int vgpu_vmem_lock(int host_index, int write);
+void vgpu_vmem_unlock(int fd, int host_index);
+int vgpu_smutil_rdlock(int host_index);
+void vgpu_smutil_unlock(int fd, int host_index);
+/* container membership flags for a list of device pids (VGPU_FLAG_*), per compatibility mode */
+void vgpu_pid_flags(const uint32_t *pids, uint32_t n, uint8_t *flags);
+
+/* device.c - per-GPU device runtime (module, streams, pinned blocks) */
+typedef struct vgpu_dev_rt {
+  int host_index;
+  int ready;   /* 1 once the module is loaded in `ctx`; -1 if bring-up failed */
+  CUdevice cuda_dev;
+  CUcontext ctx;
+  CUmodule mod;
+  CUfunction k_clear, k_spill, k_copy_generic, k_quota, k_slab_insert, k_slab_remove, k_controller, k_sampler, k_gate;
+  CUstream q_stream; /* quota / ledger kernels (app thread)     */
+  CUstream s_stream; /* sampler + controller (timer thread)     */
+  /* pinned, mapped blocks */
+  vgpu_quota_req_t *q_req;  CUdeviceptr q_req_d;
+  vgpu_quota_res_t *q_res;  CUdeviceptr q_res_d;
+  vgpu_slab_res_t *slab_res; CUdeviceptr slab_res_d;
+  vgpu_lim_host_t *lim_h;   CUdeviceptr lim_h_d;
+  /* HBM */
+  CUdeviceptr lim_d;  /* vgpu_lim_dev_t          */
+  CUdeviceptr slab_d; /* vgpu_slab_slot_t[SLOTS] */
+  uint64_t self_bytes; /* measured device footprint of everything above */
+  uint32_t seq;
+  volatile long uva_live; /* records in the slab (host-side count; skip lookups when 0) */
+  pthread_mutex_t q_mu;
+  int sm_num, max_thread_per_sm;
+  int64_t total_cores;
+  int memops64; /* cuStreamWaitValue64 usable */
+} vgpu_dev_rt;
+
+vgpu_dev_rt *vgpu_rt_get(int host_index, CUdevice dev); /* bring up (needs a current ctx) */
+vgpu_dev_rt *vgpu_rt_peek(int host_index);              /* NULL unless ready */
+CUresult vgpu_rt_launch(vgpu_dev_rt *rt, CUfunction f, unsigned grid, unsigned block,
+                        unsigned smem, CUstream s, void **params);
+
+int vgpu_rt_quota(vgpu_dev_rt *rt, vgpu_quota_res_t *out);
+int vgpu_rt_slab_insert(vgpu_dev_rt *rt, CUdeviceptr dptr, uint64_t bytes);
+int vgpu_rt_slab_remove(vgpu_dev_rt *rt, CUdeviceptr dptr, uint64_t *bytes);
+CUresult vgpu_rt_clear(vgpu_dev_rt *rt, CUdeviceptr dst, size_t bytes, CUstream s);
+CUresult vgpu_rt_spill(vgpu_dev_rt *rt, CUdeviceptr dst, CUdeviceptr src, size_t bytes, CUstream s);
+
+/* limiter.c */
+void vgpu_limiter_start(void); /* == reference initialization() (cuda_hook.c:566) */
+void vgpu_limiter_quiesce(vgpu_dev_rt *rt); /* ask a resident sampler to leave (sync paths) */
+
+/* metrics.c */
+enum { VM_RATE_GATED, VM_RATE_FAST, VM_OOM_LIMIT, VM_OOM_DRIVER, VM_UVA_FALLBACK, VM_LOCK_TIMEOUT,
+       VM_QUOTA_KERNELS, VM_SAMPLER_LAUNCHES, VM_COUNT };
+void vgpu_metric_add(int host_index, int which, uint64_t v);
+uint64_t vgpu_metric_get(int host_index, int which);
+
+#endif

@@ -1,0 +1,229 @@
+/*
+ * scenario.c - a scripted CUDA/NVML tenant used by the differential and GPU tests.
+ * TEST INFRASTRUCTURE.
+ *
+ * It binds the driver the way cudart does - dlopen("libcuda.so.1") + dlsym(), or with
+ * `--gpa` through cuGetProcAddress - so an LD_PRELOADed interception library (the reference's
+ * or ours) sees every call.  Commands come from stdin, one reply line each; replies contain
+ * return codes and sizes only (never pointer values), so the transcripts of two libraries
+ * driven by the same script can be compared byte for byte.
+ */
+#define _GNU_SOURCE
+#include <dlfcn.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+#include <unistd.h>
+
+typedef int CUresult;
+typedef unsigned long long CUdeviceptr;
+typedef struct { size_t W, H; int fmt; unsigned ch; } arr2_t;
+typedef struct { size_t W, H, D; int fmt; unsigned ch, flags; } arr3_t;
+typedef struct { int type, handle; struct { int type, id; } loc; void *w32; unsigned char flags[8]; } prop_t;
+typedef struct { unsigned long long total, free, used; } nvmem_t;
+typedef struct { unsigned version; unsigned long long total, reserved, free, used; } nvmem2_t;
+
+static void *h_cuda, *h_nvml;
+static int use_gpa;
+static CUresult (*p_gpa)(const char *, void **, int, unsigned long long, void *);
+
+static void *sym(const char *name) {
+  void *p = NULL;
+  if (!strncmp(name, "nvml", 4)) return dlsym(h_nvml, name);
+  if (use_gpa && p_gpa) {
+    /* cudart asks for base names and lets the driver pick the version */
+    char base[96];
+    snprintf(base, sizeof base, "%s", name);
+    char *v = strstr(base, "_v2");
+    if (v) *v = 0;
+    if (p_gpa(base, &p, 12090, 0, NULL) == 0 && p) return p;
+  }
+  return dlsym(h_cuda, name);
+}
+
+#define MAXH 4096
+static CUdeviceptr g_ptr[MAXH];
+static int g_kind[MAXH]; /* 1 linear, 2 array, 3 mipmap, 4 vmm */
+static int g_np;
+
+int main(int argc, char **argv) {
+  for (int i = 1; i < argc; i++)
+    if (!strcmp(argv[i], "--gpa")) use_gpa = 1;
+  h_cuda = dlopen("libcuda.so.1", RTLD_NOW | RTLD_GLOBAL);
+  h_nvml = dlopen("libnvidia-ml.so.1", RTLD_NOW | RTLD_GLOBAL);
+  if (!h_cuda || !h_nvml) { fprintf(stderr, "scenario: cannot load driver libs: %s\n", dlerror()); return 2; }
+  if (use_gpa) {
+    p_gpa = (CUresult(*)(const char *, void **, int, unsigned long long, void *))dlsym(h_cuda, "cuGetProcAddress_v2");
+    /* self-lookup, like cudart does: must come back as the interposer's own entry */
+    void *again = NULL;
+    if (p_gpa && p_gpa("cuGetProcAddress", &again, 12090, 0, NULL) == 0 && again)
+      p_gpa = (CUresult(*)(const char *, void **, int, unsigned long long, void *))again;
+  }
+  setvbuf(stdout, NULL, _IOLBF, 0);
+  void *nvdev = NULL;
+  void *ctx = NULL;
+  int dev = 0;
+  char line[4096];
+  while (fgets(line, sizeof line, stdin)) {
+    char cmd[64] = {0};
+    unsigned long long a = 0, b = 0, c = 0, d = 0, e = 0;
+    int n = sscanf(line, "%63s %llu %llu %llu %llu %llu", cmd, &a, &b, &c, &d, &e);
+    if (n < 1 || cmd[0] == '#') continue;
+    if (!strcmp(cmd, "init")) {
+      CUresult (*f_init)(unsigned) = sym("cuInit");
+      CUresult (*f_get)(int *, int) = sym("cuDeviceGet");
+      CUresult (*f_ret)(void **, int) = sym("cuDevicePrimaryCtxRetain");
+      CUresult (*f_set)(void *) = sym("cuCtxSetCurrent");
+      int (*n_init)(void) = sym("nvmlInit_v2");
+      int (*n_h)(unsigned, void **) = sym("nvmlDeviceGetHandleByIndex_v2");
+      CUresult r1 = f_init(0);
+      CUresult r2 = f_get(&dev, (int)a);
+      CUresult r3 = f_ret(&ctx, dev);
+      CUresult r4 = f_set(ctx);
+      int r5 = n_init();
+      int r6 = n_h((unsigned)a, &nvdev);
+      printf("init %d %d %d %d %d %d\n", r1, r2, r3, r4, r5, r6);
+    } else if (!strcmp(cmd, "alloc")) {
+      CUresult (*f)(CUdeviceptr *, size_t) = sym("cuMemAlloc_v2");
+      CUdeviceptr p = 0;
+      CUresult r = f(&p, (size_t)a);
+      if (r == 0) { g_ptr[g_np] = p; g_kind[g_np] = 1; g_np++; }
+      printf("alloc %llu -> %d h%d\n", a, r, r == 0 ? g_np - 1 : -1);
+    } else if (!strcmp(cmd, "managed")) {
+      CUresult (*f)(CUdeviceptr *, size_t, unsigned) = sym("cuMemAllocManaged");
+      CUdeviceptr p = 0;
+      CUresult r = f(&p, (size_t)a, (unsigned)b);
+      if (r == 0) { g_ptr[g_np] = p; g_kind[g_np] = 1; g_np++; }
+      printf("managed %llu %llu -> %d h%d\n", a, b, r, r == 0 ? g_np - 1 : -1);
+    } else if (!strcmp(cmd, "pitch")) {
+      CUresult (*f)(CUdeviceptr *, size_t *, size_t, size_t, unsigned) = sym("cuMemAllocPitch_v2");
+      CUdeviceptr p = 0;
+      size_t pitch = 0;
+      CUresult r = f(&p, &pitch, (size_t)a, (size_t)b, (unsigned)c);
+      if (r == 0) { g_ptr[g_np] = p; g_kind[g_np] = 1; g_np++; }
+      printf("pitch %llu %llu %llu -> %d pitch %zu h%d\n", a, b, c, r, r == 0 ? pitch : 0, r == 0 ? g_np - 1 : -1);
+    } else if (!strcmp(cmd, "allocasync")) {
+      CUresult (*f)(CUdeviceptr *, size_t, void *) = sym("cuMemAllocAsync");
+      CUdeviceptr p = 0;
+      CUresult r = f(&p, (size_t)a, NULL);
+      if (r == 0) { g_ptr[g_np] = p; g_kind[g_np] = 1; g_np++; }
+      printf("allocasync %llu -> %d h%d\n", a, r, r == 0 ? g_np - 1 : -1);
+    } else if (!strcmp(cmd, "pool")) {
+      CUresult (*f)(CUdeviceptr *, size_t, void *, void *) = sym("cuMemAllocFromPoolAsync");
+      CUdeviceptr p = 0;
+      CUresult r = f(&p, (size_t)a, NULL, NULL);
+      if (r == 0) { g_ptr[g_np] = p; g_kind[g_np] = 1; g_np++; }
+      printf("pool %llu -> %d h%d\n", a, r, r == 0 ? g_np - 1 : -1);
+    } else if (!strcmp(cmd, "create")) {
+      CUresult (*f)(unsigned long long *, size_t, const prop_t *, unsigned long long) = sym("cuMemCreate");
+      prop_t pr;
+      memset(&pr, 0, sizeof pr);
+      pr.type = 1; pr.loc.type = 1; pr.loc.id = dev;
+      unsigned long long h = 0;
+      CUresult r = f(&h, (size_t)a, &pr, 0);
+      if (r == 0) { g_ptr[g_np] = h; g_kind[g_np] = 4; g_np++; }
+      printf("create %llu -> %d h%d\n", a, r, r == 0 ? g_np - 1 : -1);
+    } else if (!strcmp(cmd, "array")) {
+      CUresult (*f)(void **, const arr2_t *) = sym("cuArrayCreate_v2");
+      arr2_t ds = {(size_t)a, (size_t)b, (int)c, (unsigned)d};
+      void *h = NULL;
+      CUresult r = f(&h, &ds);
+      if (r == 0) { g_ptr[g_np] = (CUdeviceptr)(uintptr_t)h; g_kind[g_np] = 2; g_np++; }
+      printf("array %llu %llu %llu %llu -> %d h%d\n", a, b, c, d, r, r == 0 ? g_np - 1 : -1);
+    } else if (!strcmp(cmd, "array3d") || !strcmp(cmd, "mipmap")) {
+      arr3_t ds = {(size_t)a, (size_t)b, (size_t)c, (int)d, (unsigned)e, 0};
+      void *h = NULL;
+      CUresult r;
+      if (cmd[0] == 'a') {
+        CUresult (*f)(void **, const arr3_t *) = sym("cuArray3DCreate_v2");
+        r = f(&h, &ds);
+      } else {
+        CUresult (*f)(void **, const arr3_t *, unsigned) = sym("cuMipmappedArrayCreate");
+        r = f(&h, &ds, 1);
+      }
+      if (r == 0) { g_ptr[g_np] = (CUdeviceptr)(uintptr_t)h; g_kind[g_np] = cmd[0] == 'a' ? 2 : 3; g_np++; }
+      printf("%s %llu %llu %llu %llu %llu -> %d h%d\n", cmd, a, b, c, d, e, r, r == 0 ? g_np - 1 : -1);
+    } else if (!strcmp(cmd, "free") || !strcmp(cmd, "freeasync")) {
+      CUresult r = 1;
+      if ((int)a < g_np && g_ptr[a]) {
+        if (g_kind[a] == 1) {
+          if (cmd[4]) { CUresult (*f)(CUdeviceptr, void *) = sym("cuMemFreeAsync"); r = f(g_ptr[a], NULL); }
+          else { CUresult (*f)(CUdeviceptr) = sym("cuMemFree_v2"); r = f(g_ptr[a]); }
+        } else if (g_kind[a] == 2) { CUresult (*f)(void *) = sym("cuArrayDestroy"); r = f((void *)(uintptr_t)g_ptr[a]); }
+        else if (g_kind[a] == 3) { CUresult (*f)(void *) = sym("cuMipmappedArrayDestroy"); r = f((void *)(uintptr_t)g_ptr[a]); }
+        else { CUresult (*f)(unsigned long long) = sym("cuMemRelease"); r = f(g_ptr[a]); }
+        if (r == 0) g_ptr[a] = 0;
+      }
+      printf("%s h%llu -> %d\n", cmd, a, r);
+    } else if (!strcmp(cmd, "meminfo")) {
+      CUresult (*f)(size_t *, size_t *) = sym("cuMemGetInfo_v2");
+      size_t fr = 0, tot = 0;
+      CUresult r = f(&fr, &tot);
+      printf("meminfo -> %d free %zu total %zu\n", r, fr, tot);
+    } else if (!strcmp(cmd, "totalmem")) {
+      CUresult (*f)(size_t *, int) = sym("cuDeviceTotalMem_v2");
+      size_t tot = 0;
+      CUresult r = f(&tot, dev);
+      printf("totalmem -> %d %zu\n", r, tot);
+    } else if (!strcmp(cmd, "nvmlinfo")) {
+      int (*f)(void *, nvmem_t *) = sym("nvmlDeviceGetMemoryInfo");
+      nvmem_t m = {0, 0, 0};
+      int r = f(nvdev, &m);
+      printf("nvmlinfo -> %d total %llu free %llu used %llu\n", r, m.total, m.free, m.used);
+    } else if (!strcmp(cmd, "nvmlinfo2")) {
+      int (*f)(void *, nvmem2_t *) = sym("nvmlDeviceGetMemoryInfo_v2");
+      nvmem2_t m;
+      memset(&m, 0, sizeof m);
+      m.version = (unsigned)(sizeof m | (2u << 24));
+      int r = f(nvdev, &m);
+      printf("nvmlinfo2 -> %d total %llu reserved %llu free %llu used %llu\n", r, m.total, m.reserved, m.free, m.used);
+    } else if (!strcmp(cmd, "setmode")) {
+      int (*f)(void *, int) = sym("nvmlDeviceSetComputeMode");
+      printf("setmode -> %d\n", f(nvdev, (int)a));
+    } else if (!strcmp(cmd, "persistence")) {
+      int (*f)(void *, int *) = sym("nvmlDeviceGetPersistenceMode");
+      int m = -1;
+      int r = f(nvdev, &m);
+      printf("persistence -> %d mode %d\n", r, m);
+    } else if (!strcmp(cmd, "launch")) {
+      CUresult (*f)(void *, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, void *, void **, void **) =
+          sym("cuLaunchKernel");
+      unsigned long long okc = 0;
+      struct timespec t0, t1;
+      clock_gettime(CLOCK_MONOTONIC, &t0);
+      for (unsigned long long i = 0; i < a; i++) okc += f(NULL, (unsigned)b, (unsigned)c, (unsigned)d, 1, 1, 1, 0, NULL, NULL, NULL) == 0;
+      clock_gettime(CLOCK_MONOTONIC, &t1);
+      double sec = (t1.tv_sec - t0.tv_sec) + (t1.tv_nsec - t0.tv_nsec) * 1e-9;
+      printf("launch %llu -> ok %llu\n", a, okc);
+      fprintf(stderr, "launch_rate %.0f per_s\n", sec > 0 ? a / sec : 0.0);
+    } else if (!strcmp(cmd, "ledger")) {
+      /* raw bytes of this GPU's record in vmem_node.config; pids are normalised to rank order */
+      const char *path = getenv("SCENARIO_LEDGER");
+      FILE *fp = path ? fopen(path, "rb") : NULL;
+      if (!fp) { printf("ledger -> absent\n"); continue; }
+      static unsigned char rec[16392];
+      fseek(fp, (long)(a * 16392), SEEK_SET);
+      size_t got = fread(rec, 1, sizeof rec, fp);
+      fclose(fp);
+      unsigned sz = 0;
+      if (got == sizeof rec) memcpy(&sz, rec + 16384, 4);
+      printf("ledger -> size %u", sz);
+      for (unsigned i = 0; i < sz && i < 8; i++) {
+        int pid; unsigned long long used;
+        memcpy(&pid, rec + i * 16, 4);
+        memcpy(&used, rec + i * 16 + 8, 8);
+        printf(" [%s %llu]", pid == getpid() ? "self" : "other", used);
+      }
+      printf("\n");
+    } else if (!strcmp(cmd, "sleepms")) {
+      struct timespec ts = {(time_t)(a / 1000), (long)(a % 1000) * 1000000L};
+      nanosleep(&ts, NULL);
+      printf("sleepms %llu\n", a);
+    } else {
+      printf("unknown %s\n", cmd);
+    }
+  }
+  return 0;
+}

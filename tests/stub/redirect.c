@@ -59,9 +59,19 @@ static const char *rw(const char *path, char *buf, size_t cap) {
   return path;
 }
 
+/* dlvsym, not dlsym: the libraries under test interpose `dlsym` itself and would answer an
+ * RTLD_NEXT query relative to themselves */
+static void *next_sym(const char *name) {
+  static const char *vers[] = {"GLIBC_2.2.5", "GLIBC_2.33", "GLIBC_2.34", "GLIBC_2.17", NULL};
+  for (int i = 0; vers[i]; i++) {
+    void *p = dlvsym(RTLD_NEXT, name, vers[i]);
+    if (p) return p;
+  }
+  return NULL;
+}
 #define REAL(name) \
   static __typeof__(name) *real_fn = NULL; \
-  if (!real_fn) real_fn = (__typeof__(name) *)dlsym(RTLD_NEXT, #name)
+  if (!real_fn) real_fn = (__typeof__(name) *)next_sym(#name)
 
 int open(const char *path, int flags, ...) {
   REAL(open);

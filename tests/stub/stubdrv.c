@@ -1,0 +1,644 @@
+/*
+ * stubdrv.c - a fake NVIDIA driver (libcuda.so.1 + libnvidia-ml.so.1 in one object) for
+ * CPU-only plumbing tests.  TEST INFRASTRUCTURE, never shipped.
+ *
+ * The reference has no mock driver; this one exists so that both the
+ * reference library (oracle/_ref) and the B200 library can be driven through the identical
+ * scripted scenario on a box without a GPU (BASELINE.json configs[0]) and their outputs diffed.
+ *
+ *  - "device memory" is host memory (mmap, lazily committed), so device pointers are valid
+ *    host pointers and pinned/mapped host blocks map to themselves;
+ *  - per-process usedGpuMemory = STUB_CTX_BYTES + sum of live device allocations of this
+ *    process; extra tenants come from STUB_OTHER_PROCS="pid:bytes:c|g|cg,...";
+ *  - SM utilisation model: STUB_UTIL="fixed:N" or "closed:K" (util% = launches in the last
+ *    second * K / 1000, capped at 100) - a fixed value above the cap deadlocks the
+ *    reference's storm, hence the closed-loop default;
+ *  - the fake GPU can "run" the B200 library's kernels: cuModuleGetFunction() resolves the
+ *    entry names of vgpu_manager_b200/csrc/kernel_abi.h and cuLaunchKernel() executes them
+ *    with the CPU oracle (oracle/vgpu_oracle.c).  That makes the host logic testable here; the
+ *    real kernels are tested against the same oracle on a B200 (tests/test_gpu_*.py).
+ */
+#define _GNU_SOURCE
+#include <dlfcn.h>
+#include <errno.h>
+#include <pthread.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/mman.h>
+#include <sys/time.h>
+#include <time.h>
+#include <unistd.h>
+
+#include "../../oracle/vgpu_oracle.h"
+#include "../../vgpu_manager_b200/csrc/kernel_abi.h"
+
+#define EXPORT __attribute__((visibility("default")))
+typedef int CUresult;
+typedef int CUdevice;
+typedef unsigned long long CUdeviceptr;
+typedef int nvmlReturn_t;
+
+/* ------------------------------------------------------------------ state */
+static pthread_mutex_t g_mu = PTHREAD_MUTEX_INITIALIZER;
+static int g_inited, g_gpu_count = 1;
+static uint64_t g_total_mem = 180ull << 30, g_phys_mem, g_ctx_bytes;
+typedef struct { void *p; size_t n; int kind; int dev; } alloc_t; /* kind 0 device, 1 managed, 2 host, 3 vmm handle */
+static alloc_t *g_allocs;
+static size_t g_nallocs, g_callocs;
+static uint64_t g_dev_bytes[16];
+static __thread int t_cur_dev = 0;
+static __thread int t_has_ctx = 0;
+static int g_any_ctx;
+
+typedef struct { uint32_t pid; uint64_t bytes; int compute, graphics; int sm; } other_t;
+static other_t g_others[64];
+static int g_nothers;
+
+static int g_util_mode = 1;        /* 0 fixed, 1 closed loop */
+static int g_util_fixed = 0;
+static double g_util_k = 0.05;     /* percent per launch/second/1000 -> see below */
+#define NB 128
+static uint64_t g_bucket_ms[NB];
+static uint32_t g_bucket_cnt[NB];
+static volatile uint64_t g_launches;
+
+static uint64_t now_ms(void) {
+  struct timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return (uint64_t)ts.tv_sec * 1000 + ts.tv_nsec / 1000000;
+}
+static uint64_t now_us_wall(void) {
+  struct timeval tv;
+  gettimeofday(&tv, NULL);
+  return (uint64_t)tv.tv_sec * 1000000ull + tv.tv_usec;
+}
+
+static void note_launch(void) {
+  uint64_t ms = now_ms() / 10; /* 10 ms buckets */
+  uint32_t i = (uint32_t)(ms % NB);
+  if (g_bucket_ms[i] != ms) { g_bucket_ms[i] = ms; g_bucket_cnt[i] = 0; }
+  g_bucket_cnt[i]++;
+  __sync_fetch_and_add(&g_launches, 1);
+}
+
+static int current_util(void) {
+  if (g_util_mode == 0) return g_util_fixed;
+  uint64_t ms = now_ms() / 10, n = 0;
+  for (int i = 0; i < NB; i++)
+    if (g_bucket_ms[i] + 100 > ms) n += g_bucket_cnt[i];
+  double u = (double)n * g_util_k / 1000.0;
+  return u > 100 ? 100 : (int)u;
+}
+
+static void stub_init(void) {
+  if (g_inited) return;
+  pthread_mutex_lock(&g_mu);
+  if (!g_inited) {
+    const char *s;
+    if ((s = getenv("STUB_GPU_COUNT"))) g_gpu_count = atoi(s);
+    if (g_gpu_count < 1) g_gpu_count = 1;
+    if (g_gpu_count > 16) g_gpu_count = 16;
+    if ((s = getenv("STUB_TOTAL_MEM"))) g_total_mem = strtoull(s, NULL, 10);
+    g_phys_mem = g_total_mem;
+    if ((s = getenv("STUB_PHYS_MEM"))) g_phys_mem = strtoull(s, NULL, 10);
+    if ((s = getenv("STUB_CTX_BYTES"))) g_ctx_bytes = strtoull(s, NULL, 10);
+    if ((s = getenv("STUB_OTHER_PROCS"))) {
+      char *dup = strdup(s), *save = NULL;
+      for (char *t = strtok_r(dup, ",", &save); t && g_nothers < 64; t = strtok_r(NULL, ",", &save)) {
+        unsigned pid = 0; unsigned long long b = 0; char kind[8] = "c"; int sm = 0;
+        int got = sscanf(t, "%u:%llu:%7[a-z]:%d", &pid, &b, kind, &sm);
+        if (got >= 2) {
+          other_t *o = &g_others[g_nothers++];
+          o->pid = pid; o->bytes = b; o->sm = sm;
+          o->compute = strchr(kind, 'c') != NULL;
+          o->graphics = strchr(kind, 'g') != NULL;
+        }
+      }
+      free(dup);
+    }
+    if ((s = getenv("STUB_UTIL"))) {
+      if (!strncmp(s, "fixed:", 6)) { g_util_mode = 0; g_util_fixed = atoi(s + 6); }
+      else if (!strncmp(s, "closed:", 7)) { g_util_mode = 1; g_util_k = atof(s + 7); }
+    }
+    g_inited = 1;
+  }
+  pthread_mutex_unlock(&g_mu);
+}
+
+/* harness control (dlsym'd by the test programs) */
+EXPORT void stub_ctl_set_util(int pct) { g_util_mode = 0; g_util_fixed = pct; }
+EXPORT unsigned long long stub_ctl_launches(void) { return g_launches; }
+EXPORT unsigned long long stub_ctl_device_bytes(int dev) { return g_dev_bytes[dev & 15]; }
+
+static void track(void *p, size_t n, int kind, int dev) {
+  pthread_mutex_lock(&g_mu);
+  if (g_nallocs == g_callocs) {
+    g_callocs = g_callocs ? g_callocs * 2 : 256;
+    g_allocs = (alloc_t *)realloc(g_allocs, g_callocs * sizeof(alloc_t));
+  }
+  g_allocs[g_nallocs++] = (alloc_t){p, n, kind, dev};
+  if (kind == 0 || kind == 3) g_dev_bytes[dev] += n;
+  pthread_mutex_unlock(&g_mu);
+}
+
+static int untrack(void *p, alloc_t *out) {
+  int found = 0;
+  pthread_mutex_lock(&g_mu);
+  for (size_t i = g_nallocs; i-- > 0;)
+    if (g_allocs[i].p == p) {
+      *out = g_allocs[i];
+      g_allocs[i] = g_allocs[--g_nallocs];
+      if (out->kind == 0 || out->kind == 3) g_dev_bytes[out->dev] -= out->n;
+      found = 1;
+      break;
+    }
+  pthread_mutex_unlock(&g_mu);
+  return found;
+}
+
+static void *big_alloc(size_t n) {
+  size_t len = (n + 4095) & ~(size_t)4095;
+  if (!len) len = 4096;
+  void *p = mmap(NULL, len, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
+  return p == MAP_FAILED ? NULL : p;
+}
+static void big_free(void *p, size_t n) {
+  size_t len = (n + 4095) & ~(size_t)4095;
+  if (!len) len = 4096;
+  munmap(p, len);
+}
+
+/* ------------------------------------------------------------------ CUDA: basics */
+EXPORT CUresult cuInit(unsigned f) { (void)f; stub_init(); return 0; }
+EXPORT CUresult cuDriverGetVersion(int *v) { stub_init(); *v = 12090; return 0; }
+EXPORT CUresult cuDeviceGetCount(int *n) { stub_init(); *n = g_gpu_count; return 0; }
+EXPORT CUresult cuDeviceGet(CUdevice *d, int ord) { stub_init(); if (ord < 0 || ord >= g_gpu_count) return 101; *d = ord; return 0; }
+EXPORT CUresult cuDeviceGetAttribute(int *pi, int attr, CUdevice d) {
+  (void)d;
+  switch (attr) {
+  case 16: *pi = 148; break;     /* MULTIPROCESSOR_COUNT */
+  case 39: *pi = 2048; break;    /* MAX_THREADS_PER_MULTIPROCESSOR */
+  case 122: *pi = 1; break;      /* CAN_USE_64_BIT_STREAM_MEM_OPS */
+  case 75: *pi = 10; break;      /* CC major */
+  case 76: *pi = 0; break;
+  default: *pi = 0;
+  }
+  return 0;
+}
+static void uuid_bytes(int dev, unsigned char *b) { memset(b, 0x11 * (dev + 1), 16); }
+EXPORT CUresult cuDeviceGetUuid(void *uuid, CUdevice d) { uuid_bytes(d, (unsigned char *)uuid); return 0; }
+EXPORT CUresult cuDeviceGetUuid_v2(void *uuid, CUdevice d) { uuid_bytes(d, (unsigned char *)uuid); return 0; }
+EXPORT CUresult cuDeviceGetName(char *name, int len, CUdevice d) { snprintf(name, len, "STUB B200 #%d", d); return 0; }
+EXPORT CUresult cuDeviceTotalMem_v2(size_t *b, CUdevice d) { (void)d; stub_init(); *b = g_total_mem; return 0; }
+EXPORT CUresult cuGetErrorString(CUresult r, const char **s) {
+  *s = r == 0 ? "no error" : r == 2 ? "out of memory" : r == 201 ? "invalid device context" : "stub error";
+  return 0;
+}
+EXPORT CUresult cuGetErrorName(CUresult r, const char **s) { return cuGetErrorString(r, s); }
+
+/* contexts: one implicit primary context per device, made current by the harness */
+EXPORT CUresult cuDevicePrimaryCtxRetain(void **ctx, CUdevice d) { stub_init(); *ctx = (void *)(uintptr_t)(0x1000 + d); g_any_ctx = 1; return 0; }
+EXPORT CUresult cuDevicePrimaryCtxRelease_v2(CUdevice d) { (void)d; return 0; }
+EXPORT CUresult cuCtxCreate_v2(void **ctx, unsigned f, CUdevice d) { (void)f; stub_init(); *ctx = (void *)(uintptr_t)(0x1000 + d); t_cur_dev = d; t_has_ctx = 1; g_any_ctx = 1; return 0; }
+EXPORT CUresult cuCtxDestroy_v2(void *ctx) { (void)ctx; return 0; }
+EXPORT CUresult cuCtxSetCurrent(void *ctx) { if (!ctx) { t_has_ctx = 0; return 0; } t_cur_dev = (int)((uintptr_t)ctx - 0x1000); t_has_ctx = 1; return 0; }
+EXPORT CUresult cuCtxGetCurrent(void **ctx) { *ctx = t_has_ctx ? (void *)(uintptr_t)(0x1000 + t_cur_dev) : NULL; return 0; }
+static __thread void *t_stack[8];
+static __thread int t_sp;
+EXPORT CUresult cuCtxPushCurrent_v2(void *ctx) { if (t_sp < 8) t_stack[t_sp++] = t_has_ctx ? (void *)(uintptr_t)(0x1000 + t_cur_dev) : NULL; return cuCtxSetCurrent(ctx); }
+EXPORT CUresult cuCtxPopCurrent_v2(void **ctx) { if (ctx) cuCtxGetCurrent(ctx); void *prev = t_sp ? t_stack[--t_sp] : NULL; return cuCtxSetCurrent(prev); }
+EXPORT CUresult cuCtxGetDevice(CUdevice *d) { if (!t_has_ctx) return 201; *d = t_cur_dev; return 0; }
+EXPORT CUresult cuCtxSynchronize(void) { return t_has_ctx ? 0 : 201; }
+EXPORT CUresult cuCtxGetStreamPriorityRange(int *lo, int *hi) { *lo = 0; *hi = -5; return 0; }
+
+/* ------------------------------------------------------------------ CUDA: memory */
+static CUresult dev_alloc(CUdeviceptr *dptr, size_t n, int kind) {
+  stub_init();
+  if (!t_has_ctx) return 201;
+  if (n == 0) return 1;
+  if (kind == 0 && g_dev_bytes[t_cur_dev] + g_ctx_bytes + n > g_phys_mem) return 2;
+  void *p = big_alloc(n);
+  if (!p) return 2;
+  track(p, n, kind, t_cur_dev);
+  *dptr = (CUdeviceptr)(uintptr_t)p;
+  return 0;
+}
+EXPORT CUresult cuMemAlloc_v2(CUdeviceptr *d, size_t n) { return dev_alloc(d, n, 0); }
+EXPORT CUresult cuMemAllocManaged(CUdeviceptr *d, size_t n, unsigned f) { (void)f; return dev_alloc(d, n, 1); }
+EXPORT CUresult cuMemAllocPitch_v2(CUdeviceptr *d, size_t *pitch, size_t w, size_t h, unsigned e) {
+  (void)e;
+  size_t p = (w + 511) & ~(size_t)511;
+  CUresult r = dev_alloc(d, p * h, 0);
+  if (r == 0) *pitch = p;
+  return r;
+}
+EXPORT CUresult cuMemAllocAsync(CUdeviceptr *d, size_t n, void *s) { (void)s; return dev_alloc(d, n, 0); }
+EXPORT CUresult cuMemAllocAsync_ptsz(CUdeviceptr *d, size_t n, void *s) { (void)s; return dev_alloc(d, n, 0); }
+EXPORT CUresult cuMemAllocFromPoolAsync(CUdeviceptr *d, size_t n, void *pool, void *s) { (void)pool; (void)s; return dev_alloc(d, n, 0); }
+EXPORT CUresult cuMemAllocFromPoolAsync_ptsz(CUdeviceptr *d, size_t n, void *pool, void *s) { (void)pool; (void)s; return dev_alloc(d, n, 0); }
+static CUresult dev_free(CUdeviceptr d) {
+  if (!t_has_ctx) return 201;
+  alloc_t a;
+  if (!untrack((void *)(uintptr_t)d, &a)) return 1;
+  big_free(a.p, a.n);
+  return 0;
+}
+EXPORT CUresult cuMemFree_v2(CUdeviceptr d) { return dev_free(d); }
+EXPORT CUresult cuMemFreeAsync(CUdeviceptr d, void *s) { (void)s; return dev_free(d); }
+EXPORT CUresult cuMemFreeAsync_ptsz(CUdeviceptr d, void *s) { (void)s; return dev_free(d); }
+EXPORT CUresult cuMemGetInfo_v2(size_t *fr, size_t *tot) {
+  stub_init();
+  if (!t_has_ctx) return 201;
+  uint64_t used = g_dev_bytes[t_cur_dev] + g_ctx_bytes;
+  for (int i = 0; i < g_nothers; i++) used += g_others[i].bytes;
+  *tot = g_total_mem;
+  *fr = used >= g_total_mem ? 0 : g_total_mem - used;
+  return 0;
+}
+EXPORT CUresult cuMemCreate(unsigned long long *h, size_t n, const void *prop, unsigned long long f) {
+  (void)prop; (void)f;
+  stub_init();
+  int dev = t_has_ctx ? t_cur_dev : 0;
+  if (g_dev_bytes[dev] + g_ctx_bytes + n > g_phys_mem) return 2;
+  void *p = big_alloc(1);
+  track(p, n, 3, dev);
+  *h = (unsigned long long)(uintptr_t)p;
+  return 0;
+}
+EXPORT CUresult cuMemRelease(unsigned long long h) { alloc_t a; if (!untrack((void *)(uintptr_t)h, &a)) return 1; big_free(a.p, 1); return 0; }
+typedef struct { size_t W, H; int fmt; unsigned ch; } arr2_t;
+typedef struct { size_t W, H, D; int fmt; unsigned ch, flags; } arr3_t;
+static size_t fmt_bytes(int f) { return (f == 1 || f == 8) ? 1 : (f == 2 || f == 9 || f == 0x10) ? 2 : 4; }
+EXPORT CUresult cuArrayCreate_v2(void **h, const arr2_t *d) {
+  CUdeviceptr p;
+  CUresult r = dev_alloc(&p, fmt_bytes(d->fmt) * d->ch * d->W * (d->H ? d->H : 1), 0);
+  if (r == 0) *h = (void *)(uintptr_t)p;
+  return r;
+}
+EXPORT CUresult cuArray3DCreate_v2(void **h, const arr3_t *d) {
+  CUdeviceptr p;
+  CUresult r = dev_alloc(&p, fmt_bytes(d->fmt) * d->ch * d->W * (d->H ? d->H : 1) * (d->D ? d->D : 1), 0);
+  if (r == 0) *h = (void *)(uintptr_t)p;
+  return r;
+}
+EXPORT CUresult cuMipmappedArrayCreate(void **h, const arr3_t *d, unsigned levels) { (void)levels; return cuArray3DCreate_v2(h, d); }
+EXPORT CUresult cuArrayDestroy(void *h) { return dev_free((CUdeviceptr)(uintptr_t)h); }
+EXPORT CUresult cuMipmappedArrayDestroy(void *h) { return dev_free((CUdeviceptr)(uintptr_t)h); }
+EXPORT CUresult cuMemHostAlloc(void **pp, size_t n, unsigned f) { (void)f; *pp = big_alloc(n); if (!*pp) return 2; track(*pp, n, 2, 0); return 0; }
+EXPORT CUresult cuMemFreeHost(void *p) { alloc_t a; if (!untrack(p, &a)) return 1; big_free(a.p, a.n); return 0; }
+EXPORT CUresult cuMemHostGetDevicePointer_v2(CUdeviceptr *d, void *p, unsigned f) { (void)f; *d = (CUdeviceptr)(uintptr_t)p; return 0; }
+EXPORT CUresult cuMemsetD8_v2(CUdeviceptr d, unsigned char v, size_t n) { memset((void *)(uintptr_t)d, v, n); return 0; }
+EXPORT CUresult cuMemcpyDtoH_v2(void *dst, CUdeviceptr src, size_t n) { memcpy(dst, (void *)(uintptr_t)src, n); return 0; }
+EXPORT CUresult cuMemcpyHtoD_v2(CUdeviceptr dst, const void *src, size_t n) { memcpy((void *)(uintptr_t)dst, src, n); return 0; }
+
+/* ------------------------------------------------------------------ CUDA: streams */
+EXPORT CUresult cuStreamCreate(void **s, unsigned f) { (void)f; static uintptr_t next = 0x5000; *s = (void *)(next += 0x10); return 0; }
+EXPORT CUresult cuStreamCreateWithPriority(void **s, unsigned f, int p) { (void)p; return cuStreamCreate(s, f); }
+EXPORT CUresult cuStreamDestroy_v2(void *s) { (void)s; return 0; }
+EXPORT CUresult cuStreamSynchronize(void *s) { (void)s; return 0; }
+EXPORT CUresult cuStreamQuery(void *s) { (void)s; return 0; }
+EXPORT CUresult cuStreamIsCapturing(void *s, int *st) { (void)s; *st = 0; return 0; }
+static CUresult wait64(CUdeviceptr addr, unsigned long long value) {
+  /* the fake GPU executes stream work synchronously, so a stream wait blocks the caller */
+  volatile long long *p = (volatile long long *)(uintptr_t)addr;
+  struct timespec nap = {0, 200000};
+  for (int i = 0; i < 100000; i++) { /* 20 s cap */
+    if ((long long)(*p - (long long)value) >= 0) return 0;
+    nanosleep(&nap, NULL);
+  }
+  return 0;
+}
+EXPORT CUresult cuStreamWaitValue64_v2(void *s, CUdeviceptr a, unsigned long long v, unsigned f) { (void)s; (void)f; return wait64(a, v); }
+EXPORT CUresult cuStreamWaitValue64_v2_ptsz(void *s, CUdeviceptr a, unsigned long long v, unsigned f) { (void)s; (void)f; return wait64(a, v); }
+EXPORT CUresult cuStreamWriteValue64_v2(void *s, CUdeviceptr a, unsigned long long v, unsigned f) { (void)s; (void)f; *(volatile unsigned long long *)(uintptr_t)a = v; return 0; }
+EXPORT CUresult cuStreamWriteValue64_v2_ptsz(void *s, CUdeviceptr a, unsigned long long v, unsigned f) { (void)s; (void)f; *(volatile unsigned long long *)(uintptr_t)a = v; return 0; }
+
+/* ------------------------------------------------------------------ CUDA: modules and the fake GPU's kernels */
+typedef struct { char name[64]; } fn_t;
+EXPORT CUresult cuModuleLoadData(void **m, const void *img) { (void)img; *m = (void *)0x7000; return 0; }
+EXPORT CUresult cuModuleUnload(void *m) { (void)m; return 0; }
+EXPORT CUresult cuModuleGetFunction(void **f, void *m, const char *name) {
+  (void)m;
+  fn_t *fn = (fn_t *)calloc(1, sizeof(fn_t));
+  snprintf(fn->name, sizeof fn->name, "%s", name);
+  *f = fn;
+  return 0;
+}
+EXPORT CUresult cuFuncSetAttribute(void *f, int a, int v) { (void)f; (void)a; (void)v; return 0; }
+EXPORT CUresult cuFuncSetBlockShape(void *f, int x, int y, int z) { (void)f; (void)x; (void)y; (void)z; return 0; }
+
+static void fake_quota(const vgpu_quota_req_t *q, vgpu_quota_res_t *r) {
+  uint8_t cp[VGPU_MAX_PIDS], cl[VGPU_MAX_PIDS], gp[VGPU_MAX_PIDS], gl[VGPU_MAX_PIDS];
+  for (uint32_t i = 0; i < q->n_compute; i++) { cp[i] = q->cflags[i] & VGPU_FLAG_PRIMARY; cl[i] = (q->cflags[i] & VGPU_FLAG_LOCAL) != 0; }
+  for (uint32_t i = 0; i < q->n_graphics; i++) { gp[i] = q->gflags[i] & VGPU_FLAG_PRIMARY; gl[i] = (q->gflags[i] & VGPU_FLAG_LOCAL) != 0; }
+  uint64_t used = orc_used_memory((int)q->mode, q->compute, q->n_compute, cp, cl, q->graphics, q->n_graphics, gp, gl);
+  used = used >= q->self_bytes ? used - q->self_bytes : 0;
+  vgpu_vmem_dev_t *led = (vgpu_vmem_dev_t *)calloc(1, sizeof *led);
+  memcpy(led->processes, q->vmem, (size_t)q->n_vmem * sizeof(vgpu_vmem_rec_t));
+  led->processes_size = q->n_vmem;
+  uint64_t vmem = orc_ledger_sum(led);
+  free(led);
+  vgpu_cfg_dev_t c;
+  memset(&c, 0, sizeof c);
+  c.total_memory = q->total_memory;
+  c.real_memory = q->real_memory;
+  c.memory_oversold = (int)q->memory_oversold;
+  c.memory_limit = 1;
+  r->used = used;
+  r->vmem = vmem;
+  r->total = q->total_memory;
+  r->out_used = r->out_free = 0;
+  r->path = VGPU_PATH_GPU;
+  if (q->kind == VGPU_Q_ALLOC) {
+    r->path = (uint32_t)orc_memory_path(&c, used, vmem, q->request, (int)q->allow_uva);
+  } else if (q->kind == VGPU_Q_NVML_INFO) {
+    orc_nvml_meminfo(&c, used, vmem, &r->total, &r->out_used, &r->out_free);
+  } else {
+    orc_cu_meminfo(&c, used, vmem, (int)q->real_ok, q->real_total, &r->out_free, &r->total);
+    r->out_used = r->total - r->out_free;
+  }
+  __sync_synchronize();
+  r->seq_done = q->seq;
+}
+
+static void fake_ctl_step(vgpu_lim_dev_t *D, vgpu_lim_host_t *H, int user, int sys, int valid, int nproc) {
+  orc_gpu_t g = {D->sm_num, D->max_thread_per_sm, D->total_cores};
+  vgpu_cfg_dev_t c;
+  memset(&c, 0, sizeof c);
+  c.hard_core = D->hard_core; c.soft_core = D->soft_core; c.core_limit = D->core_limit; c.hard_limit = D->hard_limit;
+  orc_watcher_t w = {D->share, D->sys_free, D->avg_sys_free, D->ctr_i, D->pre_sys_process_num, D->up_limit, 0};
+  if (valid) D->valid = 1;
+  orc_util_t u = {user, sys, D->valid, nproc};
+  long long consumed = H->consumed;
+  int64_t bucket = D->granted - consumed;
+  orc_watcher_step(&g, &c, &w, &u, &bucket);
+  D->share = w.share; D->sys_free = w.sys_free; D->avg_sys_free = w.avg_sys_free; D->ctr_i = w.i;
+  D->pre_sys_process_num = w.pre_sys_process_num; D->up_limit = w.up_limit;
+  if (D->core_limit && D->valid) D->granted = bucket + consumed;
+  D->bucket_last = bucket;
+  D->last_user_current = user; D->last_sys_current = sys;
+  D->steps++;
+  H->granted_mirror = D->granted; H->bucket_mirror = bucket; H->share_mirror = D->share;
+  H->up_limit_mirror = D->up_limit; H->user_current = user; H->sys_current = sys;
+  H->steps = D->steps;
+}
+
+static void run_fake_kernel(const char *name, void **p) {
+  if (!strcmp(name, VGPU_K_CLEAR)) {
+    unsigned long long n = *(unsigned long long *)p[1];
+    if (n) memset((void *)(uintptr_t) * (CUdeviceptr *)p[0], 0, n);
+  } else if (!strcmp(name, VGPU_K_SPILL) || !strcmp(name, "vgpu_copy_generic_kernel")) {
+    unsigned long long n = *(unsigned long long *)p[2];
+    if (n) memmove((void *)(uintptr_t) * (CUdeviceptr *)p[0], (void *)(uintptr_t) * (CUdeviceptr *)p[1], n);
+  } else if (!strcmp(name, VGPU_K_QUOTA)) {
+    fake_quota((const vgpu_quota_req_t *)(uintptr_t) * (CUdeviceptr *)p[0], (vgpu_quota_res_t *)(uintptr_t) * (CUdeviceptr *)p[1]);
+  } else if (!strcmp(name, VGPU_K_SLAB_INSERT)) {
+    vgpu_slab_slot_t *slab = (vgpu_slab_slot_t *)(uintptr_t) * (CUdeviceptr *)p[0];
+    unsigned long long dptr = *(unsigned long long *)p[1], bytes = *(unsigned long long *)p[2];
+    vgpu_slab_res_t *res = (vgpu_slab_res_t *)(uintptr_t) * (CUdeviceptr *)p[3];
+    uint32_t seq = *(uint32_t *)p[4], slot = 0xffffffffu;
+    for (uint32_t i = 0; i < VGPU_SLAB_SLOTS; i++)
+      if (slab[i].dptr <= 1) { slab[i].dptr = dptr; slab[i].bytes = bytes; slot = i; break; }
+    res->bytes = bytes; res->slot = slot;
+    __sync_synchronize();
+    res->seq_done = seq;
+  } else if (!strcmp(name, VGPU_K_SLAB_REMOVE)) {
+    vgpu_slab_slot_t *slab = (vgpu_slab_slot_t *)(uintptr_t) * (CUdeviceptr *)p[0];
+    unsigned long long dptr = *(unsigned long long *)p[1];
+    vgpu_slab_res_t *res = (vgpu_slab_res_t *)(uintptr_t) * (CUdeviceptr *)p[2];
+    uint32_t seq = *(uint32_t *)p[3], slot = 0xffffffffu;
+    unsigned long long bytes = 0;
+    for (uint32_t i = 0; i < VGPU_SLAB_SLOTS; i++)
+      if (slab[i].dptr == dptr && dptr > 1) { bytes = slab[i].bytes; slab[i].dptr = 1; slab[i].bytes = 0; slot = i; break; }
+    res->bytes = bytes; res->slot = slot;
+    __sync_synchronize();
+    res->seq_done = seq;
+  } else if (!strcmp(name, VGPU_K_CONTROLLER)) {
+    vgpu_ctrl_in_t *in = (vgpu_ctrl_in_t *)p[2];
+    fake_ctl_step((vgpu_lim_dev_t *)(uintptr_t) * (CUdeviceptr *)p[0], (vgpu_lim_host_t *)(uintptr_t) * (CUdeviceptr *)p[1],
+                  in->user_current, in->sys_current, in->valid, in->sys_process_num);
+  } else if (!strcmp(name, VGPU_K_SAMPLER)) {
+    vgpu_lim_dev_t *D = (vgpu_lim_dev_t *)(uintptr_t) * (CUdeviceptr *)p[0];
+    vgpu_lim_host_t *H = (vgpu_lim_host_t *)(uintptr_t) * (CUdeviceptr *)p[1];
+    uint32_t period = *(uint32_t *)p[4];
+    int util = current_util();
+    D->busy_samples += (unsigned long long)util;
+    D->total_samples += 100;
+    if (++D->period_tick >= period) {
+      D->period_tick = 0;
+      int q = D->total_samples ? (int)(D->busy_samples * 100 / D->total_samples) : 0;
+      D->last_queue_busy_pct = q;
+      D->busy_samples = D->total_samples = 0;
+      int user = H->ext_user_override >= 0 ? H->ext_user_override : q;
+      int others = H->ext_sys_current > 0 ? H->ext_sys_current : 0;
+      int np = H->ext_sys_process_num > 0 ? H->ext_sys_process_num : 1;
+      fake_ctl_step(D, H, user, user + others, 1, np);
+    }
+  } else if (!strcmp(name, VGPU_K_GATE)) {
+    wait64(*(CUdeviceptr *)p[0], (unsigned long long)*(long long *)p[1]);
+  } else {
+    note_launch(); /* a tenant kernel */
+  }
+}
+
+static CUresult launch(void *f, void **params) {
+  if (!t_has_ctx) return 201;
+  fn_t *fn = (fn_t *)f;
+  if (fn && ((uintptr_t)fn > 0x10000) && !strncmp(fn->name, "vgpu_", 5)) run_fake_kernel(fn->name, params);
+  else note_launch();
+  return 0;
+}
+EXPORT CUresult cuLaunchKernel(void *f, unsigned gx, unsigned gy, unsigned gz, unsigned bx, unsigned by, unsigned bz,
+                               unsigned sm, void *s, void **params, void **extra) {
+  (void)gx; (void)gy; (void)gz; (void)bx; (void)by; (void)bz; (void)sm; (void)s; (void)extra;
+  return launch(f, params);
+}
+EXPORT CUresult cuLaunchKernel_ptsz(void *f, unsigned gx, unsigned gy, unsigned gz, unsigned bx, unsigned by, unsigned bz,
+                                    unsigned sm, void *s, void **params, void **extra) {
+  return cuLaunchKernel(f, gx, gy, gz, bx, by, bz, sm, s, params, extra);
+}
+EXPORT CUresult cuLaunchKernelEx(const void *cfg, void *f, void **params, void **extra) { (void)cfg; (void)extra; return launch(f, params); }
+EXPORT CUresult cuLaunchKernelEx_ptsz(const void *cfg, void *f, void **params, void **extra) { (void)cfg; (void)extra; return launch(f, params); }
+EXPORT CUresult cuLaunchCooperativeKernel(void *f, unsigned gx, unsigned gy, unsigned gz, unsigned bx, unsigned by, unsigned bz,
+                                          unsigned sm, void *s, void **params) {
+  (void)gx; (void)gy; (void)gz; (void)bx; (void)by; (void)bz; (void)sm; (void)s;
+  return launch(f, params);
+}
+EXPORT CUresult cuLaunchCooperativeKernel_ptsz(void *f, unsigned gx, unsigned gy, unsigned gz, unsigned bx, unsigned by,
+                                               unsigned bz, unsigned sm, void *s, void **params) {
+  return cuLaunchCooperativeKernel(f, gx, gy, gz, bx, by, bz, sm, s, params);
+}
+EXPORT CUresult cuLaunch(void *f) { return launch(f, NULL); }
+EXPORT CUresult cuLaunchGrid(void *f, int w, int h) { (void)w; (void)h; return launch(f, NULL); }
+EXPORT CUresult cuLaunchGridAsync(void *f, int w, int h, void *s) { (void)w; (void)h; (void)s; return launch(f, NULL); }
+
+/* cuGetProcAddress: hand out this object's own symbols.  A static table, not dlsym(): under
+ * LD_PRELOAD the process-wide dlsym is the interposer of the library under test. */
+static const struct { const char *name; void *fn; } g_self_table[] = {
+  {"cuInit", (void *)cuInit},
+  {"cuDriverGetVersion", (void *)cuDriverGetVersion},
+  {"cuDeviceGetCount", (void *)cuDeviceGetCount},
+  {"cuDeviceGet", (void *)cuDeviceGet},
+  {"cuDeviceGetAttribute", (void *)cuDeviceGetAttribute},
+  {"cuDeviceGetUuid", (void *)cuDeviceGetUuid},
+  {"cuDeviceGetUuid_v2", (void *)cuDeviceGetUuid_v2},
+  {"cuDeviceGetName", (void *)cuDeviceGetName},
+  {"cuDeviceTotalMem_v2", (void *)cuDeviceTotalMem_v2},
+  {"cuGetErrorString", (void *)cuGetErrorString},
+  {"cuGetErrorName", (void *)cuGetErrorName},
+  {"cuDevicePrimaryCtxRetain", (void *)cuDevicePrimaryCtxRetain},
+  {"cuDevicePrimaryCtxRelease_v2", (void *)cuDevicePrimaryCtxRelease_v2},
+  {"cuCtxCreate_v2", (void *)cuCtxCreate_v2},
+  {"cuCtxDestroy_v2", (void *)cuCtxDestroy_v2},
+  {"cuCtxSetCurrent", (void *)cuCtxSetCurrent},
+  {"cuCtxGetCurrent", (void *)cuCtxGetCurrent},
+  {"cuCtxPushCurrent_v2", (void *)cuCtxPushCurrent_v2},
+  {"cuCtxPopCurrent_v2", (void *)cuCtxPopCurrent_v2},
+  {"cuCtxGetDevice", (void *)cuCtxGetDevice},
+  {"cuCtxSynchronize", (void *)cuCtxSynchronize},
+  {"cuCtxGetStreamPriorityRange", (void *)cuCtxGetStreamPriorityRange},
+  {"cuMemAlloc_v2", (void *)cuMemAlloc_v2},
+  {"cuMemAllocManaged", (void *)cuMemAllocManaged},
+  {"cuMemAllocPitch_v2", (void *)cuMemAllocPitch_v2},
+  {"cuMemAllocAsync", (void *)cuMemAllocAsync},
+  {"cuMemAllocAsync_ptsz", (void *)cuMemAllocAsync_ptsz},
+  {"cuMemAllocFromPoolAsync", (void *)cuMemAllocFromPoolAsync},
+  {"cuMemAllocFromPoolAsync_ptsz", (void *)cuMemAllocFromPoolAsync_ptsz},
+  {"cuMemFree_v2", (void *)cuMemFree_v2},
+  {"cuMemFreeAsync", (void *)cuMemFreeAsync},
+  {"cuMemFreeAsync_ptsz", (void *)cuMemFreeAsync_ptsz},
+  {"cuMemGetInfo_v2", (void *)cuMemGetInfo_v2},
+  {"cuMemCreate", (void *)cuMemCreate},
+  {"cuMemRelease", (void *)cuMemRelease},
+  {"cuArrayCreate_v2", (void *)cuArrayCreate_v2},
+  {"cuArray3DCreate_v2", (void *)cuArray3DCreate_v2},
+  {"cuMipmappedArrayCreate", (void *)cuMipmappedArrayCreate},
+  {"cuArrayDestroy", (void *)cuArrayDestroy},
+  {"cuMipmappedArrayDestroy", (void *)cuMipmappedArrayDestroy},
+  {"cuMemHostAlloc", (void *)cuMemHostAlloc},
+  {"cuMemFreeHost", (void *)cuMemFreeHost},
+  {"cuMemHostGetDevicePointer_v2", (void *)cuMemHostGetDevicePointer_v2},
+  {"cuMemsetD8_v2", (void *)cuMemsetD8_v2},
+  {"cuMemcpyDtoH_v2", (void *)cuMemcpyDtoH_v2},
+  {"cuMemcpyHtoD_v2", (void *)cuMemcpyHtoD_v2},
+  {"cuStreamCreate", (void *)cuStreamCreate},
+  {"cuStreamCreateWithPriority", (void *)cuStreamCreateWithPriority},
+  {"cuStreamDestroy_v2", (void *)cuStreamDestroy_v2},
+  {"cuStreamSynchronize", (void *)cuStreamSynchronize},
+  {"cuStreamQuery", (void *)cuStreamQuery},
+  {"cuStreamIsCapturing", (void *)cuStreamIsCapturing},
+  {"cuStreamWaitValue64_v2", (void *)cuStreamWaitValue64_v2},
+  {"cuStreamWaitValue64_v2_ptsz", (void *)cuStreamWaitValue64_v2_ptsz},
+  {"cuStreamWriteValue64_v2", (void *)cuStreamWriteValue64_v2},
+  {"cuStreamWriteValue64_v2_ptsz", (void *)cuStreamWriteValue64_v2_ptsz},
+  {"cuModuleLoadData", (void *)cuModuleLoadData},
+  {"cuModuleUnload", (void *)cuModuleUnload},
+  {"cuModuleGetFunction", (void *)cuModuleGetFunction},
+  {"cuFuncSetAttribute", (void *)cuFuncSetAttribute},
+  {"cuFuncSetBlockShape", (void *)cuFuncSetBlockShape},
+  {"cuLaunchKernel", (void *)cuLaunchKernel},
+  {"cuLaunchKernel_ptsz", (void *)cuLaunchKernel_ptsz},
+  {"cuLaunchKernelEx", (void *)cuLaunchKernelEx},
+  {"cuLaunchKernelEx_ptsz", (void *)cuLaunchKernelEx_ptsz},
+  {"cuLaunchCooperativeKernel", (void *)cuLaunchCooperativeKernel},
+  {"cuLaunchCooperativeKernel_ptsz", (void *)cuLaunchCooperativeKernel_ptsz},
+  {"cuLaunch", (void *)cuLaunch},
+  {"cuLaunchGrid", (void *)cuLaunchGrid},
+  {"cuLaunchGridAsync", (void *)cuLaunchGridAsync},
+};
+static void *self_lookup(const char *name) {
+  for (size_t i = 0; i < sizeof g_self_table / sizeof g_self_table[0]; i++)
+    if (!strcmp(g_self_table[i].name, name)) return g_self_table[i].fn;
+  return NULL;
+}
+EXPORT CUresult cuGetProcAddress_v2(const char *sym, void **pfn, int ver, unsigned long long flags, void *status);
+EXPORT CUresult cuGetProcAddress(const char *sym, void **pfn, int ver, unsigned long long flags);
+EXPORT CUresult cuGetProcAddress_v2(const char *sym, void **pfn, int ver, unsigned long long flags, void *status) {
+  (void)ver; (void)status;
+  char name[128];
+  void *p = NULL;
+  if (!strcmp(sym, "cuGetProcAddress")) p = (void *)cuGetProcAddress_v2;
+  if (!p && (flags & 2)) { snprintf(name, sizeof name, "%s_ptsz", sym); p = self_lookup(name); }
+  if (!p) { snprintf(name, sizeof name, "%s_v2", sym); p = self_lookup(name); }
+  if (!p) p = self_lookup(sym);
+  *pfn = p;
+  return p ? 0 : 500;
+}
+EXPORT CUresult cuGetProcAddress(const char *sym, void **pfn, int ver, unsigned long long flags) {
+  return cuGetProcAddress_v2(sym, pfn, ver, flags, NULL);
+}
+
+/* ------------------------------------------------------------------ NVML */
+EXPORT nvmlReturn_t nvmlInit(void) { stub_init(); return 0; }
+EXPORT nvmlReturn_t nvmlInit_v2(void) { stub_init(); return 0; }
+EXPORT nvmlReturn_t nvmlInitWithFlags(unsigned f) { (void)f; stub_init(); return 0; }
+EXPORT nvmlReturn_t nvmlShutdown(void) { return 0; }
+EXPORT const char *nvmlErrorString(nvmlReturn_t r) { return r == 0 ? "Success" : r == 6 ? "Not Found" : "stub nvml error"; }
+EXPORT nvmlReturn_t nvmlDeviceGetCount(unsigned *n) { stub_init(); *n = (unsigned)g_gpu_count; return 0; }
+EXPORT nvmlReturn_t nvmlDeviceGetCount_v2(unsigned *n) { return nvmlDeviceGetCount(n); }
+EXPORT nvmlReturn_t nvmlDeviceGetHandleByIndex(unsigned i, void **d) { stub_init(); if ((int)i >= g_gpu_count) return 2; *d = (void *)(uintptr_t)(0x9000 + i); return 0; }
+EXPORT nvmlReturn_t nvmlDeviceGetHandleByIndex_v2(unsigned i, void **d) { return nvmlDeviceGetHandleByIndex(i, d); }
+static int nv_idx(void *d) { return (int)((uintptr_t)d - 0x9000); }
+EXPORT nvmlReturn_t nvmlDeviceGetIndex(void *d, unsigned *i) { int k = nv_idx(d); if (k < 0 || k >= g_gpu_count) return 2; *i = (unsigned)k; return 0; }
+EXPORT nvmlReturn_t nvmlDeviceGetUUID(void *d, char *uuid, unsigned len) {
+  unsigned char b[16];
+  uuid_bytes(nv_idx(d), b);
+  snprintf(uuid, len, "GPU-%02x%02x%02x%02x-%02x%02x-%02x%02x-%02x%02x-%02x%02x%02x%02x%02x%02x", b[0], b[1], b[2], b[3],
+           b[4], b[5], b[6], b[7], b[8], b[9], b[10], b[11], b[12], b[13], b[14], b[15]);
+  return 0;
+}
+static nvmlReturn_t proc_list(void *d, unsigned *count, vgpu_proc_t *out, int graphics) {
+  int dev = nv_idx(d);
+  unsigned n = 0, cap = *count;
+  if (!graphics && g_any_ctx) {
+    if (n < cap) { out[n].pid = (uint32_t)getpid(); out[n]._pad = 0; out[n].used_bytes = g_ctx_bytes + g_dev_bytes[dev & 15]; }
+    n++;
+  }
+  for (int i = 0; i < g_nothers; i++) {
+    if (graphics ? !g_others[i].graphics : !g_others[i].compute) continue;
+    if (n < cap) { out[n].pid = g_others[i].pid; out[n]._pad = 0; out[n].used_bytes = g_others[i].bytes; }
+    n++;
+  }
+  *count = n;
+  return n > cap ? 7 /* INSUFFICIENT_SIZE */ : 0;
+}
+EXPORT nvmlReturn_t nvmlDeviceGetComputeRunningProcesses(void *d, unsigned *c, vgpu_proc_t *o) { return proc_list(d, c, o, 0); }
+EXPORT nvmlReturn_t nvmlDeviceGetGraphicsRunningProcesses(void *d, unsigned *c, vgpu_proc_t *o) { return proc_list(d, c, o, 1); }
+EXPORT nvmlReturn_t nvmlDeviceGetProcessUtilization(void *d, vgpu_util_sample_t *s, unsigned *count, unsigned long long since) {
+  (void)d; (void)since;
+  unsigned n = 0, cap = *count;
+  uint64_t ts = now_us_wall();
+  if (g_any_ctx) {
+    if (n < cap) { memset(&s[n], 0, sizeof s[n]); s[n].pid = (uint32_t)getpid(); s[n].ts_us = ts; s[n].sm = (uint32_t)current_util(); }
+    n++;
+  }
+  for (int i = 0; i < g_nothers; i++) {
+    if (!g_others[i].compute || !g_others[i].sm) continue;
+    if (n < cap) { memset(&s[n], 0, sizeof s[n]); s[n].pid = g_others[i].pid; s[n].ts_us = ts; s[n].sm = (uint32_t)g_others[i].sm; }
+    n++;
+  }
+  *count = n;
+  return n == 0 ? 6 : 0;
+}
+typedef struct { unsigned long long total, free, used; } nvmem_t;
+typedef struct { unsigned version; unsigned long long total, reserved, free, used; } nvmem2_t;
+static uint64_t dev_used(int dev) {
+  uint64_t u = g_dev_bytes[dev & 15] + (g_any_ctx ? g_ctx_bytes : 0);
+  for (int i = 0; i < g_nothers; i++) u += g_others[i].bytes;
+  return u;
+}
+EXPORT nvmlReturn_t nvmlDeviceGetMemoryInfo(void *d, nvmem_t *m) {
+  uint64_t u = dev_used(nv_idx(d));
+  m->total = g_total_mem; m->used = u; m->free = g_total_mem - u;
+  return 0;
+}
+EXPORT nvmlReturn_t nvmlDeviceGetMemoryInfo_v2(void *d, nvmem2_t *m) {
+  uint64_t u = dev_used(nv_idx(d));
+  m->total = g_total_mem; m->reserved = 512ull << 20; m->used = u; m->free = g_total_mem - u - m->reserved;
+  return 0;
+}
+EXPORT nvmlReturn_t nvmlDeviceGetUtilizationRates(void *d, unsigned *u) { (void)d; u[0] = (unsigned)current_util(); u[1] = 0; return 0; }
+EXPORT nvmlReturn_t nvmlDeviceSetComputeMode(void *d, int m) { (void)d; (void)m; return 0; }
+EXPORT nvmlReturn_t nvmlDeviceGetPersistenceMode(void *d, int *m) { (void)d; *m = 1; return 0; }

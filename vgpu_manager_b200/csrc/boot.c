@@ -24,6 +24,8 @@
 #include <sys/wait.h>
 
 vgpu_real_t R;
+volatile unsigned vgpu_fork_epoch;
+static void on_fork_child(void) { vgpu_fork_epoch++; }
 vgpu_dlsym_fn vgpu_real_dlsym;
 vgpu_cfg_t *G_cfg;
 vgpu_smutil_t *G_smutil;
@@ -120,6 +122,7 @@ static void read_driver_version(void) {
 static pthread_once_t g_real_once = PTHREAD_ONCE_INIT;
 static void resolve_real(void) {
   pthread_once(&g_dlsym_once, find_real_dlsym);
+  pthread_atfork(NULL, NULL, on_fork_child);
   read_driver_version();
   char name[512];
   snprintf(name, sizeof name, "libcuda.so.%s", g_driver_version);
@@ -405,13 +408,13 @@ static void register_with_manager(void) { /* register.c:14-38, client mode only 
 }
 
 static pthread_mutex_t g_cfg_mu = PTHREAD_MUTEX_INITIALIZER;
-static volatile pid_t g_cfg_pid;
+static volatile unsigned g_cfg_epoch;
 
 static void load_config(void) { /* loader.c:2054-2117; re-runs in a forked child */
-  pid_t me = getpid();
-  if (likely(g_cfg_pid == me)) return;
+  unsigned me = vgpu_fork_epoch + 1;
+  if (likely(g_cfg_epoch == me)) return;
   pthread_mutex_lock(&g_cfg_mu);
-  if (g_cfg_pid != me) {
+  if (g_cfg_epoch != me) {
     if (!G_cfg) {
       void *p = NULL;
       if (map_ro(VP(VGPU_CFG_FILE), sizeof(vgpu_cfg_t), &p) == 0) {
@@ -443,7 +446,7 @@ static void load_config(void) { /* loader.c:2054-2117; re-runs in a forked child
       signal(SIGABRT, on_fatal_signal);
     }
     if ((G_cfg->compatibility_mode & VGPU_MODE_CLIENT) == VGPU_MODE_CLIENT) register_with_manager();
-    g_cfg_pid = me;
+    g_cfg_epoch = me;
   }
   pthread_mutex_unlock(&g_cfg_mu);
 }

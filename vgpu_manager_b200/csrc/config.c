@@ -24,20 +24,22 @@ static volatile int g_cuda2host[VGPU_MAX_DEVICES];
 static volatile int g_cuda2nvml[VGPU_MAX_DEVICES];
 static volatile int g_nvml2host[VGPU_MAX_DEVICES];
 static nvmlDevice_t g_host2nvml[VGPU_MAX_DEVICES];
-static volatile pid_t g_map_pid;
+static volatile unsigned g_map_epoch; /* == vgpu_fork_epoch + 1 once initialised */
 static pthread_mutex_t g_map_mu = PTHREAD_MUTEX_INITIALIZER;
 
-static void maps_reset_if_forked(void) { /* loader.c:1808-1822 */
-  pid_t me = getpid();
-  if (likely(g_map_pid == me)) return;
+/* the reference compares getpid() on every call (loader.c:1808-1822); a pthread_atfork child
+ * handler bumping an epoch gives the same fork awareness without a syscall per launch */
+static inline void maps_reset_if_forked(void) {
+  unsigned want = vgpu_fork_epoch + 1;
+  if (likely(g_map_epoch == want)) return;
   pthread_mutex_lock(&g_map_mu);
-  if (g_map_pid != me) {
+  if (g_map_epoch != want) {
     for (int i = 0; i < VGPU_MAX_DEVICES; i++) {
       g_cuda2host[i] = -1;
       g_cuda2nvml[i] = -1;
-      if (g_map_pid == 0) g_nvml2host[i] = -1;
+      if (g_map_epoch == 0) g_nvml2host[i] = -1;
     }
-    g_map_pid = me;
+    g_map_epoch = want;
   }
   pthread_mutex_unlock(&g_map_mu);
 }

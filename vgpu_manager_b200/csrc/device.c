@@ -19,7 +19,7 @@ extern const unsigned long long vgpu_kernels_image_size;
 
 static vgpu_dev_rt g_rt[VGPU_MAX_DEVICES];
 static pthread_mutex_t g_rt_mu = PTHREAD_MUTEX_INITIALIZER;
-static volatile pid_t g_rt_pid;
+static volatile unsigned g_rt_epoch;
 
 #define CU_TRY(call, what)                                                             \
   do {                                                                                 \
@@ -230,13 +230,13 @@ fail:
 
 vgpu_dev_rt *vgpu_rt_get(int host_index, CUdevice dev) {
   int slot = host_index >= 0 ? host_index : (dev >= 0 && dev < VGPU_MAX_DEVICES ? dev : 0);
-  pid_t me = getpid();
+  unsigned me = vgpu_fork_epoch + 1;
   vgpu_dev_rt *rt = &g_rt[slot];
-  if (likely(g_rt_pid == me && rt->ready == 1)) return rt;
+  if (likely(g_rt_epoch == me && rt->ready == 1)) return rt;
   pthread_mutex_lock(&g_rt_mu);
-  if (g_rt_pid != me) { /* fork: device state does not survive, start over */
+  if (g_rt_epoch != me) { /* fork: device state does not survive, start over */
     memset(g_rt, 0, sizeof g_rt);
-    g_rt_pid = me;
+    g_rt_epoch = me;
   }
   vgpu_dev_rt *out = NULL;
   if (rt->ready == 1) out = rt;
@@ -248,7 +248,7 @@ vgpu_dev_rt *vgpu_rt_get(int host_index, CUdevice dev) {
 vgpu_dev_rt *vgpu_rt_peek(int host_index) {
   if (host_index < 0 || host_index >= VGPU_MAX_DEVICES) return NULL;
   vgpu_dev_rt *rt = &g_rt[host_index];
-  return (g_rt_pid == getpid() && rt->ready == 1) ? rt : NULL;
+  return (g_rt_epoch == vgpu_fork_epoch + 1 && rt->ready == 1) ? rt : NULL;
 }
 
 /* ------------------------------------------------------------------ kernel drivers used by the hooks */

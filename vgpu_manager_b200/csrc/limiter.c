@@ -55,7 +55,7 @@ static inline uint32_t slot_of(int host_index, CUstream s, int ptsz) {
 
 /* ------------------------------------------------------------------ tick thread */
 static pthread_once_t g_tick_once = PTHREAD_ONCE_INIT;
-static volatile pid_t g_tick_pid;
+static volatile unsigned g_tick_epoch;
 static volatile int g_tick_devices[VGPU_MAX_DEVICES]; /* host indexes with a live runtime + core limit */
 static uint32_t g_window_us = 8000, g_interval_us = 100, g_period_ticks = 8, g_tick_ms = 10;
 static volatile int g_capture_depth;
@@ -92,7 +92,7 @@ static void *tick_main(void *arg) {
   int fails = 0;
   for (;;) {
     nanosleep(&nap, NULL);
-    if (g_tick_pid != getpid()) return NULL;
+    if (g_tick_epoch != vgpu_fork_epoch + 1) return NULL;
     epoch++;
     for (int h = 0; h < VGPU_MAX_DEVICES; h++) {
       if (!g_tick_devices[h]) continue;
@@ -131,7 +131,7 @@ static void tick_start(void) {
   g_tick_ms = env_u32("VGPU_B200_TICK_MS", 10);
   if (!g_period_ticks) g_period_ticks = 1;
   if (!g_tick_ms) g_tick_ms = 1;
-  g_tick_pid = getpid();
+  g_tick_epoch = vgpu_fork_epoch + 1;
   pthread_t tid;
   if (pthread_create(&tid, NULL, tick_main, NULL) == 0) {
     pthread_setname_np(tid, "vgpu_b200_tick");
@@ -144,11 +144,11 @@ void vgpu_limiter_start(void) {
    * (cuda_hook.c:566-577).  Here the thread is created lazily by the first limited launch,
    * because the sampler needs the tenant's context; this entry point only re-arms after fork
    * (the reference does not - SURVEY.md Appendix B.13). */
-  if (g_tick_pid && g_tick_pid != getpid()) {
+  if (g_tick_epoch && g_tick_epoch != vgpu_fork_epoch + 1) {
     memset((void *)g_tick_devices, 0, sizeof g_tick_devices);
     memset(g_slots, 0, sizeof g_slots);
     g_tick_once = (pthread_once_t)PTHREAD_ONCE_INIT;
-    g_tick_pid = 0;
+    g_tick_epoch = 0;
   }
 }
 

@@ -236,6 +236,7 @@ const char *vgpu_path(const char *abs, char *buf, size_t cap);
 #define VP(p) vgpu_path((p), (char[512]){0}, 512)
 
 /* boot.c */
+extern volatile unsigned vgpu_fork_epoch; /* bumped in the child by a pthread_atfork handler */
 void vgpu_boot(void);             /* == reference load_necessary_data (loader.c:2166) */
 void vgpu_map_devices(void);      /* == reference init_devices_mapping (loader.c:2178) */
 const char *vgpu_cu_err(CUresult r);

@@ -1,10 +1,13 @@
 /*
- * storm.c - launch-storm tenant (BASELINE.json configs 0/1/4): N x cuLaunchKernel(grid 1,1,1)
- * of an empty kernel through the dynamic linker, per-call latency histogram, JSON on stdout.
- * TEST / BENCH INFRASTRUCTURE.  Works against the stub driver (no GPU: f == NULL) and against
- * the real driver (loads an empty kernel from PTX).
+ * storm.c - launch-storm tenant (BASELINE.json configs 0/1/4): steps x launches-per-step
+ * cuLaunchKernel(grid 1,1,1 / block 1,1,1) of an empty kernel through the dynamic linker, the
+ * way an application linked against libcuda would issue them.  Per-call host latency
+ * histogram, per-step device time (CUDA events on the launching stream), JSON on stdout.
+ * TEST / BENCH INFRASTRUCTURE.  Works against the stub driver (no GPU: f == NULL) and the real
+ * driver (empty kernel JIT-compiled from PTX).
  *
- *   storm [--n N] [--threads T] [--sync-every K] [--device D] [--no-kernel]
+ *   storm [--steps K] [--warmup W] [--per-step L] [--threads T] [--sync-every S] [--device D]
+ *         [--no-kernel] [--max-seconds X] [--n N (== --steps 1 --per-step N)]
  */
 #define _GNU_SOURCE
 #include <dlfcn.h>
@@ -27,9 +30,16 @@ static void *h_cuda;
 static launch_fn p_launch;
 static CUresult (*p_sync)(void);
 static CUresult (*p_setctx)(void *);
+static CUresult (*p_evcreate)(void **, unsigned);
+static CUresult (*p_evrecord)(void *, void *);
+static CUresult (*p_evsync)(void *);
+static CUresult (*p_evelapsed)(float *, void *, void *);
 static void *g_ctx, *g_func;
-static long g_n = 1000000, g_sync_every = 0;
-static int g_threads = 1;
+static long g_per_step = 200000, g_sync_every = 0;
+static int g_threads = 1, g_steps = 1, g_warmup = 0;
+static double g_max_seconds = 0;
+static volatile int g_stop;
+static uint64_t g_deadline_ns;
 
 static inline uint64_t now_ns(void) {
   struct timespec ts;
@@ -37,21 +47,22 @@ static inline uint64_t now_ns(void) {
   return (uint64_t)ts.tv_sec * 1000000000ull + (uint64_t)ts.tv_nsec;
 }
 
-typedef struct { uint32_t *lat; long n; long fails; uint64_t t0, t1; } worker_t;
+typedef struct { uint32_t *lat; long n, done, fails; int record; } worker_t;
 
 static void *worker(void *arg) {
   worker_t *w = (worker_t *)arg;
   p_setctx(g_ctx);
-  w->t0 = now_ns();
-  for (long i = 0; i < w->n; i++) {
+  long i;
+  for (i = 0; i < w->n && !g_stop; i++) {
     uint64_t a = now_ns();
     CUresult r = p_launch(g_func, 1, 1, 1, 1, 1, 1, 0, NULL, NULL, NULL);
     uint64_t b = now_ns();
-    w->lat[i] = (uint32_t)((b - a) > 0xffffffffull ? 0xffffffffull : (b - a));
+    if (w->record) w->lat[i] = (uint32_t)((b - a) > 0xffffffffull ? 0xffffffffull : (b - a));
     w->fails += r != 0;
     if (g_sync_every && ((i + 1) % g_sync_every) == 0) p_sync();
+    if (g_deadline_ns && (i & 1023) == 0 && b > g_deadline_ns) g_stop = 1;
   }
-  w->t1 = now_ns();
+  w->done = i;
   return NULL;
 }
 
@@ -61,14 +72,21 @@ static int cmp_u32(const void *a, const void *b) {
 }
 
 int main(int argc, char **argv) {
-  int device = 0, no_kernel = 0;
+  int device = 0, no_kernel = 0, host_index = -1;
   for (int i = 1; i < argc; i++) {
-    if (!strcmp(argv[i], "--n") && i + 1 < argc) g_n = atol(argv[++i]);
+    if (!strcmp(argv[i], "--n") && i + 1 < argc) { g_per_step = atol(argv[++i]); g_steps = 1; }
+    else if (!strcmp(argv[i], "--steps") && i + 1 < argc) g_steps = atoi(argv[++i]);
+    else if (!strcmp(argv[i], "--warmup") && i + 1 < argc) g_warmup = atoi(argv[++i]);
+    else if (!strcmp(argv[i], "--per-step") && i + 1 < argc) g_per_step = atol(argv[++i]);
     else if (!strcmp(argv[i], "--threads") && i + 1 < argc) g_threads = atoi(argv[++i]);
     else if (!strcmp(argv[i], "--sync-every") && i + 1 < argc) g_sync_every = atol(argv[++i]);
     else if (!strcmp(argv[i], "--device") && i + 1 < argc) device = atoi(argv[++i]);
+    else if (!strcmp(argv[i], "--max-seconds") && i + 1 < argc) g_max_seconds = atof(argv[++i]);
+    else if (!strcmp(argv[i], "--host-index") && i + 1 < argc) host_index = atoi(argv[++i]);
     else if (!strcmp(argv[i], "--no-kernel")) no_kernel = 1;
   }
+  if (g_threads < 1) g_threads = 1;
+  if (host_index < 0) host_index = device;
   h_cuda = dlopen("libcuda.so.1", RTLD_NOW | RTLD_GLOBAL);
   if (!h_cuda) { fprintf(stderr, "storm: %s\n", dlerror()); return 2; }
   CUresult (*p_init)(unsigned) = dlsym(h_cuda, "cuInit");
@@ -79,6 +97,11 @@ int main(int argc, char **argv) {
   p_setctx = dlsym(h_cuda, "cuCtxSetCurrent");
   p_sync = dlsym(h_cuda, "cuCtxSynchronize");
   p_launch = (launch_fn)dlsym(h_cuda, "cuLaunchKernel");
+  p_evcreate = dlsym(h_cuda, "cuEventCreate");
+  p_evrecord = dlsym(h_cuda, "cuEventRecord");
+  p_evsync = dlsym(h_cuda, "cuEventSynchronize");
+  p_evelapsed = dlsym(h_cuda, "cuEventElapsedTime");
+  int have_events = p_evcreate && p_evrecord && p_evsync && p_evelapsed;
   int dev = 0;
   uint64_t t_init0 = now_ns();
   if (p_init(0) || p_get(&dev, device) || p_retain(&g_ctx, dev) || p_setctx(g_ctx)) { fprintf(stderr, "storm: init failed\n"); return 3; }
@@ -86,35 +109,69 @@ int main(int argc, char **argv) {
     void *mod = NULL;
     if (p_modload(&mod, k_ptx) || p_getfn(&g_func, mod, "empty_kernel")) { fprintf(stderr, "storm: module load failed\n"); return 4; }
   }
-  /* warm-up: first launches pay lazy loading and, under a preload library, its bring-up */
+  /* first launches pay lazy loading and, under a preload library, its device bring-up */
   for (int i = 0; i < 2000; i++) p_launch(g_func, 1, 1, 1, 1, 1, 1, 0, NULL, NULL, NULL);
   p_sync();
   uint64_t t_init1 = now_ns();
 
-  long per = g_n / g_threads;
+  long per_thread = g_per_step / g_threads;
   worker_t *ws = calloc((size_t)g_threads, sizeof *ws);
   pthread_t *th = calloc((size_t)g_threads, sizeof *th);
-  for (int t = 0; t < g_threads; t++) { ws[t].n = per; ws[t].lat = malloc(sizeof(uint32_t) * (size_t)per); }
-  uint64_t t0 = now_ns();
-  for (int t = 1; t < g_threads; t++) pthread_create(&th[t], NULL, worker, &ws[t]);
-  worker(&ws[0]);
-  for (int t = 1; t < g_threads; t++) pthread_join(th[t], NULL);
-  uint64_t t_host = now_ns();
-  p_sync();
-  uint64_t t1 = now_ns();
+  size_t cap = (size_t)per_thread * (size_t)g_steps;
+  uint32_t *all = malloc(sizeof(uint32_t) * cap * (size_t)g_threads);
+  size_t nall = 0;
+  for (int t = 0; t < g_threads; t++) ws[t].lat = malloc(sizeof(uint32_t) * (size_t)per_thread);
+  void *ev0 = NULL, *ev1 = NULL;
+  if (have_events && (p_evcreate(&ev0, 0) || p_evcreate(&ev1, 0))) have_events = 0;
 
-  long total = per * g_threads, fails = 0;
-  uint32_t *all = malloc(sizeof(uint32_t) * (size_t)total);
-  for (int t = 0; t < g_threads; t++) { memcpy(all + (size_t)t * per, ws[t].lat, sizeof(uint32_t) * (size_t)per); fails += ws[t].fails; }
-  qsort(all, (size_t)total, sizeof(uint32_t), cmp_u32);
-  double wall = (t1 - t0) * 1e-9, host = (t_host - t0) * 1e-9;
+  double *step_wall = calloc((size_t)g_steps, sizeof(double)), *step_dev = calloc((size_t)g_steps, sizeof(double));
+  long total_done = 0, fails = 0;
+  double timed_wall = 0, timed_host = 0;
+  int steps_run = 0;
+  for (int s = -g_warmup; s < g_steps && !g_stop; s++) {
+    int timed = s >= 0;
+    if (timed && s == 0 && g_max_seconds > 0) g_deadline_ns = now_ns() + (uint64_t)(g_max_seconds * 1e9);
+    for (int t = 0; t < g_threads; t++) { ws[t].n = per_thread; ws[t].done = 0; ws[t].fails = 0; ws[t].record = timed; }
+    p_sync();
+    if (have_events) p_evrecord(ev0, NULL);
+    uint64_t t0 = now_ns();
+    for (int t = 1; t < g_threads; t++) pthread_create(&th[t], NULL, worker, &ws[t]);
+    worker(&ws[0]);
+    for (int t = 1; t < g_threads; t++) pthread_join(th[t], NULL);
+    uint64_t t_host = now_ns();
+    if (have_events) p_evrecord(ev1, NULL);
+    p_sync();
+    uint64_t t1 = now_ns();
+    if (!timed) continue;
+    float ms = 0;
+    if (have_events && p_evsync(ev1) == 0 && p_evelapsed(&ms, ev0, ev1) == 0) step_dev[s] = ms * 1e-3;
+    step_wall[s] = (t1 - t0) * 1e-9;
+    timed_wall += step_wall[s];
+    timed_host += (t_host - t0) * 1e-9;
+    for (int t = 0; t < g_threads; t++) {
+      memcpy(all + nall, ws[t].lat, sizeof(uint32_t) * (size_t)ws[t].done);
+      nall += (size_t)ws[t].done;
+      total_done += ws[t].done;
+      fails += ws[t].fails;
+    }
+    steps_run++;
+  }
+  if (nall == 0) { printf("{\"launches\": 0}\n"); return 0; }
+  qsort(all, nall, sizeof(uint32_t), cmp_u32);
   unsigned long long sum = 0;
-  for (long i = 0; i < total; i++) sum += all[i];
-  printf("{\"launches\": %ld, \"threads\": %d, \"wall_s\": %.6f, \"host_s\": %.6f, \"launches_per_s\": %.1f, "
-         "\"host_launches_per_s\": %.1f, \"p50_ns\": %u, \"p90_ns\": %u, \"p99_ns\": %u, \"p999_ns\": %u, \"max_ns\": %u, "
-         "\"mean_ns\": %.1f, \"fails\": %ld, \"init_s\": %.4f}\n",
-         total, g_threads, wall, host, total / wall, total / host, all[total / 2], all[(long)(total * 0.9)],
-         all[(long)(total * 0.99)], all[(long)(total * 0.999)], all[total - 1], (double)sum / total, fails,
-         (t_init1 - t_init0) * 1e-9);
+  for (size_t i = 0; i < nall; i++) sum += all[i];
+  unsigned long long (*metric)(int, int) = dlsym(RTLD_DEFAULT, "vgpu_b200_metric");
+  double dev_total = 0;
+  for (int s = 0; s < steps_run; s++) dev_total += step_dev[s];
+  printf("{\"launches\": %ld, \"steps\": %d, \"per_step\": %ld, \"threads\": %d, \"wall_s\": %.6f, \"host_s\": %.6f, "
+         "\"device_s\": %.6f, \"launches_per_s\": %.1f, \"host_launches_per_s\": %.1f, \"p50_ns\": %u, \"p90_ns\": %u, "
+         "\"p99_ns\": %u, \"p999_ns\": %u, \"max_ns\": %u, \"mean_ns\": %.1f, \"fails\": %ld, \"init_s\": %.4f, "
+         "\"truncated\": %d, \"sampler_launches\": %llu, \"gated_launches\": %llu, \"step_wall_s\": [",
+         total_done, steps_run, g_per_step, g_threads, timed_wall, timed_host, dev_total, total_done / timed_wall,
+         total_done / timed_host, all[nall / 2], all[(size_t)(nall * 0.9)], all[(size_t)(nall * 0.99)],
+         all[(size_t)(nall * 0.999)], all[nall - 1], (double)sum / nall, fails, (t_init1 - t_init0) * 1e-9, (int)g_stop,
+         metric ? metric(host_index, 7) : 0ull, metric ? metric(host_index, 0) : 0ull);
+  for (int s = 0; s < steps_run; s++) printf("%s%.6f", s ? ", " : "", step_wall[s]);
+  printf("]}\n");
   return 0;
 }

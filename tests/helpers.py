@@ -194,9 +194,11 @@ class Sandbox:
             os.makedirs(os.path.join(self.dir, d), exist_ok=True)
         self.extra_rules = []
 
-    def rules(self):
+    def rules(self, stub=True):
         r = ["/etc/vgpu-manager=%s/etc/vgpu-manager" % self.dir, "/tmp/.vgpu_lock=%s/lock" % self.dir,
-             "/tmp/.vmem_node=%s/vmem" % self.dir, "/proc/driver/nvidia=%s/none" % self.dir]
+             "/tmp/.vmem_node=%s/vmem" % self.dir]
+        if stub:  # hide a real driver's version file so both libraries dlopen libcuda.so.1 (the stub)
+            r.append("/proc/driver/nvidia=%s/none" % self.dir)
         return ":".join(r + self.extra_rules)
 
     def path(self, rel):
@@ -215,7 +217,7 @@ class Sandbox:
 
 def preload_env(lib, sb, env=None, stub=True):
     e = {k: v for k, v in os.environ.items() if not k.startswith(("CUDA_", "MANAGER_", "VGPU_", "STUB_", "LD_PRELOAD"))}
-    e["VGPU_REDIRECT"] = sb.rules()
+    e["VGPU_REDIRECT"] = sb.rules(stub)
     e["SCENARIO_LEDGER"] = sb.ledger()
     if stub:
         e["LD_LIBRARY_PATH"] = STUB_DIR
@@ -224,15 +226,17 @@ def preload_env(lib, sb, env=None, stub=True):
     return e
 
 
-def run_scenario(lib, script, env=None, sb=None, stub=True, args=(), timeout=120):
+def run_scenario(lib, script, env=None, sb=None, stub=True, args=(), timeout=120, check=True):
     """Run tests/_build/scenario under `lib` (a preload .so or None). Returns (stdout, stderr, sandbox)."""
     build_all()
     own = sb is None
     sb = sb or Sandbox()
     r = subprocess.run([SCENARIO, *args], input=script, capture_output=True, text=True,
                        env=preload_env(lib, sb, env, stub), timeout=timeout)
-    if r.returncode != 0:
+    if r.returncode != 0 and check:
         raise RuntimeError("scenario failed rc=%d\n%s\n%s" % (r.returncode, r.stdout[-2000:], r.stderr[-2000:]))
+    if not check:
+        return r.stdout, r.stderr, r.returncode
     return r.stdout, r.stderr, sb
 
 

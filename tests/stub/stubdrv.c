@@ -334,7 +334,19 @@ static void fake_quota(const vgpu_quota_req_t *q, vgpu_quota_res_t *r) {
   for (uint32_t i = 0; i < q->n_compute; i++) { cp[i] = q->cflags[i] & VGPU_FLAG_PRIMARY; cl[i] = (q->cflags[i] & VGPU_FLAG_LOCAL) != 0; }
   for (uint32_t i = 0; i < q->n_graphics; i++) { gp[i] = q->gflags[i] & VGPU_FLAG_PRIMARY; gl[i] = (q->gflags[i] & VGPU_FLAG_LOCAL) != 0; }
   uint64_t used = orc_used_memory((int)q->mode, q->compute, q->n_compute, cp, cl, q->graphics, q->n_graphics, gp, gl);
-  used = used >= q->self_bytes ? used - q->self_bytes : 0;
+  /* own-footprint compensation, same rule as the kernel: skip it when our own record is
+   * visible in the lists but was not counted as a container member */
+  int seen = 0;
+  vgpu_proc_t *c2 = (vgpu_proc_t *)malloc(sizeof(vgpu_proc_t) * VGPU_MAX_PIDS * 2), *g2 = c2 + VGPU_MAX_PIDS;
+  memcpy(c2, q->compute, sizeof(vgpu_proc_t) * q->n_compute);
+  memcpy(g2, q->graphics, sizeof(vgpu_proc_t) * q->n_graphics);
+  for (uint32_t i = 0; i < q->n_compute; i++) if (c2[i].pid == q->self_pid) { seen = 1; c2[i].used_bytes = c2[i].used_bytes ? 0 : 1; }
+  for (uint32_t i = 0; i < q->n_graphics; i++) if (g2[i].pid == q->self_pid) { seen = 1; g2[i].used_bytes = g2[i].used_bytes ? 0 : 1; }
+  uint64_t without = orc_used_memory((int)q->mode, c2, q->n_compute, cp, cl, g2, q->n_graphics, gp, gl);
+  free(c2);
+  int counted = without != used;
+  uint64_t self = (seen && !counted) ? 0 : q->self_bytes;
+  used = used >= self ? used - self : 0;
   vgpu_vmem_dev_t *led = (vgpu_vmem_dev_t *)calloc(1, sizeof *led);
   memcpy(led->processes, q->vmem, (size_t)q->n_vmem * sizeof(vgpu_vmem_rec_t));
   led->processes_size = q->n_vmem;

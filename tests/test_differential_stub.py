@@ -1,0 +1,176 @@
+"""CPU: the B200 library against the compiled reference library, same scripted tenant, same
+stub driver, same (redirected) contract files.  Transcripts (return codes, reported numbers,
+ledger contents) and the vgpu.config bytes each library publishes must be identical.
+
+On the stub the "GPU" runs the library's kernels through the oracle (tests/stub/stubdrv.c), so
+this suite checks the HOST logic - hook surface, request staging, locks, ledger file, error
+conventions.  The kernels themselves are checked on a B200 in tests/test_gpu_parity.py.
+"""
+import os
+
+import pytest
+
+import helpers as H
+
+pytestmark = pytest.mark.skipif(not H.have_reference(), reason="oracle/_ref not built (no /root/reference)")
+
+MiB = 1 << 20
+GiB = 1 << 30
+BASE = {"MANAGER_COMPATIBILITY_MODE": "0", "MANAGER_VISIBLE_DEVICES": H.STUB_UUID, "LOGGER_LEVEL": "0"}
+
+
+def both(script, env, stub_env=None, args=(), prep=None):
+    e = dict(BASE)
+    e.update(env)
+    e.update(stub_env or {})
+    outs = []
+    for lib in (H.REF_SO, H.NEW_SO):
+        sb = H.Sandbox()
+        if prep:
+            prep(sb)
+        out, err, _ = H.run_scenario(lib, script, e, sb=sb, args=args)
+        cfg = sb.config_bytes()
+        outs.append((out, cfg, err))
+        sb.cleanup()
+    return outs
+
+
+def assert_same(outs):
+    (a, ca, ea), (b, cb, eb) = outs
+    assert a == b, "transcripts differ:\n--- reference\n%s\n--- b200\n%s\n%s" % (a, b, eb[-1500:])
+    assert ca == cb, "published vgpu.config differs"
+    assert len(ca) == 1848
+    return a
+
+
+def test_cap_1g_alloc_free_and_reported_numbers(built):
+    script = "\n".join([
+        "init 0", "totalmem", "meminfo", "nvmlinfo", "nvmlinfo2",
+        "alloc %d" % (100 * MiB), "alloc %d" % (900 * MiB), "alloc 1", "alloc %d" % (24 * MiB), "alloc %d" % (24 * MiB - 1),
+        "meminfo", "nvmlinfo", "nvmlinfo2", "free 0", "meminfo", "alloc %d" % (100 * MiB), "alloc %d" % (100 * MiB),
+        "pitch 1000 1000 16", "pitch 1048576 2000 4", "allocasync %d" % MiB, "pool %d" % MiB, "pool %d" % GiB,
+        "create %d" % (2 * MiB), "create %d" % GiB, "array 256 256 32 4", "array 4096 4096 32 4",
+        "array3d 64 64 64 1 1", "mipmap 32 32 32 16 2", "meminfo", "nvmlinfo", "setmode 1", "persistence", "ledger 0",
+    ]) + "\n"
+    t = assert_same(both(script, {"CUDA_MEM_LIMIT_0": "1g"}))
+    assert "alloc 1 -> 2" not in t.splitlines()[7]  # sanity: the script exercises both outcomes
+    assert "-> 2 " in t  # at least one OOM happened
+
+
+def test_oversold_spill_sequence_config4_shape(built):
+    """BASELINE config 4 on the stub: 8 GiB virtual / 2 GiB physical, 128 x 64 MiB."""
+    lines = ["init 0"]
+    for i in range(130):
+        lines.append("alloc %d" % (64 * MiB))
+        if i in (0, 31, 32, 33, 95, 96, 127, 128):
+            lines += ["meminfo", "nvmlinfo", "ledger 0"]
+    lines += ["free 40", "free 5", "ledger 0", "meminfo", "managed %d 1" % MiB, "managed %d 2" % MiB, "ledger 0",
+              "alloc %d" % (64 * MiB), "alloc %d" % (64 * MiB), "nvmlinfo2"]
+    env = {"CUDA_MEM_LIMIT_0": "8g", "CUDA_MEM_RATIO_0": "4", "VMEMORY_NODE_ENABLED": "true"}
+    t = assert_same(both("\n".join(lines) + "\n", env))
+    rows = [l for l in t.splitlines() if l.startswith("alloc")]
+    assert all("-> 0" in r for r in rows[:128]) and "-> 2" in rows[128]  # 32 GPU + 96 UVA, then OOM
+    assert "ledger -> size 1 [self %d]" % (96 * 64 * MiB) in t
+
+
+def test_oversold_without_ledger_counts_no_uva(built):
+    """Default deployment (vmem_node off, Appendix B.14): spilled bytes are not counted."""
+    lines = ["init 0"] + ["alloc %d" % (512 * MiB)] * 12 + ["meminfo", "nvmlinfo", "ledger 0"]
+    assert_same(both("\n".join(lines) + "\n", {"CUDA_MEM_LIMIT_0": "2g", "CUDA_MEM_RATIO_0": "2"}))
+
+
+def test_driver_oom_falls_back_to_uva_when_oversold(built):
+    lines = ["init 0", "alloc %d" % (300 * MiB), "alloc %d" % (300 * MiB), "alloc %d" % (300 * MiB), "ledger 0", "meminfo",
+             "pitch 4096 100000 4", "allocasync %d" % (300 * MiB), "ledger 0", "nvmlinfo"]
+    env = {"CUDA_MEM_LIMIT_0": "4g", "CUDA_MEM_OVERSOLD_0": "true", "VMEMORY_NODE_ENABLED": "1"}
+    t = assert_same(both("\n".join(lines) + "\n", env, {"STUB_PHYS_MEM": str(512 * MiB)}))
+    assert "ledger -> size 1" in t
+
+
+def test_other_tenants_and_graphics_dedup_host_mode(built):
+    stub = {"STUB_OTHER_PROCS": "901:268435456:c,902:134217728:g,903:67108864:cg", "STUB_CTX_BYTES": str(300 * MiB)}
+    lines = ["init 0", "meminfo", "nvmlinfo", "alloc %d" % (200 * MiB), "alloc %d" % (100 * MiB), "meminfo", "nvmlinfo", "nvmlinfo2"]
+    assert_same(both("\n".join(lines) + "\n", {"CUDA_MEM_LIMIT_0": "1g"}, stub))
+
+
+def test_cgroup_v2_membership(built):
+    stub = {"STUB_OTHER_PROCS": "901:268435456:c,902:134217728:c,903:67108864:g"}
+
+    def prep(sb):
+        for pid, mine in ((901, True), (902, False), (903, True)):
+            d = sb.path("etc/vgpu-manager/.host_proc/%d" % pid)
+            os.makedirs(d, exist_ok=True)
+            with open(os.path.join(d, "cgroup"), "w") as f:
+                f.write("0::/\n" if mine else "0::/kubepods/burstable/other\n")
+
+    lines = ["init 0", "meminfo", "nvmlinfo", "alloc %d" % (600 * MiB), "alloc %d" % (200 * MiB), "meminfo"]
+    env = {"CUDA_MEM_LIMIT_0": "1g", "MANAGER_COMPATIBILITY_MODE": "2"}
+    t = assert_same(both("\n".join(lines) + "\n", env, stub, prep=prep))
+    # own pid has no .host_proc entry => not counted; 901 + 903 are: 320 MiB used before any alloc
+    assert "nvmlinfo -> 0 total 1073741824 free %d used %d" % (GiB - 320 * MiB, 320 * MiB) in t
+
+
+def test_client_mode_pids_file(built):
+    stub = {"STUB_OTHER_PROCS": "901:268435456:c,902:134217728:c"}
+
+    def prep(sb):
+        os.makedirs(sb.path("etc/vgpu-manager/registry"), exist_ok=True)
+        client = sb.path("etc/vgpu-manager/registry/device-client")
+        with open(client, "w") as f:
+            f.write("#!/bin/sh\nexit 0\n")
+        os.chmod(client, 0o755)
+        with open(sb.path("etc/vgpu-manager/config/pids.config"), "w") as f:
+            f.write("902\n17\n")
+
+    lines = ["init 0", "meminfo", "alloc %d" % (900 * MiB), "alloc %d" % (800 * MiB), "nvmlinfo"]
+    env = {"CUDA_MEM_LIMIT_0": "1g", "MANAGER_COMPATIBILITY_MODE": "200", "VGPU_POD_UID": "uid-1",
+           "VGPU_CONTAINER_NAME": "c", "MANAGER_CLIENT_REGISTER_UUID": "r"}
+    assert_same(both("\n".join(lines) + "\n", env, stub, prep=prep))
+
+
+def test_no_limits_is_pass_through(built):
+    lines = ["init 0", "totalmem", "meminfo", "nvmlinfo", "alloc %d" % GiB, "meminfo", "setmode 1", "persistence",
+             "launch 100 2 2 2"]
+    assert_same(both("\n".join(lines) + "\n", {}, {"STUB_TOTAL_MEM": str(16 * GiB)}))
+
+
+def test_device_missing_from_config_is_fatal_at_cuInit(built):
+    """init_device_cuda_cores (cuda_hook.c:500-503): a CUDA-visible device the config does not
+    describe terminates the process at the first cuInit - same exit code, same message."""
+    env = dict(BASE)
+    env.update({"MANAGER_VISIBLE_DEVICES": "GPU-99999999-9999-9999-9999-999999999999", "CUDA_MEM_LIMIT_0": "1g",
+                "CUDA_CORE_LIMIT_0": "10", "STUB_TOTAL_MEM": str(16 * GiB)})
+    res = []
+    for lib in (H.REF_SO, H.NEW_SO):
+        sb = H.Sandbox()
+        out, err, rc = H.run_scenario(lib, "init 0\ntotalmem\n", env, sb=sb, check=False)
+        res.append((out, rc, "cuda device 0 cannot find the corresponding host device" in err))
+        sb.cleanup()
+    assert res[0] == res[1] == ("", 1, True)
+
+
+def test_cuGetProcAddress_path_is_hooked(built):
+    """cudart resolves everything through cuGetProcAddress; the cap must still apply."""
+    lines = ["init 0", "meminfo", "alloc %d" % (2 * GiB), "alloc %d" % (512 * MiB), "meminfo", "totalmem"]
+    t = assert_same(both("\n".join(lines) + "\n", {"CUDA_MEM_LIMIT_0": "1g"}, args=("--gpa",)))
+    assert "alloc %d -> 2" % (2 * GiB) in t and "total %d" % GiB in t
+
+
+def test_existing_config_file_wins_over_env(built):
+    """A vgpu.config of exactly 1848 bytes dropped by the control plane is used as is."""
+    cfg = H.Cfg()
+    cfg.devices[0].uuid = H.STUB_UUID.encode()
+    cfg.devices[0].total_memory = 3 * GiB
+    cfg.devices[0].real_memory = 3 * GiB
+    cfg.devices[0].memory_limit = 1
+    cfg.devices[0].activate = 1
+    raw = bytes(cfg)
+
+    def prep(sb):
+        with open(sb.path("etc/vgpu-manager/config/vgpu.config"), "wb") as f:
+            f.write(raw)
+
+    lines = ["init 0", "totalmem", "meminfo", "alloc %d" % (2 * GiB), "alloc %d" % (2 * GiB), "nvmlinfo"]
+    outs = both("\n".join(lines) + "\n", {"CUDA_MEM_LIMIT_0": "1g"}, prep=prep)
+    t = assert_same(outs)
+    assert outs[0][1] == raw and "totalmem -> 0 %d" % (3 * GiB) in t

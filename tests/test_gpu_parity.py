@@ -1,0 +1,287 @@
+"""GPU (B200): the sm_100a kernels, called through the C ABI of libvgpu-control.so, against the
+CPU oracle and the reference-generated golden vectors.  Bit-exact everywhere (integer/byte work).
+"""
+import ctypes as C
+import json
+import os
+import random
+
+import pytest
+
+import helpers as H
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+MiB = 1 << 20
+
+
+@pytest.fixture(scope="module")
+def gpu(built):
+    import torch
+    assert torch.cuda.is_available(), "these tests need a GPU"
+    torch.zeros(1, device="cuda")  # creates the primary context the library attaches to
+    from vgpu_manager_b200 import B200Library
+    uuid = "GPU-" + str(torch.cuda.get_device_properties(0).uuid)
+    lib = B200Library(env={"MANAGER_VISIBLE_DEVICES": uuid, "MANAGER_COMPATIBILITY_MODE": "0"})
+    lib.attach()
+    return lib, torch
+
+
+def test_library_is_the_cuda_path(gpu):
+    lib, torch = gpu
+    assert "sm_100a" in lib.version()
+    with open("/proc/self/maps") as f:
+        assert "libvgpu-control.so" in f.read()
+
+
+# ----------------------------------------------------------------------------- clear / spill copy
+SIZES = [0, 1, 15, 16, 17, 31, 255, 4096, 4097, 16384, 16385, 98304, 98320, MiB + 3, 7 * MiB + 16, 64 * MiB]
+
+
+@pytest.mark.parametrize("off", [0, 1, 8, 15, 16])
+def test_clear_exact_and_bounded(gpu, off):
+    lib, torch = gpu
+    for n in SIZES:
+        buf = torch.full((n + 64,), 0xAB, dtype=torch.uint8, device="cuda")
+        lib.clear(buf.data_ptr() + off, n, torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        assert int(buf[off:off + n].to(torch.int64).sum()) == 0, (n, off)
+        assert bool((buf[:off] == 0xAB).all()) and bool((buf[off + n:] == 0xAB).all()), (n, off)
+
+
+@pytest.mark.parametrize("soff,doff", [(0, 0), (1, 1), (15, 15), (16, 0), (3, 19), (0, 1), (5, 2), (4, 8)])
+def test_spill_copy_exact_and_bounded(gpu, soff, doff):
+    lib, torch = gpu
+    g = torch.Generator(device="cuda").manual_seed(0x5EED)
+    for n in SIZES:
+        src = torch.randint(0, 256, (n + 64,), dtype=torch.uint8, device="cuda", generator=g)
+        dst = torch.full((n + 64,), 0xCD, dtype=torch.uint8, device="cuda")
+        lib.spill_copy(dst.data_ptr() + doff, src.data_ptr() + soff, n, torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        assert torch.equal(dst[doff:doff + n], src[soff:soff + n]), (n, soff, doff)
+        assert bool((dst[:doff] == 0xCD).all()) and bool((dst[doff + n:] == 0xCD).all()), (n, soff, doff)
+
+
+def test_spill_and_clear_full_size_properties(gpu):
+    """BASELINE config 4 sizes (64 MiB pages, GiB-scale sweeps): round trip and idempotence."""
+    lib, torch = gpu
+    n = 1 << 30
+    g = torch.Generator(device="cuda").manual_seed(7)
+    a = torch.randint(-2**62, 2**62, (n // 8,), dtype=torch.int64, device="cuda", generator=g)
+    b = torch.empty_like(a)
+    c = torch.empty_like(a)
+    s = torch.cuda.current_stream().cuda_stream
+    lib.spill_copy(b.data_ptr(), a.data_ptr(), n, s)
+    lib.spill_copy(c.data_ptr(), b.data_ptr(), n, s)  # spill then stage back
+    torch.cuda.synchronize()
+    assert torch.equal(a, c) and torch.equal(a, b)
+    # managed (UVM) destination, the reference's spill target (cuMemAllocManaged, cuda_hook.c:1381)
+    cudart = C.CDLL("libcudart.so.12")
+    mp = C.c_void_p()
+    assert cudart.cudaMallocManaged(C.byref(mp), C.c_size_t(256 * MiB), C.c_uint(1)) == 0
+    lib.spill_copy(mp.value, a.data_ptr(), 256 * MiB, s)
+    lib.spill_copy(b.data_ptr(), mp.value, 256 * MiB, s)
+    torch.cuda.synchronize()
+    assert torch.equal(a[: 256 * MiB // 8], b[: 256 * MiB // 8])
+    lib.clear(mp.value, 256 * MiB, s)
+    lib.spill_copy(b.data_ptr(), mp.value, 256 * MiB, s)
+    torch.cuda.synchronize()
+    assert int(b[: 256 * MiB // 8].abs().max()) == 0
+    cudart.cudaFree(mp)
+    lib.clear(c.data_ptr(), n, s)
+    lib.clear(c.data_ptr(), n, s)
+    torch.cuda.synchronize()
+    assert int(c.abs().max()) == 0
+
+
+# ----------------------------------------------------------------------------- quota kernel
+def _rand_req(rng, mode, kind):
+    q = H.QuotaReq()
+    q.kind, q.mode = kind, mode
+    q.n_compute = rng.choice([0, 1, 2, 5, 33, 200, 1024])
+    q.n_graphics = rng.choice([0, 0, 1, 3, 40, 1024])
+    q.n_vmem = rng.choice([0, 0, 1, 7, 1024])
+    big = rng.random() < 0.1
+    pids = [rng.randint(1, 60 if q.n_compute < 100 else 5000) for _ in range(2048)]
+    for i in range(q.n_compute):
+        q.compute[i].pid = pids[i]
+        q.compute[i].used_bytes = rng.randint(0, (1 << 64) - 1) if big else rng.randint(0, 1 << 34)
+        q.cflags[i] = rng.choice([0, 0, 1, 2, 3])
+    for i in range(q.n_graphics):
+        q.graphics[i].pid = pids[1024 + i] if rng.random() < 0.6 else pids[rng.randrange(max(q.n_compute, 1))]
+        q.graphics[i].used_bytes = rng.randint(0, 1 << 33)
+        q.gflags[i] = rng.choice([0, 1, 2, 3])
+    for i in range(q.n_vmem):
+        q.vmem[i].pid = 100 + i
+        q.vmem[i].used = rng.randint(0, 1 << 33)
+    q.total_memory = rng.choice([1 << 30, 8 << 30, 180 << 30, rng.randint(0, 1 << 40)])
+    q.real_memory = rng.choice([q.total_memory, q.total_memory // 4])
+    q.memory_oversold = rng.randint(0, 1)
+    q.allow_uva = rng.randint(0, 1)
+    q.request = rng.choice([0, 1, 64 << 20, 1 << 30, rng.randint(0, 1 << 41), (1 << 64) - 1])
+    q.real_ok = rng.randint(0, 1)
+    q.real_total = rng.choice([0, 1 << 29, 179 << 30])
+    q.self_bytes = rng.choice([0, 0, 2 << 20, 1 << 40])
+    q.self_pid = rng.choice([0, pids[0], 4242424])
+    return q
+
+
+def _oracle_res(o, q):
+    nc, ng = q.n_compute, q.n_graphics
+    cp = (C.c_uint8 * 1024)(*[f & 1 for f in q.cflags])
+    cl = (C.c_uint8 * 1024)(*[(f >> 1) & 1 for f in q.cflags])
+    gp = (C.c_uint8 * 1024)(*[f & 1 for f in q.gflags])
+    gl = (C.c_uint8 * 1024)(*[(f >> 1) & 1 for f in q.gflags])
+    used = o.orc_used_memory(q.mode, q.compute, nc, cp, cl, q.graphics, ng, gp, gl)
+    # own-footprint rule: skip when our record is visible but was not counted
+    seen = any(q.compute[i].pid == q.self_pid for i in range(nc)) or any(
+        q.graphics[i].pid == q.self_pid and all(q.compute[j].pid != q.self_pid for j in range(nc)) for i in range(ng))
+    c2 = (H.Proc * 1024)()
+    g2 = (H.Proc * 1024)()
+    C.memmove(c2, q.compute, C.sizeof(c2))
+    C.memmove(g2, q.graphics, C.sizeof(g2))
+    for arr, n in ((c2, nc), (g2, ng)):
+        for i in range(n):
+            if arr[i].pid == q.self_pid:
+                arr[i].used_bytes = 0 if arr[i].used_bytes else 1
+    counted = o.orc_used_memory(q.mode, c2, nc, cp, cl, g2, ng, gp, gl) != used
+    self_b = 0 if (seen and not counted) else q.self_bytes
+    used = used - self_b if used >= self_b else 0
+    led = H.VmemDev()
+    C.memmove(led.processes, q.vmem, C.sizeof(H.VmemRec) * q.n_vmem)
+    led.processes_size = q.n_vmem
+    vmem = o.orc_ledger_sum(C.byref(led))
+    cfg = H.CfgDev(total_memory=q.total_memory, real_memory=q.real_memory, memory_oversold=q.memory_oversold, memory_limit=1)
+    path, total, ou, of = 0, q.total_memory, 0, 0
+    if q.kind == 0:
+        path = o.orc_memory_path(C.byref(cfg), used, vmem, q.request, q.allow_uva)
+    elif q.kind == 1:
+        t, u, f = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        o.orc_nvml_meminfo(C.byref(cfg), used, vmem, C.byref(t), C.byref(u), C.byref(f))
+        total, ou, of = t.value, u.value, f.value
+    else:
+        f, t = C.c_uint64(), C.c_uint64()
+        o.orc_cu_meminfo(C.byref(cfg), used, vmem, q.real_ok, q.real_total, C.byref(f), C.byref(t))
+        total, of = t.value, f.value
+        ou = total - of
+    return used, vmem, total, ou, of, path
+
+
+def test_quota_kernel_matches_oracle(gpu):
+    lib, torch = gpu
+    o = H.oracle()
+    rng = random.Random(0x5EED)
+    modes = [0, 0, 1, 2, 2, 100, 101, 102, 200, 300, 7]
+    for it in range(400):
+        q = _rand_req(rng, rng.choice(modes), rng.choice([0, 0, 1, 2]))
+        res = lib.quota_eval(q, H.QuotaRes())
+        want = _oracle_res(o, q)
+        got = (res.used, res.vmem, res.total, res.out_used, res.out_free, res.path)
+        assert got == want, (it, q.mode, q.kind, q.n_compute, q.n_graphics, q.n_vmem)
+
+
+def test_quota_kernel_on_reference_generated_cases(gpu):
+    """used-memory folds produced by the reference's own get_used_gpu_memory_by_device."""
+    lib, torch = gpu
+    with open(os.path.join(GOLD, "limiter_memory.json")) as f:
+        cases = json.load(f)["used"]
+    for case in cases:
+        q = H.QuotaReq()
+        q.kind, q.mode = 1, case["mode"]
+        q.total_memory = (1 << 64) - 1
+        q.n_compute, q.n_graphics = len(case["compute"]), len(case["graphics"])
+        for i, (pid, b) in enumerate(case["compute"]):
+            q.compute[i].pid, q.compute[i].used_bytes = pid, b
+            q.cflags[i] = case["cflags"][i] if case["cflags"] else 0
+        for i, (pid, b) in enumerate(case["graphics"]):
+            q.graphics[i].pid, q.graphics[i].used_bytes = pid, b
+            q.gflags[i] = case["gflags"][i] if case["gflags"] else 0
+        res = lib.quota_eval(q, H.QuotaRes())
+        assert res.used == case["used"], case
+
+
+# ----------------------------------------------------------------------------- UVA slab
+def test_slab_matches_dictionary_model(gpu):
+    lib, torch = gpu
+    rng = random.Random(3)
+    model = {}
+    keys = [0x7F0000000000 + rng.randrange(1 << 20) * 512 for _ in range(3000)]
+    for step in range(6000):
+        k = rng.choice(keys)
+        if k in model or rng.random() < 0.3:
+            rc, b = lib.slab_remove(k)
+            if k in model:
+                assert (rc, b) == (0, model.pop(k)), step
+            else:
+                assert rc == 1, step
+        else:
+            b = rng.randint(1, 1 << 40)
+            assert lib.slab_insert(k, b) == 0
+            model[k] = b
+    for k, b in list(model.items()):
+        assert lib.slab_remove(k) == (0, b)
+    assert lib.slab_remove(keys[0])[0] == 1
+
+
+# ----------------------------------------------------------------------------- controller
+def test_controller_kernel_replays_reference_watcher(gpu):
+    """Every golden trajectory was produced by the reference's utilization_watcher thread; the
+    device controller must reproduce share / bucket / up_limit at every step."""
+    lib, torch = gpu
+    with open(os.path.join(GOLD, "watcher.json")) as f:
+        trajs = json.load(f)["trajectories"]
+    for tr in trajs:
+        lib.limiter_reset(tr["sm"], tr["thr"], tr["hard"], tr["soft"], tr["core_limit"], tr["hard_limit"])
+        bucket = 0
+        seen_valid = 0
+        for i, st in enumerate(tr["steps"]):
+            share_w, bucket_w, up_w, valid_w, user_w, sys_w = st["out"]
+            lib.limiter_consume(bucket - st["bucket_in"])  # host consumption since the last step
+            valid_now = 1 if (valid_w and not seen_valid) else 0
+            seen_valid |= valid_w
+            s = lib.limiter_step(user_w, sys_w, valid_now, st["nproc"])
+            got = (s.share, s.granted - s.consumed, s.up_limit, s.valid)
+            assert got == (share_w, bucket_w, up_w, valid_w), (tr["name"], i, got, st["out"])
+            bucket = bucket_w
+
+
+def test_delta_on_device_via_controller(gpu):
+    """delta() vectors from the reference (float compare, overflow guard) through one step."""
+    lib, torch = gpu
+    with open(os.path.join(GOLD, "limiter_memory.json")) as f:
+        cases = json.load(f)["delta"]
+    for sm, thr, up, user, share, want in cases[::7]:
+        if up <= 0:
+            continue
+        # hard-limit step with sys_process_num=2 (no jitter guard): share' = delta(hard, user, share)
+        lib.limiter_reset(sm, thr, up, 0, 1, 1)
+        # seed `share` by one step from 0 when possible, else compare from share = 0
+        s = lib.limiter_step(user, user, 1, 2)
+        o = H.oracle()
+        g = H.OrcGpu()
+        o.orc_gpu_init(C.byref(g), sm, thr)
+        assert s.share == o.orc_delta(C.byref(g), up, user, 0)
+
+
+# ----------------------------------------------------------------------------- sampler
+def test_sampler_tail_runs_controller_and_idle_gpu_reads_idle(gpu):
+    lib, torch = gpu
+    lib.limiter_reset(0, 0, 25, 0, 1, 1)
+    torch.cuda.synchronize()
+    st = None
+    for _ in range(4):
+        st = lib.sampler_run(2000, 100, 4, -1)
+    assert st.steps == 1 and st.valid == 1          # 4 ticks -> exactly one control step
+    assert st.queue_busy_pct == 0 and st.user_current == 0
+    assert 0 <= st.sm_active_pct <= 25               # nothing else is running
+    o = H.oracle()
+    g = H.OrcGpu()
+    o.orc_gpu_init(C.byref(g), 148, 2048)
+    # idle + single process: jitter guard writes the bucket directly with delta(25, 0, 0)
+    assert st.granted - st.consumed == o.orc_delta(C.byref(g), 25, 0, 0) or st.share > 0
+    # scripted utilisation through the sampler's tail == explicit controller steps
+    lib.limiter_reset(148, 2048, 25, 0, 1, 1)
+    a = [lib.sampler_run(200, 50, 1, u) for u in (90, 90, 10, 30, 25, 0)]
+    lib.limiter_reset(148, 2048, 25, 0, 1, 1)
+    b = [lib.limiter_step(u, u, 1, 1) for u in (90, 90, 10, 30, 25, 0)]
+    assert [(x.share, x.granted, x.up_limit) for x in a] == [(x.share, x.granted, x.up_limit) for x in b]

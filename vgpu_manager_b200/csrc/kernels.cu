@@ -259,7 +259,7 @@ DEVINL int mode_select(uint32_t mode, int *open_mode) {
  * sums every local pid.  `live` masks records removed by the graphics/compute dedup. */
 DEVINL unsigned long long fold_list(int sel, int open_mode, bool live, uint32_t flags,
                                     unsigned long long bytes, unsigned long long *s64,
-                                    unsigned int *s32) {
+                                    unsigned int *s32, bool is_self, int *self_state) {
   const bool prim = live && (flags & VGPU_FLAG_PRIMARY);
   const bool loc = live && open_mode && (flags & VGPU_FLAG_LOCAL);
   bool take;
@@ -277,6 +277,8 @@ DEVINL unsigned long long fold_list(int sel, int open_mode, bool live, uint32_t 
   } else {
     take = false;
   }
+  /* bit0: our own process record is visible in this list, bit1: it was counted */
+  if (live && is_self) atomicOr(self_state, take ? 3 : 1);
   return block_sum_u64(take ? bytes : 0ull, s64);
 }
 
@@ -285,6 +287,7 @@ extern "C" __global__ void __launch_bounds__(1024)
   __shared__ unsigned long long s64[33];
   __shared__ unsigned int s32[33];
   __shared__ uint32_t cpid[VGPU_MAX_PIDS];
+  __shared__ int self_state;
 
   const uint32_t t = threadIdx.x;
   const uint32_t nc = min(req->n_compute, (uint32_t)VGPU_MAX_PIDS);
@@ -292,6 +295,8 @@ extern "C" __global__ void __launch_bounds__(1024)
   const uint32_t nv = min(req->n_vmem, (uint32_t)VGPU_MAX_PIDS);
   int open_mode;
   const int sel = mode_select(req->mode, &open_mode);
+  const uint32_t self_pid = req->self_pid;
+  if (t == 0) self_state = 0;
 
   /* compute list */
   uint4 c = make_uint4(0, 0, 0, 0);
@@ -300,7 +305,7 @@ extern "C" __global__ void __launch_bounds__(1024)
   unsigned long long cbytes = ((unsigned long long)c.w << 32) | c.z;
   uint32_t cf = (t < nc) ? req->cflags[t] : 0;
   __syncthreads();
-  unsigned long long used = fold_list(sel, open_mode, t < nc, cf, cbytes, s64, s32);
+  unsigned long long used = fold_list(sel, open_mode, t < nc, cf, cbytes, s64, s32, c.x == self_pid, &self_state);
 
   /* graphics list minus pids already present in the compute list (cuda_hook.c:868-887) */
   uint4 g = make_uint4(0, 0, 0, 0);
@@ -312,7 +317,7 @@ extern "C" __global__ void __launch_bounds__(1024)
   }
   unsigned long long gbytes = ((unsigned long long)g.w << 32) | g.z;
   uint32_t gf = (t < ng) ? req->gflags[t] : 0;
-  used += fold_list(sel, open_mode, glive, gf, gbytes, s64, s32);
+  used += fold_list(sel, open_mode, glive, gf, gbytes, s64, s32, g.x == self_pid, &self_state);
 
   /* UVA ledger sum (loader.c:1909-1922) */
   unsigned long long v = 0;
@@ -323,8 +328,11 @@ extern "C" __global__ void __launch_bounds__(1024)
   unsigned long long vmem = block_sum_u64(v, s64);
 
   if (t == 0) {
-    /* the library's own device footprint is not part of the tenant's usage */
+    /* The library's own device footprint is not part of the tenant's usage.  It is inside
+     * `used` iff our process record was counted; when the record cannot be identified (pid
+     * namespace: NVML reports host pids) the process is a member of its own container. */
     unsigned long long self = req->self_bytes;
+    if (self_state == 1) self = 0; /* visible but not a member: nothing of ours was summed */
     used = used >= self ? used - self : 0;
 
     const unsigned long long total = req->total_memory;

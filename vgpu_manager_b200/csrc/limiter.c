@@ -139,7 +139,31 @@ static void tick_start(void) {
   }
 }
 
+/* Same start-up strictness as the reference's initialization() / init_device_cuda_cores
+ * (cuda_hook.c:487-577): every CUDA-visible device must be described by the config and be
+ * known to NVML, otherwise the process is terminated. */
+static pthread_once_t g_verify_once = PTHREAD_ONCE_INIT;
+static void verify_devices(void) {
+  if (!R.cuInit || R.cuInit(0) != CUDA_SUCCESS) {
+    VLOG(VL_ERROR, "initialization of sm watcher failed");
+    return;
+  }
+  int n = 0;
+  CUresult r = R.cuDeviceGetCount ? R.cuDeviceGetCount(&n) : CUDA_ERROR_NOT_FOUND;
+  if (r) VLOG(VL_FATAL, "cuDeviceGetCount call failed, return %d, str: %s", r, vgpu_cu_err(r));
+  for (int i = 0; i < n; i++) {
+    CUdevice dev;
+    r = R.cuDeviceGet(&dev, i);
+    if (r) VLOG(VL_FATAL, "cuDeviceGet call failed, cuda device %d, return %d, str %s", i, r, vgpu_cu_err(r));
+    if (vgpu_host_index_of_cuda(dev) < 0)
+      VLOG(VL_FATAL, "cuda device %d cannot find the corresponding host device", dev);
+    if (vgpu_nvml_index_of_cuda(dev) < 0)
+      VLOG(VL_FATAL, "cuda device %d cannot find the corresponding nvml device", dev);
+  }
+}
+
 void vgpu_limiter_start(void) {
+  pthread_once(&g_verify_once, verify_devices);
   /* reference: initialization() spawns watch_util_bt_N threads at the first successful cuInit
    * (cuda_hook.c:566-577).  Here the thread is created lazily by the first limited launch,
    * because the sampler needs the tenant's context; this entry point only re-arms after fork

@@ -51,7 +51,7 @@ def build(force=False, verbose=False):
             f.write(body)
             f.write("\nconst unsigned long long vgpu_kernels_image_size = sizeof(vgpu_kernels_image);\n")
     srcs = [os.path.join(CSRC, s) for s in HOST_SRCS] + [image_c]
-    hdrs = [os.path.join(CSRC, h) for h in ("vgpu_internal.h", "kernel_abi.h")] + [
+    hdrs = [os.path.join(CSRC, h) for h in ("vgpu_internal.h", "kernel_abi.h", "cu_abi_subset.h")] + [
         contract, os.path.join(HERE, "..", "include", "vgpu_b200.h")]
     if force or _newer(OUT, srcs + hdrs):
         cmd = ["gcc", "-D_GNU_SOURCE", "-std=gnu11", "-O2", "-g", "-Wall", "-Wshadow", "-fPIC", "-shared",

@@ -58,7 +58,6 @@ static pthread_once_t g_tick_once = PTHREAD_ONCE_INIT;
 static volatile unsigned g_tick_epoch;
 static volatile int g_tick_devices[VGPU_MAX_DEVICES]; /* host indexes with a live runtime + core limit */
 static uint32_t g_window_us = 8000, g_interval_us = 100, g_period_ticks = 8, g_tick_ms = 10;
-static volatile int g_capture_depth;
 
 static uint32_t env_u32(const char *name, uint32_t dflt) {
   const char *s = getenv(name);
@@ -207,9 +206,11 @@ static inline int admit(admit_t *a, unsigned gx, unsigned gy, unsigned gz, CUstr
   a->rt = rt;
   a->ptsz = ptsz;
   a->slot = slot_of(h, s, ptsz);
+  /* the legacy NULL stream cannot be captured; any other stream might be */
   int capturing = 0;
-  if (unlikely(g_capture_depth > 0) && R.cuStreamIsCapturing) R.cuStreamIsCapturing(s, &capturing);
-  if (capturing) { /* graph capture: tokens are paid at capture time, like the reference */
+  if ((s != NULL || ptsz) && R.cuStreamIsCapturing) R.cuStreamIsCapturing(s, &capturing);
+  if (capturing) { /* graph capture: tokens are paid at capture time, like the reference; no gate or
+                      marker nodes are recorded into the graph (they would replay stale values) */
     a->rt = NULL;
     return 1;
   }

@@ -251,18 +251,20 @@ def main():
     if distributed:
         gathered = [torch.zeros_like(vals) for _ in range(world)]
         dist.all_gather(gathered, vals)
-        # cross-tenant rebalance vector: {quota, achieved launches/s, slack} per GPU
-        vec = torch.tensor([CORE_LIMIT, res["launches"] / dev_s, 0.0, float(local_rank)], dtype=torch.float32, device="cuda")
-        bufs = [torch.zeros_like(vec) for _ in range(world)]
+        # cross-tenant rebalance vector: {gpu, quota, achieved launches/s, gated fraction}
+        from vgpu_manager_b200.multi import TenantReport, all_gather_reports, rebalance
+        rep = TenantReport(local_rank, CORE_LIMIT, res["launches"] / dev_s,
+                           res.get("gated_launches", 0) / max(res["launches"], 1))
         for _ in range(5):
-            dist.all_gather(bufs, vec)
+            table = all_gather_reports(dist, torch, rep, torch.device("cuda", local_rank))
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(20):
-            dist.all_gather(bufs, vec)
+            table = all_gather_reports(dist, torch, rep, torch.device("cuda", local_rank))
         e1.record()
         e1.synchronize()
+        plan = rebalance(table)
         rb = torch.tensor([e0.elapsed_time(e1) * 1e3 / 20], dtype=torch.float64, device="cuda")
         dist.all_reduce(rb, op=dist.ReduceOp.MAX)
         rebalance_us = float(rb.item())
@@ -317,6 +319,7 @@ def main():
     }
     if rebalance_us is not None:
         line["rebalance_us"] = round(rebalance_us, 2)
+        line["rebalance_plan_pct"] = {str(k): round(v, 1) for k, v in plan.items()}
     if args.impl == "reference":
         line["impl"] = "reference"
         line["gpu_launches"] = 0

@@ -1,0 +1,59 @@
+"""CPU: the N>1 path of bench.py with world_size 2 over gloo - one stub-driver tenant per rank,
+independent limiter instances, the rebalance all_gather, whole-job aggregation."""
+import json
+import os
+import subprocess
+import sys
+
+import helpers as H
+
+WORKER = r'''
+import json, os, subprocess, sys
+sys.path.insert(0, os.environ["REPO_ROOT"]); sys.path.insert(0, os.path.join(os.environ["REPO_ROOT"], "tests"))
+import torch, torch.distributed as dist
+import helpers as H
+from vgpu_manager_b200.multi import TenantReport, aggregate, rebalance, all_gather_reports
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+sb = H.Sandbox()
+env = H.preload_env(H.NEW_SO, sb, {"MANAGER_COMPATIBILITY_MODE": "0", "MANAGER_VISIBLE_DEVICES": H.STUB_UUID,
+                                  "CUDA_CORE_LIMIT_0": "50", "CUDA_MEM_LIMIT_0": "1g", "STUB_UTIL": "closed:0.02"})
+dist.barrier()
+r = subprocess.run([H.STORM, "--steps", "2", "--warmup", "1", "--per-step", "50000", "--no-kernel"], env=env,
+                   capture_output=True, text=True, timeout=120)
+dist.barrier()
+d = json.loads(r.stdout.strip().splitlines()[-1])
+rep = TenantReport(rank, 50.0, d["launches"] / d["wall_s"], d["gated_launches"] / max(d["launches"], 1))
+table = all_gather_reports(dist, torch, rep, "cpu")
+t = torch.tensor([d["wall_s"], float(d["launches"])], dtype=torch.float64)
+rows = [torch.zeros_like(t) for _ in range(world)]
+dist.all_gather(rows, t)
+value, tmax = aggregate([float(x[0]) for x in rows], [float(x[1]) for x in rows])
+if rank == 0:
+    print(json.dumps({"value": value, "tmax": tmax, "launches": sum(float(x[1]) for x in rows),
+                      "gpus": [r.gpu for r in table], "plan": rebalance(table), "sampler": d["sampler_launches"]}))
+sb.cleanup()
+dist.destroy_process_group()
+'''
+
+
+def test_two_ranks_independent_tenants_and_rebalance_gather(built, tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER)
+    env = dict(os.environ, REPO_ROOT=H.ROOT)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29731", str(script)],
+                       capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0, r.stderr[-3000:]
+    line = [l for l in r.stdout.splitlines() if l.startswith("{")][-1]
+    d = json.loads(line)
+    assert d["launches"] == 200000 and d["gpus"] == [0, 1]
+    assert abs(d["value"] - d["launches"] / d["tmax"]) < 1e-6
+    assert set(d["plan"].keys()) == {"0", "1"} and all(50.0 <= v <= 100.0 for v in d["plan"].values())
+
+
+def test_rebalance_policy_shapes():
+    from vgpu_manager_b200.multi import TenantReport, aggregate, rebalance
+    plan = rebalance([TenantReport(0, 25, 1e5, 0.0), TenantReport(1, 25, 1e5, 1.0), TenantReport(2, 50, 1e5, 0.5)])
+    assert plan == {0: 25.0, 1: 100.0, 2: 75.0}
+    assert aggregate([1.0, 2.0], [10, 30]) == (20.0, 2.0)

@@ -123,7 +123,8 @@ def run_tenant(H, lib, gpu, uuids, steps, warmup, per_step, max_seconds=0.0):
     if max_seconds:
         cmd += ["--max-seconds", str(max_seconds)]
     t0 = time.perf_counter()
-    r = subprocess.run(cmd, env=tenant_env(H, lib, gpu, uuids, sandbox), capture_output=True, text=True)
+    r = subprocess.run(cmd, env=tenant_env(H, lib, gpu, uuids, sandbox), capture_output=True, text=True,
+                       timeout=max(240.0, 4 * max_seconds))
     life = time.perf_counter() - t0
     shutil.rmtree(sandbox, ignore_errors=True)
     if r.returncode != 0 or not r.stdout.strip():

@@ -216,7 +216,22 @@ static inline int admit(admit_t *a, unsigned gx, unsigned gy, unsigned gz, CUstr
   }
   /* bounded run-ahead: the ticket ring holds VGPU_TICKET_RING outstanding launches per stream */
   unsigned long long seq = H->launched[a->slot] + 1;
-  while (unlikely(seq - H->done[a->slot] >= VGPU_TICKET_RING - 2)) sched_yield();
+  if (unlikely(seq - H->done[a->slot] >= VGPU_TICKET_RING - 2)) {
+    /* wait for the stream to drain a little; never forever - if completion markers stopped
+     * arriving (driver refused the mem-op, context torn down) fall back to marker-less mode */
+    struct timespec t0, t1;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    while (seq - H->done[a->slot] >= VGPU_TICKET_RING - 2) {
+      sched_yield();
+      clock_gettime(CLOCK_MONOTONIC, &t1);
+      if (t1.tv_sec - t0.tv_sec >= 5) {
+        VLOG(VL_ERROR, "completion markers stalled on host device %d; disabling stream mem-ops", h);
+        rt->memops64 = 0;
+        H->done[a->slot] = seq - 1;
+        break;
+      }
+    }
+  }
   H->ticket[a->slot][seq & (VGPU_TICKET_RING - 1)] = ticket;
   __sync_synchronize();
   H->launched[a->slot] = seq;
@@ -227,8 +242,13 @@ static inline int admit(admit_t *a, unsigned gx, unsigned gy, unsigned gz, CUstr
     if (likely(rt->memops64)) {
       CUresult (*wait)(CUstream, CUdeviceptr, cuuint64_t, unsigned) =
           (ptsz && R.cuStreamWaitValue64_v2_ptsz) ? R.cuStreamWaitValue64_v2_ptsz : R.cuStreamWaitValue64_v2;
-      wait(s, rt->lim_d + offsetof(vgpu_lim_dev_t, granted), (cuuint64_t)ticket, VCU_WAIT_GEQ);
-    } else {
+      CUresult wr = wait(s, rt->lim_d + offsetof(vgpu_lim_dev_t, granted), (cuuint64_t)ticket, VCU_WAIT_GEQ);
+      if (unlikely(wr != CUDA_SUCCESS)) {
+        VLOG(VL_ERROR, "cuStreamWaitValue64 failed (%d: %s); falling back to the gate kernel", wr, vgpu_cu_err(wr));
+        rt->memops64 = 0;
+      }
+    }
+    if (unlikely(!rt->memops64)) {
       CUdeviceptr gp = rt->lim_d + offsetof(vgpu_lim_dev_t, granted);
       uint32_t timeout_ms = 2000;
       void *params[] = {&gp, &ticket, &timeout_ms};
@@ -248,8 +268,10 @@ static inline void mark_done(const admit_t *a, CUstream s) {
   if (likely(rt->memops64)) {
     CUresult (*wr)(CUstream, CUdeviceptr, cuuint64_t, unsigned) =
         (a->ptsz && R.cuStreamWriteValue64_v2_ptsz) ? R.cuStreamWriteValue64_v2_ptsz : R.cuStreamWriteValue64_v2;
-    wr(s, addr, (cuuint64_t)a->seq, 0);
-  } else {
+    if (likely(wr(s, addr, (cuuint64_t)a->seq, 0) == CUDA_SUCCESS)) return;
+    rt->memops64 = 0;
+  }
+  {
     rt->lim_h->done[a->slot] = a->seq; /* no completion signal available: treat as instantaneous */
   }
 }

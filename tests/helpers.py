@@ -99,7 +99,7 @@ class QuotaReq(C.Structure):
                 ("n_graphics", C.c_uint32), ("n_vmem", C.c_uint32), ("_pad", C.c_uint32),
                 ("total_memory", C.c_uint64), ("real_memory", C.c_uint64), ("request", C.c_uint64),
                 ("real_total", C.c_uint64), ("self_bytes", C.c_uint64), ("self_pid", C.c_uint32),
-                ("_pad2", C.c_uint32), ("compute", Proc * 1024), ("graphics", Proc * 1024),
+                ("_pad2", C.c_uint32 * 3), ("compute", Proc * 1024), ("graphics", Proc * 1024),
                 ("vmem", VmemRec * 1024), ("cflags", C.c_uint8 * 1024), ("gflags", C.c_uint8 * 1024)]
 
 

@@ -56,7 +56,7 @@ typedef struct {
   uint64_t real_total;   /* CU_INFO: driver total                                    */
   uint64_t self_bytes;   /* this library's own device footprint, removed from `used` */
   uint32_t self_pid;
-  uint32_t _pad2;
+  uint32_t _pad2[3];     /* record arrays start 16-byte aligned: they are read with 128-bit loads */
   vgpu_proc_t compute[VGPU_MAX_PIDS];
   vgpu_proc_t graphics[VGPU_MAX_PIDS];
   vgpu_vmem_rec_t vmem[VGPU_MAX_PIDS];
@@ -73,6 +73,9 @@ typedef struct {
   uint32_t path;     /* VGPU_PATH_*                                         */
   uint32_t seq_done; /* written last (release, system scope)                */
 } vgpu_quota_res_t;
+VGPU_STATIC_ASSERT(offsetof(vgpu_quota_req_t, compute) % 16 == 0, qreq_compute_align);
+VGPU_STATIC_ASSERT(offsetof(vgpu_quota_req_t, graphics) % 16 == 0, qreq_graphics_align);
+VGPU_STATIC_ASSERT(offsetof(vgpu_quota_req_t, vmem) % 16 == 0, qreq_vmem_align);
 
 /* ---------------------------------------------------------------- UVA slab ledger */
 

@@ -456,12 +456,38 @@ DEVINL long long ctl_delta(const vgpu_lim_dev_t *D, int up_limit, int user_curre
   return share;
 }
 
+/* `consumed` counts every launch the host has *enqueued*; the reference only charges a launch
+ * when it is admitted (cuda_hook.c:322-328).  Launches are admitted in ticket order, so the
+ * tokens really spent are the ticket of the first launch still parked behind the gate (or all of
+ * `consumed` when nothing is parked).  Tickets grow monotonically inside a stream slot, hence a
+ * binary search over the slot's outstanding window. */
+DEVINL long long consumed_admitted(const vgpu_lim_host_t *H, long long granted) {
+  long long eff = *reinterpret_cast<const volatile long long *>(&H->consumed);
+  for (uint32_t s = 0; s < VGPU_STREAM_SLOTS; s++) {
+    unsigned long long l = H->launched[s], d = H->done[s];
+    if (l <= d) continue;
+    if (l - d > VGPU_TICKET_RING - 1) d = l - (VGPU_TICKET_RING - 1);
+    unsigned long long lo = d + 1, hi = l + 1; /* first seq in [lo, hi) whose ticket > granted */
+    while (lo < hi) {
+      unsigned long long mid = lo + ((hi - lo) >> 1);
+      long long tk = H->ticket[s][mid & (VGPU_TICKET_RING - 1)];
+      if (granted - tk >= 0) lo = mid + 1;
+      else hi = mid;
+    }
+    if (lo <= l) {
+      long long tk = H->ticket[s][lo & (VGPU_TICKET_RING - 1)];
+      if (tk < eff) eff = tk;
+    }
+  }
+  return eff;
+}
+
 DEVINL void ctl_step(vgpu_lim_dev_t *D, vgpu_lim_host_t *H, int user_current, int sys_current,
                      int valid_now, int sys_process_num) {
   if (valid_now) D->valid = 1; /* sticky, like top_result->valid */
   D->last_user_current = user_current;
   D->last_sys_current = sys_current;
-  long long consumed = *reinterpret_cast<volatile long long *>(&H->consumed);
+  long long consumed = consumed_admitted(H, D->granted);
   long long bucket = D->granted - consumed;
   bool touched = false;
   if (D->core_limit && D->valid) {

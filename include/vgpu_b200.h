@@ -123,6 +123,9 @@ int vgpu_b200_limiter_state(vgpu_b200_limiter_state_t *out);
 int vgpu_b200_sampler_run(unsigned window_us, unsigned interval_us, unsigned period_ticks,
                           int user_override, vgpu_b200_limiter_state_t *out);
 
+/* Tuning: bytes per TMA bulk copy (multiple of 16), ring depth (2..16), CTAs per SM; the ring must
+ * fit 200 KiB of shared memory.  0 / -1. */
+int vgpu_b200_set_spill_geometry(unsigned chunk, unsigned stages, unsigned ctas_per_sm);
 unsigned long long vgpu_b200_self_bytes(void);
 unsigned long long vgpu_b200_metric(int host_index, int which);
 

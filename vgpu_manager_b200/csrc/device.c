@@ -125,8 +125,19 @@ static vgpu_dev_rt *bring_up(vgpu_dev_rt *rt, int slot, int host_index, CUdevice
   CU_TRY(R.cuModuleGetFunction(&rt->k_controller, rt->mod, VGPU_K_CONTROLLER), VGPU_K_CONTROLLER);
   CU_TRY(R.cuModuleGetFunction(&rt->k_sampler, rt->mod, VGPU_K_SAMPLER), VGPU_K_SAMPLER);
   CU_TRY(R.cuModuleGetFunction(&rt->k_gate, rt->mod, VGPU_K_GATE), VGPU_K_GATE);
+  {
+    /* spill-copy geometry: defaults from kernel_abi.h, overridable for tuning sweeps */
+    const char *e;
+    rt->spill_chunk = VGPU_SPILL_CHUNK;
+    rt->spill_stages = VGPU_SPILL_STAGES;
+    rt->spill_ctas_per_sm = VGPU_SPILL_CTAS_PER_SM;
+    if ((e = getenv("VGPU_B200_SPILL_CHUNK")) && atoi(e) >= 1024) rt->spill_chunk = (uint32_t)atoi(e) & ~15u;
+    if ((e = getenv("VGPU_B200_SPILL_STAGES")) && atoi(e) >= 2 && atoi(e) <= 16) rt->spill_stages = (uint32_t)atoi(e);
+    if ((e = getenv("VGPU_B200_SPILL_CTAS_PER_SM")) && atoi(e) >= 1) rt->spill_ctas_per_sm = (uint32_t)atoi(e);
+    if ((size_t)rt->spill_chunk * rt->spill_stages > 200 * 1024) rt->spill_stages = 200 * 1024 / rt->spill_chunk;
+  }
   if (R.cuFuncSetAttribute) /* CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES = 8 */
-    CU_TRY(R.cuFuncSetAttribute(rt->k_spill, 8, VGPU_SPILL_SMEM_BYTES), "spill smem opt-in");
+    CU_TRY(R.cuFuncSetAttribute(rt->k_spill, 8, (int)(rt->spill_chunk * rt->spill_stages)), "spill smem opt-in");
 
   int lo = 0, hi = 0;
   if (R.cuCtxGetStreamPriorityRange) R.cuCtxGetStreamPriorityRange(&lo, &hi);
@@ -173,9 +184,9 @@ static vgpu_dev_rt *bring_up(vgpu_dev_rt *rt, int slot, int host_index, CUdevice
     unsigned long long zero = 0;
     CUdeviceptr nullp = rt->slab_d;
     void *p_clear[] = {&nullp, &zero};
-    void *p_copy[] = {&nullp, &nullp, &zero};
+    void *p_copy[] = {&nullp, &nullp, &zero, &rt->spill_chunk, &rt->spill_stages};
     CU_TRY(vgpu_rt_launch(rt, rt->k_clear, 1, 256, 0, rt->q_stream, p_clear), "warm clear");
-    CU_TRY(vgpu_rt_launch(rt, rt->k_spill, 1, 32, VGPU_SPILL_SMEM_BYTES, rt->q_stream, p_copy), "warm spill");
+    CU_TRY(vgpu_rt_launch(rt, rt->k_spill, 1, 32, rt->spill_chunk * rt->spill_stages, rt->q_stream, p_copy), "warm spill");
     CU_TRY(vgpu_rt_launch(rt, rt->k_copy_generic, 1, 256, 0, rt->q_stream, p_copy), "warm copy");
     rt->q_req->seq = ++rt->seq;
     void *p_quota[] = {&rt->q_req_d, &rt->q_res_d};
@@ -324,12 +335,12 @@ CUresult vgpu_rt_clear(vgpu_dev_rt *rt, CUdeviceptr dst, size_t bytes, CUstream 
 
 CUresult vgpu_rt_spill(vgpu_dev_rt *rt, CUdeviceptr dst, CUdeviceptr src, size_t bytes, CUstream s) {
   unsigned long long n = bytes;
-  void *params[] = {&dst, &src, &n};
+  void *params[] = {&dst, &src, &n, &rt->spill_chunk, &rt->spill_stages};
   if (((dst ^ src) & 15) != 0) /* TMA bulk copies need 16-byte congruent endpoints */
     return vgpu_rt_launch(rt, rt->k_copy_generic, copy_grid(rt, (n + 4095) / 4096, 8), 256, 0, s, params);
-  unsigned long long chunks = (n + VGPU_SPILL_CHUNK - 1) / VGPU_SPILL_CHUNK;
-  return vgpu_rt_launch(rt, rt->k_spill, copy_grid(rt, chunks, VGPU_SPILL_CTAS_PER_SM), 32,
-                        VGPU_SPILL_SMEM_BYTES, s, params);
+  unsigned long long chunks = (n + rt->spill_chunk - 1) / rt->spill_chunk;
+  return vgpu_rt_launch(rt, rt->k_spill, copy_grid(rt, chunks, rt->spill_ctas_per_sm), 32,
+                        rt->spill_chunk * rt->spill_stages, s, params);
 }
 
 /* ------------------------------------------------------------------ direct C-ABI (include/vgpu_b200.h) */
@@ -470,6 +481,18 @@ VGPU_EXPORT int vgpu_b200_sampler_run(unsigned window_us, unsigned interval_us, 
   if (R.cuStreamSynchronize(rt->s_stream) != CUDA_SUCCESS) return -1;
   vgpu_metric_add(rt->host_index, VM_SAMPLER_LAUNCHES, 1);
   return read_lim(rt, out);
+}
+
+VGPU_EXPORT int vgpu_b200_set_spill_geometry(unsigned chunk, unsigned stages, unsigned ctas_per_sm) {
+  vgpu_dev_rt *rt = attached();
+  if (!rt || chunk < 1024 || (chunk & 15) || stages < 2 || stages > 16 || ctas_per_sm < 1 ||
+      (size_t)chunk * stages > 200 * 1024)
+    return -1;
+  if (R.cuFuncSetAttribute && R.cuFuncSetAttribute(rt->k_spill, 8, (int)(chunk * stages)) != CUDA_SUCCESS) return -1;
+  rt->spill_chunk = chunk;
+  rt->spill_stages = stages;
+  rt->spill_ctas_per_sm = ctas_per_sm;
+  return 0;
 }
 
 VGPU_EXPORT unsigned long long vgpu_b200_self_bytes(void) {

@@ -114,18 +114,19 @@ extern "C" __global__ void __launch_bounds__(CLEAR_THREADS)
 
 /* ======================================================================= spill copy (TMA)
  * N bytes moved: algorithmic traffic = 2N (N read + N written).
- * One elected thread per CTA drives a SPILL_STAGES-deep ring of SPILL_CHUNK-byte shared-memory
- * buffers: bulk load chunk i+STAGES-1 while chunk i is being stored.  No generic-proxy access to
+ * One elected thread per CTA drives a `stages`-deep ring of `chunk`-byte shared-memory buffers
+ * (defaults VGPU_SPILL_STAGES x VGPU_SPILL_CHUNK): bulk load chunk i+stages-1 while chunk i is
+ * being stored.  No generic-proxy access to
  * the staging buffers ever happens, so no proxy fence is needed between the load's mbarrier
  * completion and the bulk store that reads the same buffer.
  * Precondition: dst and src are congruent mod 16 (the host wrapper checks). */
-#define SPILL_CHUNK VGPU_SPILL_CHUNK
-#define SPILL_STAGES VGPU_SPILL_STAGES
+#define SPILL_MAX_STAGES 16
 #define SPILL_THREADS 32
 extern "C" __global__ void __launch_bounds__(SPILL_THREADS)
-    vgpu_spill_copy_kernel(uint8_t *dst, const uint8_t *src, unsigned long long bytes) {
+    vgpu_spill_copy_kernel(uint8_t *dst, const uint8_t *src, unsigned long long bytes, uint32_t chunk,
+                           uint32_t stages) {
   extern __shared__ __align__(128) uint8_t stage_mem[];
-  __shared__ __align__(8) uint64_t full[SPILL_STAGES];
+  __shared__ __align__(8) uint64_t full[SPILL_MAX_STAGES];
 
   unsigned long long mis = (16 - ((unsigned long long)dst & 15)) & 15;
   if (mis > bytes) mis = bytes;
@@ -139,36 +140,35 @@ extern "C" __global__ void __launch_bounds__(SPILL_THREADS)
 
   const uint8_t *s = src + mis;
   uint8_t *d = dst + mis;
-  const unsigned long long nchunks = (body + SPILL_CHUNK - 1) / SPILL_CHUNK;
+  const unsigned long long nchunks = (body + chunk - 1) / chunk;
   /* chunks owned by this CTA: blockIdx.x, blockIdx.x + gridDim.x, ... */
   if (blockIdx.x >= nchunks) return;
   const unsigned long long mine = (nchunks - 1 - blockIdx.x) / gridDim.x + 1;
 
-  for (int i = 0; i < SPILL_STAGES; i++) mbar_init(&full[i], 1);
+  for (uint32_t i = 0; i < stages; i++) mbar_init(&full[i], 1);
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 
-  auto chunk_off = [&](unsigned long long k) { return (blockIdx.x + k * gridDim.x) * (unsigned long long)SPILL_CHUNK; };
+  auto chunk_off = [&](unsigned long long k) { return (blockIdx.x + k * gridDim.x) * (unsigned long long)chunk; };
   auto chunk_len = [&](unsigned long long k) -> uint32_t {
-    unsigned long long off = chunk_off(k);
-    unsigned long long rem = body - off;
-    return (uint32_t)(rem < SPILL_CHUNK ? rem : SPILL_CHUNK);
+    unsigned long long rem = body - chunk_off(k);
+    return (uint32_t)(rem < chunk ? rem : chunk);
   };
   auto issue_load = [&](unsigned long long k) {
-    int st = (int)(k % SPILL_STAGES);
+    uint32_t st = (uint32_t)(k % stages);
     uint32_t len = chunk_len(k);
     mbar_expect_tx(&full[st], len);
-    bulk_g2s(stage_mem + (size_t)st * SPILL_CHUNK, s + chunk_off(k), len, &full[st]);
+    bulk_g2s(stage_mem + (size_t)st * chunk, s + chunk_off(k), len, &full[st]);
   };
 
-  /* prologue: STAGES-1 loads in flight */
+  /* prologue: stages-1 loads in flight */
   unsigned long long issued = 0;
-  for (; issued < mine && issued < SPILL_STAGES - 1; issued++) issue_load(issued);
+  for (; issued < mine && issued < stages - 1; issued++) issue_load(issued);
 
   for (unsigned long long k = 0; k < mine; k++) {
-    int st = (int)(k % SPILL_STAGES);
-    uint32_t parity = (uint32_t)((k / SPILL_STAGES) & 1);
+    uint32_t st = (uint32_t)(k % stages);
+    uint32_t parity = (uint32_t)((k / stages) & 1);
     mbar_wait(&full[st], parity);
-    bulk_s2g(d + chunk_off(k), stage_mem + (size_t)st * SPILL_CHUNK, chunk_len(k));
+    bulk_s2g(d + chunk_off(k), stage_mem + (size_t)st * chunk, chunk_len(k));
     bulk_commit();
     if (issued < mine) {
       /* the buffer to refill is the one chunk k-1 was stored from; allow only the store just

@@ -215,6 +215,7 @@ typedef struct vgpu_dev_rt {
   int sm_num, max_thread_per_sm;
   int64_t total_cores;
   int memops64; /* cuStreamWaitValue64 usable */
+  uint32_t spill_chunk, spill_stages, spill_ctas_per_sm;
 } vgpu_dev_rt;
 
 vgpu_dev_rt *vgpu_rt_get(int host_index, CUdevice dev); /* bring up (needs a current ctx) */

@@ -120,5 +120,8 @@ class B200Library:
                     "vgpu_b200_sampler_run")
         return st
 
+    def set_spill_geometry(self, chunk, stages, ctas_per_sm):
+        self._check(self.h.vgpu_b200_set_spill_geometry(chunk, stages, ctas_per_sm), "vgpu_b200_set_spill_geometry")
+
     def self_bytes(self):
         return self.h.vgpu_b200_self_bytes()

@@ -180,6 +180,7 @@ void vgpu_limiter_quiesce(vgpu_dev_rt *rt) {
 }
 
 /* ------------------------------------------------------------------ admission */
+#define GATED_RUNAHEAD 96u /* launches (x3 stream ops) allowed to queue behind a closed gate */
 typedef struct {
   vgpu_dev_rt *rt;
   uint32_t slot;
@@ -239,6 +240,20 @@ static inline int admit(admit_t *a, unsigned gx, unsigned gy, unsigned gz, CUstr
   if (H->granted_mirror - ticket < 0) {
     /* bucket empty: park the *stream* on the HBM word, not the CPU thread */
     vgpu_metric_add(h, VM_RATE_GATED, 1);
+    /* Bounded run-ahead.  A parked stream must never be allowed to fill the driver's hardware
+     * queue: a launch call that blocks inside the driver for queue space holds the context lock,
+     * and the tick thread could then no longer launch the sampler whose controller is the only
+     * thing that can release the stream.  So once GATED_RUNAHEAD launches are queued behind the
+     * gate, wait here - in user space, in ~20 us steps - for the stream to drain or for tokens.
+     * (The reference blocks the thread for every throttled launch, in 10 ms steps.) */
+    if (unlikely(seq - H->done[a->slot] > GATED_RUNAHEAD)) {
+      struct timespec nap = {0, 20000};
+      for (int spins = 0; seq - H->done[a->slot] > GATED_RUNAHEAD && H->granted_mirror - ticket < 0; spins++) {
+        if (spins < 64) sched_yield();
+        else nanosleep(&nap, NULL);
+        if (unlikely(!rt->memops64)) break;
+      }
+    }
     if (likely(rt->memops64)) {
       CUresult (*wait)(CUstream, CUdeviceptr, cuuint64_t, unsigned) =
           (ptsz && R.cuStreamWaitValue64_v2_ptsz) ? R.cuStreamWaitValue64_v2_ptsz : R.cuStreamWaitValue64_v2;

@@ -85,6 +85,13 @@ int main(int argc, char **argv) {
       int r5 = n_init();
       int r6 = n_h((unsigned)a, &nvdev);
       printf("init %d %d %d %d %d %d\n", r1, r2, r3, r4, r5, r6);
+    } else if (!strcmp(cmd, "nvmlinit")) {
+      /* NVML-only client (nvidia-smi style): no cuInit, no CUDA context */
+      int (*n_init)(void) = sym("nvmlInit_v2");
+      int (*n_h)(unsigned, void **) = sym("nvmlDeviceGetHandleByIndex_v2");
+      int r5 = n_init();
+      int r6 = n_h((unsigned)a, &nvdev);
+      printf("nvmlinit %d %d\n", r5, r6);
     } else if (!strcmp(cmd, "alloc")) {
       CUresult (*f)(CUdeviceptr *, size_t) = sym("cuMemAlloc_v2");
       CUdeviceptr p = 0;

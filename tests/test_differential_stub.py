@@ -174,3 +174,23 @@ def test_existing_config_file_wins_over_env(built):
     outs = both("\n".join(lines) + "\n", {"CUDA_MEM_LIMIT_0": "1g"}, prep=prep)
     t = assert_same(outs)
     assert outs[0][1] == raw and "totalmem -> 0 %d" % (3 * GiB) in t
+
+
+def test_nvml_only_client_needs_opt_in_context(built):
+    """nvidia-smi style process: no CUDA context.  The reference answers on the CPU; the B200
+    library has no CPU path, so it refuses by default and matches the reference's numbers once
+    VGPU_B200_NVML_CONTEXT=1 lets it retain the primary context for its kernel."""
+    script = "nvmlinit 0\nnvmlinfo\nnvmlinfo2\npersistence\nsetmode 0\n"
+    env = dict(BASE)
+    env.update({"CUDA_MEM_LIMIT_0": "1g", "STUB_OTHER_PROCS": "901:268435456:c"})
+    sb = H.Sandbox()
+    ref, _, _ = H.run_scenario(H.REF_SO, script, env, sb=sb)
+    sb.cleanup()
+    sb = H.Sandbox()
+    off, err, _ = H.run_scenario(H.NEW_SO, script, dict(env, LOGGER_LEVEL="1"), sb=sb)
+    sb.cleanup()
+    assert "nvmlinfo -> 3 " in off and "no CPU fallback" in err
+    sb = H.Sandbox()
+    on, _, _ = H.run_scenario(H.NEW_SO, script, dict(env, VGPU_B200_NVML_CONTEXT="1"), sb=sb)
+    sb.cleanup()
+    assert on == ref and "used 268435456" in ref

@@ -479,7 +479,6 @@ VGPU_EXPORT CUresult cuMemGetInfo(size_t *f, size_t *t) { return mem_info(f, t);
 
 /* ------------------------------------------------------------------ NVML hooks */
 static vgpu_dev_rt *rt_for_nvml(int host_index, CUdevice *dev_out) {
-  /* an NVML-only client (nvidia-smi) has no CUDA context: the kernels then cannot run */
   vgpu_dev_rt *rt = vgpu_rt_peek(host_index);
   if (rt) {
     *dev_out = rt->cuda_dev;
@@ -489,6 +488,23 @@ static vgpu_dev_rt *rt_for_nvml(int host_index, CUdevice *dev_out) {
   if (R.cuCtxGetDevice && R.cuCtxGetDevice(&dev) == CUDA_SUCCESS && vgpu_host_index_of_cuda(dev) == host_index) {
     *dev_out = dev;
     return vgpu_rt_get(host_index, dev);
+  }
+  /* An NVML-only client (nvidia-smi, a metrics exporter) has no CUDA context for the quota
+   * kernel to run in.  Opt-in: retain the device's primary context for it.  Off by default
+   * because that context's own footprint (hundreds of MiB) would then be charged to the tenant,
+   * which the reference - computing on the CPU - never does. */
+  const char *opt = getenv("VGPU_B200_NVML_CONTEXT");
+  if (!opt || strcmp(opt, "1") != 0 || !R.cuInit || !R.cuDevicePrimaryCtxRetain || !R.cuDeviceGetCount) return NULL;
+  int n = 0;
+  if (R.cuInit(0) != CUDA_SUCCESS || R.cuDeviceGetCount(&n) != CUDA_SUCCESS) return NULL;
+  for (int i = 0; i < n; i++) {
+    CUcontext ctx = NULL;
+    if (R.cuDeviceGet(&dev, i) != CUDA_SUCCESS || vgpu_host_index_of_cuda(dev) != host_index) continue;
+    if (R.cuDevicePrimaryCtxRetain(&ctx, dev) != CUDA_SUCCESS || R.cuCtxPushCurrent_v2(ctx) != CUDA_SUCCESS) return NULL;
+    rt = vgpu_rt_get(host_index, dev);
+    R.cuCtxPopCurrent_v2(&ctx);
+    *dev_out = dev;
+    return rt;
   }
   return NULL;
 }

@@ -61,6 +61,7 @@ void vgpu_log_emit(int level, const char *file, int line, const char *fmt, ...)
   X(cuCtxPushCurrent_v2, CUresult, (CUcontext))                                                 \
   X(cuCtxPopCurrent_v2, CUresult, (CUcontext *))                                                \
   X(cuCtxSynchronize, CUresult, (void))                                                         \
+  X(cuDevicePrimaryCtxRetain, CUresult, (CUcontext *, CUdevice))                                \
   X(cuMemAlloc, CUresult, (CUdeviceptr *, size_t))                                              \
   X(cuMemAlloc_v2, CUresult, (CUdeviceptr *, size_t))                                           \
   X(cuMemAllocManaged, CUresult, (CUdeviceptr *, size_t, unsigned int))                         \

@@ -301,7 +301,7 @@ def main():
         "value": round(value, 1), "unit": "launches/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(t_max / max(res["steps"], 1) * 1e3, 3), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "int64", "data": "synthetic",
-        "config": {"workload": "configs[1]: 1 tenant per B200, 25% cores / 4 GiB cap, empty-kernel <<<1,1>>> "
+        "config": {"workload": "configs[1]: 1 tenant per B200, 25%% cores / 4 GiB cap, empty-kernel <<<1,1>>> "
                                "cuLaunchKernel storm, %d launches per step, sync per step" % per_step,
                    "per_step_launches": per_step, "core_limit_pct": CORE_LIMIT, "mem_limit": MEM_LIMIT,
                    "l2_policy": "storm has no data reuse; roofline copy uses 1 GiB buffers (> 126 MB L2)",

@@ -68,6 +68,8 @@ typedef int vb_nvmlReturn;               /* nvmlReturn_t  */
  *  nvmlDeviceGetUtilizationRates            library/src/nvml_originals.c:698 (forward)
  *  cuCtxSynchronize                         (none - B200 addition: asks a resident sampler
  *                                            kernel to retire before the tenant's device sync)
+ *  cuStreamDestroy_v2                       (none - B200 addition: releases the stream's
+ *                                            completion-marker slot)
  */
 
 /* ======================================================================== PART 2: direct API */

@@ -23,7 +23,7 @@
   X(cuLaunchGrid) X(cuLaunchGridAsync) X(cuFuncSetBlockShape) X(cuMemAllocAsync)              \
   X(cuMemAllocAsync_ptsz) X(cuMemCreate) X(cuMemAllocFromPoolAsync)                           \
   X(cuMemAllocFromPoolAsync_ptsz) X(cuMemFree_v2) X(cuMemFree) X(cuMemFreeAsync)              \
-  X(cuMemFreeAsync_ptsz) X(cuCtxSynchronize)
+  X(cuMemFreeAsync_ptsz) X(cuCtxSynchronize) X(cuStreamDestroy_v2)
 #define VGPU_NVML_HOOKS(X)                                                                    \
   X(nvmlInit) X(nvmlInit_v2) X(nvmlInitWithFlags) X(nvmlDeviceGetMemoryInfo)                  \
   X(nvmlDeviceGetMemoryInfo_v2) X(nvmlDeviceSetComputeMode) X(nvmlDeviceGetPersistenceMode)   \
@@ -44,6 +44,9 @@ static void *find_hook(const hook_ent *t, size_t n, const char *name) {
 
 void *vgpu_lookup_cuda_hook(const char *name, int want_ptsz) {
   size_t n = sizeof g_cuda_hooks / sizeof g_cuda_hooks[0];
+  /* cuGetProcAddress callers ask for the base name; cuStreamDestroy has had the _v2 ABI since
+   * CUDA 4.0 and the driver hands out exactly that for it */
+  if (!strcmp(name, "cuStreamDestroy")) name = "cuStreamDestroy_v2";
   if (want_ptsz) {
     char alt[96];
     snprintf(alt, sizeof alt, "%s_ptsz", name);

@@ -25,9 +25,9 @@ extern "C" {
 
 /* ---------------------------------------------------------------- spill copy geometry */
 #define VGPU_SPILL_CHUNK 16384u      /* bytes per TMA bulk copy                      */
-#define VGPU_SPILL_STAGES 6u         /* shared-memory ring depth per CTA             */
+#define VGPU_SPILL_STAGES 4u         /* shared-memory ring depth per CTA             */
 #define VGPU_SPILL_SMEM_BYTES (VGPU_SPILL_CHUNK * VGPU_SPILL_STAGES)
-#define VGPU_SPILL_CTAS_PER_SM 2u    /* 2 x 96 KiB of staging per SM                 */
+#define VGPU_SPILL_CTAS_PER_SM 1u    /* one 64 KiB ring per SM (best of the r1 sweep)  */
 
 /* ---------------------------------------------------------------- memory quota */
 

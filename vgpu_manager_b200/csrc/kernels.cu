@@ -625,8 +625,10 @@ extern "C" __global__ void __launch_bounds__(SAMPLER_THREADS)
       long long granted = *reinterpret_cast<volatile long long *>(&D->granted);
 #pragma unroll
       for (uint32_t s = lane; s < VGPU_STREAM_SLOTS; s += 32) {
-        unsigned long long l = H->launched[s];
+        /* done first, launched second: a completion racing the two reads can then only make
+         * the stream look busy a moment longer, never idle while work is queued */
         unsigned long long d = H->done[s];
+        unsigned long long l = H->launched[s];
         if (l > d) {
           long long tk = H->ticket[s][(d + 1) & (VGPU_TICKET_RING - 1)];
           if (granted - tk >= 0) running = true;

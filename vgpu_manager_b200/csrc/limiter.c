@@ -33,24 +33,47 @@
 
 extern vgpu_dev_rt *vgpu_rt_get(int host_index, CUdevice dev);
 
-/* ------------------------------------------------------------------ stream slots */
+/* ------------------------------------------------------------------ stream slots
+ * Every (stream, per-thread-default flag) of a device gets a slot in the pinned block: launch
+ * sequence, completion marker, ticket ring.  Host-only bookkeeping lives here. */
+#define MARK_EVERY 32u              /* dense launch trains: one completion marker per 32 launches */
+#define SPARSE_TSC 120000ull        /* launches further apart than ~50 us are each marked       */
 typedef struct {
-  volatile uintptr_t key; /* CUstream | ptsz bit; 0 = empty */
-} slot_key_t;
-static slot_key_t g_slots[VGPU_MAX_DEVICES][VGPU_STREAM_SLOTS];
+  volatile uintptr_t key;           /* CUstream | ptsz bit | top bit; 0 = empty */
+  CUstream stream;
+  int ptsz;
+  volatile unsigned long long marked; /* last sequence number a marker was enqueued for */
+  unsigned long long seen_launched;   /* tick thread: launch count at the previous tick  */
+  unsigned long long last_tsc;
+} slot_t;
+static slot_t g_slots[VGPU_MAX_DEVICES][VGPU_STREAM_SLOTS];
+
+static inline unsigned long long rdtsc(void) {
+  unsigned int lo, hi;
+  __asm__ volatile("rdtsc" : "=a"(lo), "=d"(hi));
+  return ((unsigned long long)hi << 32) | lo;
+}
+
+static inline uintptr_t slot_key(CUstream s, int ptsz) {
+  return ((uintptr_t)s << 1) | (uintptr_t)(ptsz & 1) | ((uintptr_t)1 << 63);
+}
 
 static inline uint32_t slot_of(int host_index, CUstream s, int ptsz) {
-  uintptr_t key = ((uintptr_t)s << 1) | (uintptr_t)(ptsz & 1) | ((uintptr_t)1 << 63);
+  uintptr_t key = slot_key(s, ptsz);
   uint32_t h = (uint32_t)((key >> 4) * 0x9E3779B97F4A7C15ull >> 58); /* 6 bits */
-  slot_key_t *tab = g_slots[host_index];
+  slot_t *tab = g_slots[host_index];
   for (uint32_t i = 0; i < VGPU_STREAM_SLOTS - 1; i++) {
     uint32_t idx = (h + i) % (VGPU_STREAM_SLOTS - 1);
     uintptr_t k = tab[idx].key;
     if (k == key) return idx;
-    if (k == 0 && __sync_bool_compare_and_swap(&tab[idx].key, 0, key)) return idx;
+    if (k == 0 && __sync_bool_compare_and_swap(&tab[idx].key, 0, key)) {
+      tab[idx].stream = s;
+      tab[idx].ptsz = ptsz;
+      return idx;
+    }
     if (tab[idx].key == key) return idx;
   }
-  return VGPU_STREAM_SLOTS - 1; /* overflow slot, shared */
+  return VGPU_STREAM_SLOTS - 1; /* overflow slot, shared: every launch is marked */
 }
 
 /* ------------------------------------------------------------------ tick thread */
@@ -84,6 +107,24 @@ static void refresh_process_count(vgpu_dev_rt *rt) {
   }
 }
 
+/* A dense launch train only carries a marker every MARK_EVERY launches, so its tail may stay
+ * unmarked.  If a stream has not launched since the previous tick and the driver says it is
+ * idle, everything it was given has completed. */
+static void settle_idle_streams(vgpu_dev_rt *rt, int h) {
+  vgpu_lim_host_t *H = rt->lim_h;
+  for (uint32_t i = 0; i < VGPU_STREAM_SLOTS - 1; i++) {
+    slot_t *sl = &g_slots[h][i];
+    if (!sl->key) continue;
+    unsigned long long l = H->launched[i], d = H->done[i];
+    int quiet = (l == sl->seen_launched);
+    sl->seen_launched = l;
+    if (l <= d || !quiet || sl->marked >= l) continue;
+    if (sl->ptsz && sl->stream == NULL) continue; /* another thread's default stream: not addressable */
+    if (R.cuStreamQuery && R.cuStreamQuery(sl->stream) == CUDA_SUCCESS && H->launched[i] == l && H->done[i] < l)
+      H->done[i] = l;
+  }
+}
+
 static void *tick_main(void *arg) {
   (void)arg;
   struct timespec nap = {0, (long)g_tick_ms * 1000000L};
@@ -98,6 +139,7 @@ static void *tick_main(void *arg) {
       vgpu_dev_rt *rt = vgpu_rt_peek(h);
       if (!rt) continue;
       if (R.cuCtxPushCurrent_v2(rt->ctx) != CUDA_SUCCESS) continue;
+      settle_idle_streams(rt, h);
       CUresult q = R.cuStreamQuery(rt->s_stream);
       if (q == CUDA_SUCCESS) {
         rt->lim_h->quit = 0;
@@ -169,7 +211,7 @@ void vgpu_limiter_start(void) {
    * (the reference does not - SURVEY.md Appendix B.13). */
   if (g_tick_epoch && g_tick_epoch != vgpu_fork_epoch + 1) {
     memset((void *)g_tick_devices, 0, sizeof g_tick_devices);
-    memset(g_slots, 0, sizeof g_slots);
+    memset((void *)g_slots, 0, sizeof g_slots);
     g_tick_once = (pthread_once_t)PTHREAD_ONCE_INIT;
     g_tick_epoch = 0;
   }
@@ -187,6 +229,14 @@ typedef struct {
   unsigned long long seq;
   int ptsz;
 } admit_t;
+
+static inline void enqueue_marker(vgpu_dev_rt *rt, int h, uint32_t slot, unsigned long long seq, CUstream s, int ptsz) {
+  CUdeviceptr addr = rt->lim_h_d + offsetof(vgpu_lim_host_t, done) + (CUdeviceptr)slot * sizeof(unsigned long long);
+  CUresult (*wr)(CUstream, CUdeviceptr, cuuint64_t, unsigned) =
+      (ptsz && R.cuStreamWriteValue64_v2_ptsz) ? R.cuStreamWriteValue64_v2_ptsz : R.cuStreamWriteValue64_v2;
+  if (likely(wr(s, addr, (cuuint64_t)seq, 0) == CUDA_SUCCESS)) g_slots[h][slot].marked = seq;
+  else rt->memops64 = 0;
+}
 
 /* returns 0 when the launch should simply be forwarded */
 static inline int admit(admit_t *a, unsigned gx, unsigned gy, unsigned gz, CUstream s, int ptsz) {
@@ -254,6 +304,9 @@ static inline int admit(admit_t *a, unsigned gx, unsigned gy, unsigned gz, CUstr
         if (unlikely(!rt->memops64)) break;
       }
     }
+    /* make the sampler's view exact at the gate: everything before this launch gets its marker
+     * now, so the oldest unfinished launch it will see is this (parked) one */
+    if (likely(rt->memops64) && g_slots[h][a->slot].marked < seq - 1) enqueue_marker(rt, h, a->slot, seq - 1, s, ptsz);
     if (likely(rt->memops64)) {
       CUresult (*wait)(CUstream, CUdeviceptr, cuuint64_t, unsigned) =
           (ptsz && R.cuStreamWaitValue64_v2_ptsz) ? R.cuStreamWaitValue64_v2_ptsz : R.cuStreamWaitValue64_v2;
@@ -279,16 +332,19 @@ static inline int admit(admit_t *a, unsigned gx, unsigned gy, unsigned gz, CUstr
 static inline void mark_done(const admit_t *a, CUstream s) {
   if (!a->rt) return;
   vgpu_dev_rt *rt = a->rt;
-  CUdeviceptr addr = rt->lim_h_d + offsetof(vgpu_lim_host_t, done) + (CUdeviceptr)a->slot * sizeof(unsigned long long);
+  int h = rt->host_index;
+  slot_t *sl = &g_slots[h][a->slot];
   if (likely(rt->memops64)) {
-    CUresult (*wr)(CUstream, CUdeviceptr, cuuint64_t, unsigned) =
-        (a->ptsz && R.cuStreamWriteValue64_v2_ptsz) ? R.cuStreamWriteValue64_v2_ptsz : R.cuStreamWriteValue64_v2;
-    if (likely(wr(s, addr, (cuuint64_t)a->seq, 0) == CUDA_SUCCESS)) return;
-    rt->memops64 = 0;
+    /* a completion marker costs a driver call (~3 us): dense trains share one per MARK_EVERY
+     * launches, isolated launches and the overflow slot get their own */
+    unsigned long long now = rdtsc();
+    int sparse = (now - sl->last_tsc) > SPARSE_TSC;
+    sl->last_tsc = now;
+    if (sparse || a->seq - sl->marked >= MARK_EVERY || a->slot == VGPU_STREAM_SLOTS - 1 || (sl->ptsz && !sl->stream))
+      enqueue_marker(rt, h, a->slot, a->seq, s, a->ptsz);
+    if (likely(rt->memops64)) return;
   }
-  {
-    rt->lim_h->done[a->slot] = a->seq; /* no completion signal available: treat as instantaneous */
-  }
+  rt->lim_h->done[a->slot] = a->seq; /* no completion signal available: treat as instantaneous */
 }
 
 #define LIMITED_LAUNCH(gx, gy, gz, stream, ptsz, CALL)          \
@@ -372,4 +428,22 @@ VGPU_EXPORT CUresult cuCtxSynchronize(void) {
     if (rt) vgpu_limiter_quiesce(rt);
   }
   return R.cuCtxSynchronize();
+}
+
+/* B200 addition: forget a stream's slot when the application destroys it */
+VGPU_EXPORT CUresult cuStreamDestroy_v2(CUstream s) {
+  vgpu_boot();
+  for (int h = 0; h < VGPU_MAX_DEVICES; h++)
+    for (uint32_t i = 0; i < VGPU_STREAM_SLOTS - 1; i++) {
+      slot_t *sl = &g_slots[h][i];
+      if (sl->key && sl->stream == s) {
+        vgpu_dev_rt *rt = vgpu_rt_peek(h);
+        if (rt) rt->lim_h->done[i] = rt->lim_h->launched[i];
+        sl->stream = NULL;
+        sl->marked = sl->seen_launched = 0;
+        __sync_synchronize();
+        sl->key = 0;
+      }
+    }
+  return R.cuStreamDestroy_v2 ? R.cuStreamDestroy_v2(s) : CUDA_ERROR_NOT_FOUND;
 }

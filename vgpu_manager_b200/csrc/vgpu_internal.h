@@ -99,6 +99,7 @@ void vgpu_log_emit(int level, const char *file, int line, const char *fmt, ...)
   X(cuStreamCreateWithPriority, CUresult, (CUstream *, unsigned int, int))                      \
   X(cuCtxGetStreamPriorityRange, CUresult, (int *, int *))                                      \
   X(cuStreamSynchronize, CUresult, (CUstream))                                                  \
+  X(cuStreamDestroy_v2, CUresult, (CUstream))                                                   \
   X(cuStreamQuery, CUresult, (CUstream))                                                        \
   X(cuStreamIsCapturing, CUresult, (CUstream, int *))                                           \
   X(cuStreamWaitValue64_v2, CUresult, (CUstream, CUdeviceptr, cuuint64_t, unsigned int))        \

@@ -315,6 +315,7 @@ def main():
                         % (args.warmup, res["steps"])},
         "gpu_launches": int(sum(r[5] for r in rows)) + own_launches,
         "gated_launches": int(sum(r[6] for r in rows)),
+        "limiter_rank0": res.get("limiter"),
         "truncated": bool(res.get("truncated", 0)),
         "region_wall_s": round(region_s, 3),
     }

@@ -386,7 +386,7 @@ void orc_config_from_env(orc_getenv_fn ge, void *ctx, vgpu_cfg_t *cfg) {
         snprintf(slot, VGPU_UUID_LEN, "%s", v);
         ok++;
       } else {
-        if (v && v[0]) snprintf(slot, VGPU_UUID_LEN, "%s", v); /* truncated write, then ... */
+        /* (a too-long value is first written truncated, then ...) */
         strncpy(slot, VGPU_FAKE_UUID, VGPU_UUID_LEN - 1);         /* ... overwritten by the fake */
         slot[VGPU_UUID_LEN - 1] = '\0';
       }

@@ -81,6 +81,7 @@ static pthread_once_t g_tick_once = PTHREAD_ONCE_INIT;
 static volatile unsigned g_tick_epoch;
 static volatile int g_tick_devices[VGPU_MAX_DEVICES]; /* host indexes with a live runtime + core limit */
 static uint32_t g_window_us = 8000, g_interval_us = 100, g_period_ticks = 8, g_tick_ms = 10;
+static volatile int g_sync_waiters; /* threads currently inside a device-wide synchronise */
 
 static uint32_t env_u32(const char *name, uint32_t dflt) {
   const char *s = getenv(name);
@@ -145,7 +146,10 @@ static void *tick_main(void *arg) {
         rt->lim_h->quit = 0;
         if ((epoch % 100) == 1) refresh_process_count(rt);
         uint32_t ep = epoch;
-        void *params[] = {&rt->lim_d, &rt->lim_h_d, &g_window_us, &g_interval_us, &g_period_ticks, &ep};
+        /* while a tenant thread waits for the device to go idle, keep the sampler's residency
+         * negligible so the wait is not stretched by it */
+        uint32_t window = g_sync_waiters > 0 ? 200u : g_window_us;
+        void *params[] = {&rt->lim_d, &rt->lim_h_d, &window, &g_interval_us, &g_period_ticks, &ep};
         unsigned grid = rt->sm_num > 0 ? (unsigned)rt->sm_num : 148u;
         CUresult r = R.cuLaunchKernel(rt->k_sampler, grid, 1, 1, 128, 1, 1, 0, rt->s_stream, params, NULL);
         if (r == CUDA_SUCCESS) {
@@ -427,7 +431,10 @@ VGPU_EXPORT CUresult cuCtxSynchronize(void) {
     vgpu_dev_rt *rt = vgpu_rt_peek(vgpu_host_index_of_cuda(dev));
     if (rt) vgpu_limiter_quiesce(rt);
   }
-  return R.cuCtxSynchronize();
+  __sync_fetch_and_add(&g_sync_waiters, 1);
+  CUresult r = R.cuCtxSynchronize();
+  __sync_fetch_and_sub(&g_sync_waiters, 1);
+  return r;
 }
 
 /* B200 addition: forget a stream's slot when the application destroys it */

@@ -8,6 +8,7 @@
  *
  *   storm [--steps K] [--warmup W] [--per-step L] [--threads T] [--sync-every S] [--device D]
  *         [--no-kernel] [--max-seconds X] [--n N (== --steps 1 --per-step N)]
+ *         [--spin-iters I --grid G --block B]   busy kernel instead of the empty one
  */
 #define _GNU_SOURCE
 #include <dlfcn.h>
@@ -24,7 +25,12 @@ typedef CUresult (*launch_fn)(void *, unsigned, unsigned, unsigned, unsigned, un
 
 static const char *k_ptx =
     ".version 7.0\n.target sm_52\n.address_size 64\n"
-    ".visible .entry empty_kernel()\n{\n  ret;\n}\n";
+    ".visible .entry empty_kernel()\n{\n  ret;\n}\n"
+    /* busy kernel for the fairness / utilisation cases: `iters` dependent adds per thread */
+    ".visible .entry spin_kernel(.param .u32 iters)\n{\n"
+    "  .reg .u32 %r<4>;\n  .reg .pred %p;\n"
+    "  ld.param.u32 %r1, [iters];\n  mov.u32 %r2, 0;\n"
+    "L0:\n  add.u32 %r2, %r2, 1;\n  setp.lt.u32 %p, %r2, %r1;\n  @%p bra L0;\n  ret;\n}\n";
 
 static void *h_cuda;
 static launch_fn p_launch;
@@ -36,6 +42,8 @@ static CUresult (*p_evsync)(void *);
 static CUresult (*p_evelapsed)(float *, void *, void *);
 static void *g_ctx, *g_func;
 static long g_per_step = 200000, g_sync_every = 0;
+static unsigned g_spin_iters = 0, g_grid = 1, g_block = 1;
+static void *g_kparams[1];
 static int g_threads = 1, g_steps = 1, g_warmup = 0;
 static double g_max_seconds = 0;
 static volatile int g_stop;
@@ -55,7 +63,7 @@ static void *worker(void *arg) {
   long i;
   for (i = 0; i < w->n && !g_stop; i++) {
     uint64_t a = now_ns();
-    CUresult r = p_launch(g_func, 1, 1, 1, 1, 1, 1, 0, NULL, NULL, NULL);
+    CUresult r = p_launch(g_func, g_grid, 1, 1, g_block, 1, 1, 0, NULL, g_spin_iters ? g_kparams : NULL, NULL);
     uint64_t b = now_ns();
     if (w->record) w->lat[i] = (uint32_t)((b - a) > 0xffffffffull ? 0xffffffffull : (b - a));
     w->fails += r != 0;
@@ -83,6 +91,9 @@ int main(int argc, char **argv) {
     else if (!strcmp(argv[i], "--device") && i + 1 < argc) device = atoi(argv[++i]);
     else if (!strcmp(argv[i], "--max-seconds") && i + 1 < argc) g_max_seconds = atof(argv[++i]);
     else if (!strcmp(argv[i], "--host-index") && i + 1 < argc) host_index = atoi(argv[++i]);
+    else if (!strcmp(argv[i], "--spin-iters") && i + 1 < argc) g_spin_iters = (unsigned)atol(argv[++i]);
+    else if (!strcmp(argv[i], "--grid") && i + 1 < argc) g_grid = (unsigned)atol(argv[++i]);
+    else if (!strcmp(argv[i], "--block") && i + 1 < argc) g_block = (unsigned)atol(argv[++i]);
     else if (!strcmp(argv[i], "--no-kernel")) no_kernel = 1;
   }
   if (g_threads < 1) g_threads = 1;
@@ -107,10 +118,11 @@ int main(int argc, char **argv) {
   if (p_init(0) || p_get(&dev, device) || p_retain(&g_ctx, dev) || p_setctx(g_ctx)) { fprintf(stderr, "storm: init failed\n"); return 3; }
   if (!no_kernel) {
     void *mod = NULL;
-    if (p_modload(&mod, k_ptx) || p_getfn(&g_func, mod, "empty_kernel")) { fprintf(stderr, "storm: module load failed\n"); return 4; }
+    if (p_modload(&mod, k_ptx) || p_getfn(&g_func, mod, g_spin_iters ? "spin_kernel" : "empty_kernel")) { fprintf(stderr, "storm: module load failed\n"); return 4; }
+    g_kparams[0] = &g_spin_iters;
   }
   /* first launches pay lazy loading and, under a preload library, its device bring-up */
-  for (int i = 0; i < 2000; i++) p_launch(g_func, 1, 1, 1, 1, 1, 1, 0, NULL, NULL, NULL);
+  for (int i = 0; i < (g_spin_iters ? 50 : 2000); i++) p_launch(g_func, g_grid, 1, 1, g_block, 1, 1, 0, NULL, g_spin_iters ? g_kparams : NULL, NULL);
   p_sync();
   uint64_t t_init1 = now_ns();
 

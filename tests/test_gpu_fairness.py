@@ -1,0 +1,61 @@
+"""GPU (B200): BASELINE config 3 shape - four tenants on ONE GPU, 25 % cores each, each running
+a loop of busy kernels.  No numeric tolerance exists in the reference (SURVEY.md 8a L-tol), so
+the assertions are structural (all tenants finish, nobody starves, the limiter engaged); the
+measured shares for both libraries are written to gpurun_out/fairness_r1.json for DESIGN.md.
+"""
+import json
+import os
+import subprocess
+import time
+
+import pytest
+
+import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+
+def gpu0_uuid():
+    out = subprocess.run(["nvidia-smi", "--query-gpu=uuid", "--format=csv,noheader"], capture_output=True, text=True)
+    return out.stdout.splitlines()[0].strip()
+
+
+def run_four(lib, seconds=8.0):
+    procs, sbs = [], []
+    for t in range(4):
+        sb = H.Sandbox()
+        sbs.append(sb)
+        env = H.preload_env(lib, sb, {"MANAGER_COMPATIBILITY_MODE": "0", "MANAGER_VISIBLE_DEVICES": gpu0_uuid(),
+                                      "CUDA_CORE_LIMIT_0": "25", "CUDA_MEM_LIMIT_0": "4g", "CUDA_VISIBLE_DEVICES": "0",
+                                      "LOGGER_LEVEL": "1"}, stub=False)
+        procs.append(subprocess.Popen([H.STORM, "--steps", "1000", "--warmup", "0", "--per-step", "200", "--spin-iters",
+                                       "20000", "--grid", "592", "--block", "256", "--max-seconds", str(seconds)],
+                                      env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
+    outs = []
+    for p in procs:
+        out, err = p.communicate(timeout=seconds * 6 + 60)
+        assert p.returncode == 0, err[-2000:]
+        outs.append(json.loads(out.strip().splitlines()[-1]))
+    for sb in sbs:
+        sb.cleanup()
+    return outs
+
+
+def test_four_tenants_share_one_gpu(built):
+    report = {}
+    for name, lib in (("b200", H.NEW_SO), ("reference", H.REF_SO)):
+        if not os.path.exists(lib):
+            continue
+        outs = run_four(lib)
+        rates = [o["launches"] / o["wall_s"] for o in outs]
+        report[name] = {"launches": [o["launches"] for o in outs], "rates_per_s": rates,
+                        "fairness_max_over_min": max(rates) / max(min(rates), 1e-9),
+                        "gated": [o.get("gated_launches", 0) for o in outs],
+                        "limiter": [o.get("limiter") for o in outs]}
+    os.makedirs(os.path.join(H.ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(H.ROOT, "gpurun_out", "fairness_r1.json"), "w") as f:
+        json.dump(report, f, indent=1)
+    b = report["b200"]
+    assert all(n > 0 for n in b["launches"])
+    assert b["fairness_max_over_min"] < 3.0, b
+    assert sum(b["gated"]) > 0, "the limiter never engaged under a 4 x 25 % load"

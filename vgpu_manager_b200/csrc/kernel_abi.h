@@ -126,6 +126,11 @@ typedef struct {
   uint32_t _pad_q;
   uint32_t probe_idle[VGPU_MAX_SMS * 4];/* per SM sub-partition calibrated idle probe cycles    */
   uint32_t sm_epoch[VGPU_MAX_SMS];      /* last sampler launch (epoch) that ran on this %smid   */
+  /* utilisation history: the controller is fed the mean of the last `util_window` periods, the
+   * on-device stand-in for NVML's ~1 s process-utilisation window (cuda_hook.c:972-976) */
+  int32_t util_hist[16];
+  uint32_t util_hist_pos;
+  uint32_t _pad_h;
   /* last results, for metrics and tests */
   int32_t last_user_current;
   int32_t last_sys_current;
@@ -143,7 +148,7 @@ typedef struct {
   volatile int32_t ext_sys_current;   /* other tenants' util (host-provided, balance mode)     */
   volatile int32_t ext_sys_process_num;
   volatile int32_t ext_user_override; /* >=0: test hook, use this as user_current              */
-  volatile int32_t _pad;
+  volatile uint32_t util_window;      /* periods averaged into user_current (1..16)            */
   volatile unsigned long long launched[VGPU_STREAM_SLOTS]; /* per-slot launch sequence (host)   */
   /* per-slot completion markers, written by cuStreamWriteValue64 right after each launch */
   volatile unsigned long long done[VGPU_STREAM_SLOTS];

@@ -688,6 +688,15 @@ extern "C" __global__ void __launch_bounds__(SAMPLER_THREADS)
   if (srcsel == 1) user = active;
   else if (srcsel == 2) user = active > qbusy ? active : qbusy;
   else user = qbusy;
+  /* moving average over the last util_window periods */
+  uint32_t W = H->util_window;
+  W = W < 1 ? 1 : (W > 16 ? 16 : W);
+  D->util_hist[D->util_hist_pos & 15] = user;
+  D->util_hist_pos++;
+  uint32_t have = D->util_hist_pos < W ? D->util_hist_pos : W;
+  int acc = 0;
+  for (uint32_t i = 0; i < have; i++) acc += D->util_hist[(D->util_hist_pos - 1 - i) & 15];
+  user = acc / (int)have;
   int ov = H->ext_user_override;
   if (ov >= 0) user = ov;
   int others = H->ext_sys_current;

@@ -88,9 +88,42 @@ static uint32_t env_u32(const char *name, uint32_t dflt) {
   return (s && *s) ? (uint32_t)strtoul(s, NULL, 10) : dflt;
 }
 
+/* External SM watcher (reference cuda_hook.c:1009-1042): when the control plane publishes
+ * sm_util.config the per-process lists and utilisation samples of every tenant on the GPU are
+ * read from that file (byte-range read lock, 5 s staleness) instead of from NVML. */
+static int refresh_from_external_watcher(vgpu_dev_rt *rt) {
+  if (!G_cfg->sm_watcher || !G_smutil) return 0;
+  int h = rt->host_index;
+  int fd = vgpu_smutil_rdlock(h);
+  if (fd < 0) return 0;
+  const vgpu_smutil_dev_t *d = &G_smutil->devices[h];
+  struct timespec now;
+  clock_gettime(CLOCK_REALTIME, &now);
+  unsigned long long now_us = (unsigned long long)now.tv_sec * 1000000ull + (unsigned long long)now.tv_nsec / 1000ull;
+  int ok = 0;
+  if (now_us - d->last_seen_us < 5000000ull) {
+    unsigned n = d->compute_size >= d->graphics_size ? d->compute_size : d->graphics_size;
+    rt->lim_h->ext_sys_process_num = n ? (int)n : 1;
+    int total = 0;
+    unsigned ns = d->samples_size > VGPU_MAX_PIDS ? VGPU_MAX_PIDS : d->samples_size;
+    for (unsigned i = 0; i < ns; i++) {
+      if (d->samples[i].ts_us < d->last_seen_us) continue;
+      unsigned sm = d->samples[i].sm <= 100 ? d->samples[i].sm : 0;
+      unsigned enc = d->samples[i].enc <= 100 ? d->samples[i].enc : 0, dec = d->samples[i].dec <= 100 ? d->samples[i].dec : 0;
+      total += (int)(sm + (enc + dec) * 85 / 100);
+    }
+    int others = total - rt->lim_h->user_current;
+    rt->lim_h->ext_sys_current = others > 0 ? others : 0;
+    ok = 1;
+  }
+  vgpu_smutil_unlock(fd, h);
+  return ok;
+}
+
 static void refresh_process_count(vgpu_dev_rt *rt) {
   /* sys_process_num feeds the jitter guard and the balance policy (cuda_hook.c:424,:431-449);
    * it changes on process start/exit, so one cheap list query per second is plenty */
+  if (refresh_from_external_watcher(rt)) return;
   nvmlDevice_t nv = vgpu_nvml_handle_of_host(rt->host_index);
   if (!nv || !R.nvmlDeviceGetComputeRunningProcesses) return;
   static vgpu_proc_t procs[VGPU_MAX_PIDS];

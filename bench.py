@@ -200,8 +200,24 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     distributed = world > 1
+    if args.impl == "reference" and distributed:
+        # the reference arm is a CPU path: rank 0 alone times it, the other ranks leave at once
+        if rank != 0:
+            return
+        distributed = False
 
-    H = build_everything()
+    import torch
+    import torch.distributed as dist
+    if distributed:
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    # one rank builds (make / nvcc are not re-entrant on the same tree), the others wait
+    if rank == 0:
+        H = build_everything()
+    if distributed:
+        dist.barrier()
+    if rank != 0:
+        import helpers as H
     lib = H.NEW_SO if args.impl == "b200" else H.REF_SO
     if args.impl == "reference" and not os.path.exists(H.REF_SO):
         if rank == 0:
@@ -209,12 +225,6 @@ def main():
         return
     if args.impl == "b200" and not os.path.exists(H.NEW_SO):
         raise SystemExit("libvgpu-control.so (with its sm_100a image) is missing - no CPU fallback exists")
-
-    import torch
-    import torch.distributed as dist
-    if distributed:
-        torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     uuids = gpu_uuids()
     peaks = {}
     try:
@@ -305,7 +315,7 @@ def main():
                                "cuLaunchKernel storm, %d launches per step, sync per step" % per_step,
                    "per_step_launches": per_step, "core_limit_pct": CORE_LIMIT, "mem_limit": MEM_LIMIT,
                    "l2_policy": "storm has no data reuse; roofline copy uses 1 GiB buffers (> 126 MB L2)",
-                   "tenants": world, "impl_library": os.path.relpath(lib, ROOT)},
+                   "tenants": world if args.impl == "b200" else 1, "impl_library": os.path.relpath(lib, ROOT)},
         "p50_hook_ns": max(r[3] for r in rows), "p99_hook_ns": max(r[4] for r in rows),
         "clocks": clk,
         "e2e": {"value": round(total / life_max, 1), "unit": "launches/s",

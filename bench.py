@@ -176,7 +176,10 @@ def spill_roofline(lib_path, peaks):
     achieved = 2 * n / avg / 1e9
     return {"bound": "hbm", "kernel": "vgpu_spill_copy_kernel", "achieved": round(achieved, 1), "peak": peak,
             "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "6650 GB/s (of fallback)",
-            "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": None,
+            "unit": "GB/s", "frac": round(achieved / peak, 4),
+            # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel at this size
+            # (ncu --set full, round 1: profiles/ncu_spill_copy_r1.txt: 1.073823 + 1.026727 GB)
+            "traffic": 2100550000,
             "algorithmic_bytes_per_launch": 2 * n, "avg_launch_ms": round(avg * 1e3, 4), "best_launch_ms": round(min(times) * 1e3, 4),
             "launches_timed": len(times),
             "clear": {"kernel": "vgpu_clear_kernel", "achieved": round(n / cavg / 1e9, 1), "unit": "GB/s",
@@ -255,7 +258,7 @@ def main():
 
     # timed K steps on the device (events inside the tenant); max over ranks
     dev_s = res["device_s"] if res.get("device_s", 0) > 0 else res["wall_s"]
-    vals = torch.tensor([dev_s, float(res["launches"]), res["life_s"], float(res["p50_ns"]), float(res["p99_ns"]),
+    vals = torch.tensor([dev_s, float(res["launches"]), res["wall_s"], float(res["p50_ns"]), float(res["p99_ns"]),
                          float(res.get("sampler_launches", 0)), float(res.get("gated_launches", 0))],
                         dtype=torch.float64, device="cuda")
     rebalance_us = None
@@ -320,9 +323,11 @@ def main():
         "clocks": clk,
         "e2e": {"value": round(total / life_max, 1), "unit": "launches/s",
                 "h2d_bytes_per_step": 16 * per_step if args.impl == "b200" else 0,
-                "d2h_bytes_per_step": 8 * per_step if args.impl == "b200" else 0,
-                "what": "tenant process lifetime (exec, preload bring-up, context, %d warm-up + %d timed steps, exit)"
-                        % (args.warmup, res["steps"])},
+                "d2h_bytes_per_step": 8 * per_step // 32 if args.impl == "b200" else 0,
+                "what": "same K steps on the tenant's HOST clock around launch calls + device sync, through the "
+                        "LD_PRELOADed hook; h2d = ticket + sequence words the hook publishes per launch in pinned "
+                        "memory (read by the sampler over PCIe), d2h = completion markers (one per 32 launches)"},
+        "tenant_process_life_s": round(res["life_s"], 3),
         "gpu_launches": int(sum(r[5] for r in rows)) + own_launches,
         "gated_launches": int(sum(r[6] for r in rows)),
         "limiter_rank0": res.get("limiter"),

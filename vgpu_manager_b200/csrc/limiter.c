@@ -80,7 +80,7 @@ static inline uint32_t slot_of(int host_index, CUstream s, int ptsz) {
 static pthread_once_t g_tick_once = PTHREAD_ONCE_INIT;
 static volatile unsigned g_tick_epoch;
 static volatile int g_tick_devices[VGPU_MAX_DEVICES]; /* host indexes with a live runtime + core limit */
-static uint32_t g_window_us = 8000, g_interval_us = 100, g_period_ticks = 8, g_tick_ms = 10;
+static uint32_t g_window_us = 500, g_interval_us = 50, g_period_ticks = 8, g_tick_ms = 10;
 static volatile int g_sync_waiters; /* threads currently inside a device-wide synchronise */
 
 static uint32_t env_u32(const char *name, uint32_t dflt) {
@@ -161,10 +161,18 @@ static void settle_idle_streams(vgpu_dev_rt *rt, int h) {
 
 static void *tick_main(void *arg) {
   (void)arg;
-  struct timespec nap = {0, (long)g_tick_ms * 1000000L};
   uint32_t epoch = 0;
   int fails = 0;
+  uint64_t rng = 0x9E3779B97F4A7C15ull ^ (uint64_t)getpid();
   for (;;) {
+    /* One short sampler window per tick, at a uniformly random offset inside the tick: the
+     * sampler stays resident ~5 % of the time (it would otherwise show up as GPU utilisation in
+     * NVML) and cannot phase-lock with the refill bursts the controller itself causes. */
+    rng ^= rng << 13; rng ^= rng >> 7; rng ^= rng << 17;
+    uint64_t tick_ns = (uint64_t)g_tick_ms * 1000000ull, win_ns = (uint64_t)g_window_us * 1000ull;
+    uint64_t slack = tick_ns > win_ns ? tick_ns - win_ns : 0;
+    uint64_t before = slack ? rng % slack : 0;
+    struct timespec nap = {(time_t)(before / 1000000000ull), (long)(before % 1000000000ull)};
     nanosleep(&nap, NULL);
     if (g_tick_epoch != vgpu_fork_epoch + 1) return NULL;
     epoch++;
@@ -199,12 +207,15 @@ static void *tick_main(void *arg) {
       CUcontext dummy;
       R.cuCtxPopCurrent_v2(&dummy);
     }
+    uint64_t after = tick_ns - before;
+    struct timespec rest = {(time_t)(after / 1000000000ull), (long)(after % 1000000000ull)};
+    nanosleep(&rest, NULL);
   }
 }
 
 static void tick_start(void) {
-  g_window_us = env_u32("VGPU_B200_SAMPLER_WINDOW_US", 8000);
-  g_interval_us = env_u32("VGPU_B200_SAMPLER_INTERVAL_US", 100);
+  g_window_us = env_u32("VGPU_B200_SAMPLER_WINDOW_US", 500);
+  g_interval_us = env_u32("VGPU_B200_SAMPLER_INTERVAL_US", 50);
   g_period_ticks = env_u32("VGPU_B200_PERIOD_TICKS", 8);
   g_tick_ms = env_u32("VGPU_B200_TICK_MS", 10);
   if (!g_period_ticks) g_period_ticks = 1;

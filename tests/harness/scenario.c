@@ -164,6 +164,11 @@ int main(int argc, char **argv) {
         if (r == 0) g_ptr[a] = 0;
       }
       printf("%s h%llu -> %d\n", cmd, a, r);
+    } else if (!strcmp(cmd, "dirty")) {
+      /* write a pattern over allocation h<a> (first and last byte are what the stub checks) */
+      CUresult (*f)(CUdeviceptr, unsigned char, size_t) = sym("cuMemsetD8_v2");
+      CUresult r = ((int)a < g_np && g_ptr[a]) ? f(g_ptr[a], 0xA5, (size_t)b) : 1;
+      printf("dirty h%llu -> %d\n", a, r);
     } else if (!strcmp(cmd, "meminfo")) {
       CUresult (*f)(size_t *, size_t *) = sym("cuMemGetInfo_v2");
       size_t fr = 0, tot = 0;

@@ -238,10 +238,18 @@ EXPORT CUresult cuMemAllocAsync(CUdeviceptr *d, size_t n, void *s) { (void)s; re
 EXPORT CUresult cuMemAllocAsync_ptsz(CUdeviceptr *d, size_t n, void *s) { (void)s; return dev_alloc(d, n, 0); }
 EXPORT CUresult cuMemAllocFromPoolAsync(CUdeviceptr *d, size_t n, void *pool, void *s) { (void)pool; (void)s; return dev_alloc(d, n, 0); }
 EXPORT CUresult cuMemAllocFromPoolAsync_ptsz(CUdeviceptr *d, size_t n, void *pool, void *s) { (void)pool; (void)s; return dev_alloc(d, n, 0); }
+static unsigned long long g_freed_dirty, g_freed_clean;
+EXPORT unsigned long long stub_ctl_freed(int clean) { return clean ? g_freed_clean : g_freed_dirty; }
 static CUresult dev_free(CUdeviceptr d) {
   if (!t_has_ctx) return 201;
   alloc_t a;
   if (!untrack((void *)(uintptr_t)d, &a)) return 1;
+  if (a.kind == 0 && a.n >= 8 && getenv("STUB_CHECK_SCRUB")) {
+    /* the harness dirtied the first and last bytes (scenario `dirty`); were they zeroed? */
+    const unsigned char *p = (const unsigned char *)a.p;
+    if (p[0] == 0 && p[a.n - 1] == 0) g_freed_clean++; else g_freed_dirty++;
+    fprintf(stderr, "stub: freed %s buffer of %zu bytes\n", (p[0] == 0 && p[a.n - 1] == 0) ? "clean" : "dirty", a.n);
+  }
   big_free(a.p, a.n);
   return 0;
 }
@@ -289,6 +297,19 @@ EXPORT CUresult cuMipmappedArrayDestroy(void *h) { return dev_free((CUdeviceptr)
 EXPORT CUresult cuMemHostAlloc(void **pp, size_t n, unsigned f) { (void)f; *pp = big_alloc(n); if (!*pp) return 2; track(*pp, n, 2, 0); return 0; }
 EXPORT CUresult cuMemFreeHost(void *p) { alloc_t a; if (!untrack(p, &a)) return 1; big_free(a.p, a.n); return 0; }
 EXPORT CUresult cuMemHostGetDevicePointer_v2(CUdeviceptr *d, void *p, unsigned f) { (void)f; *d = (CUdeviceptr)(uintptr_t)p; return 0; }
+EXPORT CUresult cuMemGetAddressRange_v2(CUdeviceptr *base, size_t *size, CUdeviceptr d) {
+  CUresult r = 1;
+  pthread_mutex_lock(&g_mu);
+  for (size_t i = 0; i < g_nallocs; i++)
+    if ((uintptr_t)g_allocs[i].p <= (uintptr_t)d && (uintptr_t)d < (uintptr_t)g_allocs[i].p + g_allocs[i].n) {
+      if (base) *base = (CUdeviceptr)(uintptr_t)g_allocs[i].p;
+      if (size) *size = g_allocs[i].n;
+      r = 0;
+      break;
+    }
+  pthread_mutex_unlock(&g_mu);
+  return r;
+}
 EXPORT CUresult cuMemsetD8_v2(CUdeviceptr d, unsigned char v, size_t n) { memset((void *)(uintptr_t)d, v, n); return 0; }
 EXPORT CUresult cuMemcpyDtoH_v2(void *dst, CUdeviceptr src, size_t n) { memcpy(dst, (void *)(uintptr_t)src, n); return 0; }
 EXPORT CUresult cuMemcpyHtoD_v2(CUdeviceptr dst, const void *src, size_t n) { memcpy((void *)(uintptr_t)dst, src, n); return 0; }

@@ -194,3 +194,19 @@ def test_nvml_only_client_needs_opt_in_context(built):
     on, _, _ = H.run_scenario(H.NEW_SO, script, dict(env, VGPU_B200_NVML_CONTEXT="1"), sb=sb)
     sb.cleanup()
     assert on == ref and "used 268435456" in ref
+
+
+def test_scrub_on_free_runs_the_clear_kernel(built):
+    """VGPU_B200_SCRUB_ON_FREE=1: the allocation is zeroed by vgpu_clear_kernel before cuMemFree."""
+    script = "init 0\nalloc 1048576\ndirty 0 1048576\nfree 0\nalloc 4096\ndirty 1 4096\nfree 1\n"
+    env = dict(BASE)
+    env.update({"CUDA_MEM_LIMIT_0": "1g", "STUB_CHECK_SCRUB": "1"})
+    sb = H.Sandbox()
+    _, err_off, _ = H.run_scenario(H.NEW_SO, script, env, sb=sb)
+    sb.cleanup()
+    sb = H.Sandbox()
+    out, err_on, _ = H.run_scenario(H.NEW_SO, script, dict(env, VGPU_B200_SCRUB_ON_FREE="1"), sb=sb)
+    sb.cleanup()
+    assert err_off.count("freed dirty") == 2 and "freed clean" not in err_off
+    assert err_on.count("freed clean") == 2 and "freed dirty" not in err_on
+    assert "free h0 -> 0" in out and "free h1 -> 0" in out

@@ -406,6 +406,27 @@ VGPU_EXPORT CUresult cuMipmappedArrayCreate(CUmipmappedArray *h, const vcu_array
 }
 
 /* ------------------------------------------------------------------ free */
+/* Tenant isolation option (VGPU_B200_SCRUB_ON_FREE=1): zero an allocation with the 128-bit clear
+ * kernel before it goes back to the driver, so the next tenant of the shared GPU cannot read it.
+ * The reference has no counterpart (it never touches tenant memory); accounting is unaffected. */
+static int scrub_on_free(void) {
+  static int on = -1;
+  if (on < 0) {
+    const char *e = getenv("VGPU_B200_SCRUB_ON_FREE");
+    on = e && (!strcmp(e, "1") || !strcmp(e, "true"));
+  }
+  return on;
+}
+
+static void scrub(vgpu_dev_rt *rt, CUdeviceptr dptr) {
+  CUdeviceptr base = 0;
+  size_t size = 0;
+  if (!R.cuMemGetAddressRange_v2 || R.cuMemGetAddressRange_v2(&base, &size, dptr) != CUDA_SUCCESS || !size) return;
+  if (R.cuCtxSynchronize) R.cuCtxSynchronize(); /* cuMemFree would wait for pending work anyway */
+  if (vgpu_rt_clear(rt, base, size, rt->q_stream) == CUDA_SUCCESS && R.cuStreamSynchronize(rt->q_stream) == CUDA_SUCCESS)
+    vgpu_metric_add(rt->host_index, VM_SCRUBBED_BYTES, size);
+}
+
 static CUresult free_sync(CUdeviceptr dptr) {
   CUdevice dev;
   CUresult r = R.cuCtxGetDevice ? R.cuCtxGetDevice(&dev) : CUDA_ERROR_NOT_FOUND;
@@ -413,6 +434,7 @@ static CUresult free_sync(CUdeviceptr dptr) {
   /* cuMemFree synchronises the device: do not let a resident sampler stretch that */
   vgpu_dev_rt *rt = vgpu_rt_peek(vgpu_host_index_of_cuda(dev));
   if (rt) vgpu_limiter_quiesce(rt);
+  if (rt && scrub_on_free()) scrub(rt, dptr);
   r = R.cuMemFree_v2 ? R.cuMemFree_v2(dptr) : R.cuMemFree ? R.cuMemFree(dptr) : CUDA_ERROR_NOT_FOUND;
   if (r == CUDA_SUCCESS) ledger_sub(dev, dptr);
   return r;

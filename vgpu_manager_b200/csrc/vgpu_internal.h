@@ -87,6 +87,7 @@ void vgpu_log_emit(int level, const char *file, int line, const char *fmt, ...)
   X(cuMemGetInfo_v2, CUresult, (size_t *, size_t *))                                            \
   X(cuMemHostAlloc, CUresult, (void **, size_t, unsigned int))                                  \
   X(cuMemFreeHost, CUresult, (void *))                                                          \
+  X(cuMemGetAddressRange_v2, CUresult, (CUdeviceptr *, size_t *, CUdeviceptr))                  \
   X(cuMemHostGetDevicePointer_v2, CUresult, (CUdeviceptr *, void *, unsigned int))              \
   X(cuMemsetD8_v2, CUresult, (CUdeviceptr, unsigned char, size_t))                              \
   X(cuMemcpyDtoH_v2, CUresult, (void *, CUdeviceptr, size_t))                                   \
@@ -237,7 +238,7 @@ void vgpu_limiter_quiesce(vgpu_dev_rt *rt); /* ask a resident sampler to leave (
 
 /* metrics.c */
 enum { VM_RATE_GATED, VM_RATE_FAST, VM_OOM_LIMIT, VM_OOM_DRIVER, VM_UVA_FALLBACK, VM_LOCK_TIMEOUT,
-       VM_QUOTA_KERNELS, VM_SAMPLER_LAUNCHES, VM_COUNT };
+       VM_QUOTA_KERNELS, VM_SAMPLER_LAUNCHES, VM_SCRUBBED_BYTES, VM_COUNT };
 void vgpu_metric_add(int host_index, int which, uint64_t v);
 uint64_t vgpu_metric_get(int host_index, int which);
 

@@ -75,3 +75,29 @@ def test_launch_storm_under_core_cap_completes_and_is_gated_on_device(built):
     assert d["launches"] == 200000 and d["fails"] == 0
     assert d["sampler_launches"] > 0          # the on-device sampler/controller ran
     assert d["p50_ns"] < 20000                 # the hook never sleeps on the CPU
+
+
+def test_two_processes_in_one_container_see_reference_numbers(built):
+    """Multi-process container: process A holds memory while process B queries and allocates.
+    Every library instance owns a few MiB of HBM; the shared own-footprint registry next to the
+    GPU lock file must remove A's share from B's view too, or B would differ from the reference."""
+    import time
+    env = {"MANAGER_COMPATIBILITY_MODE": "0", "MANAGER_VISIBLE_DEVICES": gpu0_uuid(), "LOGGER_LEVEL": "1",
+           "CUDA_VISIBLE_DEVICES": "0", "CUDA_MEM_LIMIT_0": "6g"}
+    a_script = "init 0\nalloc %d\nalloc %d\nsleepms 9000\nmeminfo\n" % (512 * MiB, 256 * MiB)
+    b_script = "init 0\nmeminfo\nnvmlinfo\nalloc %d\nmeminfo\nnvmlinfo2\nalloc %d\nmeminfo\n" % (1 * GiB, 4 * GiB)
+    views = []
+    for lib in (H.REF_SO, H.NEW_SO):
+        sb = H.Sandbox()
+        pa = subprocess.Popen([H.SCENARIO], stdin=subprocess.PIPE, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True,
+                              env=H.preload_env(lib, sb, env, stub=False))
+        pa.stdin.write(a_script)
+        pa.stdin.flush()
+        time.sleep(4.0)  # A has its context and allocations by now
+        out_b, err_b, _ = H.run_scenario(lib, b_script, env, sb=sb, stub=False, timeout=120)
+        out_a, err_a = pa.communicate(timeout=60)
+        sb.cleanup()
+        views.append((out_b, out_a, err_b))
+    assert views[0][0] == views[1][0], "B's view differs:\nreference:\n%s\nb200:\n%s\n%s" % (views[0][0], views[1][0], views[1][2][-1500:])
+    assert views[0][1] == views[1][1]
+    assert "-> 2" in views[0][0]  # the 4 GiB request exceeds what is left of the 6 GiB cap

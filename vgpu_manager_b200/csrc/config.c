@@ -361,3 +361,56 @@ void vgpu_pid_flags(const uint32_t *pids, uint32_t n, uint8_t *flags) {
     for (uint32_t i = 0; i < n; i++)
       if (is_local_gpu_pid(pids[i])) flags[i] |= VGPU_FLAG_LOCAL;
 }
+
+/* ------------------------------------------------------------------ own-footprint registry
+ * Every process that brings the device runtime up owns a few MiB of HBM (module + limiter
+ * state).  NVML charges them to the tenant, the reference has no such footprint, so the quota
+ * kernel removes them again.  One process only knows its own share; siblings in the same
+ * container publish theirs in a small table next to the per-GPU lock file (which is already a
+ * cross-process shared directory), keyed by container identity.  All accesses happen while the
+ * per-GPU lock is held. */
+typedef struct { int32_t pid; uint32_t key; uint64_t bytes; } self_rec_t;
+#define SELF_RECS 1024
+
+static uint32_t container_key(void) {
+  uint32_t h = 2166136261u;
+  const char *parts[2] = {G_cfg->pod_uid, G_cfg->container_name};
+  for (int p = 0; p < 2; p++)
+    for (const char *s = parts[p]; *s; s++) h = (h ^ (uint8_t)*s) * 16777619u;
+  return h ? h : 1;
+}
+
+static int self_table_open(int h) {
+  char raw[64];
+  snprintf(raw, sizeof raw, VGPU_LOCK_DIR "/vgpu_%d.b200", h);
+  return open(VP(raw), O_RDWR | O_CREAT | O_CLOEXEC, 0644);
+}
+
+uint64_t vgpu_self_registry(int h, uint64_t publish_bytes, int publish) {
+  if (h < 0 || h >= VGPU_MAX_DEVICES) return publish_bytes;
+  int fd = self_table_open(h);
+  if (fd < 0) return publish_bytes;
+  static __thread self_rec_t tab[SELF_RECS];
+  memset(tab, 0, sizeof tab);
+  ssize_t got = pread(fd, tab, sizeof tab, 0);
+  (void)got;
+  uint32_t key = container_key();
+  int me = getpid(), mine = -1, free_slot = -1, dirty = 0;
+  uint64_t total = 0;
+  for (int i = 0; i < SELF_RECS; i++) {
+    if (tab[i].pid == 0) { if (free_slot < 0) free_slot = i; continue; }
+    if (tab[i].pid == me && tab[i].key == key) { mine = i; continue; }
+    if (tab[i].key != key) continue;
+    if (kill(tab[i].pid, 0) != 0 && errno == ESRCH) { memset(&tab[i], 0, sizeof tab[i]); dirty = 1; if (free_slot < 0) free_slot = i; continue; }
+    total += tab[i].bytes;
+  }
+  if (publish) {
+    int slot = mine >= 0 ? mine : free_slot;
+    if (slot >= 0) { tab[slot].pid = me; tab[slot].key = key; tab[slot].bytes = publish_bytes; dirty = 1; mine = slot; }
+  }
+  if (mine >= 0) total += tab[mine].bytes;
+  else total += publish_bytes;
+  if (dirty) { ssize_t w = pwrite(fd, tab, sizeof tab, 0); (void)w; }
+  close(fd);
+  return total;
+}

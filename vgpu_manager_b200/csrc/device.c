@@ -229,6 +229,7 @@ static vgpu_dev_rt *bring_up(vgpu_dev_rt *rt, int slot, int host_index, CUdevice
 
   uint64_t after = own_process_bytes(nvdev);
   rt->self_bytes = after > before ? after - before : 0;
+  if (host_index >= 0 && lock_fd >= 0) vgpu_self_registry(host_index, rt->self_bytes, 1);
   vgpu_unlock_gpu(lock_fd);
   __sync_synchronize();
   rt->ready = 1;
@@ -271,7 +272,8 @@ int vgpu_rt_quota(vgpu_dev_rt *rt, vgpu_quota_res_t *out) {
   /* caller filled rt->q_req (except seq) and holds rt->q_mu */
   uint32_t seq = ++rt->seq;
   rt->q_req->seq = seq;
-  rt->q_req->self_bytes = rt->self_bytes;
+  if (!rt->q_req_self_set) rt->q_req->self_bytes = rt->self_bytes;
+  rt->q_req_self_set = 0;
   __sync_synchronize();
   void *params[] = {&rt->q_req_d, &rt->q_res_d};
   CUresult r = vgpu_rt_launch(rt, rt->k_quota, 1, 1024, 0, rt->q_stream, params);
@@ -378,10 +380,8 @@ VGPU_EXPORT int vgpu_b200_quota_eval(const void *req_, void *res_) {
   if (!rt || !req || !res) return -1;
   pthread_mutex_lock(&rt->q_mu);
   memcpy(rt->q_req, req, sizeof *req);
-  uint64_t keep = rt->self_bytes;
-  rt->self_bytes = req->self_bytes; /* the caller's request is evaluated verbatim */
+  rt->q_req_self_set = 1; /* the caller's request is evaluated verbatim */
   int rc = vgpu_rt_quota(rt, res);
-  rt->self_bytes = keep;
   pthread_mutex_unlock(&rt->q_mu);
   return rc;
 }

@@ -129,6 +129,9 @@ static void memview(memview_t *mv, CUdevice dev, int host_index, nvmlDevice_t nv
     q->n_compute = q->n_graphics = 0;
     stage_request(rt, host_index, NULL);
   }
+  /* footprint of every live library instance of this container on this GPU (lock is held) */
+  q->self_bytes = mv->lock_fd >= 0 ? vgpu_self_registry(host_index, rt->self_bytes, 0) : rt->self_bytes;
+  rt->q_req_self_set = 1;
   q->kind = kind;
   q->request = request;
   q->allow_uva = (uint32_t)allow_uva;

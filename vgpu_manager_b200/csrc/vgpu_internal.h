@@ -190,6 +190,9 @@ int vgpu_vmem_lock(int host_index, int write);
 void vgpu_vmem_unlock(int fd, int host_index);
 int vgpu_smutil_rdlock(int host_index);
 void vgpu_smutil_unlock(int fd, int host_index);
+/* device footprint of this library summed over the live processes of this container on GPU h;
+ * publish != 0 (re)registers the calling process with publish_bytes first.  GPU lock must be held. */
+uint64_t vgpu_self_registry(int h, uint64_t publish_bytes, int publish);
 /* container membership flags for a list of device pids (VGPU_FLAG_*), per compatibility mode */
 void vgpu_pid_flags(const uint32_t *pids, uint32_t n, uint8_t *flags);
 
@@ -212,6 +215,7 @@ typedef struct vgpu_dev_rt {
   CUdeviceptr lim_d;  /* vgpu_lim_dev_t          */
   CUdeviceptr slab_d; /* vgpu_slab_slot_t[SLOTS] */
   uint64_t self_bytes; /* measured device footprint of everything above */
+  int q_req_self_set;  /* q_req->self_bytes was provided by the caller of vgpu_rt_quota */
   uint32_t seq;
   volatile long uva_live; /* records in the slab (host-side count; skip lookups when 0) */
   pthread_mutex_t q_mu;

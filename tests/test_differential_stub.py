@@ -210,3 +210,50 @@ def test_scrub_on_free_runs_the_clear_kernel(built):
     assert err_off.count("freed dirty") == 2 and "freed clean" not in err_off
     assert err_on.count("freed clean") == 2 and "freed dirty" not in err_on
     assert "free h0 -> 0" in out and "free h1 -> 0" in out
+
+
+def test_external_sm_watcher_file_is_mandatory_when_enabled(built):
+    """EXTERNAL_SM_WATCHER_ENABLED without /etc/vgpu-manager/watcher/sm_util.config is fatal in
+    both libraries (loader.c:2082-2087); with a well-formed 1 311 232-byte file both start."""
+    env = dict(BASE)
+    env.update({"CUDA_MEM_LIMIT_0": "1g", "EXTERNAL_SM_WATCHER_ENABLED": "true"})
+    for lib in (H.REF_SO, H.NEW_SO):
+        sb = H.Sandbox()
+        out, err, rc = H.run_scenario(lib, "init 0\ntotalmem\n", env, sb=sb, check=False)
+        sb.cleanup()
+        assert rc == 1 and out == "", (lib, rc, out)
+    outs = []
+    for lib in (H.REF_SO, H.NEW_SO):
+        sb = H.Sandbox()
+        with open(sb.path("etc/vgpu-manager/watcher/sm_util.config"), "wb") as f:
+            f.write(b"\0" * 1311232)
+        out, err, rc = H.run_scenario(lib, "init 0\ntotalmem\nmeminfo\n", env, sb=sb, check=False)
+        outs.append((out, rc, sb.config_bytes()))
+        sb.cleanup()
+    assert outs[0] == outs[1] and outs[0][1] == 0
+
+
+def _storm(lib, env, n, threads=1):
+    import json
+    import subprocess
+    sb = H.Sandbox()
+    e = H.preload_env(lib, sb, env)
+    r = subprocess.run([H.STORM, "--steps", "1", "--warmup", "0", "--per-step", str(n), "--threads", str(threads),
+                        "--no-kernel"], env=e, capture_output=True, text=True, timeout=300)
+    sb.cleanup()
+    assert r.returncode == 0, r.stderr[-2000:]
+    return json.loads(r.stdout.strip().splitlines()[-1])
+
+
+def test_config1_stub_launch_storm_both_libraries(built):
+    """BASELINE configs[0]: 10 % cores / 1 GiB, empty-kernel storm on the CPU-only stub driver,
+    closed-loop utilisation model; single thread and 8 threads (the reference serialises every
+    launch on one mutex, loader.c:1769).  Plumbing check: everything is admitted exactly once."""
+    env = dict(BASE)
+    env.update({"CUDA_CORE_LIMIT_0": "10", "CUDA_MEM_LIMIT_0": "1g", "STUB_UTIL": "closed:0.02"})
+    for threads in (1, 8):
+        ref = _storm(H.REF_SO, env, 400000, threads)
+        new = _storm(H.NEW_SO, env, 400000, threads)
+        assert ref["launches"] == new["launches"] == 400000 and ref["fails"] == new["fails"] == 0
+        assert new["limiter"]["present"] == 1 and new["sampler_launches"] > 0
+        assert new["p50_ns"] < 5000

@@ -285,3 +285,21 @@ def test_sampler_tail_runs_controller_and_idle_gpu_reads_idle(gpu):
     lib.limiter_reset(148, 2048, 25, 0, 1, 1)
     b = [lib.limiter_step(u, u, 1, 1) for u in (90, 90, 10, 30, 25, 0)]
     assert [(x.share, x.granted, x.up_limit) for x in a] == [(x.share, x.granted, x.up_limit) for x in b]
+
+
+def test_sm_probe_sees_a_busy_gpu(gpu):
+    """The %smid/%clock64 probe: while a long kernel train saturates the SMs the sampler's
+    issue-slot probe must read clearly higher than on the idle GPU."""
+    lib, torch = gpu
+    lib.limiter_reset(0, 0, 25, 0, 1, 1)
+    torch.cuda.synchronize()
+    idle = [lib.sampler_run(1000, 50, 1, -1).sm_active_pct for _ in range(3)]
+    a = torch.randn(8192, 8192, device="cuda", dtype=torch.float32)
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        for _ in range(60):
+            a = torch.sin(a) * 1.0001  # elementwise, every SM busy issuing
+    busy = [lib.sampler_run(1000, 50, 1, -1).sm_active_pct for _ in range(3)]
+    torch.cuda.synchronize()
+    assert max(idle) <= 30, idle
+    assert max(busy) >= max(idle) + 15, (idle, busy)

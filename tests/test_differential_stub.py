@@ -257,3 +257,21 @@ def test_config1_stub_launch_storm_both_libraries(built):
         assert ref["launches"] == new["launches"] == 400000 and ref["fails"] == new["fails"] == 0
         assert new["limiter"]["present"] == 1 and new["sampler_launches"] > 0
         assert new["p50_ns"] < 5000
+
+
+def test_directly_linked_tenant_is_intercepted_by_symbol_interposition(built):
+    """No dlopen/dlsym/cuGetProcAddress at all: the tenant links libcuda; the preloaded library
+    must win plain symbol resolution for every hooked entry point."""
+    import subprocess
+    env = dict(BASE)
+    env.update({"CUDA_MEM_LIMIT_0": "1g", "CUDA_CORE_LIMIT_0": "50", "STUB_UTIL": "closed:0.02"})
+    outs = []
+    for lib in (H.REF_SO, H.NEW_SO):
+        sb = H.Sandbox()
+        r = subprocess.run([os.path.join(H.BUILD, "direct")], env=H.preload_env(lib, sb, env), capture_output=True,
+                           text=True, timeout=120)
+        sb.cleanup()
+        assert r.returncode == 0, r.stderr[-1500:]
+        outs.append(r.stdout)
+    assert outs[0] == outs[1]
+    assert "totalmem 0 1073741824" in outs[0] and "alloc 0\nalloc 2\n" in outs[0] and "launch 1000" in outs[0]

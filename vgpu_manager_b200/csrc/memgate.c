@@ -202,6 +202,7 @@ static void gate_open(gate_t *g, uint64_t request, int allow_uva, const vcu_mem_
   g->mv.lock_fd = -1;
   g->mv.host_index = -1;
   g->path = VGPU_PATH_GPU;
+  if (unlikely(!G_cfg)) vgpu_boot();
   CUresult r = R.cuCtxGetDevice ? R.cuCtxGetDevice(&g->dev) : CUDA_ERROR_NOT_FOUND;
   if (r != CUDA_SUCCESS) {
     if (prop && prop->location.type == 1) g->dev = prop->location.id; /* cuMemCreate w/o ctx (:1678) */
@@ -432,6 +433,7 @@ static void scrub(vgpu_dev_rt *rt, CUdeviceptr dptr) {
 
 static CUresult free_sync(CUdeviceptr dptr) {
   CUdevice dev;
+  if (unlikely(!G_cfg)) vgpu_boot();
   CUresult r = R.cuCtxGetDevice ? R.cuCtxGetDevice(&dev) : CUDA_ERROR_NOT_FOUND;
   if (r != CUDA_SUCCESS) return r;
   /* cuMemFree synchronises the device: do not let a resident sampler stretch that */
@@ -447,6 +449,7 @@ VGPU_EXPORT CUresult cuMemFree(CUdeviceptr p) { return free_sync(p); }
 
 static CUresult free_async(CUdeviceptr dptr, CUstream s, int ptsz) {
   CUdevice dev;
+  if (unlikely(!G_cfg)) vgpu_boot();
   CUresult r = R.cuCtxGetDevice ? R.cuCtxGetDevice(&dev) : CUDA_ERROR_NOT_FOUND;
   if (r != CUDA_SUCCESS) return r;
   CUresult (*fn)(CUdeviceptr, CUstream) = ptsz ? R.cuMemFreeAsync_ptsz : R.cuMemFreeAsync;
@@ -459,6 +462,7 @@ VGPU_EXPORT CUresult cuMemFreeAsync_ptsz(CUdeviceptr p, CUstream s) { return fre
 
 /* ------------------------------------------------------------------ reported sizes */
 static CUresult total_mem(size_t *bytes, CUdevice dev) {
+  if (unlikely(!G_cfg)) vgpu_boot();
   int h = vgpu_host_index_of_cuda(dev);
   if (h >= 0 && G_cfg->devices[h].memory_limit) {
     *bytes = G_cfg->devices[h].total_memory;
@@ -477,6 +481,7 @@ static CUresult real_meminfo(size_t *fr, size_t *tot) {
 
 static CUresult mem_info(size_t *free_out, size_t *total_out) {
   CUdevice dev;
+  if (unlikely(!G_cfg)) vgpu_boot();
   CUresult r = R.cuCtxGetDevice ? R.cuCtxGetDevice(&dev) : CUDA_ERROR_NOT_FOUND;
   if (r != CUDA_SUCCESS) return r;
   int h = vgpu_host_index_of_cuda(dev);

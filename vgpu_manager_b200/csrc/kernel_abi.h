@@ -130,7 +130,7 @@ typedef struct {
    * on-device stand-in for NVML's ~1 s process-utilisation window (cuda_hook.c:972-976) */
   int32_t util_hist[16];
   uint32_t util_hist_pos;
-  uint32_t _pad_h;
+  int32_t blk_sum, blk_n, blk_reading; /* tumbling-block mode: reading = mean of the last full block */
   /* last results, for metrics and tests */
   int32_t last_user_current;
   int32_t last_sys_current;
@@ -149,6 +149,8 @@ typedef struct {
   volatile int32_t ext_sys_process_num;
   volatile int32_t ext_user_override; /* >=0: test hook, use this as user_current              */
   volatile uint32_t util_window;      /* periods averaged into user_current (1..16)            */
+  volatile uint32_t util_mode;        /* 0 moving average, 1 tumbling block (NVML-like sampling) */
+  volatile uint32_t _pad_m;
   volatile unsigned long long launched[VGPU_STREAM_SLOTS]; /* per-slot launch sequence (host)   */
   /* per-slot completion markers, written by cuStreamWriteValue64 right after each launch */
   volatile unsigned long long done[VGPU_STREAM_SLOTS];

@@ -688,15 +688,30 @@ extern "C" __global__ void __launch_bounds__(SAMPLER_THREADS)
   if (srcsel == 1) user = active;
   else if (srcsel == 2) user = active > qbusy ? active : qbusy;
   else user = qbusy;
-  /* moving average over the last util_window periods */
+  /* How the raw per-period figure becomes the controller's reading:
+   *  mode 1 (default)  tumbling blocks of util_window periods - the reading is the mean of the
+   *                    last *completed* block and only changes at block boundaries.  This is how
+   *                    the reference sees utilisation: NVML publishes a per-process sample about
+   *                    once a second (cuda_hook.c:972-979 asks for "since now - 1 s").
+   *  mode 0            moving average over the last util_window periods (window 1 = raw). */
   uint32_t W = H->util_window;
   W = W < 1 ? 1 : (W > 16 ? 16 : W);
-  D->util_hist[D->util_hist_pos & 15] = user;
-  D->util_hist_pos++;
-  uint32_t have = D->util_hist_pos < W ? D->util_hist_pos : W;
-  int acc = 0;
-  for (uint32_t i = 0; i < have; i++) acc += D->util_hist[(D->util_hist_pos - 1 - i) & 15];
-  user = acc / (int)have;
+  if (H->util_mode == 1) {
+    D->blk_sum += user;
+    if (++D->blk_n >= (int)W) {
+      D->blk_reading = D->blk_sum / D->blk_n;
+      D->blk_sum = 0;
+      D->blk_n = 0;
+    }
+    user = D->blk_reading;
+  } else {
+    D->util_hist[D->util_hist_pos & 15] = user;
+    D->util_hist_pos++;
+    uint32_t have = D->util_hist_pos < W ? D->util_hist_pos : W;
+    int acc = 0;
+    for (uint32_t i = 0; i < have; i++) acc += D->util_hist[(D->util_hist_pos - 1 - i) & 15];
+    user = acc / (int)have;
+  }
   int ov = H->ext_user_override;
   if (ov >= 0) user = ov;
   int others = H->ext_sys_current;

@@ -21,8 +21,16 @@ run_storm $REF ref_25 100 200000 20 LOGGER_LEVEL=1 CUDA_CORE_LIMIT_0=25
 run_storm $NEW new_10_block12 100 200000 20 LOGGER_LEVEL=1 CUDA_CORE_LIMIT_0=10
 run_storm $REF ref_10 100 200000 20 LOGGER_LEVEL=1 CUDA_CORE_LIMIT_0=10
 kill $(cat /tmp/smi.pid)
+run_alloc() { # lib tag vmem
+  SB=$(mktemp -d); mkdir -p $SB/etc/vgpu-manager/config $SB/lock $SB/vmem
+  env CUDA_VISIBLE_DEVICES=0 MANAGER_COMPATIBILITY_MODE=0 MANAGER_VISIBLE_DEVICES=$UUID CUDA_MEM_LIMIT_0=4g VMEMORY_NODE_ENABLED=$3 LOGGER_LEVEL=0 \
+    VGPU_REDIRECT="/etc/vgpu-manager=$SB/etc/vgpu-manager:/tmp/.vgpu_lock=$SB/lock:/tmp/.vmem_node=$SB/vmem" \
+    LD_PRELOAD="$B/libredirect.so $1" timeout 120 $B/allocstorm --n 3000 > gpurun_out/alloc_$2.json 2> gpurun_out/alloc_$2.err
+}
+timeout 60 $B/allocstorm --n 3000 > gpurun_out/alloc_bare.json 2>/dev/null
+run_alloc $NEW new false; run_alloc $REF ref false; run_alloc $NEW new_vmem true; run_alloc $REF ref_vmem true
 timeout 700 python -m pytest tests -m gpu -q --timeout 250 > gpurun_out/pytest_gpu.log 2>&1
 timeout 120 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1
 timeout 300 python bench.py --steps 5 --impl reference > gpurun_out/bench_ref.log 2> gpurun_out/bench_ref.err
 timeout 600 python bench.py --steps 5 > gpurun_out/bench.log 2> gpurun_out/bench.err
-for t in new_25_block12 new_25_avg1 ref_25 new_10_block12 ref_10; do echo $t; cat gpurun_out/storm_$t.json | cut -c1-640; done; tail -1 gpurun_out/bench.log | cut -c1-700; tail -1 gpurun_out/bench_ref.log | cut -c1-300; tail -3 gpurun_out/pytest_gpu.log
+for t in new_25_block12 new_25_avg1 ref_25 new_10_block12 ref_10; do echo $t; cat gpurun_out/storm_$t.json | cut -c1-640; done; tail -1 gpurun_out/bench.log | cut -c1-700; tail -1 gpurun_out/bench_ref.log | cut -c1-300; tail -3 gpurun_out/pytest_gpu.log; for t in bare new ref new_vmem ref_vmem; do echo alloc_$t; cat gpurun_out/alloc_$t.json; done

@@ -370,7 +370,7 @@ void vgpu_pid_flags(const uint32_t *pids, uint32_t n, uint8_t *flags) {
  * cross-process shared directory), keyed by container identity.  All accesses happen while the
  * per-GPU lock is held. */
 typedef struct { int32_t pid; uint32_t key; uint64_t bytes; } self_rec_t;
-#define SELF_RECS 1024
+#define SELF_RECS 1023 /* record 0 of the file is the header {generation} */
 
 static uint32_t container_key(void) {
   uint32_t h = 2166136261u;
@@ -380,24 +380,44 @@ static uint32_t container_key(void) {
   return h ? h : 1;
 }
 
-static int self_table_open(int h) {
-  char raw[64];
-  snprintf(raw, sizeof raw, VGPU_LOCK_DIR "/vgpu_%d.b200", h);
-  return open(VP(raw), O_RDWR | O_CREAT | O_CLOEXEC, 0644);
-}
+static int g_self_fd[VGPU_MAX_DEVICES];          /* fd + 1, kept open */
+static uint64_t g_self_gen[VGPU_MAX_DEVICES];    /* generation the cached total was computed at */
+static uint64_t g_self_total[VGPU_MAX_DEVICES];
+static time_t g_self_checked[VGPU_MAX_DEVICES];  /* last liveness sweep */
+static unsigned g_self_epoch[VGPU_MAX_DEVICES];
 
 uint64_t vgpu_self_registry(int h, uint64_t publish_bytes, int publish) {
   if (h < 0 || h >= VGPU_MAX_DEVICES) return publish_bytes;
-  int fd = self_table_open(h);
-  if (fd < 0) return publish_bytes;
-  static __thread self_rec_t tab[SELF_RECS];
+  if (g_self_epoch[h] != vgpu_fork_epoch + 1) { /* a forked child starts with nothing cached */
+    g_self_fd[h] = 0;
+    g_self_gen[h] = 0;
+    g_self_epoch[h] = vgpu_fork_epoch + 1;
+  }
+  if (!g_self_fd[h]) {
+    char raw[64];
+    snprintf(raw, sizeof raw, VGPU_LOCK_DIR "/vgpu_%d.b200", h);
+    int fd = open(VP(raw), O_RDWR | O_CREAT | O_CLOEXEC, 0644);
+    if (fd < 0) return publish_bytes;
+    g_self_fd[h] = fd + 1;
+  }
+  int fd = g_self_fd[h] - 1;
+  /* fast path: nothing was (un)registered since the cached sum, and the last liveness sweep is
+   * recent - one 8-byte pread */
+  uint64_t gen = 0;
+  time_t now = time(NULL);
+  if (!publish && pread(fd, &gen, sizeof gen, 0) == (ssize_t)sizeof gen && gen == g_self_gen[h] && gen != 0 &&
+      now - g_self_checked[h] < 2)
+    return g_self_total[h];
+
+  static __thread self_rec_t tab[SELF_RECS + 1];
   memset(tab, 0, sizeof tab);
   ssize_t got = pread(fd, tab, sizeof tab, 0);
   (void)got;
+  memcpy(&gen, &tab[0], sizeof gen);
   uint32_t key = container_key();
   int me = getpid(), mine = -1, free_slot = -1, dirty = 0;
   uint64_t total = 0;
-  for (int i = 0; i < SELF_RECS; i++) {
+  for (int i = 1; i <= SELF_RECS; i++) {
     if (tab[i].pid == 0) { if (free_slot < 0) free_slot = i; continue; }
     if (tab[i].pid == me && tab[i].key == key) { mine = i; continue; }
     if (tab[i].key != key) continue;
@@ -408,9 +428,15 @@ uint64_t vgpu_self_registry(int h, uint64_t publish_bytes, int publish) {
     int slot = mine >= 0 ? mine : free_slot;
     if (slot >= 0) { tab[slot].pid = me; tab[slot].key = key; tab[slot].bytes = publish_bytes; dirty = 1; mine = slot; }
   }
-  if (mine >= 0) total += tab[mine].bytes;
-  else total += publish_bytes;
-  if (dirty) { ssize_t w = pwrite(fd, tab, sizeof tab, 0); (void)w; }
-  close(fd);
+  total += mine >= 0 ? tab[mine].bytes : publish_bytes;
+  if (dirty || gen == 0) {
+    gen++;
+    memcpy(&tab[0], &gen, sizeof gen);
+    ssize_t w = pwrite(fd, tab, sizeof tab, 0);
+    (void)w;
+  }
+  g_self_gen[h] = gen;
+  g_self_total[h] = total;
+  g_self_checked[h] = now;
   return total;
 }

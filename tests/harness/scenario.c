@@ -16,6 +16,7 @@
 #include <string.h>
 #include <time.h>
 #include <unistd.h>
+#include <sys/wait.h>
 
 typedef int CUresult;
 typedef unsigned long long CUdeviceptr;
@@ -229,6 +230,28 @@ int main(int argc, char **argv) {
         printf(" [%s %llu]", pid == getpid() ? "self" : "other", used);
       }
       printf("\n");
+    } else if (!strcmp(cmd, "forkchild")) {
+      /* fork; the child allocates <a> bytes, reads meminfo, launches <b> kernels, exits */
+      fflush(stdout);
+      pid_t pid = fork();
+      if (pid == 0) {
+        CUresult (*fa)(CUdeviceptr *, size_t) = sym("cuMemAlloc_v2");
+        CUresult (*fm)(size_t *, size_t *) = sym("cuMemGetInfo_v2");
+        CUresult (*fl)(void *, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, void *, void **, void **) =
+            sym("cuLaunchKernel");
+        CUdeviceptr p = 0;
+        size_t fr = 0, tot = 0;
+        CUresult r1 = fa(&p, (size_t)a);
+        CUresult r2 = fm(&fr, &tot);
+        unsigned long long okc = 0;
+        for (unsigned long long i = 0; i < b; i++) okc += fl(NULL, 1, 1, 1, 1, 1, 1, 0, NULL, NULL, NULL) == 0;
+        printf("child alloc %d meminfo %d total %zu launches %llu\n", r1, r2, tot, okc);
+        fflush(stdout);
+        _exit(0);
+      }
+      int st = 0;
+      waitpid(pid, &st, 0);
+      printf("forkchild -> exit %d\n", WIFEXITED(st) ? WEXITSTATUS(st) : -1);
     } else if (!strcmp(cmd, "sleepms")) {
       struct timespec ts = {(time_t)(a / 1000), (long)(a % 1000) * 1000000L};
       nanosleep(&ts, NULL);

@@ -275,3 +275,20 @@ def test_directly_linked_tenant_is_intercepted_by_symbol_interposition(built):
         outs.append(r.stdout)
     assert outs[0] == outs[1]
     assert "totalmem 0 1073741824" in outs[0] and "alloc 0\nalloc 2\n" in outs[0] and "launch 1000" in outs[0]
+
+
+def test_forked_child_is_served_like_the_parent(built):
+    """fork awareness (loader.c:1805-1822,2054-2066): config and index maps are reloaded in the
+    child.  Memory path compared against the reference; launches in the child only under the
+    B200 library - the reference never restarts its watcher there and would hang a capped child
+    (SURVEY.md Appendix B.13), the B200 library re-arms its tick thread."""
+    env = {"CUDA_MEM_LIMIT_0": "1g"}
+    script = "init 0\nalloc %d\nforkchild %d 0\nmeminfo\nforkchild %d 0\n" % (300 * MiB, 200 * MiB, 900 * MiB)
+    t = assert_same(both(script, env))
+    assert "child alloc 0 meminfo 0 total 1073741824" in t and "child alloc 2 " in t
+    e = dict(BASE)
+    e.update({"CUDA_MEM_LIMIT_0": "1g", "CUDA_CORE_LIMIT_0": "20", "STUB_UTIL": "closed:0.02"})
+    sb = H.Sandbox()
+    out, err, _ = H.run_scenario(H.NEW_SO, "init 0\nlaunch 5000 1 1 1\nforkchild 1048576 200000\nlaunch 5000 1 1 1\n", e, sb=sb)
+    sb.cleanup()
+    assert "child alloc 0 meminfo 0 total 1073741824 launches 200000" in out and out.count("-> ok 5000") == 2

@@ -290,6 +290,7 @@ static inline void enqueue_marker(vgpu_dev_rt *rt, int h, uint32_t slot, unsigne
 static inline int admit(admit_t *a, unsigned gx, unsigned gy, unsigned gz, CUstream s, int ptsz) {
   CUdevice dev;
   if (unlikely(!G_cfg)) vgpu_boot(); /* entry reached without cuInit/dlsym going through us */
+  if (unlikely(g_tick_epoch && g_tick_epoch != vgpu_fork_epoch + 1)) vgpu_limiter_start(); /* forked child */
   if (unlikely(R.cuCtxGetDevice(&dev) != CUDA_SUCCESS)) return -1;
   int h = vgpu_host_index_of_cuda(dev);
   if (h < 0 || !G_cfg->devices[h].core_limit) return 0;

@@ -1,7 +1,9 @@
 """GPU (B200): the reference's OWN smoke tests (library/test/test_*.c, test_runtime_launch.cu),
 compiled from /root/reference by oracle/Makefile into oracle/_ref/ref_tests/, run the way the
 reference's run_all_tests.sh runs them - LD_PRELOAD=<lib> ./test_x, pass = exit 0 within 120 s -
-once under the reference library and once under the B200 library, under an active cap.
+once under the reference library and once under the B200 library, under an active cap.  The
+B200 library must exit with the reference's code for every test (one of them, test_alloc_managed,
+fails under BOTH libraries with this 8 GiB cap: managed allocations are ledgered and hit it).
 For the deterministic single-threaded memory tests the printed NVML usage figures must also be
 identical between the two libraries.
 """
@@ -49,7 +51,7 @@ def test_reference_smoke_suite_passes_under_both_libraries(built):
         rc_new, out_new, err_new = run_under(H.NEW_SO, exe)
         same = out_ref == out_new
         report[name] = {"rc_reference": rc_ref, "rc_b200": rc_new, "stdout_identical": same}
-        if rc_new != 0 or rc_new != rc_ref:
+        if rc_new != rc_ref or (rc_ref == 0 and rc_new != 0):
             failures.append((name, rc_ref, rc_new, err_new[-800:]))
         elif name in SAME_STDOUT and not same:
             failures.append((name, "stdout differs", out_ref[-600:], out_new[-600:]))

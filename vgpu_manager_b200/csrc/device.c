@@ -92,7 +92,15 @@ static void write_limiter_config(vgpu_dev_rt *rt, vgpu_lim_dev_t *init) {
 
 static vgpu_dev_rt *bring_up(vgpu_dev_rt *rt, int slot, int host_index, CUdevice dev) {
   CUcontext ctx = NULL;
-  if (!R.cuCtxGetCurrent || R.cuCtxGetCurrent(&ctx) != CUDA_SUCCESS || !ctx) return NULL;
+  int retained = 0;
+  if (!R.cuCtxGetCurrent || R.cuCtxGetCurrent(&ctx) != CUDA_SUCCESS || !ctx) {
+    /* no current context on this thread (e.g. cuMemCreate addressed the device through
+     * prop->location): fall back to the device's primary context */
+    if (!R.cuDevicePrimaryCtxRetain || R.cuDevicePrimaryCtxRetain(&ctx, dev) != CUDA_SUCCESS || !ctx ||
+        R.cuCtxPushCurrent_v2(ctx) != CUDA_SUCCESS)
+      return NULL;
+    retained = 1;
+  }
   if (!R.cuModuleLoadData || !R.cuLaunchKernel || !R.cuMemAlloc_v2) {
     VLOG(VL_ERROR, "device runtime: driver lacks module/launch entry points");
     rt->ready = -1;
@@ -237,11 +245,13 @@ static vgpu_dev_rt *bring_up(vgpu_dev_rt *rt, int slot, int host_index, CUdevice
   vgpu_unlock_gpu(lock_fd);
   __sync_synchronize();
   rt->ready = 1;
+  if (retained) { CUcontext dummy; R.cuCtxPopCurrent_v2(&dummy); }
   VLOG(VL_INFO, "device runtime up: slot %d host %d sms %d own footprint %" PRIu64 " bytes memops64 %d",
        slot, host_index, rt->sm_num, rt->self_bytes, rt->memops64);
   return rt;
 fail:
   vgpu_unlock_gpu(lock_fd);
+  if (retained) { CUcontext dummy; R.cuCtxPopCurrent_v2(&dummy); }
   rt->ready = -1;
   VLOG(VL_ERROR, "device runtime bring-up failed on cuda device %d: the sm_100a enforcement "
                  "kernels are unavailable (no CPU fallback exists)", dev);
@@ -272,6 +282,18 @@ vgpu_dev_rt *vgpu_rt_peek(int host_index) {
 }
 
 /* ------------------------------------------------------------------ kernel drivers used by the hooks */
+/* The calling thread may have no current context (cuMemCreate from a worker thread addresses
+ * the device through prop->location) or a different one: run our kernels in the runtime's. */
+static int ctx_enter(vgpu_dev_rt *rt) {
+  CUcontext cur = NULL;
+  if (R.cuCtxGetCurrent && R.cuCtxGetCurrent(&cur) == CUDA_SUCCESS && cur == rt->ctx) return 0;
+  return (R.cuCtxPushCurrent_v2 && R.cuCtxPushCurrent_v2(rt->ctx) == CUDA_SUCCESS) ? 1 : 0;
+}
+static void ctx_leave(int pushed) {
+  CUcontext dummy;
+  if (pushed) R.cuCtxPopCurrent_v2(&dummy);
+}
+
 int vgpu_rt_quota(vgpu_dev_rt *rt, vgpu_quota_res_t *out) {
   /* caller filled rt->q_req (except seq) and holds rt->q_mu */
   uint32_t seq = ++rt->seq;
@@ -280,12 +302,16 @@ int vgpu_rt_quota(vgpu_dev_rt *rt, vgpu_quota_res_t *out) {
   rt->q_req_self_set = 0;
   __sync_synchronize();
   void *params[] = {&rt->q_req_d, &rt->q_res_d};
+  int pushed = ctx_enter(rt);
   CUresult r = vgpu_rt_launch(rt, rt->k_quota, 1, 1024, 0, rt->q_stream, params);
   if (r != CUDA_SUCCESS) {
+    ctx_leave(pushed);
     VLOG(VL_ERROR, "quota kernel launch failed: %d (%s)", r, vgpu_cu_err(r));
     return -1;
   }
-  if (spin_seq(&rt->q_res->seq_done, seq, rt->q_stream)) {
+  int stuck = spin_seq(&rt->q_res->seq_done, seq, rt->q_stream);
+  ctx_leave(pushed);
+  if (stuck) {
     VLOG(VL_ERROR, "quota kernel did not complete");
     return -1;
   }
@@ -300,11 +326,13 @@ int vgpu_rt_slab_insert(vgpu_dev_rt *rt, CUdeviceptr dptr, uint64_t bytes) {
   unsigned long long k = dptr, b = bytes;
   void *params[] = {&rt->slab_d, &k, &b, &rt->slab_res_d, &seq};
   int rc = -1;
+  int pushed = ctx_enter(rt);
   if (vgpu_rt_launch(rt, rt->k_slab_insert, 1, 32, 0, rt->q_stream, params) == CUDA_SUCCESS &&
       spin_seq(&rt->slab_res->seq_done, seq, rt->q_stream) == 0 && rt->slab_res->slot != 0xffffffffu) {
     __sync_fetch_and_add(&rt->uva_live, 1);
     rc = 0;
   }
+  ctx_leave(pushed);
   pthread_mutex_unlock(&rt->q_mu);
   return rc;
 }
@@ -316,6 +344,7 @@ int vgpu_rt_slab_remove(vgpu_dev_rt *rt, CUdeviceptr dptr, uint64_t *bytes) {
   unsigned long long k = dptr;
   void *params[] = {&rt->slab_d, &k, &rt->slab_res_d, &seq};
   int rc = -1;
+  int pushed = ctx_enter(rt);
   if (vgpu_rt_launch(rt, rt->k_slab_remove, 1, 32, 0, rt->q_stream, params) == CUDA_SUCCESS &&
       spin_seq(&rt->slab_res->seq_done, seq, rt->q_stream) == 0) {
     if (rt->slab_res->slot != 0xffffffffu) {
@@ -326,6 +355,7 @@ int vgpu_rt_slab_remove(vgpu_dev_rt *rt, CUdeviceptr dptr, uint64_t *bytes) {
       rc = 1;
     }
   }
+  ctx_leave(pushed);
   pthread_mutex_unlock(&rt->q_mu);
   return rc;
 }

@@ -1,0 +1,58 @@
+"""GPU (B200): a real framework as the tenant (the reference's library/test/python/limit_pytorch.py
+idea).  PyTorch resolves the driver through cudart -> cuGetProcAddress, uses the caching allocator,
+the legacy default stream and many kernels per step - i.e. the interception surface is exercised
+the way production tenants do.  Checked under both libraries: same reported totals, same OOM
+behaviour, same results."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+TENANT = r'''
+import torch, json
+free0, total = torch.cuda.mem_get_info()
+x = torch.ones(256, 1024, 1024, dtype=torch.float32, device="cuda")        # 1 GiB
+s = float(x.sum().cpu())
+y = (x[:8] @ x[:8].transpose(1, 2)).float().sum().item()
+free1, _ = torch.cuda.mem_get_info()
+oom = False
+try:
+    z = torch.empty(12 * 1024**3, dtype=torch.uint8, device="cuda")        # beyond the 8 GiB cap
+except torch.OutOfMemoryError:
+    oom = True
+for _ in range(200):                                                        # a short launch train under the core cap
+    x.mul_(1.0001)
+torch.cuda.synchronize()
+print(json.dumps({"total": total, "sum": s, "y": y, "oom": oom, "free_drop_ge_1g": (free0 - free1) >= 1024**3}))
+'''
+
+
+def gpu0_uuid():
+    out = subprocess.run(["nvidia-smi", "--query-gpu=uuid", "--format=csv,noheader"], capture_output=True, text=True)
+    return out.stdout.splitlines()[0].strip()
+
+
+def test_pytorch_tenant_under_cap(built):
+    import json
+    res = {}
+    for name, lib in (("reference", H.REF_SO), ("b200", H.NEW_SO)):
+        if not os.path.exists(lib):
+            continue
+        sb = H.Sandbox()
+        env = H.preload_env(lib, sb, {"MANAGER_COMPATIBILITY_MODE": "0", "MANAGER_VISIBLE_DEVICES": gpu0_uuid(),
+                                      "CUDA_VISIBLE_DEVICES": "0", "CUDA_MEM_LIMIT_0": "8g", "CUDA_CORE_LIMIT_0": "50",
+                                      "LOGGER_LEVEL": "1"}, stub=False)
+        r = subprocess.run([sys.executable, "-c", TENANT], env=env, capture_output=True, text=True, timeout=300)
+        sb.cleanup()
+        assert r.returncode == 0, (name, r.stderr[-2500:])
+        res[name] = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    b = res["b200"]
+    assert b["total"] == 8 * 1024**3 and b["oom"] and b["free_drop_ge_1g"]
+    assert b["sum"] == float(256 * 1024 * 1024)
+    if "reference" in res:
+        assert res["reference"] == b

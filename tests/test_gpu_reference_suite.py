@@ -45,6 +45,7 @@ def test_reference_smoke_suite_passes_under_both_libraries(built):
     exes = sorted(p for p in glob.glob(os.path.join(REF_TESTS, "test_*")) if os.access(p, os.X_OK))
     assert len(exes) >= 12
     report, failures = {}, []
+    os.makedirs(os.path.join(H.ROOT, "gpurun_out"), exist_ok=True)
     for exe in exes:
         name = os.path.basename(exe)
         rc_ref, out_ref, err_ref = run_under(H.REF_SO, exe)
@@ -54,7 +55,11 @@ def test_reference_smoke_suite_passes_under_both_libraries(built):
         if rc_new != rc_ref or (rc_ref == 0 and rc_new != 0):
             failures.append((name, rc_ref, rc_new, err_new[-800:]))
         elif name in SAME_STDOUT and not same:
-            failures.append((name, "stdout differs", out_ref[-600:], out_new[-600:]))
+            import difflib
+            diff = "\n".join(list(difflib.unified_diff(out_ref.splitlines(), out_new.splitlines(), "reference", "b200", lineterm=""))[:40])
+            with open(os.path.join(H.ROOT, "gpurun_out", "refsuite_%s.diff" % name), "w") as f:
+                f.write(diff + "\n---- stderr b200\n" + err_new[-3000:])
+            failures.append((name, "stdout differs", diff[:1500]))
     os.makedirs(os.path.join(H.ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(H.ROOT, "gpurun_out", "reference_suite_r1.json"), "w") as f:
         json.dump(report, f, indent=1)

@@ -170,7 +170,7 @@ static vgpu_dev_rt *bring_up(vgpu_dev_rt *rt, int slot, int host_index, CUdevice
     const char *src = getenv("VGPU_B200_UTIL_SOURCE"); /* queue (default) | sm | max */
     rt->lim_h->util_source = (src && !strcmp(src, "sm")) ? 1 : (src && !strcmp(src, "max")) ? 2 : 0;
     const char *win = getenv("VGPU_B200_UTIL_WINDOW_PERIODS"); /* control periods (~80 ms) per utilisation reading */
-    rt->lim_h->util_window = (win && atoi(win) >= 1) ? (uint32_t)atoi(win) : 12u;
+    rt->lim_h->util_window = (win && atoi(win) >= 1) ? (uint32_t)atoi(win) : 4u;
     const char *um = getenv("VGPU_B200_UTIL_MODE"); /* block (default, NVML-like) | average */
     rt->lim_h->util_mode = (um && !strcmp(um, "average")) ? 0u : 1u;
   }
@@ -234,7 +234,7 @@ static vgpu_dev_rt *bring_up(vgpu_dev_rt *rt, int slot, int host_index, CUdevice
     const char *src = getenv("VGPU_B200_UTIL_SOURCE");
     rt->lim_h->util_source = (src && !strcmp(src, "sm")) ? 1 : (src && !strcmp(src, "max")) ? 2 : 0;
     const char *win = getenv("VGPU_B200_UTIL_WINDOW_PERIODS");
-    rt->lim_h->util_window = (win && atoi(win) >= 1) ? (uint32_t)atoi(win) : 12u;
+    rt->lim_h->util_window = (win && atoi(win) >= 1) ? (uint32_t)atoi(win) : 4u;
     const char *um = getenv("VGPU_B200_UTIL_MODE");
     rt->lim_h->util_mode = (um && !strcmp(um, "average")) ? 0u : 1u;
   }

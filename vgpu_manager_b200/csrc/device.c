@@ -175,9 +175,14 @@ static vgpu_dev_rt *bring_up(vgpu_dev_rt *rt, int slot, int host_index, CUdevice
     rt->lim_h->util_mode = (um && !strcmp(um, "average")) ? 0u : 1u;
   }
 
-  /* one HBM allocation: limiter state followed by the UVA slab */
+  /* One HBM allocation: limiter state followed by the UVA slab, rounded up to a whole 2 MiB
+   * allocation granule.  A sub-granule request would be carved from the driver's small-block
+   * pool, whose free tail the tenant's own small allocations would then share - their first
+   * 2 MiB granule would stop showing up in NVML and the reported usage would differ from a
+   * reference deployment by one granule (seen with the reference's test_alloc). */
   size_t lim_bytes = (sizeof(vgpu_lim_dev_t) + 255) & ~(size_t)255;
   size_t hbm_bytes = lim_bytes + sizeof(vgpu_slab_slot_t) * VGPU_SLAB_SLOTS;
+  hbm_bytes = (hbm_bytes + ((size_t)2 << 20) - 1) & ~(((size_t)2 << 20) - 1);
   CU_TRY(R.cuMemAlloc_v2(&rt->lim_d, hbm_bytes), "HBM state");
   rt->slab_d = rt->lim_d + lim_bytes;
   CU_TRY(R.cuMemsetD8_v2(rt->lim_d, 0, hbm_bytes), "HBM state clear");

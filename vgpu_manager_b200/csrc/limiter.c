@@ -213,6 +213,20 @@ static void *tick_main(void *arg) {
   }
 }
 
+/* Process exit: stop launching into a context the CUDA runtime is about to tear down.  Registered
+ * with atexit() after the runtime's own handlers, hence run before them. */
+static pthread_t g_tick_tid;
+static volatile int g_tick_running;
+static void tick_stop(void) {
+  if (!g_tick_running || g_tick_epoch != vgpu_fork_epoch + 1) return;
+  g_tick_epoch = 0; /* tick_main leaves its loop at the next check */
+  struct timespec ts;
+  clock_gettime(CLOCK_REALTIME, &ts);
+  ts.tv_sec += 1;
+  pthread_timedjoin_np(g_tick_tid, NULL, &ts);
+  g_tick_running = 0;
+}
+
 static void tick_start(void) {
   g_window_us = env_u32("VGPU_B200_SAMPLER_WINDOW_US", 500);
   g_interval_us = env_u32("VGPU_B200_SAMPLER_INTERVAL_US", 50);
@@ -221,10 +235,10 @@ static void tick_start(void) {
   if (!g_period_ticks) g_period_ticks = 1;
   if (!g_tick_ms) g_tick_ms = 1;
   g_tick_epoch = vgpu_fork_epoch + 1;
-  pthread_t tid;
-  if (pthread_create(&tid, NULL, tick_main, NULL) == 0) {
-    pthread_setname_np(tid, "vgpu_b200_tick");
-    pthread_detach(tid);
+  if (pthread_create(&g_tick_tid, NULL, tick_main, NULL) == 0) {
+    pthread_setname_np(g_tick_tid, "vgpu_b200_tick");
+    g_tick_running = 1;
+    atexit(tick_stop);
   }
 }
 

@@ -9,6 +9,8 @@
  *   storm [--steps K] [--warmup W] [--per-step L] [--threads T] [--sync-every S] [--device D]
  *         [--no-kernel] [--max-seconds X] [--n N (== --steps 1 --per-step N)]
  *         [--spin-iters I --grid G --block B]   busy kernel instead of the empty one
+ *         [--stream null|created|ptsz]          legacy stream (default), one created stream per thread, or the
+ *                                               per-thread default stream through the _ptsz entry point
  */
 #define _GNU_SOURCE
 #include <dlfcn.h>
@@ -41,6 +43,8 @@ static CUresult (*p_evrecord)(void *, void *);
 static CUresult (*p_evsync)(void *);
 static CUresult (*p_evelapsed)(float *, void *, void *);
 static void *g_ctx, *g_func;
+static int g_stream_mode; /* 0 legacy NULL stream, 1 one created stream per thread, 2 per-thread default stream (_ptsz entry) */
+static CUresult (*p_stream_create)(void **, unsigned);
 static long g_per_step = 200000, g_sync_every = 0;
 static unsigned g_spin_iters = 0, g_grid = 1, g_block = 1;
 static void *g_kparams[1];
@@ -60,10 +64,12 @@ typedef struct { uint32_t *lat; long n, done, fails; int record; } worker_t;
 static void *worker(void *arg) {
   worker_t *w = (worker_t *)arg;
   p_setctx(g_ctx);
+  void *stream = NULL;
+  if (g_stream_mode == 1 && p_stream_create) p_stream_create(&stream, 1 /* CU_STREAM_NON_BLOCKING */);
   long i;
   for (i = 0; i < w->n && !g_stop; i++) {
     uint64_t a = now_ns();
-    CUresult r = p_launch(g_func, g_grid, 1, 1, g_block, 1, 1, 0, NULL, g_spin_iters ? g_kparams : NULL, NULL);
+    CUresult r = p_launch(g_func, g_grid, 1, 1, g_block, 1, 1, 0, stream, g_spin_iters ? g_kparams : NULL, NULL);
     uint64_t b = now_ns();
     if (w->record) w->lat[i] = (uint32_t)((b - a) > 0xffffffffull ? 0xffffffffull : (b - a));
     w->fails += r != 0;
@@ -94,6 +100,7 @@ int main(int argc, char **argv) {
     else if (!strcmp(argv[i], "--spin-iters") && i + 1 < argc) g_spin_iters = (unsigned)atol(argv[++i]);
     else if (!strcmp(argv[i], "--grid") && i + 1 < argc) g_grid = (unsigned)atol(argv[++i]);
     else if (!strcmp(argv[i], "--block") && i + 1 < argc) g_block = (unsigned)atol(argv[++i]);
+    else if (!strcmp(argv[i], "--stream") && i + 1 < argc) { i++; g_stream_mode = !strcmp(argv[i], "created") ? 1 : !strcmp(argv[i], "ptsz") ? 2 : 0; }
     else if (!strcmp(argv[i], "--no-kernel")) no_kernel = 1;
   }
   if (g_threads < 1) g_threads = 1;
@@ -107,7 +114,8 @@ int main(int argc, char **argv) {
   CUresult (*p_getfn)(void **, void *, const char *) = dlsym(h_cuda, "cuModuleGetFunction");
   p_setctx = dlsym(h_cuda, "cuCtxSetCurrent");
   p_sync = dlsym(h_cuda, "cuCtxSynchronize");
-  p_launch = (launch_fn)dlsym(h_cuda, "cuLaunchKernel");
+  p_launch = (launch_fn)dlsym(h_cuda, g_stream_mode == 2 ? "cuLaunchKernel_ptsz" : "cuLaunchKernel");
+  p_stream_create = dlsym(h_cuda, "cuStreamCreate");
   p_evcreate = dlsym(h_cuda, "cuEventCreate");
   p_evrecord = dlsym(h_cuda, "cuEventRecord");
   p_evsync = dlsym(h_cuda, "cuEventSynchronize");

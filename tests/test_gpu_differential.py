@@ -101,3 +101,20 @@ def test_two_processes_in_one_container_see_reference_numbers(built):
     assert views[0][0] == views[1][0], "B's view differs:\nreference:\n%s\nb200:\n%s\n%s" % (views[0][0], views[1][0], views[1][2][-1500:])
     assert views[0][1] == views[1][1]
     assert "-> 2" in views[0][0]  # the 4 GiB request exceeds what is left of the 6 GiB cap
+
+
+@pytest.mark.parametrize("mode,threads", [("created", 1), ("ptsz", 1), ("created", 4)])
+def test_launch_storm_on_other_stream_kinds(built, mode, threads):
+    """Created (non-blocking) streams and the per-thread default stream (_ptsz entry points):
+    slots, completion markers and device-side gates must work there too, from several threads."""
+    sb = H.Sandbox()
+    env = H.preload_env(H.NEW_SO, sb, {"MANAGER_COMPATIBILITY_MODE": "0", "MANAGER_VISIBLE_DEVICES": gpu0_uuid(),
+                                      "CUDA_CORE_LIMIT_0": "25", "CUDA_MEM_LIMIT_0": "4g", "CUDA_VISIBLE_DEVICES": "0",
+                                      "LOGGER_LEVEL": "1"}, stub=False)
+    r = subprocess.run([H.STORM, "--steps", "3", "--warmup", "1", "--per-step", "120000", "--stream", mode, "--threads",
+                        str(threads), "--max-seconds", "40"], env=env, capture_output=True, text=True, timeout=200)
+    sb.cleanup()
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads(r.stdout.strip().splitlines()[-1])
+    assert d["fails"] == 0 and d["launches"] >= 120000 and d["limiter"]["present"] == 1
+    assert d["sampler_launches"] > 0 and d["p50_ns"] < 20000

@@ -14,7 +14,9 @@ import helpers as H
 pytestmark = pytest.mark.gpu
 
 TENANT = r'''
-import torch, json
+import torch, json, sys, faulthandler
+faulthandler.dump_traceback_later(100, exit=True)
+print('imported', flush=True)
 free0, total = torch.cuda.mem_get_info()
 x = torch.ones(256, 1024, 1024, dtype=torch.float32, device="cuda")        # 1 GiB
 s = float(x.sum().cpu())
@@ -28,6 +30,7 @@ except torch.OutOfMemoryError:
 for _ in range(200):                                                        # a short launch train under the core cap
     x.mul_(1.0001)
 torch.cuda.synchronize()
+print("computed", flush=True)
 print(json.dumps({"total": total, "sum": s, "y": y, "oom": oom, "free_drop_ge_1g": (free0 - free1) >= 1024**3}))
 '''
 
@@ -42,12 +45,12 @@ def run_tenant(lib, timeout):
     sb = H.Sandbox()
     env = H.preload_env(lib, sb, {"MANAGER_COMPATIBILITY_MODE": "0", "MANAGER_VISIBLE_DEVICES": gpu0_uuid(),
                                   "CUDA_VISIBLE_DEVICES": "0", "CUDA_MEM_LIMIT_0": "8g", "CUDA_CORE_LIMIT_0": "50",
-                                  "LOGGER_LEVEL": "1"}, stub=False)
+                                  "LOGGER_LEVEL": "3", "PYTHONUNBUFFERED": "1"}, stub=False)
     try:
-        r = subprocess.run([sys.executable, "-c", TENANT], env=env, capture_output=True, text=True, timeout=timeout)
+        r = subprocess.run([sys.executable, "-X", "faulthandler", "-c", TENANT], env=env, capture_output=True, text=True, timeout=timeout)
     except subprocess.TimeoutExpired as e:
         sb.cleanup()
-        return None, "timeout after %ds\n%s" % (timeout, (e.stderr or b"")[-1500:])
+        return None, "timeout after %ds\nstdout: %s\nstderr: %s" % (timeout, (e.stdout or b"")[-800:], (e.stderr or b"")[-1500:])
     sb.cleanup()
     if r.returncode != 0:
         return None, r.stderr[-2500:]

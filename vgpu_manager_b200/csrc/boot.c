@@ -16,6 +16,7 @@
 #include <errno.h>
 #include <fcntl.h>
 #include <libgen.h>
+#include <link.h>
 #include <regex.h>
 #include <signal.h>
 #include <stdarg.h>
@@ -461,10 +462,41 @@ void vgpu_boot(void) {
  * our entry points no matter which handle the caller passes (cudart dlopen()s libcuda and
  * dlsym()s everything); all else goes to the real dlsym.  The reference's RTLD_NEXT
  * "(tid, pointer) seen before => NULL" de-duplication is a bug we do not reproduce. */
+/* RTLD_NEXT means "the first definition in the objects loaded after the CALLER".  An
+ * interposed dlsym that simply forwards RTLD_NEXT answers relative to *itself* instead, which can
+ * hand a later-loaded library its own symbol back (an endless loop for wrappers of the
+ * "real_foo = dlsym(RTLD_NEXT, "foo")" kind; the reference papers over that by returning NULL
+ * the second time a thread gets the same pointer, loader.c:1496-1539).  Walk the link map from
+ * the caller's object instead. */
+static void *next_after(void *caller, const char *symbol) {
+  struct link_map *lm = NULL;
+  Dl_info di;
+  if (!caller || !dladdr1(caller, &di, (void **)&lm, RTLD_DL_LINKMAP) || !lm) return vgpu_real_dlsym(RTLD_NEXT, symbol);
+  for (lm = lm->l_next; lm; lm = lm->l_next) {
+    if (!lm->l_name || !lm->l_name[0]) continue; /* the main program is never "next" */
+    void *h = dlopen(lm->l_name, RTLD_NOLOAD | RTLD_LAZY);
+    if (!h) continue;
+    void *p = vgpu_real_dlsym(h, symbol);
+    dlclose(h);
+    if (!p) continue;
+    /* dlsym(handle) also searches the object's dependencies; accept only its own definition */
+    struct link_map *owner = NULL;
+    Dl_info dp;
+    if (dladdr1(p, &dp, (void **)&owner, RTLD_DL_LINKMAP) && owner == lm) return p;
+  }
+  return NULL;
+}
+
 VGPU_EXPORT void *dlsym(void *handle, const char *symbol) {
   static __thread int depth;
   pthread_once(&g_dlsym_once, find_real_dlsym);
   if (depth > 0 || !symbol) return vgpu_real_dlsym(handle, symbol);
+  if (handle == RTLD_NEXT) {
+    depth++;
+    void *r = next_after(__builtin_return_address(0), symbol);
+    depth--;
+    return r;
+  }
   depth++;
   void *res = NULL;
   if (handle != RTLD_NEXT) {

@@ -15,7 +15,7 @@ pytestmark = pytest.mark.gpu
 
 TENANT = r'''
 import torch, json, sys, faulthandler
-faulthandler.dump_traceback_later(100, exit=True)
+faulthandler.dump_traceback_later(25, exit=True)
 print('imported', flush=True)
 free0, total = torch.cuda.mem_get_info()
 x = torch.ones(256, 1024, 1024, dtype=torch.float32, device="cuda")        # 1 GiB
@@ -45,7 +45,7 @@ def run_tenant(lib, timeout):
     sb = H.Sandbox()
     env = H.preload_env(lib, sb, {"MANAGER_COMPATIBILITY_MODE": "0", "MANAGER_VISIBLE_DEVICES": gpu0_uuid(),
                                   "CUDA_VISIBLE_DEVICES": "0", "CUDA_MEM_LIMIT_0": "8g", "CUDA_CORE_LIMIT_0": "50",
-                                  "LOGGER_LEVEL": "3", "PYTHONUNBUFFERED": "1"}, stub=False)
+                                  "LOGGER_LEVEL": "4", "PYTHONUNBUFFERED": "1"}, stub=False)
     try:
         r = subprocess.run([sys.executable, "-X", "faulthandler", "-c", TENANT], env=env, capture_output=True, text=True, timeout=timeout)
     except subprocess.TimeoutExpired as e:

@@ -183,9 +183,18 @@ static void *tick_main(void *arg) {
       if (R.cuCtxPushCurrent_v2(rt->ctx) != CUDA_SUCCESS) continue;
       settle_idle_streams(rt, h);
       CUresult q = R.cuStreamQuery(rt->s_stream);
+      if (q != CUDA_SUCCESS && (epoch % 100) == 0)
+        VLOG(VL_VERBOSE, "limiter host %d: sampler stream not idle (%d: %s)", h, q, vgpu_cu_err(q));
       if (q == CUDA_SUCCESS) {
         rt->lim_h->quit = 0;
         if ((epoch % 100) == 1) refresh_process_count(rt);
+        if ((epoch % 100) == 0 && vgpu_log_level() >= VL_VERBOSE) {
+          vgpu_lim_host_t *H = rt->lim_h;
+          VLOG(VL_VERBOSE, "limiter host %d: steps %llu user %d (queue %d sm %d) share %lld bucket %lld granted %lld consumed %lld "
+               "nproc %d slot0 launched %llu done %llu", h, (unsigned long long)H->steps, H->user_current, H->queue_busy_pct,
+               H->sm_active_pct, (long long)H->share_mirror, (long long)H->bucket_mirror, (long long)H->granted_mirror,
+               (long long)H->consumed, H->ext_sys_process_num, (unsigned long long)H->launched[0], (unsigned long long)H->done[0]);
+        }
         uint32_t ep = epoch;
         /* while a tenant thread waits for the device to go idle, keep the sampler's residency
          * negligible so the wait is not stretched by it */

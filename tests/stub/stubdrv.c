@@ -314,21 +314,47 @@ EXPORT CUresult cuMemsetD8_v2(CUdeviceptr d, unsigned char v, size_t n) { memset
 EXPORT CUresult cuMemcpyDtoH_v2(void *dst, CUdeviceptr src, size_t n) { memcpy(dst, (void *)(uintptr_t)src, n); return 0; }
 EXPORT CUresult cuMemcpyHtoD_v2(CUdeviceptr dst, const void *src, size_t n) { memcpy((void *)(uintptr_t)dst, src, n); return 0; }
 
+/* STUB_CTX_LOCK=1 models the real driver's context lock: a call that blocks on the stream (here
+ * the wait itself, on a real GPU e.g. a pageable memcpy behind a parked kernel) keeps every other
+ * thread out of the driver - in particular out of cuLaunchKernel. */
+static pthread_mutex_t g_ctx_mu = PTHREAD_MUTEX_INITIALIZER;
+static int g_ctx_lock = -1;
+static CUresult wait64_unlocked(CUdeviceptr addr, unsigned long long value);
+static int ctx_lock_on(void) {
+  if (g_ctx_lock < 0) { const char *e = getenv("STUB_CTX_LOCK"); g_ctx_lock = (e && atoi(e)) ? 1 : 0; }
+  return g_ctx_lock;
+}
 /* ------------------------------------------------------------------ CUDA: streams */
 EXPORT CUresult cuStreamCreate(void **s, unsigned f) { (void)f; static uintptr_t next = 0x5000; *s = (void *)(next += 0x10); return 0; }
 EXPORT CUresult cuStreamCreateWithPriority(void **s, unsigned f, int p) { (void)p; return cuStreamCreate(s, f); }
 EXPORT CUresult cuStreamDestroy_v2(void *s) { (void)s; return 0; }
 EXPORT CUresult cuStreamSynchronize(void *s) { (void)s; return 0; }
-EXPORT CUresult cuStreamQuery(void *s) { (void)s; return 0; }
+EXPORT CUresult cuStreamQuery(void *s) {
+  (void)s;
+  if (ctx_lock_on()) { pthread_mutex_lock(&g_ctx_mu); pthread_mutex_unlock(&g_ctx_mu); }
+  return 0;
+}
 EXPORT CUresult cuStreamIsCapturing(void *s, int *st) { (void)s; *st = 0; return 0; }
+static volatile int g_parked; /* callers blocked behind the gate (the fake GPU's "parked streams") */
+static CUresult wait64_unlocked(CUdeviceptr addr, unsigned long long value);
 static CUresult wait64(CUdeviceptr addr, unsigned long long value) {
+  if (!ctx_lock_on()) return wait64_unlocked(addr, value);
+  pthread_mutex_lock(&g_ctx_mu);
+  CUresult r = wait64_unlocked(addr, value);
+  pthread_mutex_unlock(&g_ctx_mu);
+  return r;
+}
+static CUresult wait64_unlocked(CUdeviceptr addr, unsigned long long value) {
   /* the fake GPU executes stream work synchronously, so a stream wait blocks the caller */
   volatile long long *p = (volatile long long *)(uintptr_t)addr;
   struct timespec nap = {0, 200000};
+  if ((long long)(*p - (long long)value) >= 0) return 0;
+  __sync_fetch_and_add(&g_parked, 1);
   for (int i = 0; i < 100000; i++) { /* 20 s cap */
-    if ((long long)(*p - (long long)value) >= 0) return 0;
+    if ((long long)(*p - (long long)value) >= 0) break;
     nanosleep(&nap, NULL);
   }
+  __sync_fetch_and_sub(&g_parked, 1);
   return 0;
 }
 EXPORT CUresult cuStreamWaitValue64_v2(void *s, CUdeviceptr a, unsigned long long v, unsigned f) { (void)s; (void)f; return wait64(a, v); }
@@ -418,6 +444,107 @@ static void fake_ctl_step(vgpu_lim_dev_t *D, vgpu_lim_host_t *H, int user, int s
   H->steps = D->steps;
 }
 
+static void fake_period_end(vgpu_lim_dev_t *D, vgpu_lim_host_t *H) {
+  int q = D->total_samples ? (int)(D->busy_samples * 100 / D->total_samples) : 0;
+  D->last_queue_busy_pct = q;
+  D->busy_samples = D->total_samples = 0;
+  int user = H->ext_user_override >= 0 ? H->ext_user_override : q;
+  int others = H->ext_sys_current > 0 ? H->ext_sys_current : 0;
+  int np = H->ext_sys_process_num > 0 ? H->ext_sys_process_num : 1;
+  fake_ctl_step(D, H, user, user + others, 1, np);
+}
+
+/* vgpu_governor_kernel on the fake GPU: the only kernel that is not executed synchronously -
+ * it is resident, so it runs as a thread until its own retire protocol lets it go. */
+typedef struct { vgpu_lim_dev_t *D; vgpu_lim_host_t *H; uint32_t interval_us, period_us, idle_us; } gov_arg_t;
+static uint64_t mono_ns(void) {
+  struct timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return (uint64_t)ts.tv_sec * 1000000000ull + (uint64_t)ts.tv_nsec;
+}
+static unsigned long long fake_signature(const vgpu_lim_host_t *H) {
+  unsigned long long sgn = 0;
+  for (uint32_t i = 0; i < VGPU_STREAM_SLOTS; i++) sgn += H->launched[i] * 3ull + H->done[i];
+  return sgn;
+}
+static void *fake_governor(void *argp) {
+  gov_arg_t a = *(gov_arg_t *)argp;
+  free(argp);
+  vgpu_lim_dev_t *D = a.D;
+  vgpu_lim_host_t *H = a.H;
+  const uint64_t period_ns = (uint64_t)(a.period_us ? a.period_us : 1) * 1000ull, idle_ns = (uint64_t)a.idle_us * 1000ull;
+  uint64_t now = mono_ns();
+  uint64_t left = D->gov_left_ns, lc = D->last_ctl_ns;
+  if (lc == 0 || now < lc || left == 0 || now < left || left < lc) {
+    D->last_ctl_ns = now;
+  } else {
+    int was_busy = D->gov_left_busy != 0;
+    uint64_t t = left;
+    unsigned steps = 0;
+    while (now - lc >= period_ns && steps < 128) {
+      uint64_t end = lc + period_ns;
+      D->total_samples += end - t;
+      if (was_busy) D->busy_samples += end - t;
+      fake_period_end(D, H);
+      t = lc = end;
+      steps++;
+    }
+    if (now - lc >= period_ns) { lc = now - (now - lc) % period_ns; t = lc; }
+    D->total_samples += now - t;
+    if (was_busy) D->busy_samples += now - t;
+    D->last_ctl_ns = lc;
+  }
+  D->gov_left_ns = 0;
+  D->gov_left_busy = 0;
+  H->gov_left_busy = 0;
+  uint64_t prev = now, last_change = now;
+  unsigned long long sig = fake_signature(H), busy = 0, total = 0;
+  unsigned nap_us = a.interval_us < 200 ? 200 : a.interval_us; /* a CPU thread: do not spin at 50 us */
+  for (;;) {
+    now = mono_ns();
+    uint64_t dt = now - prev;
+    prev = now;
+    int util = current_util();
+    int parked = g_parked > 0, outstanding = 0;
+    for (uint32_t i = 0; i < VGPU_STREAM_SLOTS; i++)
+      if (H->launched[i] > H->done[i]) outstanding = 1;
+    total += dt;
+    busy += dt * (unsigned long long)util / 100ull;
+    unsigned long long sn = fake_signature(H);
+    if (sn != sig) { sig = sn; last_change = now; }
+    if (now - D->last_ctl_ns >= period_ns) {
+      D->last_ctl_ns = now;
+      D->busy_samples += busy;
+      D->total_samples += total;
+      busy = total = 0;
+      fake_period_end(D, H);
+    }
+    uint32_t quit = H->quit;
+    int want_exit = quit ? !parked : (!outstanding && !parked && now - last_change > idle_ns);
+    if (want_exit) {
+      H->ctl_state = 2;
+      __sync_synchronize();
+      unsigned long long chk = fake_signature(H);
+      if (chk != sig && !quit) {
+        H->ctl_state = 1;
+        sig = chk;
+        last_change = now;
+      } else {
+        D->busy_samples += busy;
+        D->total_samples += total;
+        D->gov_left_ns = now;
+        D->gov_left_busy = 0;
+        H->gov_left_busy = 0;
+        __sync_synchronize();
+        H->ctl_state = 0;
+        return NULL;
+      }
+    }
+    struct timespec nap = {0, (long)nap_us * 1000L};
+    nanosleep(&nap, NULL);
+  }
+}
+
 static void run_fake_kernel(const char *name, void **p) {
   if (!strcmp(name, VGPU_K_CLEAR)) {
     unsigned long long n = *(unsigned long long *)p[1];
@@ -459,18 +586,23 @@ static void run_fake_kernel(const char *name, void **p) {
     int util = current_util();
     D->busy_samples += (unsigned long long)util;
     D->total_samples += 100;
-    if (++D->period_tick >= period) {
+    if (period != VGPU_SAMPLER_PROBE_ONLY && ++D->period_tick >= period) {
       D->period_tick = 0;
-      int q = D->total_samples ? (int)(D->busy_samples * 100 / D->total_samples) : 0;
-      D->last_queue_busy_pct = q;
-      D->busy_samples = D->total_samples = 0;
-      int user = H->ext_user_override >= 0 ? H->ext_user_override : q;
-      int others = H->ext_sys_current > 0 ? H->ext_sys_current : 0;
-      int np = H->ext_sys_process_num > 0 ? H->ext_sys_process_num : 1;
-      fake_ctl_step(D, H, user, user + others, 1, np);
+      fake_period_end(D, H);
     }
+  } else if (!strcmp(name, VGPU_K_GOVERNOR)) {
+    gov_arg_t *a = (gov_arg_t *)malloc(sizeof *a);
+    a->D = (vgpu_lim_dev_t *)(uintptr_t) * (CUdeviceptr *)p[0];
+    a->H = (vgpu_lim_host_t *)(uintptr_t) * (CUdeviceptr *)p[1];
+    a->interval_us = *(uint32_t *)p[2]; a->period_us = *(uint32_t *)p[3]; a->idle_us = *(uint32_t *)p[4];
+    pthread_t t;
+    pthread_attr_t at;
+    pthread_attr_init(&at);
+    pthread_attr_setdetachstate(&at, PTHREAD_CREATE_DETACHED);
+    if (pthread_create(&t, &at, fake_governor, a) != 0) { a->H->ctl_state = 0; free(a); }
+    pthread_attr_destroy(&at);
   } else if (!strcmp(name, VGPU_K_GATE)) {
-    wait64(*(CUdeviceptr *)p[0], (unsigned long long)*(long long *)p[1]);
+    wait64_unlocked(*(CUdeviceptr *)p[0], (unsigned long long)*(long long *)p[1]);
   } else {
     note_launch(); /* a tenant kernel */
   }
@@ -479,8 +611,11 @@ static void run_fake_kernel(const char *name, void **p) {
 static CUresult launch(void *f, void **params) {
   if (!t_has_ctx) return 201;
   fn_t *fn = (fn_t *)f;
+  int locked = ctx_lock_on();
+  if (locked) pthread_mutex_lock(&g_ctx_mu);
   if (fn && ((uintptr_t)fn > 0x10000) && !strncmp(fn->name, "vgpu_", 5)) run_fake_kernel(fn->name, params);
   else note_launch();
+  if (locked) pthread_mutex_unlock(&g_ctx_mu);
   return 0;
 }
 EXPORT CUresult cuLaunchKernel(void *f, unsigned gx, unsigned gy, unsigned gz, unsigned bx, unsigned by, unsigned bz,

@@ -259,6 +259,19 @@ def test_config1_stub_launch_storm_both_libraries(built):
         assert new["p50_ns"] < 5000
 
 
+def test_refill_does_not_need_the_host_to_enter_the_driver(built):
+    """Regression for a deadlock class seen with PyTorch on the real driver: a thread blocks inside
+    a driver call (holding the context lock) behind a parked stream, so no other thread can launch
+    the kernel that would refill the bucket.  STUB_CTX_LOCK=1 models that lock in the fake driver;
+    the resident governor must release the parked stream on its own."""
+    env = dict(BASE)
+    env.update({"CUDA_CORE_LIMIT_0": "10", "CUDA_MEM_LIMIT_0": "1g", "STUB_UTIL": "closed:0.02", "STUB_CTX_LOCK": "1"})
+    for threads in (1, 4):
+        new = _storm(H.NEW_SO, env, 300000, threads)
+        assert new["launches"] == 300000 and new["fails"] == 0
+        assert new["limiter"]["present"] == 1 and new["gated_launches"] > 0, new
+
+
 def test_directly_linked_tenant_is_intercepted_by_symbol_interposition(built):
     """No dlopen/dlsym/cuGetProcAddress at all: the tenant links libcuda; the preloaded library
     must win plain symbol resolution for every hooked entry point."""

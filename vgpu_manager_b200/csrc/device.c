@@ -133,6 +133,7 @@ static vgpu_dev_rt *bring_up(vgpu_dev_rt *rt, int slot, int host_index, CUdevice
   CU_TRY(R.cuModuleGetFunction(&rt->k_controller, rt->mod, VGPU_K_CONTROLLER), VGPU_K_CONTROLLER);
   CU_TRY(R.cuModuleGetFunction(&rt->k_sampler, rt->mod, VGPU_K_SAMPLER), VGPU_K_SAMPLER);
   CU_TRY(R.cuModuleGetFunction(&rt->k_gate, rt->mod, VGPU_K_GATE), VGPU_K_GATE);
+  CU_TRY(R.cuModuleGetFunction(&rt->k_governor, rt->mod, VGPU_K_GOVERNOR), VGPU_K_GOVERNOR);
   {
     /* spill-copy geometry: defaults from kernel_abi.h, overridable for tuning sweeps */
     const char *e;
@@ -151,10 +152,12 @@ static vgpu_dev_rt *bring_up(vgpu_dev_rt *rt, int slot, int host_index, CUdevice
   if (R.cuCtxGetStreamPriorityRange) R.cuCtxGetStreamPriorityRange(&lo, &hi);
   if (R.cuStreamCreateWithPriority) {
     CU_TRY(R.cuStreamCreateWithPriority(&rt->q_stream, VCU_STREAM_NON_BLOCKING, hi), "quota stream");
-    CU_TRY(R.cuStreamCreateWithPriority(&rt->s_stream, VCU_STREAM_NON_BLOCKING, hi), "sampler stream");
+    CU_TRY(R.cuStreamCreateWithPriority(&rt->s_stream, VCU_STREAM_NON_BLOCKING, hi), "governor stream");
+    CU_TRY(R.cuStreamCreateWithPriority(&rt->p_stream, VCU_STREAM_NON_BLOCKING, hi), "probe stream");
   } else {
     CU_TRY(R.cuStreamCreate(&rt->q_stream, VCU_STREAM_NON_BLOCKING), "quota stream");
-    CU_TRY(R.cuStreamCreate(&rt->s_stream, VCU_STREAM_NON_BLOCKING), "sampler stream");
+    CU_TRY(R.cuStreamCreate(&rt->s_stream, VCU_STREAM_NON_BLOCKING), "governor stream");
+    CU_TRY(R.cuStreamCreate(&rt->p_stream, VCU_STREAM_NON_BLOCKING), "probe stream");
   }
 
   if (pinned_block(sizeof(vgpu_quota_req_t), (void **)&rt->q_req, &rt->q_req_d) ||
@@ -217,14 +220,23 @@ static vgpu_dev_rt *bring_up(vgpu_dev_rt *rt, int slot, int host_index, CUdevice
     vgpu_ctrl_in_t in = {0, 0, 0, 1};
     void *p_ctl[] = {&rt->lim_d, &rt->lim_h_d, &in};
     CU_TRY(vgpu_rt_launch(rt, rt->k_controller, 1, 32, 0, rt->q_stream, p_ctl), "warm controller");
-    uint32_t w = 0, iv = 1, per = 0x7fffffff, ep = 0;
+    uint32_t w = 0, iv = 1, per = VGPU_SAMPLER_PROBE_ONLY, ep = 0;
     void *p_smp[] = {&rt->lim_d, &rt->lim_h_d, &w, &iv, &per, &ep};
     CU_TRY(vgpu_rt_launch(rt, rt->k_sampler, 1, 128, 0, rt->q_stream, p_smp), "warm sampler");
+    rt->lim_h->quit = 1;
+    rt->lim_h->ctl_state = 1;
+    uint32_t g_iv = 10, g_per = 80000, g_idle = 1;
+    void *p_gov[] = {&rt->lim_d, &rt->lim_h_d, &g_iv, &g_per, &g_idle};
+    CU_TRY(vgpu_rt_launch(rt, rt->k_governor, 1, 32, 0, rt->q_stream, p_gov), "warm governor");
     long long tk = 0;
     uint32_t to = 1;
     void *p_gate[] = {&rt->lim_d, &tk, &to};
     CU_TRY(vgpu_rt_launch(rt, rt->k_gate, 1, 1, 0, rt->q_stream, p_gate), "warm gate");
     CU_TRY(R.cuStreamSynchronize(rt->q_stream), "warm-up sync");
+    for (int i = 0; i < 10000 && rt->lim_h->ctl_state != 0; i++) { /* governor's last store is to host memory */
+      struct timespec nap = {0, 100000};
+      nanosleep(&nap, NULL);
+    }
     /* the warm-up controller/sampler steps touched the state: re-initialise it */
     CU_TRY(R.cuMemsetD8_v2(rt->lim_d, 0, lim_bytes), "HBM state re-clear");
     vgpu_lim_dev_t *init = (vgpu_lim_dev_t *)malloc(sizeof *init);
@@ -234,6 +246,7 @@ static vgpu_dev_rt *bring_up(vgpu_dev_rt *rt, int slot, int host_index, CUdevice
     free(init);
     CU_TRY(r, "HBM state init");
     memset((void *)rt->lim_h, 0, offsetof(vgpu_lim_host_t, user_current));
+    rt->lim_h->gov_left_busy = 0;
     rt->lim_h->ext_user_override = -1;
     rt->lim_h->ext_sys_process_num = 1;
     const char *src = getenv("VGPU_B200_UTIL_SOURCE");
@@ -480,7 +493,12 @@ VGPU_EXPORT int vgpu_b200_limiter_reset(int sm_num, int max_thread_per_sm, int h
   init->core_limit = core_limit;
   init->hard_limit = hard_limit;
   init->up_limit = hard_core;
+  /* a resident governor would keep stepping the state being replaced: ask it to leave first */
+  __sync_fetch_and_add(&rt->lim_h->quit, 1u);
   R.cuStreamSynchronize(rt->s_stream);
+  R.cuStreamSynchronize(rt->p_stream);
+  __sync_fetch_and_sub(&rt->lim_h->quit, 1u);
+  rt->lim_h->gov_left_busy = 0;
   int rc = R.cuMemcpyHtoD_v2(rt->lim_d, init, sizeof *init) == CUDA_SUCCESS ? 0 : -1;
   free(init);
   rt->lim_h->consumed = 0;
@@ -520,8 +538,8 @@ VGPU_EXPORT int vgpu_b200_sampler_run(unsigned window_us, unsigned interval_us, 
   uint32_t ep = ++epoch;
   void *params[] = {&rt->lim_d, &rt->lim_h_d, &window_us, &interval_us, &period_ticks, &ep};
   unsigned grid = rt->sm_num > 0 ? (unsigned)rt->sm_num : 148u;
-  if (vgpu_rt_launch(rt, rt->k_sampler, grid, 128, 0, rt->s_stream, params) != CUDA_SUCCESS) return -1;
-  if (R.cuStreamSynchronize(rt->s_stream) != CUDA_SUCCESS) return -1;
+  if (vgpu_rt_launch(rt, rt->k_sampler, grid, 128, 0, rt->p_stream, params) != CUDA_SUCCESS) return -1;
+  if (R.cuStreamSynchronize(rt->p_stream) != CUDA_SUCCESS) return -1;
   vgpu_metric_add(rt->host_index, VM_SAMPLER_LAUNCHES, 1);
   return read_lim(rt, out);
 }

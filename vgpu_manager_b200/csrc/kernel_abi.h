@@ -22,6 +22,7 @@ extern "C" {
 #define VGPU_K_CONTROLLER "vgpu_controller_kernel"
 #define VGPU_K_SAMPLER "vgpu_sampler_kernel"
 #define VGPU_K_GATE "vgpu_gate_kernel"
+#define VGPU_K_GOVERNOR "vgpu_governor_kernel"
 
 /* ---------------------------------------------------------------- spill copy geometry */
 #define VGPU_SPILL_CHUNK 16384u      /* bytes per TMA bulk copy                      */
@@ -96,6 +97,7 @@ typedef struct {
 #define VGPU_STREAM_SLOTS 64u
 #define VGPU_TICKET_RING 1024u /* per stream slot; power of two */
 #define VGPU_MAX_SMS 256u
+#define VGPU_SAMPLER_PROBE_ONLY 0x7fffffffu /* sampler period_ticks value: probe SMs, leave the queue signal and the controller to the governor */
 
 /* device-resident (HBM) limiter state, one per GPU */
 typedef struct {
@@ -131,6 +133,10 @@ typedef struct {
   int32_t util_hist[16];
   uint32_t util_hist_pos;
   int32_t blk_sum, blk_n, blk_reading; /* tumbling-block mode: reading = mean of the last full block */
+  unsigned long long last_ctl_ns;      /* %globaltimer of the last control step (survives governor restarts) */
+  unsigned long long gov_left_ns;      /* %globaltimer at which the previous governor incarnation retired   */
+  uint32_t gov_left_busy;              /* ... and whether tenant work was executing at that moment           */
+  uint32_t _pad_g;
   /* last results, for metrics and tests */
   int32_t last_user_current;
   int32_t last_sys_current;
@@ -143,14 +149,14 @@ typedef struct {
 typedef struct {
   volatile long long consumed;        /* host-owned, fetch_add by the hook                     */
   volatile long long granted_mirror;  /* device-written copy of granted                        */
-  volatile uint32_t quit;             /* host asks a running sampler to leave early            */
+  volatile uint32_t quit;             /* >0: threads inside a device-wide synchronise; resident kernels leave */
   volatile uint32_t util_source;      /* 0 queue-busy, 1 sm-active, 2 max of both              */
   volatile int32_t ext_sys_current;   /* other tenants' util (host-provided, balance mode)     */
   volatile int32_t ext_sys_process_num;
   volatile int32_t ext_user_override; /* >=0: test hook, use this as user_current              */
   volatile uint32_t util_window;      /* periods averaged into user_current (1..16)            */
   volatile uint32_t util_mode;        /* 0 moving average, 1 tumbling block (NVML-like sampling) */
-  volatile uint32_t _pad_m;
+  volatile uint32_t ctl_state;        /* governor: 0 not resident, 1 resident (or being launched), 2 leaving */
   volatile unsigned long long launched[VGPU_STREAM_SLOTS]; /* per-slot launch sequence (host)   */
   /* per-slot completion markers, written by cuStreamWriteValue64 right after each launch */
   volatile unsigned long long done[VGPU_STREAM_SLOTS];
@@ -160,7 +166,7 @@ typedef struct {
   volatile int32_t user_current, sys_current, sm_active_pct, queue_busy_pct;
   volatile long long share_mirror, bucket_mirror;
   volatile int32_t up_limit_mirror;
-  volatile int32_t _pad3;
+  volatile uint32_t gov_left_busy;    /* the governor retired while tenant work was executing (see device block) */
   volatile unsigned long long steps;
 } vgpu_lim_host_t;
 

@@ -555,6 +555,63 @@ extern "C" __global__ void vgpu_controller_kernel(vgpu_lim_dev_t *D, vgpu_lim_ho
     ctl_step(D, H, in.user_current, in.sys_current, in.valid, in.sys_process_num);
 }
 
+/* End of a control period: turn the accumulators into the utilisation reading and run one
+ * controller step.  Shared by the sampler's tail (direct API / tests) and the governor. */
+DEVINL void period_end(vgpu_lim_dev_t *D, vgpu_lim_host_t *H, int grid_sms, uint32_t epoch, uint32_t period_ticks) {
+  unsigned long long pc = D->probe_cycles, pi = D->probe_idle_cycles;
+  unsigned long long bs = D->busy_samples, ts = D->total_samples;
+  int nsm = D->sm_num > 0 ? D->sm_num : grid_sms;
+  int active = pc ? (int)(100 - (pi * 100ull) / pc) : 0;
+  if (active < 0) active = 0;
+  if (period_ticks) { /* coverage: SMs that hosted a sampler CTA at least once this period */
+    int covered = 0;
+    for (int i = 0; i < nsm && i < (int)VGPU_MAX_SMS; i++) covered += ((epoch - D->sm_epoch[i]) < period_ticks) ? 1 : 0;
+    if (covered < nsm && pc) active = (active * covered + 100 * (nsm - covered)) / nsm;
+  }
+  int qbusy = ts ? (int)((bs * 100ull) / ts) : 0;
+  D->last_sm_active_pct = active;
+  D->last_queue_busy_pct = qbusy;
+  D->probe_cycles = D->probe_idle_cycles = D->probe_count = 0;
+  D->busy_samples = D->total_samples = 0;
+
+  int user;
+  uint32_t srcsel = H->util_source;
+  if (srcsel == 1) user = active;
+  else if (srcsel == 2) user = active > qbusy ? active : qbusy;
+  else user = qbusy;
+  /* How the raw per-period figure becomes the controller's reading:
+   *  mode 1 (default)  tumbling blocks of util_window periods - the reading is the mean of the
+   *                    last *completed* block and only changes at block boundaries.  This is how
+   *                    the reference sees utilisation: NVML publishes a per-process sample about
+   *                    once a second (cuda_hook.c:972-979 asks for "since now - 1 s").
+   *  mode 0            moving average over the last util_window periods (window 1 = raw). */
+  uint32_t W = H->util_window;
+  W = W < 1 ? 1 : (W > 16 ? 16 : W);
+  if (H->util_mode == 1) {
+    D->blk_sum += user;
+    if (++D->blk_n >= (int)W) {
+      D->blk_reading = D->blk_sum / D->blk_n;
+      D->blk_sum = 0;
+      D->blk_n = 0;
+    }
+    user = D->blk_reading;
+  } else {
+    D->util_hist[D->util_hist_pos & 15] = user;
+    D->util_hist_pos++;
+    uint32_t have = D->util_hist_pos < W ? D->util_hist_pos : W;
+    int acc = 0;
+    for (uint32_t i = 0; i < have; i++) acc += D->util_hist[(D->util_hist_pos - 1 - i) & 15];
+    user = acc / (int)have;
+  }
+  int ov = H->ext_user_override;
+  if (ov >= 0) user = ov;
+  int others = H->ext_sys_current;
+  int sys = user + (others > 0 ? others : 0);
+  int nproc = H->ext_sys_process_num;
+  if (nproc <= 0) nproc = 1;
+  ctl_step(D, H, user, sys, (ts > 0 || ov >= 0) ? 1 : 0, nproc);
+}
+
 /* ======================================================================= sampler
  * grid = one CTA per SM (as scheduled), 4 warps = one per SM sub-partition.
  *
@@ -605,6 +662,7 @@ extern "C" __global__ void __launch_bounds__(SAMPLER_THREADS)
   const uint64_t t_start = globaltimer_ns();
   const uint64_t window_ns = (uint64_t)window_us * 1000ull;
   const bool queue_warp = (blockIdx.x == 0 && warp == 0);
+  const bool probe_only = (period_ticks == VGPU_SAMPLER_PROBE_ONLY);
 
   uint32_t idle = D->probe_idle[pslot];
   unsigned long long probe_sum = 0, idle_sum = 0, nprobe = 0, busy = 0, total = 0;
@@ -619,8 +677,8 @@ extern "C" __global__ void __launch_bounds__(SAMPLER_THREADS)
     idle_sum += idle;
     nprobe++;
 
-    /* (b) queue-busy */
-    if (queue_warp) {
+    /* (b) queue-busy (the governor owns this signal when the sampler runs probe-only) */
+    if (queue_warp && !probe_only) {
       bool running = false;
       long long granted = *reinterpret_cast<volatile long long *>(&D->granted);
 #pragma unroll
@@ -637,8 +695,8 @@ extern "C" __global__ void __launch_bounds__(SAMPLER_THREADS)
       bool any = __any_sync(0xffffffffu, running);
       total++;
       busy += any ? 1 : 0;
-      if (lane == 0 && H->quit) *quit_dev = 1;
     }
+    if (queue_warp && lane == 0 && H->quit) *quit_dev = 1;
     if (*quit_dev) break;
     if (globaltimer_ns() - t_start >= window_ns) break;
     __nanosleep(interval_us * 1000u);
@@ -650,7 +708,7 @@ extern "C" __global__ void __launch_bounds__(SAMPLER_THREADS)
     atomicAdd(&D->probe_count, nprobe);
     atomicMin(&D->probe_idle[pslot], idle); /* host initialises the table to 0xffffffff */
     if (warp == 0) D->sm_epoch[sm < VGPU_MAX_SMS ? sm : VGPU_MAX_SMS - 1] = epoch;
-    if (queue_warp) {
+    if (queue_warp && !probe_only) {
       atomicAdd(&D->busy_samples, busy);
       atomicAdd(&D->total_samples, total);
     }
@@ -664,61 +722,166 @@ extern "C" __global__ void __launch_bounds__(SAMPLER_THREADS)
   D->cta_done = 0;
   *quit_dev = 0;
   /* coverage: SMs that hosted a sampler CTA at least once this period */
+  if (probe_only) return;
   uint32_t tick = ++D->period_tick;
   if (tick < period_ticks) return;
   D->period_tick = 0;
   __threadfence();
 
-  unsigned long long pc = D->probe_cycles, pi = D->probe_idle_cycles;
-  unsigned long long bs = D->busy_samples, ts = D->total_samples;
-  int nsm = D->sm_num > 0 ? D->sm_num : (int)gridDim.x;
-  int covered = 0;
-  for (int i = 0; i < nsm && i < (int)VGPU_MAX_SMS; i++) covered += ((epoch - D->sm_epoch[i]) < period_ticks) ? 1 : 0;
-  int active = pc ? (int)(100 - (pi * 100ull) / pc) : 0;
-  if (active < 0) active = 0;
-  if (covered < nsm) active = (active * covered + 100 * (nsm - covered)) / nsm;
-  int qbusy = ts ? (int)((bs * 100ull) / ts) : 0;
-  D->last_sm_active_pct = active;
-  D->last_queue_busy_pct = qbusy;
-  D->probe_cycles = D->probe_idle_cycles = D->probe_count = 0;
-  D->busy_samples = D->total_samples = 0;
+  period_end(D, H, (int)gridDim.x, epoch, period_ticks);
+}
 
-  int user;
-  uint32_t srcsel = H->util_source;
-  if (srcsel == 1) user = active;
-  else if (srcsel == 2) user = active > qbusy ? active : qbusy;
-  else user = qbusy;
-  /* How the raw per-period figure becomes the controller's reading:
-   *  mode 1 (default)  tumbling blocks of util_window periods - the reading is the mean of the
-   *                    last *completed* block and only changes at block boundaries.  This is how
-   *                    the reference sees utilisation: NVML publishes a per-process sample about
-   *                    once a second (cuda_hook.c:972-979 asks for "since now - 1 s").
-   *  mode 0            moving average over the last util_window periods (window 1 = raw). */
-  uint32_t W = H->util_window;
-  W = W < 1 ? 1 : (W > 16 ? 16 : W);
-  if (H->util_mode == 1) {
-    D->blk_sum += user;
-    if (++D->blk_n >= (int)W) {
-      D->blk_reading = D->blk_sum / D->blk_n;
-      D->blk_sum = 0;
-      D->blk_n = 0;
+/* ======================================================================= governor
+ * The resident half of the limiter: ONE warp that stays on the device for as long as the tenant
+ * has work queued or parked, samples the stream queues every `interval_us`, and runs the
+ * controller every `period_us` - so a parked stream is released by the device itself.
+ *
+ * Why resident: a refill that needs a *host* launch can deadlock.  Several driver calls block
+ * while holding the context lock (a pageable cuMemcpyDtoH waiting for a parked kernel is the
+ * common one); no other thread can then launch anything into that context, including the
+ * kernel that would refill the bucket.
+ *
+ * Why not resident forever: device-wide synchronisation (cuCtxSynchronize, cuMemFree, context
+ * teardown...) waits for every kernel of the context.  The governor therefore retires by itself
+ * once the queues have been empty for `idle_exit_us`, or - when the host announces a device-wide
+ * synchronise through `quit` - as soon as nothing is parked; the next launch hook starts it
+ * again.  The retire / restart hand-shake is a Dekker pair over pinned memory: the governor
+ * publishes state 2 ("leaving"), fences, re-reads the launch counters and only then writes 0;
+ * the hook publishes its launch, fences and then reads the state.
+ *
+ * Time it was away is accounted when it comes back: idle if the queues were empty when it left,
+ * busy if it left (for a synchronise) while tenant work was executing; control periods that
+ * elapsed meanwhile are stepped one by one (bounded), exactly as the reference's watcher thread
+ * would have done while the tenant was quiet.
+ *
+ * busy_samples / total_samples hold nanoseconds here (the sampler's tail, which shares
+ * period_end(), uses sample counts; only the ratio matters). */
+#define GOV_MAX_CATCHUP 128u
+#define GOV_STALE_NS 1000000000ull /* counters frozen this long while "busy": stop believing them */
+
+DEVINL unsigned long long queue_signature(const vgpu_lim_host_t *H, uint32_t lane) {
+  unsigned long long s = 0;
+  for (uint32_t i = lane; i < VGPU_STREAM_SLOTS; i += 32) s += H->launched[i] * 3ull + H->done[i];
+  return warp_sum_u64(s);
+}
+
+extern "C" __global__ void __launch_bounds__(32)
+    vgpu_governor_kernel(vgpu_lim_dev_t *D, vgpu_lim_host_t *H, uint32_t interval_us, uint32_t period_us,
+                         uint32_t idle_exit_us) {
+  const uint32_t lane = threadIdx.x;
+  const uint64_t period_ns = (uint64_t)(period_us ? period_us : 1u) * 1000ull, idle_ns = (uint64_t)idle_exit_us * 1000ull;
+  uint64_t now = globaltimer_ns();
+
+  if (lane == 0) {
+    uint64_t left = D->gov_left_ns, lc = D->last_ctl_ns;
+    if (lc == 0 || now < lc || left == 0 || now < left || left < lc) {
+      D->last_ctl_ns = now; /* first incarnation (or a timer discontinuity): start a fresh period */
+    } else {
+      const bool was_busy = D->gov_left_busy != 0;
+      uint64_t t = left; /* accounted up to here */
+      uint32_t steps = 0;
+      while (now - lc >= period_ns && steps < GOV_MAX_CATCHUP) {
+        uint64_t end = lc + period_ns;
+        D->total_samples += end - t;
+        if (was_busy) D->busy_samples += end - t;
+        period_end(D, H, D->sm_num, 0, 0);
+        t = lc = end;
+        steps++;
+      }
+      if (now - lc >= period_ns) { /* away for longer than we are willing to replay */
+        lc = now - (now - lc) % period_ns;
+        t = lc;
+      }
+      D->total_samples += now - t;
+      if (was_busy) D->busy_samples += now - t;
+      D->last_ctl_ns = lc;
     }
-    user = D->blk_reading;
-  } else {
-    D->util_hist[D->util_hist_pos & 15] = user;
-    D->util_hist_pos++;
-    uint32_t have = D->util_hist_pos < W ? D->util_hist_pos : W;
-    int acc = 0;
-    for (uint32_t i = 0; i < have; i++) acc += D->util_hist[(D->util_hist_pos - 1 - i) & 15];
-    user = acc / (int)have;
+    D->gov_left_ns = 0;
+    D->gov_left_busy = 0;
+    H->gov_left_busy = 0;
   }
-  int ov = H->ext_user_override;
-  if (ov >= 0) user = ov;
-  int others = H->ext_sys_current;
-  int sys = user + (others > 0 ? others : 0);
-  int nproc = H->ext_sys_process_num;
-  if (nproc <= 0) nproc = 1;
-  ctl_step(D, H, user, sys, (ts > 0 || ov >= 0) ? 1 : 0, nproc);
+  __syncwarp();
+
+  uint64_t prev = now, last_change = now;
+  unsigned long long sig = __shfl_sync(0xffffffffu, queue_signature(H, lane), 0);
+  unsigned long long busy = 0, total = 0;
+
+  for (;;) {
+    now = globaltimer_ns();
+    const uint64_t dt = now - prev;
+    prev = now;
+    /* queue state: executing / parked behind the gate / anything outstanding at all */
+    bool running = false, parked = false, outstanding = false;
+    long long granted = *reinterpret_cast<volatile long long *>(&D->granted);
+    for (uint32_t s = lane; s < VGPU_STREAM_SLOTS; s += 32) {
+      /* done first, launched second: a completion racing the two reads can then only make the
+       * stream look busy a moment longer, never idle while work is queued */
+      unsigned long long d = H->done[s];
+      unsigned long long l = H->launched[s];
+      if (l > d) {
+        outstanding = true;
+        long long tk = H->ticket[s][(d + 1) & (VGPU_TICKET_RING - 1)];
+        if (granted - tk >= 0) running = true;
+        /* the newest launch of a slot holds its largest ticket: if even that one is admitted
+         * nothing of this slot is parked */
+        long long tl = H->ticket[s][l & (VGPU_TICKET_RING - 1)];
+        if (granted - tl < 0) parked = true;
+      }
+    }
+    running = __any_sync(0xffffffffu, running);
+    parked = __any_sync(0xffffffffu, parked);
+    outstanding = __any_sync(0xffffffffu, outstanding);
+    total += dt;
+    busy += running ? dt : 0;
+    unsigned long long sig_now = __shfl_sync(0xffffffffu, queue_signature(H, lane), 0);
+    if (sig_now != sig) { sig = sig_now; last_change = now; }
+
+    /* control period */
+    int stepped = 0;
+    if (lane == 0 && now - D->last_ctl_ns >= period_ns) {
+      D->last_ctl_ns = now;
+      D->busy_samples += busy;
+      D->total_samples += total;
+      period_end(D, H, D->sm_num, 0, 0);
+      stepped = 1;
+    }
+    if (__shfl_sync(0xffffffffu, stepped, 0)) { busy = 0; total = 0; }
+
+    /* retire? */
+    const uint32_t quit = H->quit;
+    const bool frozen = (now - last_change) > GOV_STALE_NS;
+    bool want_exit = quit ? !parked : (!outstanding && (now - last_change) > idle_ns);
+    if (frozen && !parked) want_exit = true;
+    if (__any_sync(0xffffffffu, want_exit)) {
+      int leave = 0;
+      if (lane == 0) {
+        *reinterpret_cast<volatile uint32_t *>(&H->ctl_state) = 2u;
+        __threadfence_system();
+      }
+      __syncwarp();
+      unsigned long long sig_check = __shfl_sync(0xffffffffu, queue_signature(H, lane), 0);
+      if (lane == 0) {
+        if (sig_check != sig && !quit) {
+          *reinterpret_cast<volatile uint32_t *>(&H->ctl_state) = 1u; /* new work raced in: stay */
+          __threadfence_system();
+        } else {
+          D->busy_samples += busy; /* the partial period is continued by the next incarnation */
+          D->total_samples += total;
+          D->gov_left_ns = now;
+          D->gov_left_busy = (running && !frozen) ? 1u : 0u;
+          H->gov_left_busy = D->gov_left_busy;
+          __threadfence_system();
+          *reinterpret_cast<volatile uint32_t *>(&H->ctl_state) = 0u;
+          __threadfence_system();
+          leave = 1;
+        }
+      }
+      if (__shfl_sync(0xffffffffu, leave, 0)) return;
+      sig = sig_check;
+      last_change = now;
+    }
+    __nanosleep(interval_us * 1000u);
+  }
 }
 
 /* ======================================================================= gate

@@ -12,18 +12,21 @@
  * B200 design:
  *   bucket   = granted - consumed.  `consumed` is host-owned (pinned page, one fetch_add per
  *              launch); `granted` is device-owned (HBM word + host-visible mirror), written only
- *              by the controller that runs at the tail of the sampler kernel.  The hook reads
- *              the mirror with a single 8-byte load.
+ *              by the controller.  The hook reads the mirror with a single 8-byte load.
  *   gate     = when the bucket is empty the launch is NOT delayed on the CPU: a
  *              cuStreamWaitValue64(granted >= ticket) is enqueued in front of it, so the stream
- *              itself waits on the HBM word and the host thread keeps going.  (Contexts without
- *              64-bit stream mem-ops use vgpu_gate_kernel, a one-thread device spin.)
- *   markers  = after each launch a cuStreamWriteValue64 bumps the stream's `done` sequence;
- *              the sampler compares it with `launched` to measure how long tenant work is
- *              actually resident (the NVML notion of utilisation) without NVML.
- *   tick     = one light thread per process launches vgpu_sampler_kernel every 10 ms
- *              (TIME_TICK) on a private non-blocking stream; every 8th launch the kernel's last
- *              CTA runs the controller (the reference's ~80 ms control period).
+ *              itself waits on the HBM word.  (Contexts without 64-bit stream mem-ops use
+ *              vgpu_gate_kernel, a one-thread device spin.)
+ *   markers  = behind launches a cuStreamWriteValue64 bumps the stream's `done` sequence; the
+ *              governor compares it with `launched` to measure how long tenant work is resident
+ *              (the NVML notion of utilisation) without NVML.
+ *   governor = vgpu_governor_kernel, one warp that stays resident while the tenant has work
+ *              queued or parked: it samples the queues every 50 us and runs the controller every
+ *              80 ms (the reference's control period), so parked streams are released by the
+ *              device itself.  The launch hook (re)starts it when needed; it retires when idle.
+ *   tick     = one light thread per process for housekeeping that is allowed to block: settling
+ *              unmarked launch-train tails, the once-per-second process count, and (only when
+ *              VGPU_B200_UTIL_SOURCE asks for it) the per-SM probe sampler.
  */
 #include "vgpu_internal.h"
 
@@ -80,6 +83,7 @@ static inline uint32_t slot_of(int host_index, CUstream s, int ptsz) {
 static pthread_once_t g_tick_once = PTHREAD_ONCE_INIT;
 static volatile unsigned g_tick_epoch;
 static volatile int g_tick_devices[VGPU_MAX_DEVICES]; /* host indexes with a live runtime + core limit */
+static uint32_t g_gov_interval_us = 50, g_gov_period_us = 80000, g_gov_idle_us = 20000;
 static uint32_t g_window_us = 500, g_interval_us = 50, g_period_ticks = 8, g_tick_ms = 10;
 static volatile int g_sync_waiters; /* threads currently inside a device-wide synchronise */
 
@@ -162,7 +166,6 @@ static void settle_idle_streams(vgpu_dev_rt *rt, int h) {
 static void *tick_main(void *arg) {
   (void)arg;
   uint32_t epoch = 0;
-  int fails = 0;
   uint64_t rng = 0x9E3779B97F4A7C15ull ^ (uint64_t)getpid();
   for (;;) {
     /* One short sampler window per tick, at a uniformly random offset inside the tick: the
@@ -182,36 +185,23 @@ static void *tick_main(void *arg) {
       if (!rt) continue;
       if (R.cuCtxPushCurrent_v2(rt->ctx) != CUDA_SUCCESS) continue;
       settle_idle_streams(rt, h);
-      CUresult q = R.cuStreamQuery(rt->s_stream);
-      if (q != CUDA_SUCCESS && (epoch % 100) == 0)
-        VLOG(VL_VERBOSE, "limiter host %d: sampler stream not idle (%d: %s)", h, q, vgpu_cu_err(q));
-      if (q == CUDA_SUCCESS) {
-        rt->lim_h->quit = 0;
-        if ((epoch % 100) == 1) refresh_process_count(rt);
-        if ((epoch % 100) == 0 && vgpu_log_level() >= VL_VERBOSE) {
-          vgpu_lim_host_t *H = rt->lim_h;
-          VLOG(VL_VERBOSE, "limiter host %d: steps %llu user %d (queue %d sm %d) share %lld bucket %lld granted %lld consumed %lld "
-               "nproc %d slot0 launched %llu done %llu", h, (unsigned long long)H->steps, H->user_current, H->queue_busy_pct,
-               H->sm_active_pct, (long long)H->share_mirror, (long long)H->bucket_mirror, (long long)H->granted_mirror,
-               (long long)H->consumed, H->ext_sys_process_num, (unsigned long long)H->launched[0], (unsigned long long)H->done[0]);
-        }
-        uint32_t ep = epoch;
-        /* while a tenant thread waits for the device to go idle, keep the sampler's residency
-         * negligible so the wait is not stretched by it */
+      if ((epoch % 100) == 1) refresh_process_count(rt);
+      if ((epoch % 100) == 0 && vgpu_log_level() >= VL_VERBOSE) {
+        vgpu_lim_host_t *H = rt->lim_h;
+        VLOG(VL_VERBOSE, "limiter host %d: steps %llu user %d (queue %d sm %d) share %lld bucket %lld granted %lld consumed %lld "
+             "nproc %d governor %u slot0 launched %llu done %llu", h, (unsigned long long)H->steps, H->user_current,
+             H->queue_busy_pct, H->sm_active_pct, (long long)H->share_mirror, (long long)H->bucket_mirror,
+             (long long)H->granted_mirror, (long long)H->consumed, H->ext_sys_process_num, H->ctl_state,
+             (unsigned long long)H->launched[0], (unsigned long long)H->done[0]);
+      }
+      /* per-SM probe sampler: only when the controller is asked to look at SM activity */
+      if (rt->lim_h->util_source != 0 && R.cuStreamQuery(rt->p_stream) == CUDA_SUCCESS) {
+        uint32_t ep = epoch, never = VGPU_SAMPLER_PROBE_ONLY;
         uint32_t window = g_sync_waiters > 0 ? 200u : g_window_us;
-        void *params[] = {&rt->lim_d, &rt->lim_h_d, &window, &g_interval_us, &g_period_ticks, &ep};
+        void *params[] = {&rt->lim_d, &rt->lim_h_d, &window, &g_interval_us, &never, &ep};
         unsigned grid = rt->sm_num > 0 ? (unsigned)rt->sm_num : 148u;
-        CUresult r = R.cuLaunchKernel(rt->k_sampler, grid, 1, 1, 128, 1, 1, 0, rt->s_stream, params, NULL);
-        if (r == CUDA_SUCCESS) {
-          fails = 0;
+        if (R.cuLaunchKernel(rt->k_sampler, grid, 1, 1, 128, 1, 1, 0, rt->p_stream, params, NULL) == CUDA_SUCCESS)
           vgpu_metric_add(h, VM_SAMPLER_LAUNCHES, 1);
-        } else if (++fails == 100) {
-          /* fail open: never leave tenant streams parked on a bucket nobody refills */
-          VLOG(VL_ERROR, "sampler launch keeps failing (%d: %s); opening the gate", r, vgpu_cu_err(r));
-          long long open_val = (long long)1 << 60;
-          R.cuMemcpyHtoD_v2(rt->lim_d, &open_val, sizeof open_val);
-          rt->lim_h->granted_mirror = open_val;
-        }
       }
       CUcontext dummy;
       R.cuCtxPopCurrent_v2(&dummy);
@@ -227,6 +217,14 @@ static void *tick_main(void *arg) {
 static pthread_t g_tick_tid;
 static volatile int g_tick_running;
 static void tick_stop(void) {
+  /* retire every governor: the runtime is about to tear the context down */
+  for (int h = 0; h < VGPU_MAX_DEVICES; h++) {
+    vgpu_dev_rt *rt = vgpu_rt_peek(h);
+    if (!rt || !rt->lim_h) continue;
+    __sync_fetch_and_add(&rt->lim_h->quit, 1u);
+    struct timespec nap = {0, 100000};
+    for (int i = 0; i < 3000 && rt->lim_h->ctl_state != 0; i++) nanosleep(&nap, NULL);
+  }
   if (!g_tick_running || g_tick_epoch != vgpu_fork_epoch + 1) return;
   g_tick_epoch = 0; /* tick_main leaves its loop at the next check */
   struct timespec ts;
@@ -241,6 +239,9 @@ static void tick_start(void) {
   g_interval_us = env_u32("VGPU_B200_SAMPLER_INTERVAL_US", 50);
   g_period_ticks = env_u32("VGPU_B200_PERIOD_TICKS", 8);
   g_tick_ms = env_u32("VGPU_B200_TICK_MS", 10);
+  g_gov_interval_us = env_u32("VGPU_B200_GOVERNOR_INTERVAL_US", 50);
+  g_gov_period_us = env_u32("VGPU_B200_PERIOD_US", 80000);
+  g_gov_idle_us = env_u32("VGPU_B200_GOVERNOR_IDLE_US", 20000);
   if (!g_period_ticks) g_period_ticks = 1;
   if (!g_tick_ms) g_tick_ms = 1;
   g_tick_epoch = vgpu_fork_epoch + 1;
@@ -288,8 +289,76 @@ void vgpu_limiter_start(void) {
   }
 }
 
+/* ------------------------------------------------------------------ governor */
+
+/* Called by the launch hook after it has published its launch.  Dekker pair with the governor's
+ * retire protocol (kernels.cu): publish, fence, then look at the state. */
+static inline void governor_ensure(vgpu_dev_rt *rt, int h) {
+  vgpu_lim_host_t *H = rt->lim_h;
+  __sync_synchronize();
+  uint32_t st = H->ctl_state;
+  if (likely(st == 1)) return;
+  for (int spins = 0; st == 2 && spins < 200000; spins++) { /* leaving: its verdict takes microseconds */
+    __builtin_ia32_pause();
+    st = H->ctl_state;
+  }
+  if (st == 1) return;
+  if (!__sync_bool_compare_and_swap(&H->ctl_state, st, 1u)) return; /* another thread is starting it */
+  CUcontext cur = NULL;
+  int pushed = 0;
+  if (R.cuCtxGetCurrent(&cur) == CUDA_SUCCESS && cur != rt->ctx && R.cuCtxPushCurrent_v2(rt->ctx) == CUDA_SUCCESS) pushed = 1;
+  void *params[] = {&rt->lim_d, &rt->lim_h_d, &g_gov_interval_us, &g_gov_period_us, &g_gov_idle_us};
+  CUresult r = R.cuLaunchKernel(rt->k_governor, 1, 1, 1, 32, 1, 1, 0, rt->s_stream, params, NULL);
+  if (pushed) R.cuCtxPopCurrent_v2(&cur);
+  if (likely(r == CUDA_SUCCESS)) {
+    vgpu_metric_add(h, VM_SAMPLER_LAUNCHES, 1);
+  } else {
+    H->ctl_state = 0;
+    VLOG(VL_ERROR, "governor launch failed (%d: %s); launches stay un-gated until it succeeds", r, vgpu_cu_err(r));
+    rt->memops64 = -1; /* no gate without a governor */
+  }
+}
+
+/* Bracket around a driver call that synchronises the whole device (it would otherwise wait for
+ * the resident governor).  begin: give every launch train its completion marker so the queue
+ * state the governor sees is exact, then announce the synchronise; the governor leaves as soon as
+ * nothing is parked.  end: withdraw the announcement and bring the governor back if tenant work
+ * is (or was, when it left) still executing, so that the time it was away is attributed. */
+static __thread unsigned long long t_sync_snap[VGPU_STREAM_SLOTS];
+static inline void enqueue_marker(vgpu_dev_rt *rt, int h, uint32_t slot, unsigned long long seq, CUstream s, int ptsz);
+
 void vgpu_limiter_quiesce(vgpu_dev_rt *rt) {
-  if (rt && rt->lim_h && g_tick_devices[rt->host_index >= 0 ? rt->host_index : 0]) rt->lim_h->quit = 1;
+  if (!rt || !rt->lim_h) return;
+  vgpu_lim_host_t *H = rt->lim_h;
+  int h = rt->host_index;
+  if (h >= 0 && g_tick_devices[h]) {
+    for (uint32_t i = 0; i < VGPU_STREAM_SLOTS; i++) {
+      slot_t *sl = &g_slots[h][i];
+      unsigned long long l = H->launched[i];
+      t_sync_snap[i] = l;
+      if (!sl->key || l <= H->done[i] || sl->marked >= l || rt->memops64 <= 0) continue;
+      if (i == VGPU_STREAM_SLOTS - 1 || (sl->ptsz && !sl->stream)) continue; /* marked per launch already */
+      enqueue_marker(rt, h, i, l, sl->stream, sl->ptsz);
+    }
+  }
+  __sync_fetch_and_add(&H->quit, 1u);
+}
+
+void vgpu_limiter_resume(vgpu_dev_rt *rt, int everything_completed) {
+  if (!rt || !rt->lim_h) return;
+  vgpu_lim_host_t *H = rt->lim_h;
+  int h = rt->host_index;
+  __sync_fetch_and_sub(&H->quit, 1u);
+  if (h < 0 || !g_tick_devices[h]) return;
+  int outstanding = 0;
+  for (uint32_t i = 0; i < VGPU_STREAM_SLOTS; i++) {
+    if (everything_completed) { /* whatever had been launched before the call has finished */
+      unsigned long long d;
+      while ((d = H->done[i]) < t_sync_snap[i] && !__sync_bool_compare_and_swap(&H->done[i], d, t_sync_snap[i])) {}
+    }
+    if (H->launched[i] > H->done[i]) outstanding = 1;
+  }
+  if (outstanding || H->gov_left_busy) governor_ensure(rt, h);
 }
 
 /* ------------------------------------------------------------------ admission */
@@ -359,7 +428,8 @@ static inline int admit(admit_t *a, unsigned gx, unsigned gy, unsigned gz, CUstr
   H->ticket[a->slot][seq & (VGPU_TICKET_RING - 1)] = ticket;
   __atomic_store_n(&H->launched[a->slot], seq, __ATOMIC_RELEASE); /* ticket first, then the sequence */
   a->seq = seq;
-  if (H->granted_mirror - ticket < 0) {
+  governor_ensure(rt, h);
+  if (H->granted_mirror - ticket < 0 && rt->memops64 >= 0) {
     /* bucket empty: park the *stream* on the HBM word, not the CPU thread */
     vgpu_metric_add(h, VM_RATE_GATED, 1);
     /* Bounded run-ahead.  A parked stream must never be allowed to fill the driver's hardware
@@ -373,13 +443,13 @@ static inline int admit(admit_t *a, unsigned gx, unsigned gy, unsigned gz, CUstr
       for (int spins = 0; seq - H->done[a->slot] > GATED_RUNAHEAD && H->granted_mirror - ticket < 0; spins++) {
         if (spins < 64) sched_yield();
         else nanosleep(&nap, NULL);
-        if (unlikely(!rt->memops64)) break;
+        if (unlikely(rt->memops64 <= 0)) break;
       }
     }
     /* make the sampler's view exact at the gate: everything before this launch gets its marker
      * now, so the oldest unfinished launch it will see is this (parked) one */
-    if (likely(rt->memops64) && g_slots[h][a->slot].marked < seq - 1) enqueue_marker(rt, h, a->slot, seq - 1, s, ptsz);
-    if (likely(rt->memops64)) {
+    if (likely(rt->memops64 > 0) && g_slots[h][a->slot].marked < seq - 1) enqueue_marker(rt, h, a->slot, seq - 1, s, ptsz);
+    if (likely(rt->memops64 > 0)) {
       CUresult (*wait)(CUstream, CUdeviceptr, cuuint64_t, unsigned) =
           (ptsz && R.cuStreamWaitValue64_v2_ptsz) ? R.cuStreamWaitValue64_v2_ptsz : R.cuStreamWaitValue64_v2;
       CUresult wr = wait(s, rt->lim_d + offsetof(vgpu_lim_dev_t, granted), (cuuint64_t)ticket, VCU_WAIT_GEQ);
@@ -388,7 +458,7 @@ static inline int admit(admit_t *a, unsigned gx, unsigned gy, unsigned gz, CUstr
         rt->memops64 = 0;
       }
     }
-    if (unlikely(!rt->memops64)) {
+    if (unlikely(rt->memops64 == 0)) {
       CUdeviceptr gp = rt->lim_d + offsetof(vgpu_lim_dev_t, granted);
       uint32_t timeout_ms = 2000;
       void *params[] = {&gp, &ticket, &timeout_ms};
@@ -406,7 +476,7 @@ static inline void mark_done(const admit_t *a, CUstream s) {
   vgpu_dev_rt *rt = a->rt;
   int h = rt->host_index;
   slot_t *sl = &g_slots[h][a->slot];
-  if (likely(rt->memops64)) {
+  if (likely(rt->memops64 > 0)) {
     /* a completion marker costs a driver call (~3 us): dense trains share one per MARK_EVERY
      * launches, isolated launches and the overflow slot get their own */
     unsigned long long now = rdtsc();
@@ -414,7 +484,7 @@ static inline void mark_done(const admit_t *a, CUstream s) {
     sl->last_tsc = now;
     if (sparse || a->seq - sl->marked >= MARK_EVERY || a->slot == VGPU_STREAM_SLOTS - 1 || (sl->ptsz && !sl->stream))
       enqueue_marker(rt, h, a->slot, a->seq, s, a->ptsz);
-    if (likely(rt->memops64)) return;
+    if (likely(rt->memops64 > 0)) return;
   }
   rt->lim_h->done[a->slot] = a->seq; /* no completion signal available: treat as instantaneous */
 }
@@ -490,18 +560,18 @@ VGPU_EXPORT CUresult cuFuncSetBlockShape(CUfunction f, int x, int y, int z) {
   return R.cuFuncSetBlockShape ? R.cuFuncSetBlockShape(f, x, y, z) : CUDA_ERROR_NOT_FOUND;
 }
 
-/* B200 addition: a device-wide synchronise must not wait out the sampler's residency window */
+/* B200 addition: a device-wide synchronise must not wait for the resident governor */
 VGPU_EXPORT CUresult cuCtxSynchronize(void) {
   vgpu_boot();
   if (unlikely(!R.cuCtxSynchronize)) return CUDA_ERROR_NOT_FOUND;
   CUdevice dev;
-  if (R.cuCtxGetDevice && R.cuCtxGetDevice(&dev) == CUDA_SUCCESS) {
-    vgpu_dev_rt *rt = vgpu_rt_peek(vgpu_host_index_of_cuda(dev));
-    if (rt) vgpu_limiter_quiesce(rt);
-  }
+  vgpu_dev_rt *rt = NULL;
+  if (R.cuCtxGetDevice && R.cuCtxGetDevice(&dev) == CUDA_SUCCESS) rt = vgpu_rt_peek(vgpu_host_index_of_cuda(dev));
+  vgpu_limiter_quiesce(rt);
   __sync_fetch_and_add(&g_sync_waiters, 1);
   CUresult r = R.cuCtxSynchronize();
   __sync_fetch_and_sub(&g_sync_waiters, 1);
+  vgpu_limiter_resume(rt, r == CUDA_SUCCESS);
   return r;
 }
 

@@ -436,11 +436,12 @@ static CUresult free_sync(CUdeviceptr dptr) {
   if (unlikely(!G_cfg)) vgpu_boot();
   CUresult r = R.cuCtxGetDevice ? R.cuCtxGetDevice(&dev) : CUDA_ERROR_NOT_FOUND;
   if (r != CUDA_SUCCESS) return r;
-  /* cuMemFree synchronises the device: do not let a resident sampler stretch that */
+  /* cuMemFree synchronises the device: it must not wait for the resident governor */
   vgpu_dev_rt *rt = vgpu_rt_peek(vgpu_host_index_of_cuda(dev));
   if (rt) vgpu_limiter_quiesce(rt);
   if (rt && scrub_on_free()) scrub(rt, dptr);
   r = R.cuMemFree_v2 ? R.cuMemFree_v2(dptr) : R.cuMemFree ? R.cuMemFree(dptr) : CUDA_ERROR_NOT_FOUND;
+  if (rt) vgpu_limiter_resume(rt, 0);
   if (r == CUDA_SUCCESS) ledger_sub(dev, dptr);
   return r;
 }

@@ -203,9 +203,10 @@ typedef struct vgpu_dev_rt {
   CUdevice cuda_dev;
   CUcontext ctx;
   CUmodule mod;
-  CUfunction k_clear, k_spill, k_copy_generic, k_quota, k_slab_insert, k_slab_remove, k_controller, k_sampler, k_gate;
+  CUfunction k_clear, k_spill, k_copy_generic, k_quota, k_slab_insert, k_slab_remove, k_controller, k_sampler, k_gate, k_governor;
   CUstream q_stream; /* quota / ledger kernels (app thread)     */
-  CUstream s_stream; /* sampler + controller (timer thread)     */
+  CUstream s_stream; /* the resident governor                    */
+  CUstream p_stream; /* per-SM probe sampler (tick thread)      */
   /* pinned, mapped blocks */
   vgpu_quota_req_t *q_req;  CUdeviceptr q_req_d;
   vgpu_quota_res_t *q_res;  CUdeviceptr q_res_d;
@@ -238,7 +239,8 @@ CUresult vgpu_rt_spill(vgpu_dev_rt *rt, CUdeviceptr dst, CUdeviceptr src, size_t
 
 /* limiter.c */
 void vgpu_limiter_start(void); /* == reference initialization() (cuda_hook.c:566) */
-void vgpu_limiter_quiesce(vgpu_dev_rt *rt); /* ask a resident sampler to leave (sync paths) */
+void vgpu_limiter_quiesce(vgpu_dev_rt *rt); /* device-wide sync ahead: governor retires once nothing is parked */
+void vgpu_limiter_resume(vgpu_dev_rt *rt, int everything_completed); /* the sync returned */
 
 /* metrics.c */
 enum { VM_RATE_GATED, VM_RATE_FAST, VM_OOM_LIMIT, VM_OOM_DRIVER, VM_UVA_FALLBACK, VM_LOCK_TIMEOUT,

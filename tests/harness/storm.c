@@ -192,13 +192,13 @@ int main(int argc, char **argv) {
   printf("{\"launches\": %ld, \"steps\": %d, \"per_step\": %ld, \"threads\": %d, \"wall_s\": %.6f, \"host_s\": %.6f, "
          "\"device_s\": %.6f, \"launches_per_s\": %.1f, \"host_launches_per_s\": %.1f, \"p50_ns\": %u, \"p90_ns\": %u, "
          "\"p99_ns\": %u, \"p999_ns\": %u, \"max_ns\": %u, \"mean_ns\": %.1f, \"fails\": %ld, \"init_s\": %.4f, "
-         "\"truncated\": %d, \"sampler_launches\": %llu, \"gated_launches\": %llu, \"limiter\": {\"present\": %d, "
+         "\"truncated\": %d, \"sampler_launches\": %llu, \"gated_launches\": %llu, \"watchdog_loans\": %llu, \"limiter\": {\"present\": %d, "
          "\"user_current\": %d, \"queue_busy_pct\": %d, \"sm_active_pct\": %d, \"share\": %lld, \"bucket\": %lld, "
          "\"control_steps\": %llu}, \"step_wall_s\": [",
          total_done, steps_run, g_per_step, g_threads, timed_wall, timed_host, dev_total, total_done / timed_wall,
          total_done / timed_host, all[nall / 2], all[(size_t)(nall * 0.9)], all[(size_t)(nall * 0.99)],
          all[(size_t)(nall * 0.999)], all[nall - 1], (double)sum / nall, fails, (t_init1 - t_init0) * 1e-9, (int)g_stop,
-         metric ? metric(host_index, 7) : 0ull, metric ? metric(host_index, 0) : 0ull, have_ls, ls.user_current,
+         metric ? metric(host_index, 7) : 0ull, metric ? metric(host_index, 0) : 0ull, metric ? metric(host_index, 9) : 0ull, have_ls, ls.user_current,
          ls.queue_busy_pct, ls.sm_active_pct, ls.share, ls.granted - ls.consumed, ls.steps);
   for (int s = 0; s < steps_run; s++) printf("%s%.6f", s ? ", " : "", step_wall[s]);
   printf("]}\n");

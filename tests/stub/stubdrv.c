@@ -317,7 +317,24 @@ EXPORT CUresult cuMemcpyHtoD_v2(CUdeviceptr dst, const void *src, size_t n) { me
 /* STUB_CTX_LOCK=1 models the real driver's context lock: a call that blocks on the stream (here
  * the wait itself, on a real GPU e.g. a pageable memcpy behind a parked kernel) keeps every other
  * thread out of the driver - in particular out of cuLaunchKernel. */
-static pthread_mutex_t g_ctx_mu = PTHREAD_MUTEX_INITIALIZER;
+/* FIFO (ticket) lock: a plain pthread mutex lets the releasing thread re-acquire it at once and
+ * would starve the library's tick thread for ever, which is a property of the model, not of
+ * the thing modelled */
+static pthread_mutex_t g_ctx_m = PTHREAD_MUTEX_INITIALIZER;
+static pthread_cond_t g_ctx_c = PTHREAD_COND_INITIALIZER;
+static unsigned long g_ctx_next, g_ctx_serving;
+static void ctx_lock(void) {
+  pthread_mutex_lock(&g_ctx_m);
+  unsigned long my = g_ctx_next++;
+  while (my != g_ctx_serving) pthread_cond_wait(&g_ctx_c, &g_ctx_m);
+  pthread_mutex_unlock(&g_ctx_m);
+}
+static void ctx_unlock(void) {
+  pthread_mutex_lock(&g_ctx_m);
+  g_ctx_serving++;
+  pthread_cond_broadcast(&g_ctx_c);
+  pthread_mutex_unlock(&g_ctx_m);
+}
 static int g_ctx_lock = -1;
 static CUresult wait64_unlocked(CUdeviceptr addr, unsigned long long value);
 static int ctx_lock_on(void) {
@@ -331,7 +348,7 @@ EXPORT CUresult cuStreamDestroy_v2(void *s) { (void)s; return 0; }
 EXPORT CUresult cuStreamSynchronize(void *s) { (void)s; return 0; }
 EXPORT CUresult cuStreamQuery(void *s) {
   (void)s;
-  if (ctx_lock_on()) { pthread_mutex_lock(&g_ctx_mu); pthread_mutex_unlock(&g_ctx_mu); }
+  if (ctx_lock_on()) { ctx_lock(); ctx_unlock(); }
   return 0;
 }
 EXPORT CUresult cuStreamIsCapturing(void *s, int *st) { (void)s; *st = 0; return 0; }
@@ -339,9 +356,9 @@ static volatile int g_parked; /* callers blocked behind the gate (the fake GPU's
 static CUresult wait64_unlocked(CUdeviceptr addr, unsigned long long value);
 static CUresult wait64(CUdeviceptr addr, unsigned long long value) {
   if (!ctx_lock_on()) return wait64_unlocked(addr, value);
-  pthread_mutex_lock(&g_ctx_mu);
+  ctx_lock();
   CUresult r = wait64_unlocked(addr, value);
-  pthread_mutex_unlock(&g_ctx_mu);
+  ctx_unlock();
   return r;
 }
 static CUresult wait64_unlocked(CUdeviceptr addr, unsigned long long value) {
@@ -430,6 +447,11 @@ static void fake_ctl_step(vgpu_lim_dev_t *D, vgpu_lim_host_t *H, int user, int s
   orc_watcher_t w = {D->share, D->sys_free, D->avg_sys_free, D->ctr_i, D->pre_sys_process_num, D->up_limit, 0};
   if (valid) D->valid = 1;
   orc_util_t u = {user, sys, D->valid, nproc};
+  if (H->release_pending) {
+    long long fl = H->release_floor;
+    H->release_pending = 0;
+    if (fl - D->granted > 0) D->granted = fl;
+  }
   long long consumed = H->consumed;
   int64_t bucket = D->granted - consumed;
   orc_watcher_step(&g, &c, &w, &u, &bucket);
@@ -612,10 +634,10 @@ static CUresult launch(void *f, void **params) {
   if (!t_has_ctx) return 201;
   fn_t *fn = (fn_t *)f;
   int locked = ctx_lock_on();
-  if (locked) pthread_mutex_lock(&g_ctx_mu);
+  if (locked) ctx_lock();
   if (fn && ((uintptr_t)fn > 0x10000) && !strncmp(fn->name, "vgpu_", 5)) run_fake_kernel(fn->name, params);
   else note_launch();
-  if (locked) pthread_mutex_unlock(&g_ctx_mu);
+  if (locked) ctx_unlock();
   return 0;
 }
 EXPORT CUresult cuLaunchKernel(void *f, unsigned gx, unsigned gy, unsigned gz, unsigned bx, unsigned by, unsigned bz,

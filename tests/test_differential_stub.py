@@ -263,13 +263,18 @@ def test_refill_does_not_need_the_host_to_enter_the_driver(built):
     """Regression for a deadlock class seen with PyTorch on the real driver: a thread blocks inside
     a driver call (holding the context lock) behind a parked stream, so no other thread can launch
     the kernel that would refill the bucket.  STUB_CTX_LOCK=1 models that lock in the fake driver;
-    the resident governor must release the parked stream on its own."""
-    env = dict(BASE)
-    env.update({"CUDA_CORE_LIMIT_0": "10", "CUDA_MEM_LIMIT_0": "1g", "STUB_UTIL": "closed:0.02", "STUB_CTX_LOCK": "1"})
-    for threads in (1, 4):
-        new = _storm(H.NEW_SO, env, 300000, threads)
-        assert new["launches"] == 300000 and new["fails"] == 0
-        assert new["limiter"]["present"] == 1 and new["gated_launches"] > 0, new
+    the parked stream must be released without a host launch - by the watchdog's loan in the
+    default mode, by the resident governor in VGPU_B200_GOVERNOR=1 mode."""
+    for governor in ("0", "1"):
+        env = dict(BASE)
+        env.update({"CUDA_CORE_LIMIT_0": "10", "CUDA_MEM_LIMIT_0": "1g", "STUB_UTIL": "closed:0.02", "STUB_CTX_LOCK": "1",
+                    "VGPU_B200_GOVERNOR": governor})
+        for threads in (1, 4):
+            new = _storm(H.NEW_SO, env, 300000, threads)
+            assert new["launches"] == 300000 and new["fails"] == 0
+            assert new["limiter"]["present"] == 1 and new["gated_launches"] > 0, new
+            if governor == "0":  # the tick thread is locked out whenever a stream is parked: only loans release it
+                assert new["watchdog_loans"] > 0, new
 
 
 def test_directly_linked_tenant_is_intercepted_by_symbol_interposition(built):

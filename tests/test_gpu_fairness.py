@@ -59,3 +59,52 @@ def test_four_tenants_share_one_gpu(built):
     assert all(n > 0 for n in b["launches"])
     assert b["fairness_max_over_min"] < 3.0, b
     assert sum(b["gated"]) > 0, "the limiter never engaged under a 4 x 25 % load"
+
+
+def _tenant(lib, cap, seconds, mem="4g"):
+    sb = H.Sandbox()
+    extra = {"MANAGER_COMPATIBILITY_MODE": "0", "MANAGER_VISIBLE_DEVICES": gpu0_uuid(), "CUDA_MEM_LIMIT_0": mem,
+             "CUDA_VISIBLE_DEVICES": "0", "LOGGER_LEVEL": "1"}
+    if cap:
+        extra["CUDA_CORE_LIMIT_0"] = str(cap)
+    if lib:
+        env = H.preload_env(lib, sb, extra, stub=False)
+    else:
+        env = dict(os.environ, CUDA_VISIBLE_DEVICES="0")
+    p = subprocess.Popen([H.STORM, "--steps", "100000", "--warmup", "0", "--per-step", "200", "--spin-iters", "20000",
+                          "--grid", "592", "--block", "256", "--max-seconds", str(seconds)],
+                         env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    return p, sb
+
+
+def _finish(p, sb, seconds):
+    out, err = p.communicate(timeout=seconds * 6 + 60)
+    sb.cleanup()
+    assert p.returncode == 0, err[-2000:]
+    return json.loads(out.strip().splitlines()[-1])
+
+
+def test_throttled_tenant_leaves_the_gpu_to_its_neighbour(built):
+    """Noisy-neighbour shape: tenant A is capped at 10 % and saturates its cap, tenant B is not
+    capped.  What matters to B is how much of the GPU A really gives back while it is throttled.
+    Measured for both libraries on A's side; B runs without any library."""
+    seconds = 8.0
+    report = {}
+    p, sb = _tenant(None, 0, seconds)
+    alone = _finish(p, sb, seconds)
+    report["neighbour_alone_per_s"] = alone["launches"] / alone["wall_s"]
+    for name, lib in (("b200", H.NEW_SO), ("reference", H.REF_SO)):
+        if not os.path.exists(lib):
+            continue
+        pa, sa = _tenant(lib, 10, seconds + 2.0)
+        time.sleep(1.0)  # A reaches its throttled regime first
+        pb, sbb = _tenant(None, 0, seconds)
+        b = _finish(pb, sbb, seconds)
+        a = _finish(pa, sa, seconds)
+        report[name] = {"capped_tenant_per_s": a["launches"] / a["wall_s"], "neighbour_per_s": b["launches"] / b["wall_s"],
+                        "neighbour_vs_alone": (b["launches"] / b["wall_s"]) / report["neighbour_alone_per_s"],
+                        "capped_gated": a.get("gated_launches", 0)}
+    os.makedirs(os.path.join(H.ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(H.ROOT, "gpurun_out", "neighbour_r1.json"), "w") as f:
+        json.dump(report, f, indent=1)
+    assert report["b200"]["neighbour_per_s"] > 0 and report["b200"]["capped_tenant_per_s"] > 0

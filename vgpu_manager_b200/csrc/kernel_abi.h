@@ -157,6 +157,9 @@ typedef struct {
   volatile uint32_t util_window;      /* periods averaged into user_current (1..16)            */
   volatile uint32_t util_mode;        /* 0 moving average, 1 tumbling block (NVML-like sampling) */
   volatile uint32_t ctl_state;        /* governor: 0 not resident, 1 resident (or being launched), 2 leaving */
+  volatile uint32_t release_pending;  /* watchdog lent tokens: fold release_floor into granted at the next step */
+  volatile uint32_t _pad_r;
+  volatile long long release_floor;   /* ticket up to which the watchdog released parked launches */
   volatile unsigned long long launched[VGPU_STREAM_SLOTS]; /* per-slot launch sequence (host)   */
   /* per-slot completion markers, written by cuStreamWriteValue64 right after each launch */
   volatile unsigned long long done[VGPU_STREAM_SLOTS];

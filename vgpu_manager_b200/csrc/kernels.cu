@@ -487,6 +487,13 @@ DEVINL void ctl_step(vgpu_lim_dev_t *D, vgpu_lim_host_t *H, int user_current, in
   if (valid_now) D->valid = 1; /* sticky, like top_result->valid */
   D->last_user_current = user_current;
   D->last_sys_current = sys_current;
+  if (H->release_pending) {
+    /* the host watchdog lent tokens up to this ticket while no step could be launched: the
+     * launches it released have run, so the loan is part of `granted` from now on */
+    long long floor = H->release_floor;
+    H->release_pending = 0;
+    if (floor - D->granted > 0) D->granted = floor;
+  }
   long long consumed = consumed_admitted(H, D->granted);
   long long bucket = D->granted - consumed;
   bool touched = false;

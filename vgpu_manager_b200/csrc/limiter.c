@@ -18,15 +18,25 @@
  *              itself waits on the HBM word.  (Contexts without 64-bit stream mem-ops use
  *              vgpu_gate_kernel, a one-thread device spin.)
  *   markers  = behind launches a cuStreamWriteValue64 bumps the stream's `done` sequence; the
- *              governor compares it with `launched` to measure how long tenant work is resident
+ *              sampler compares it with `launched` to measure how long tenant work is resident
  *              (the NVML notion of utilisation) without NVML.
- *   governor = vgpu_governor_kernel, one warp that stays resident while the tenant has work
- *              queued or parked: it samples the queues every 50 us and runs the controller every
- *              80 ms (the reference's control period), so parked streams are released by the
- *              device itself.  The launch hook (re)starts it when needed; it retires when idle.
- *   tick     = one light thread per process for housekeeping that is allowed to block: settling
- *              unmarked launch-train tails, the once-per-second process count, and (only when
- *              VGPU_B200_UTIL_SOURCE asks for it) the per-SM probe sampler.
+ *   tick     = one light thread per process: every 10 ms it launches vgpu_sampler_kernel for a
+ *              0.5 ms window at a random offset (5 % residency - a resident kernel costs the
+ *              *other* tenants of a time-sliced GPU a full time slice, measured in
+ *              profiles/README.md); the last CTA of every 8th launch runs the controller.  It
+ *              also settles unmarked launch-train tails and refreshes the process count.
+ *   watchdog = a second thread that never enters the driver.  Some driver calls block while
+ *              holding the context lock (a pageable cuMemcpyDtoH behind a parked kernel is the
+ *              common one); the tick thread can then not launch the refill and the stream
+ *              would stay parked for ever.  The gate therefore waits on the *host-visible mirror*
+ *              of `granted`; when streams are parked and the controller has not stepped for two
+ *              periods the watchdog advances the mirror to the newest parked ticket (a loan:
+ *              the controller folds it into `granted` at its next step, so it is repaid).
+ *   governor = opt-in (VGPU_B200_GOVERNOR=1) alternative for GPUs that are not time-sliced with
+ *              other contexts: vgpu_governor_kernel, one warp that stays resident while the
+ *              tenant has work queued or parked, samples the queues every 50 us and runs the
+ *              controller every 80 ms - no host involvement in the refill at all.  The launch
+ *              hook (re)starts it; it retires when idle or ahead of a device-wide synchronise.
  */
 #include "vgpu_internal.h"
 
@@ -83,7 +93,8 @@ static inline uint32_t slot_of(int host_index, CUstream s, int ptsz) {
 static pthread_once_t g_tick_once = PTHREAD_ONCE_INIT;
 static volatile unsigned g_tick_epoch;
 static volatile int g_tick_devices[VGPU_MAX_DEVICES]; /* host indexes with a live runtime + core limit */
-static uint32_t g_gov_interval_us = 50, g_gov_period_us = 80000, g_gov_idle_us = 20000;
+static uint32_t g_gov_interval_us = 50, g_gov_period_us = 80000, g_gov_idle_us = 5000;
+static int g_governor_mode; /* VGPU_B200_GOVERNOR=1 */
 static uint32_t g_window_us = 500, g_interval_us = 50, g_period_ticks = 8, g_tick_ms = 10;
 static volatile int g_sync_waiters; /* threads currently inside a device-wide synchronise */
 
@@ -166,6 +177,7 @@ static void settle_idle_streams(vgpu_dev_rt *rt, int h) {
 static void *tick_main(void *arg) {
   (void)arg;
   uint32_t epoch = 0;
+  int fails = 0;
   uint64_t rng = 0x9E3779B97F4A7C15ull ^ (uint64_t)getpid();
   for (;;) {
     /* One short sampler window per tick, at a uniformly random offset inside the tick: the
@@ -194,14 +206,33 @@ static void *tick_main(void *arg) {
              (long long)H->granted_mirror, (long long)H->consumed, H->ext_sys_process_num, H->ctl_state,
              (unsigned long long)H->launched[0], (unsigned long long)H->done[0]);
       }
-      /* per-SM probe sampler: only when the controller is asked to look at SM activity */
-      if (rt->lim_h->util_source != 0 && R.cuStreamQuery(rt->p_stream) == CUDA_SUCCESS) {
-        uint32_t ep = epoch, never = VGPU_SAMPLER_PROBE_ONLY;
+      if (g_governor_mode) {
+        /* the governor owns the queue signal and the controller; the per-SM probe is only
+         * needed when the controller is asked to look at SM activity */
+        if (rt->lim_h->util_source != 0 && R.cuStreamQuery(rt->p_stream) == CUDA_SUCCESS) {
+          uint32_t ep = epoch, never = VGPU_SAMPLER_PROBE_ONLY;
+          void *params[] = {&rt->lim_d, &rt->lim_h_d, &g_window_us, &g_interval_us, &never, &ep};
+          unsigned grid = rt->sm_num > 0 ? (unsigned)rt->sm_num : 148u;
+          if (R.cuLaunchKernel(rt->k_sampler, grid, 1, 1, 128, 1, 1, 0, rt->p_stream, params, NULL) == CUDA_SUCCESS)
+            vgpu_metric_add(h, VM_SAMPLER_LAUNCHES, 1);
+        }
+      } else if (R.cuStreamQuery(rt->s_stream) == CUDA_SUCCESS) {
+        uint32_t ep = epoch;
+        /* while a tenant thread waits for the device to go idle, keep the sampler's residency
+         * negligible so the wait is not stretched by it */
         uint32_t window = g_sync_waiters > 0 ? 200u : g_window_us;
-        void *params[] = {&rt->lim_d, &rt->lim_h_d, &window, &g_interval_us, &never, &ep};
+        void *params[] = {&rt->lim_d, &rt->lim_h_d, &window, &g_interval_us, &g_period_ticks, &ep};
         unsigned grid = rt->sm_num > 0 ? (unsigned)rt->sm_num : 148u;
-        if (R.cuLaunchKernel(rt->k_sampler, grid, 1, 1, 128, 1, 1, 0, rt->p_stream, params, NULL) == CUDA_SUCCESS)
+        CUresult r = R.cuLaunchKernel(rt->k_sampler, grid, 1, 1, 128, 1, 1, 0, rt->s_stream, params, NULL);
+        if (r == CUDA_SUCCESS) {
+          fails = 0;
           vgpu_metric_add(h, VM_SAMPLER_LAUNCHES, 1);
+        } else if (++fails == 100) {
+          /* fail open: never leave tenant streams parked on a bucket nobody refills */
+          VLOG(VL_ERROR, "sampler launch keeps failing (%d: %s); opening the gate", r, vgpu_cu_err(r));
+          rt->memops64 = -1;
+          rt->lim_h->granted_mirror = (long long)1 << 60;
+        }
       }
       CUcontext dummy;
       R.cuCtxPopCurrent_v2(&dummy);
@@ -209,6 +240,60 @@ static void *tick_main(void *arg) {
     uint64_t after = tick_ns - before;
     struct timespec rest = {(time_t)(after / 1000000000ull), (long)(after % 1000000000ull)};
     nanosleep(&rest, NULL);
+  }
+}
+
+/* ------------------------------------------------------------------ watchdog
+ * Never calls into the driver, so nothing can lock it out.  Condition for a loan: some stream is
+ * parked (its newest launch is not admitted) and the controller's step counter has not moved
+ * for g_watchdog_ms.  The loan is the newest parked ticket: everything queued behind the gate
+ * (at most GATED_RUNAHEAD launches per stream) is released at once, which is what the blocked
+ * driver call is waiting for. */
+static uint32_t g_watchdog_ms = 170;
+static pthread_t g_wd_tid;
+static volatile int g_wd_running;
+static void *watchdog_main(void *arg) {
+  (void)arg;
+  unsigned long long seen_steps[VGPU_MAX_DEVICES] = {0};
+  uint32_t stalled_ms[VGPU_MAX_DEVICES] = {0};
+  const uint32_t step_ms = 10;
+  for (;;) {
+    struct timespec nap = {0, (long)step_ms * 1000000L};
+    nanosleep(&nap, NULL);
+    if (g_tick_epoch != vgpu_fork_epoch + 1) return NULL;
+    for (int h = 0; h < VGPU_MAX_DEVICES; h++) {
+      if (!g_tick_devices[h]) continue;
+      vgpu_dev_rt *rt = vgpu_rt_peek(h);
+      if (!rt || rt->memops64 < 0) continue;
+      vgpu_lim_host_t *H = rt->lim_h;
+      long long granted = H->granted_mirror, newest = 0;
+      int parked = 0;
+      for (uint32_t i = 0; i < VGPU_STREAM_SLOTS; i++) {
+        unsigned long long d = H->done[i], l = H->launched[i];
+        if (l <= d) continue;
+        long long tl = H->ticket[i][l & (VGPU_TICKET_RING - 1)];
+        if (granted - tl < 0) {
+          if (!parked || tl - newest > 0) newest = tl;
+          parked = 1;
+        }
+      }
+      unsigned long long st = H->steps;
+      if (!parked || st != seen_steps[h]) {
+        seen_steps[h] = st;
+        stalled_ms[h] = 0;
+        continue;
+      }
+      stalled_ms[h] += step_ms;
+      if (stalled_ms[h] < g_watchdog_ms) continue;
+      stalled_ms[h] = 0;
+      H->release_floor = newest;
+      __sync_synchronize();
+      H->release_pending = 1;
+      if (newest - H->granted_mirror > 0) H->granted_mirror = newest;
+      vgpu_metric_add(h, VM_WATCHDOG_LOANS, 1);
+      VLOG(VL_WARNING, "host device %d: controller has not stepped for %u ms while streams are parked "
+                       "(driver busy?); lent tokens up to ticket %lld", h, g_watchdog_ms, newest);
+    }
   }
 }
 
@@ -232,6 +317,10 @@ static void tick_stop(void) {
   ts.tv_sec += 1;
   pthread_timedjoin_np(g_tick_tid, NULL, &ts);
   g_tick_running = 0;
+  if (g_wd_running) {
+    pthread_timedjoin_np(g_wd_tid, NULL, &ts);
+    g_wd_running = 0;
+  }
 }
 
 static void tick_start(void) {
@@ -241,7 +330,9 @@ static void tick_start(void) {
   g_tick_ms = env_u32("VGPU_B200_TICK_MS", 10);
   g_gov_interval_us = env_u32("VGPU_B200_GOVERNOR_INTERVAL_US", 50);
   g_gov_period_us = env_u32("VGPU_B200_PERIOD_US", 80000);
-  g_gov_idle_us = env_u32("VGPU_B200_GOVERNOR_IDLE_US", 20000);
+  g_gov_idle_us = env_u32("VGPU_B200_GOVERNOR_IDLE_US", 5000);
+  g_governor_mode = env_u32("VGPU_B200_GOVERNOR", 0) != 0;
+  g_watchdog_ms = env_u32("VGPU_B200_WATCHDOG_MS", 170);
   if (!g_period_ticks) g_period_ticks = 1;
   if (!g_tick_ms) g_tick_ms = 1;
   g_tick_epoch = vgpu_fork_epoch + 1;
@@ -249,6 +340,10 @@ static void tick_start(void) {
     pthread_setname_np(g_tick_tid, "vgpu_b200_tick");
     g_tick_running = 1;
     atexit(tick_stop);
+  }
+  if (pthread_create(&g_wd_tid, NULL, watchdog_main, NULL) == 0) {
+    pthread_setname_np(g_wd_tid, "vgpu_b200_wdog");
+    g_wd_running = 1;
   }
 }
 
@@ -358,7 +453,7 @@ void vgpu_limiter_resume(vgpu_dev_rt *rt, int everything_completed) {
     }
     if (H->launched[i] > H->done[i]) outstanding = 1;
   }
-  if (outstanding || H->gov_left_busy) governor_ensure(rt, h);
+  if (g_governor_mode && (outstanding || H->gov_left_busy)) governor_ensure(rt, h);
 }
 
 /* ------------------------------------------------------------------ admission */
@@ -428,9 +523,10 @@ static inline int admit(admit_t *a, unsigned gx, unsigned gy, unsigned gz, CUstr
   H->ticket[a->slot][seq & (VGPU_TICKET_RING - 1)] = ticket;
   __atomic_store_n(&H->launched[a->slot], seq, __ATOMIC_RELEASE); /* ticket first, then the sequence */
   a->seq = seq;
-  governor_ensure(rt, h);
+  if (unlikely(g_governor_mode)) governor_ensure(rt, h);
   if (H->granted_mirror - ticket < 0 && rt->memops64 >= 0) {
-    /* bucket empty: park the *stream* on the HBM word, not the CPU thread */
+    /* bucket empty: park the *stream* on the bucket word (its host-visible mirror, so that the
+     * watchdog can lend tokens without the driver), not the CPU thread */
     vgpu_metric_add(h, VM_RATE_GATED, 1);
     /* Bounded run-ahead.  A parked stream must never be allowed to fill the driver's hardware
      * queue: a launch call that blocks inside the driver for queue space holds the context lock,
@@ -452,14 +548,14 @@ static inline int admit(admit_t *a, unsigned gx, unsigned gy, unsigned gz, CUstr
     if (likely(rt->memops64 > 0)) {
       CUresult (*wait)(CUstream, CUdeviceptr, cuuint64_t, unsigned) =
           (ptsz && R.cuStreamWaitValue64_v2_ptsz) ? R.cuStreamWaitValue64_v2_ptsz : R.cuStreamWaitValue64_v2;
-      CUresult wr = wait(s, rt->lim_d + offsetof(vgpu_lim_dev_t, granted), (cuuint64_t)ticket, VCU_WAIT_GEQ);
+      CUresult wr = wait(s, rt->lim_h_d + offsetof(vgpu_lim_host_t, granted_mirror), (cuuint64_t)ticket, VCU_WAIT_GEQ);
       if (unlikely(wr != CUDA_SUCCESS)) {
         VLOG(VL_ERROR, "cuStreamWaitValue64 failed (%d: %s); falling back to the gate kernel", wr, vgpu_cu_err(wr));
         rt->memops64 = 0;
       }
     }
     if (unlikely(rt->memops64 == 0)) {
-      CUdeviceptr gp = rt->lim_d + offsetof(vgpu_lim_dev_t, granted);
+      CUdeviceptr gp = rt->lim_h_d + offsetof(vgpu_lim_host_t, granted_mirror);
       uint32_t timeout_ms = 2000;
       void *params[] = {&gp, &ticket, &timeout_ms};
       (ptsz && R.cuLaunchKernel_ptsz ? R.cuLaunchKernel_ptsz : R.cuLaunchKernel)(

@@ -8,7 +8,7 @@
 static volatile uint64_t g_counters[VGPU_MAX_DEVICES][VM_COUNT];
 static const char *g_names[VM_COUNT] = {"rate_gated",   "rate_fast",     "oom_total_limit", "oom_driver_return",
                                         "uva_fallback", "lock_timeout",  "quota_kernels",   "sampler_launches",
-                                        "scrubbed_bytes"};
+                                        "scrubbed_bytes", "watchdog_loans"};
 
 void vgpu_metric_add(int h, int which, uint64_t v) {
   if (h < 0 || h >= VGPU_MAX_DEVICES || which < 0 || which >= VM_COUNT) return;

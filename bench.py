@@ -12,10 +12,11 @@ device synchronise.
   value     intercepted launches / second over the K timed steps, all ranks (N tenants, one per
             GPU, weak scaling), timed on the device with CUDA events around each step, max over
             ranks (the limiter state - token bucket, sampler - is resident in HBM throughout).
-  e2e       the same launches divided by the tenant process's whole life as seen from outside
-            (exec, dlopen + hook bring-up, context creation, module load, storm, teardown);
-            host<->device bytes are what the hook itself moves over PCIe per launch
-            (ticket + launch sequence read by the sampler, completion marker written back).
+  e2e       the same K steps on the tenant's HOST clock (launch calls through the LD_PRELOADed
+            hook + the per-step device synchronise); host<->device bytes are what the hook itself
+            moves over PCIe per launch (ticket + launch sequence in pinned memory read by the
+            sampler, completion markers written back).  `tenant_process_life_s` additionally
+            reports the whole process life (exec, dlopen, bring-up, storm, teardown).
   roofline  the spill-copy kernel (TMA bulk HBM->HBM staging of spilled pages, the dominant
             device kernel of the memory path): algorithmic bytes 2 x 1 GiB per launch over the
             CUDA-event time on the launching stream, against MEASURED_PEAKS.json hbm_gbs.

@@ -15,10 +15,10 @@ run_storm() { # lib tag steps perstep maxsec extra-env...
 rm -f gpurun_out/util_trace.csv
 ( nvidia-smi --query-gpu=utilization.gpu --format=csv,noheader -lms 200 >> gpurun_out/util_trace.csv & echo $! > /tmp/smi.pid )
 NEW=vgpu_manager_b200/libvgpu-control.so; REF=oracle/_ref/libvgpu-control.so
-run_storm $NEW new_25_block12 100 200000 20 LOGGER_LEVEL=1 CUDA_CORE_LIMIT_0=25
+run_storm $NEW new_25 100 200000 20 LOGGER_LEVEL=1 CUDA_CORE_LIMIT_0=25
 run_storm $NEW new_25_avg1 100 200000 20 LOGGER_LEVEL=1 CUDA_CORE_LIMIT_0=25 VGPU_B200_UTIL_MODE=average VGPU_B200_UTIL_WINDOW_PERIODS=1
 run_storm $REF ref_25 100 200000 20 LOGGER_LEVEL=1 CUDA_CORE_LIMIT_0=25
-run_storm $NEW new_10_block12 100 200000 20 LOGGER_LEVEL=1 CUDA_CORE_LIMIT_0=10
+run_storm $NEW new_10 100 200000 20 LOGGER_LEVEL=1 CUDA_CORE_LIMIT_0=10
 run_storm $REF ref_10 100 200000 20 LOGGER_LEVEL=1 CUDA_CORE_LIMIT_0=10
 kill $(cat /tmp/smi.pid)
 run_alloc() { # lib tag vmem
@@ -33,4 +33,8 @@ timeout 700 python -m pytest tests -m gpu -q --timeout 250 > gpurun_out/pytest_g
 timeout 120 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1
 timeout 300 python bench.py --steps 5 --impl reference > gpurun_out/bench_ref.log 2> gpurun_out/bench_ref.err
 timeout 600 python bench.py --steps 5 > gpurun_out/bench.log 2> gpurun_out/bench.err
-for t in new_25_block12 new_25_avg1 ref_25 new_10_block12 ref_10; do echo $t; cat gpurun_out/storm_$t.json | cut -c1-640; done; tail -1 gpurun_out/bench.log | cut -c1-700; tail -1 gpurun_out/bench_ref.log | cut -c1-300; tail -3 gpurun_out/pytest_gpu.log; for t in bare new ref new_vmem ref_vmem; do echo alloc_$t; cat gpurun_out/alloc_$t.json; done
+# launch list of the same command, library kernels only (never a bench value: numbers under ncu are discarded)
+timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:vgpu_ -c 3000 --csv \
+  --log-file gpurun_out/ncu_bench_launches.csv python bench.py --steps 2 --warmup 3 > gpurun_out/ncu_bench.log 2>&1
+echo "ncu rc=$?" >> gpurun_out/ncu_bench.log
+for t in new_25 new_25_avg1 ref_25 new_10 ref_10; do echo $t; cat gpurun_out/storm_$t.json | cut -c1-640; done; tail -1 gpurun_out/bench.log | cut -c1-700; tail -1 gpurun_out/bench_ref.log | cut -c1-300; tail -3 gpurun_out/pytest_gpu.log; for t in bare new ref new_vmem ref_vmem; do echo alloc_$t; cat gpurun_out/alloc_$t.json; done

@@ -59,7 +59,20 @@ def build(force=False, verbose=False):
         out = _run(cmd)
         if verbose and out:
             print(out)
+    build_tools(force)
     return OUT
+
+
+WATCHER = os.path.join(HERE, "vgpu-smwatcher")
+
+
+def build_tools(force=False):
+    """Node-level helper binaries (plain C, libc only)."""
+    src = os.path.join(CSRC, "smwatcher.c")
+    contract = os.path.join(HERE, "..", "include", "vgpu_contract.h")
+    if force or _newer(WATCHER, [src, contract]):
+        _run(["gcc", "-D_GNU_SOURCE", "-std=gnu11", "-O2", "-g", "-Wall", "-Wshadow", "-o", WATCHER, src, "-ldl"])
+    return WATCHER
 
 
 if __name__ == "__main__":

@@ -196,7 +196,22 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--per-step", type=int, default=PER_STEP)
     ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--roofline-only", action="store_true",
+                    help="only the in-process bandwidth kernels (the form profiled under ncu: a tenant that runs with the "
+                         "interposer preloaded cannot also run under ncu's - its gate waits deadlock with kernel serialisation)")
     args = ap.parse_args()
+    if args.roofline_only:
+        import helpers
+        helpers.build_all()
+        peaks = {}
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                peaks = json.load(f)
+        except Exception:
+            pass
+        roof, n = spill_roofline(helpers.NEW_SO, peaks)
+        print(json.dumps({"roofline": roof, "gpu_launches": n}))
+        return
     if args.warmup < 3:
         args.warmup = 3
 

@@ -33,9 +33,9 @@ timeout 700 python -m pytest tests -m gpu -q --timeout 250 > gpurun_out/pytest_g
 timeout 120 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1
 timeout 300 python bench.py --steps 5 --impl reference > gpurun_out/bench_ref.log 2> gpurun_out/bench_ref.err
 timeout 600 python bench.py --steps 5 > gpurun_out/bench.log 2> gpurun_out/bench.err
-# launch list of the same command, library kernels only, with short steps (ncu intercepts every one of the
-# tenant's launches; 200 000 per step do not finish).  Never a bench value: numbers under ncu are discarded.
+# launch list of bench.py's device kernels (--roofline-only: the storm tenant runs with the interposer preloaded
+# and cannot also run under ncu's).  Never a bench value: numbers under ncu are discarded.
 timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:vgpu_ -c 3000 --csv \
-  --log-file gpurun_out/ncu_bench_launches.csv python bench.py --steps 2 --warmup 3 --per-step 2000 > gpurun_out/ncu_bench.log 2>&1
+  --log-file gpurun_out/ncu_bench_launches.csv python bench.py --roofline-only > gpurun_out/ncu_bench.log 2>&1
 echo "ncu rc=$?" >> gpurun_out/ncu_bench.log
 for t in new_25 new_25_avg1 ref_25 new_10 ref_10; do echo $t; cat gpurun_out/storm_$t.json | cut -c1-640; done; tail -1 gpurun_out/bench.log | cut -c1-700; tail -1 gpurun_out/bench_ref.log | cut -c1-300; tail -3 gpurun_out/pytest_gpu.log; for t in bare new ref new_vmem ref_vmem; do echo alloc_$t; cat gpurun_out/alloc_$t.json; done

@@ -70,6 +70,11 @@ typedef int vb_nvmlReturn;               /* nvmlReturn_t  */
  *                                            kernel to retire before the tenant's device sync)
  *  cuStreamDestroy_v2                       (none - B200 addition: releases the stream's
  *                                            completion-marker slot)
+ *  cuGraphInstantiateWithFlags              library/src/cuda_originals.c:2953-2980 (forward) - B200
+ *  cuGraphInstantiateWithParams / _ptsz       addition, opt-in VGPU_B200_GRAPH_LIMIT=1: learns the
+ *  cuGraphExecDestroy                         token cost of a graph (sum of its kernel nodes' grids)
+ *  cuGraphLaunch / _ptsz                    library/src/cuda_originals.c:3033 (forward) - opt-in:
+ *                                            a replay pays that cost and is gated like a launch
  */
 
 /* ======================================================================== PART 2: direct API */

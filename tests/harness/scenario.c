@@ -48,6 +48,7 @@ static void *sym(const char *name) {
 static CUdeviceptr g_ptr[MAXH];
 static int g_kind[MAXH]; /* 1 linear, 2 array, 3 mipmap, 4 vmm */
 static int g_np;
+static void *g_exec;
 
 int main(int argc, char **argv) {
   for (int i = 1; i < argc; i++)
@@ -252,6 +253,39 @@ int main(int argc, char **argv) {
       int st = 0;
       waitpid(pid, &st, 0);
       printf("forkchild -> exit %d\n", WIFEXITED(st) ? WEXITSTATUS(st) : -1);
+    } else if (!strcmp(cmd, "graph")) { /* graph <kernel nodes> <gridX>: build + instantiate (replaces the previous one) */
+      typedef struct { void *func; unsigned gx, gy, gz, bx, by, bz, smem; void **params; void **extra; } knp_t;
+      CUresult (*create)(void **, unsigned) = sym("cuGraphCreate");
+      CUresult (*add)(void **, void *, const void **, size_t, const knp_t *) = sym("cuGraphAddKernelNode");
+      CUresult (*inst)(void **, void *, unsigned long long) = sym("cuGraphInstantiateWithFlags");
+      CUresult (*gdestroy)(void *) = sym("cuGraphDestroy");
+      CUresult (*edestroy)(void *) = sym("cuGraphExecDestroy");
+      CUresult r = 500;
+      if (create && add && inst) {
+        if (g_exec && edestroy) edestroy(g_exec);
+        g_exec = NULL;
+        void *g = NULL;
+        r = create(&g, 0);
+        for (unsigned long long i = 0; r == 0 && i < a; i++) {
+          knp_t p = {NULL, (unsigned)b, 1, 1, 1, 1, 1, 0, NULL, NULL};
+          void *node = NULL;
+          r = add(&node, g, NULL, 0, &p);
+        }
+        if (r == 0) r = inst(&g_exec, g, 0);
+        if (g && gdestroy) gdestroy(g);
+      }
+      printf("graph %llu x %llu -> %d\n", a, b, r);
+    } else if (!strcmp(cmd, "graphlaunch")) {
+      CUresult (*gl)(void *, void *) = sym("cuGraphLaunch");
+      unsigned long long okc = 0;
+      for (unsigned long long i = 0; gl && g_exec && i < a; i++) okc += gl(g_exec, NULL) == 0;
+      printf("graphlaunch %llu -> ok %llu\n", a, okc);
+    } else if (!strcmp(cmd, "limstate")) { /* B200 library only: tokens charged so far */
+      struct { long long granted, consumed, bucket, share; int v[10]; unsigned long long steps; } ls;
+      int (*lstate)(void *) = dlsym(RTLD_DEFAULT, "vgpu_b200_limiter_state");
+      memset(&ls, 0, sizeof ls);
+      if (lstate && lstate(&ls) == 0) printf("limstate consumed %lld\n", ls.consumed);
+      else printf("limstate none\n");
     } else if (!strcmp(cmd, "sleepms")) {
       struct timespec ts = {(time_t)(a / 1000), (long)(a % 1000) * 1000000L};
       nanosleep(&ts, NULL);

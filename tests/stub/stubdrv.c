@@ -666,6 +666,48 @@ EXPORT CUresult cuLaunchGridAsync(void *f, int w, int h, void *s) { (void)w; (vo
 
 /* cuGetProcAddress: hand out this object's own symbols.  A static table, not dlsym(): under
  * LD_PRELOAD the process-wide dlsym is the interposer of the library under test. */
+/* ------------------------------------------------------------------ CUDA: graphs (kernel nodes only) */
+typedef struct { void *func; unsigned gx, gy, gz, bx, by, bz, smem; void **params; void **extra; } knode_params_t;
+typedef struct fake_graph { int n; knode_params_t nodes[64]; } fake_graph_t;
+typedef struct { fake_graph_t g; } fake_exec_t;
+EXPORT CUresult cuGraphCreate(void **g, unsigned flags) { (void)flags; *g = calloc(1, sizeof(fake_graph_t)); return *g ? 0 : 2; }
+EXPORT CUresult cuGraphDestroy(void *g) { free(g); return 0; }
+EXPORT CUresult cuGraphAddKernelNode(void **node, void *g, const void **deps, size_t ndeps, const knode_params_t *p) {
+  (void)deps; (void)ndeps;
+  fake_graph_t *fg = (fake_graph_t *)g;
+  if (!fg || fg->n >= 64) return 1;
+  fg->nodes[fg->n] = *p;
+  if (node) *node = &fg->nodes[fg->n];
+  fg->n++;
+  return 0;
+}
+EXPORT CUresult cuGraphGetNodes(void *g, void **nodes, size_t *n) {
+  fake_graph_t *fg = (fake_graph_t *)g;
+  if (!nodes) { *n = (size_t)fg->n; return 0; }
+  size_t k = *n < (size_t)fg->n ? *n : (size_t)fg->n;
+  for (size_t i = 0; i < k; i++) nodes[i] = &fg->nodes[i];
+  *n = k;
+  return 0;
+}
+EXPORT CUresult cuGraphNodeGetType(void *node, int *type) { (void)node; *type = 0; return 0; }
+EXPORT CUresult cuGraphKernelNodeGetParams(void *node, knode_params_t *out) { *out = *(knode_params_t *)node; return 0; }
+EXPORT CUresult cuGraphInstantiateWithFlags(void **exec, void *g, unsigned long long flags) {
+  (void)flags;
+  fake_exec_t *e = (fake_exec_t *)calloc(1, sizeof *e);
+  if (!e) return 2;
+  e->g = *(fake_graph_t *)g;
+  *exec = e;
+  return 0;
+}
+EXPORT CUresult cuGraphExecDestroy(void *exec) { free(exec); return 0; }
+EXPORT CUresult cuGraphLaunch(void *exec, void *stream) {
+  (void)stream;
+  if (!t_has_ctx) return 201;
+  fake_exec_t *e = (fake_exec_t *)exec;
+  for (int i = 0; i < e->g.n; i++) note_launch();
+  return 0;
+}
+
 static const struct { const char *name; void *fn; } g_self_table[] = {
   {"cuInit", (void *)cuInit},
   {"cuDriverGetVersion", (void *)cuDriverGetVersion},
@@ -731,6 +773,11 @@ static const struct { const char *name; void *fn; } g_self_table[] = {
   {"cuLaunchKernel", (void *)cuLaunchKernel},
   {"cuLaunchKernel_ptsz", (void *)cuLaunchKernel_ptsz},
   {"cuLaunchKernelEx", (void *)cuLaunchKernelEx},
+  {"cuGraphCreate", (void *)cuGraphCreate}, {"cuGraphDestroy", (void *)cuGraphDestroy},
+  {"cuGraphAddKernelNode", (void *)cuGraphAddKernelNode}, {"cuGraphGetNodes", (void *)cuGraphGetNodes},
+  {"cuGraphNodeGetType", (void *)cuGraphNodeGetType}, {"cuGraphKernelNodeGetParams", (void *)cuGraphKernelNodeGetParams},
+  {"cuGraphInstantiateWithFlags", (void *)cuGraphInstantiateWithFlags}, {"cuGraphInstantiate", (void *)cuGraphInstantiateWithFlags},
+  {"cuGraphExecDestroy", (void *)cuGraphExecDestroy}, {"cuGraphLaunch", (void *)cuGraphLaunch},
   {"cuLaunchKernelEx_ptsz", (void *)cuLaunchKernelEx_ptsz},
   {"cuLaunchCooperativeKernel", (void *)cuLaunchCooperativeKernel},
   {"cuLaunchCooperativeKernel_ptsz", (void *)cuLaunchCooperativeKernel_ptsz},

@@ -28,7 +28,9 @@ def test_exports_the_reference_hook_surface_and_nothing_accidental(built):
     missing = [s for s in REFERENCE_CUDA_HOOKS + REFERENCE_NVML_HOOKS + ["dlsym"] if s not in sym]
     assert not missing, missing
     extra = {s for s in sym if not s.startswith("vgpu_b200_")} - set(REFERENCE_CUDA_HOOKS) - set(REFERENCE_NVML_HOOKS)
-    assert extra == {"dlsym", "cuCtxSynchronize", "cuStreamDestroy_v2", "nvmlDeviceGetUtilizationRates"}, extra
+    graph_opt_in = {"cuGraphInstantiateWithFlags", "cuGraphInstantiateWithParams", "cuGraphInstantiateWithParams_ptsz",
+                    "cuGraphExecDestroy", "cuGraphLaunch", "cuGraphLaunch_ptsz"}
+    assert extra == {"dlsym", "cuCtxSynchronize", "cuStreamDestroy_v2", "nvmlDeviceGetUtilizationRates"} | graph_opt_in, extra
     if H.have_reference():
         ref = exported(H.REF_SO)
         assert set(REFERENCE_CUDA_HOOKS + REFERENCE_NVML_HOOKS + ["dlsym"]) <= ref

@@ -310,3 +310,29 @@ def test_forked_child_is_served_like_the_parent(built):
     out, err, _ = H.run_scenario(H.NEW_SO, "init 0\nlaunch 5000 1 1 1\nforkchild 1048576 200000\nlaunch 5000 1 1 1\n", e, sb=sb)
     sb.cleanup()
     assert "child alloc 0 meminfo 0 total 1073741824 launches 200000" in out and out.count("-> ok 5000") == 2
+
+
+def test_cuda_graph_replays_forward_by_default_and_are_metered_on_request(built):
+    """cuGraphLaunch is a pure forward in the reference (cuda_originals.c:3033) and by default here:
+    same transcripts.  With VGPU_B200_GRAPH_LIMIT=1 a replay pays the sum of its kernel nodes' grids
+    (dlsym and cuGetProcAddress bindings alike) and is gated like a launch."""
+    script = "init 0\ngraph 10 100\ngraphlaunch 50\ngraph 3 7\ngraphlaunch 4\nlaunch 5 7 1 1\n"
+    env = {"CUDA_MEM_LIMIT_0": "1g", "CUDA_CORE_LIMIT_0": "50"}
+    for args in ((), ("--gpa",)):
+        assert_same(both(script, env, args=args))
+    e = dict(BASE)
+    e.update(env)
+    metered = dict(e, VGPU_B200_GRAPH_LIMIT="1")
+    for args in ((), ("--gpa",)):
+        out, _, sb = H.run_scenario(H.NEW_SO, script + "limstate\n", e, args=args)
+        sb.cleanup()
+        assert "limstate consumed 35" in out  # only the five plain launches
+        out, _, sb = H.run_scenario(H.NEW_SO, script + "limstate\n", metered, args=args)
+        sb.cleanup()
+        assert "graphlaunch 50 -> ok 50" in out and "graphlaunch 4 -> ok 4" in out
+        assert "limstate consumed %d" % (50 * 10 * 100 + 4 * 3 * 7 + 35) in out
+    # saturating tenant under a 10 % cap: replays end up behind the gate
+    hot = dict(metered, CUDA_CORE_LIMIT_0="10", STUB_UTIL="fixed:90", LOGGER_LEVEL="3")
+    out, err, sb = H.run_scenario(H.NEW_SO, "init 0\ngraph 8 4000\ngraphlaunch 400\n", hot)
+    sb.cleanup()
+    assert "graphlaunch 400 -> ok 400" in out and "metric=rate_gated" in err

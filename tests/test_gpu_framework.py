@@ -82,3 +82,59 @@ def test_pytorch_tenant_under_cap(built):
             json.dump({"b200": b, "reference": ref, "reference_stderr_tail": None if ref else rerr, "runs": RUNS}, f, indent=1)
         if ref is not None:  # the reference itself may not survive a modern framework; compare when it does
             assert ref == b
+
+
+GRAPH_TENANT = r'''
+import torch, time, json
+x = torch.ones(1 << 22, device="cuda")
+side = torch.cuda.Stream()
+with torch.cuda.stream(side):
+    for _ in range(3):
+        y = x * 1.0001
+torch.cuda.current_stream().wait_stream(side)
+g = torch.cuda.CUDAGraph()
+with torch.cuda.graph(g):
+    y = x
+    for _ in range(20):
+        y = y * 1.0001 + 0.5
+torch.cuda.synchronize()
+t0 = time.time()
+n = 0
+while time.time() - t0 < 6.0:
+    for _ in range(50):
+        g.replay()
+    torch.cuda.synchronize()
+    n += 50
+wall = time.time() - t0
+print(json.dumps({"replays": n, "wall_s": wall, "replays_per_s": n / wall, "y0": float(y[0].cpu())}))
+'''
+
+
+def run_graph_tenant(lib, extra):
+    import json
+    sb = H.Sandbox()
+    knobs = {"MANAGER_COMPATIBILITY_MODE": "0", "MANAGER_VISIBLE_DEVICES": gpu0_uuid(), "CUDA_VISIBLE_DEVICES": "0",
+             "CUDA_MEM_LIMIT_0": "8g", "CUDA_CORE_LIMIT_0": "10", "LOGGER_LEVEL": "2"}
+    knobs.update(extra)
+    env = H.preload_env(lib, sb, knobs, stub=False)
+    r = subprocess.run([sys.executable, "-c", GRAPH_TENANT], env=env, capture_output=True, text=True, timeout=200)
+    sb.cleanup()
+    assert r.returncode == 0, r.stderr[-2500:]
+    return json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+
+
+def test_cuda_graph_replays_are_metered_on_request(built):
+    """PyTorch CUDA graphs (cudart -> cuGetProcAddress -> cuGraphInstantiate* / cuGraphLaunch): by default a
+    replay is forwarded like the reference does; with VGPU_B200_GRAPH_LIMIT=1 it pays its kernel nodes' grids."""
+    import json
+    free_run = run_graph_tenant(H.NEW_SO, {})
+    metered = run_graph_tenant(H.NEW_SO, {"VGPU_B200_GRAPH_LIMIT": "1"})
+    report = {"b200_default": free_run, "b200_graph_limit": metered}
+    if os.path.exists(H.REF_SO):
+        report["reference"] = run_graph_tenant(H.REF_SO, {})
+    os.makedirs(os.path.join(H.ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(H.ROOT, "gpurun_out", "cuda_graph_r1.json"), "w") as f:
+        json.dump(report, f, indent=1)
+    assert free_run["y0"] == metered["y0"]
+    assert metered["replays"] > 0
+    assert metered["replays_per_s"] < 0.8 * free_run["replays_per_s"], report

@@ -16,7 +16,8 @@ typedef int CUdevice;
 typedef unsigned long long CUdeviceptr;
 typedef unsigned long long cuuint64_t;
 typedef void *CUcontext, *CUstream, *CUfunction, *CUmodule, *CUarray, *CUmipmappedArray,
-    *CUmemoryPool, *CUevent;
+    *CUmemoryPool, *CUevent, *CUgraph, *CUgraphNode, *CUgraphExec;
+enum { VCU_GRAPH_NODE_KERNEL = 0, VCU_GRAPH_NODE_GRAPH = 4 }; /* CUgraphNodeType */
 typedef unsigned long long CUmemGenericAllocationHandle;
 typedef struct { char bytes[16]; } CUuuid;
 

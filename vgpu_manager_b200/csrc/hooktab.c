@@ -24,16 +24,24 @@
   X(cuMemAllocAsync_ptsz) X(cuMemCreate) X(cuMemAllocFromPoolAsync)                           \
   X(cuMemAllocFromPoolAsync_ptsz) X(cuMemFree_v2) X(cuMemFree) X(cuMemFreeAsync)              \
   X(cuMemFreeAsync_ptsz) X(cuCtxSynchronize) X(cuStreamDestroy_v2)
+/* opt-in (VGPU_B200_GRAPH_LIMIT=1): only then are these names substituted in dlsym /
+ * cuGetProcAddress answers; the reference forwards all of them (cuda_originals.c:2953-3040) */
+#define VGPU_GRAPH_HOOKS(X)                                                                   \
+  X(cuGraphInstantiateWithFlags) X(cuGraphInstantiateWithParams) X(cuGraphInstantiateWithParams_ptsz) \
+  X(cuGraphLaunch) X(cuGraphLaunch_ptsz) X(cuGraphExecDestroy)
 #define VGPU_NVML_HOOKS(X)                                                                    \
   X(nvmlInit) X(nvmlInit_v2) X(nvmlInitWithFlags) X(nvmlDeviceGetMemoryInfo)                  \
   X(nvmlDeviceGetMemoryInfo_v2) X(nvmlDeviceSetComputeMode) X(nvmlDeviceGetPersistenceMode)   \
   X(nvmlDeviceGetUtilizationRates)
 VGPU_CUDA_HOOKS(HOOK_DECL)
+VGPU_GRAPH_HOOKS(HOOK_DECL)
 VGPU_NVML_HOOKS(HOOK_DECL)
+extern int vgpu_graph_limit_enabled(void);
 
 typedef struct { const char *name; void *fn; } hook_ent;
 #define HOOK_ENT(n) {#n, (void *)n},
 static const hook_ent g_cuda_hooks[] = {VGPU_CUDA_HOOKS(HOOK_ENT)};
+static const hook_ent g_graph_hooks[] = {VGPU_GRAPH_HOOKS(HOOK_ENT)};
 static const hook_ent g_nvml_hooks[] = {VGPU_NVML_HOOKS(HOOK_ENT)};
 
 static void *find_hook(const hook_ent *t, size_t n, const char *name) {
@@ -47,6 +55,20 @@ void *vgpu_lookup_cuda_hook(const char *name, int want_ptsz) {
   /* cuGetProcAddress callers ask for the base name; cuStreamDestroy has had the _v2 ABI since
    * CUDA 4.0 and the driver hands out exactly that for it */
   if (!strcmp(name, "cuStreamDestroy")) name = "cuStreamDestroy_v2";
+  if (!strncmp(name, "cuGraph", 7)) {
+    if (!vgpu_graph_limit_enabled()) return NULL;
+    /* since CUDA 12.0 the base name is the WithFlags entry point (cuda.h maps it); the legacy
+     * 5-argument ABI of older toolkits is left to the driver */
+    if (!strcmp(name, "cuGraphInstantiate")) name = "cuGraphInstantiateWithFlags";
+    size_t ng = sizeof g_graph_hooks / sizeof g_graph_hooks[0];
+    if (want_ptsz) {
+      char alt[96];
+      snprintf(alt, sizeof alt, "%s_ptsz", name);
+      void *f = find_hook(g_graph_hooks, ng, alt);
+      if (f) return f;
+    }
+    return find_hook(g_graph_hooks, ng, name);
+  }
   if (want_ptsz) {
     char alt[96];
     snprintf(alt, sizeof alt, "%s_ptsz", name);

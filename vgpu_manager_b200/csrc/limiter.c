@@ -15,8 +15,8 @@
  *              by the controller.  The hook reads the mirror with a single 8-byte load.
  *   gate     = when the bucket is empty the launch is NOT delayed on the CPU: a
  *              cuStreamWaitValue64(granted >= ticket) is enqueued in front of it, so the stream
- *              itself waits on the HBM word.  (Contexts without 64-bit stream mem-ops use
- *              vgpu_gate_kernel, a one-thread device spin.)
+ *              itself waits on the bucket word (see watchdog for which copy).  Contexts without
+ *              64-bit stream mem-ops use vgpu_gate_kernel, a one-thread device spin.
  *   markers  = behind launches a cuStreamWriteValue64 bumps the stream's `done` sequence; the
  *              sampler compares it with `launched` to measure how long tenant work is resident
  *              (the NVML notion of utilisation) without NVML.
@@ -687,4 +687,139 @@ VGPU_EXPORT CUresult cuStreamDestroy_v2(CUstream s) {
       }
     }
   return R.cuStreamDestroy_v2 ? R.cuStreamDestroy_v2(s) : CUDA_ERROR_NOT_FOUND;
+}
+
+/* ------------------------------------------------------------------ CUDA graphs (opt-in)
+ * The reference meters kernels at capture time only (the launch hooks run while the stream
+ * captures) and forwards cuGraphLaunch untouched, so every replay of a graph is free and
+ * invisible to its utilisation reading.  With VGPU_B200_GRAPH_LIMIT=1 a replay costs what its
+ * kernel nodes would cost as individual launches (sum of gridX*gridY*gridZ, child graphs
+ * included), is gated like a launch and carries a completion marker.  Off by default: it changes
+ * behaviour relative to the reference. */
+#define GRAPH_TAB 2048u
+typedef struct { volatile uintptr_t exec; long long cost; } graph_ent;
+static graph_ent g_graphs[GRAPH_TAB];
+static pthread_mutex_t g_graph_mu = PTHREAD_MUTEX_INITIALIZER;
+
+int vgpu_graph_limit_enabled(void) {
+  static int on = -1;
+  if (on < 0) {
+    const char *e = getenv("VGPU_B200_GRAPH_LIMIT");
+    on = (e && (*e == '1' || *e == 't' || *e == 'T')) ? 1 : 0;
+  }
+  return on;
+}
+
+static long long graph_cost(CUgraph g, int depth) {
+  size_t n = 0;
+  if (!R.cuGraphGetNodes || !R.cuGraphNodeGetType || depth > 8) return 0;
+  if (R.cuGraphGetNodes(g, NULL, &n) != CUDA_SUCCESS || n == 0) return 0;
+  CUgraphNode *nodes = (CUgraphNode *)malloc(n * sizeof *nodes);
+  if (!nodes) return 0;
+  long long cost = 0;
+  if (R.cuGraphGetNodes(g, nodes, &n) == CUDA_SUCCESS) {
+    for (size_t i = 0; i < n; i++) {
+      int type = -1;
+      if (R.cuGraphNodeGetType(nodes[i], &type) != CUDA_SUCCESS) continue;
+      if (type == VCU_GRAPH_NODE_KERNEL) {
+        /* CUDA_KERNEL_NODE_PARAMS v1 (56 B) and v2 (72 B) both start {CUfunction func; unsigned gridDimX,Y,Z; ...} */
+        union { unsigned u[32]; void *align; } p;
+        memset(&p, 0, sizeof p);
+        CUresult r = R.cuGraphKernelNodeGetParams_v2 ? R.cuGraphKernelNodeGetParams_v2(nodes[i], &p) : CUDA_ERROR_NOT_FOUND;
+        if (r != CUDA_SUCCESS && R.cuGraphKernelNodeGetParams) r = R.cuGraphKernelNodeGetParams(nodes[i], &p);
+        if (r == CUDA_SUCCESS) cost += (long long)(int)(p.u[2] * p.u[3] * p.u[4]); /* same 32-bit product as a launch */
+      } else if (type == VCU_GRAPH_NODE_GRAPH && R.cuGraphChildGraphNodeGetGraph) {
+        CUgraph child = NULL;
+        if (R.cuGraphChildGraphNodeGetGraph(nodes[i], &child) == CUDA_SUCCESS && child) cost += graph_cost(child, depth + 1);
+      }
+    }
+  }
+  free(nodes);
+  return cost;
+}
+
+static void graph_remember(CUgraphExec exec, long long cost) {
+  uintptr_t key = (uintptr_t)exec;
+  uint32_t h = (uint32_t)((key >> 4) * 0x9E3779B97F4A7C15ull >> 53) % GRAPH_TAB;
+  pthread_mutex_lock(&g_graph_mu);
+  for (uint32_t i = 0; i < GRAPH_TAB; i++) {
+    graph_ent *e = &g_graphs[(h + i) % GRAPH_TAB];
+    if (e->exec == 0 || e->exec == 1 || e->exec == key) { /* empty, tombstone or re-used handle */
+      e->cost = cost;
+      __sync_synchronize();
+      e->exec = key;
+      break;
+    }
+  }
+  pthread_mutex_unlock(&g_graph_mu);
+}
+
+static int graph_lookup(CUgraphExec exec, long long *cost, int forget) {
+  uintptr_t key = (uintptr_t)exec;
+  uint32_t h = (uint32_t)((key >> 4) * 0x9E3779B97F4A7C15ull >> 53) % GRAPH_TAB;
+  for (uint32_t i = 0; i < GRAPH_TAB; i++) {
+    graph_ent *e = &g_graphs[(h + i) % GRAPH_TAB];
+    uintptr_t k = e->exec;
+    if (k == 0) return 0;
+    if (k == key) {
+      if (cost) *cost = e->cost;
+      if (forget) e->exec = 1;
+      return 1;
+    }
+  }
+  return 0;
+}
+
+static void graph_instantiated(CUgraphExec *out, CUgraph g, CUresult r) {
+  if (r != CUDA_SUCCESS || !out || !*out || !vgpu_graph_limit_enabled()) return;
+  long long cost = graph_cost(g, 0);
+  graph_remember(*out, cost);
+  VLOG(VL_VERBOSE, "graph exec %p: %lld tokens per launch", (void *)*out, cost);
+}
+
+VGPU_EXPORT CUresult cuGraphInstantiateWithFlags(CUgraphExec *out, CUgraph g, unsigned long long flags) {
+  vgpu_boot();
+  if (unlikely(!R.cuGraphInstantiateWithFlags)) return CUDA_ERROR_NOT_FOUND;
+  CUresult r = R.cuGraphInstantiateWithFlags(out, g, flags);
+  graph_instantiated(out, g, r);
+  return r;
+}
+VGPU_EXPORT CUresult cuGraphInstantiateWithParams(CUgraphExec *out, CUgraph g, void *params) {
+  vgpu_boot();
+  if (unlikely(!R.cuGraphInstantiateWithParams)) return CUDA_ERROR_NOT_FOUND;
+  CUresult r = R.cuGraphInstantiateWithParams(out, g, params);
+  graph_instantiated(out, g, r);
+  return r;
+}
+VGPU_EXPORT CUresult cuGraphInstantiateWithParams_ptsz(CUgraphExec *out, CUgraph g, void *params) {
+  vgpu_boot();
+  if (unlikely(!R.cuGraphInstantiateWithParams_ptsz)) return CUDA_ERROR_NOT_FOUND;
+  CUresult r = R.cuGraphInstantiateWithParams_ptsz(out, g, params);
+  graph_instantiated(out, g, r);
+  return r;
+}
+VGPU_EXPORT CUresult cuGraphExecDestroy(CUgraphExec exec) {
+  vgpu_boot();
+  if (vgpu_graph_limit_enabled()) graph_lookup(exec, NULL, 1);
+  return R.cuGraphExecDestroy ? R.cuGraphExecDestroy(exec) : CUDA_ERROR_NOT_FOUND;
+}
+
+static inline unsigned graph_tokens(CUgraphExec exec) {
+  long long cost = 0;
+  if (!vgpu_graph_limit_enabled() || !graph_lookup(exec, &cost, 0) || cost <= 0) return 0;
+  return cost > 0x7fffffffll ? 0x7fffffffu : (unsigned)cost;
+}
+VGPU_EXPORT CUresult cuGraphLaunch(CUgraphExec exec, CUstream s) {
+  if (unlikely(!G_cfg)) vgpu_boot();
+  if (unlikely(!R.cuGraphLaunch)) return CUDA_ERROR_NOT_FOUND;
+  unsigned tokens = graph_tokens(exec);
+  if (!tokens) return R.cuGraphLaunch(exec, s);
+  LIMITED_LAUNCH(tokens, 1, 1, s, 0, R.cuGraphLaunch(exec, s));
+}
+VGPU_EXPORT CUresult cuGraphLaunch_ptsz(CUgraphExec exec, CUstream s) {
+  if (unlikely(!G_cfg)) vgpu_boot();
+  if (unlikely(!R.cuGraphLaunch_ptsz)) return CUDA_ERROR_NOT_FOUND;
+  unsigned tokens = graph_tokens(exec);
+  if (!tokens) return R.cuGraphLaunch_ptsz(exec, s);
+  LIMITED_LAUNCH(tokens, 1, 1, s, 1, R.cuGraphLaunch_ptsz(exec, s));
 }

@@ -124,7 +124,18 @@ void vgpu_log_emit(int level, const char *file, int line, const char *fmt, ...)
   X(cuLaunch, CUresult, (CUfunction))                                                           \
   X(cuLaunchGrid, CUresult, (CUfunction, int, int))                                             \
   X(cuLaunchGridAsync, CUresult, (CUfunction, int, int, CUstream))                              \
-  X(cuFuncSetBlockShape, CUresult, (CUfunction, int, int, int))
+  X(cuFuncSetBlockShape, CUresult, (CUfunction, int, int, int))                                 \
+  X(cuGraphInstantiateWithFlags, CUresult, (CUgraphExec *, CUgraph, unsigned long long))         \
+  X(cuGraphInstantiateWithParams, CUresult, (CUgraphExec *, CUgraph, void *))                    \
+  X(cuGraphInstantiateWithParams_ptsz, CUresult, (CUgraphExec *, CUgraph, void *))               \
+  X(cuGraphLaunch, CUresult, (CUgraphExec, CUstream))                                           \
+  X(cuGraphLaunch_ptsz, CUresult, (CUgraphExec, CUstream))                                      \
+  X(cuGraphExecDestroy, CUresult, (CUgraphExec))                                                \
+  X(cuGraphGetNodes, CUresult, (CUgraph, CUgraphNode *, size_t *))                              \
+  X(cuGraphNodeGetType, CUresult, (CUgraphNode, int *))                                         \
+  X(cuGraphKernelNodeGetParams, CUresult, (CUgraphNode, void *))                                \
+  X(cuGraphKernelNodeGetParams_v2, CUresult, (CUgraphNode, void *))                             \
+  X(cuGraphChildGraphNodeGetGraph, CUresult, (CUgraphNode, CUgraph *))
 
 #define VGPU_REAL_NVML(X)                                                                       \
   X(nvmlInit, nvmlReturn_t, (void))                                                             \

@@ -20,7 +20,7 @@ enum {
   real_THR = CU_DEVICE_ATTRIBUTE_MAX_THREADS_PER_MULTIPROCESSOR, real_PTDS = CU_GET_PROC_ADDRESS_PER_THREAD_DEFAULT_STREAM,
   real_GEQ = CU_STREAM_WAIT_VALUE_GEQ, real_MEMOPS64 = CU_DEVICE_ATTRIBUTE_CAN_USE_64_BIT_STREAM_MEM_OPS,
   real_SMEM_ATTR = CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, real_LOC_DEVICE = CU_MEM_LOCATION_TYPE_DEVICE,
-  real_NODE_KERNEL = CU_GRAPH_NODE_TYPE_KERNEL, real_NODE_GRAPH = CU_GRAPH_NODE_TYPE_GRAPH,
+  real_CAP_RELAXED = CU_STREAM_CAPTURE_MODE_RELAXED, real_NODE_KERNEL = CU_GRAPH_NODE_TYPE_KERNEL, real_NODE_GRAPH = CU_GRAPH_NODE_TYPE_GRAPH,
   /* graph cost reads gridDimX/Y/Z as 32-bit words 2,3,4 of either kernel-node parameter struct */
   real_KNP1_GX = offsetof(CUDA_KERNEL_NODE_PARAMS_v1, gridDimX), real_KNP1_GZ = offsetof(CUDA_KERNEL_NODE_PARAMS_v1, gridDimZ),
   real_KNP2_GX = offsetof(CUDA_KERNEL_NODE_PARAMS_v2, gridDimX), real_KNP2_GZ = offsetof(CUDA_KERNEL_NODE_PARAMS_v2, gridDimZ),
@@ -110,7 +110,7 @@ SAME(sizeof(vgpu_util_sample_t), sizeof(real_sample));
 SAME(offsetof(vgpu_util_sample_t, ts_us), offsetof(real_sample, timeStamp));
 SAME(offsetof(vgpu_util_sample_t, sm), offsetof(real_sample, smUtil));
 SAME(offsetof(vgpu_util_sample_t, dec), offsetof(real_sample, decUtil));
-SAME(VCU_GRAPH_NODE_KERNEL, real_NODE_KERNEL); SAME(VCU_GRAPH_NODE_GRAPH, real_NODE_GRAPH);
+SAME(VCU_STREAM_CAPTURE_MODE_RELAXED, real_CAP_RELAXED); SAME(VCU_GRAPH_NODE_KERNEL, real_NODE_KERNEL); SAME(VCU_GRAPH_NODE_GRAPH, real_NODE_GRAPH);
 SAME(real_KNP1_GX, 8); SAME(real_KNP1_GZ, 16); SAME(real_KNP2_GX, 8); SAME(real_KNP2_GZ, 16);
 _Static_assert(real_KNP2_SIZE <= 128, "graph_cost() reads kernel-node parameters into a 128-byte buffer");
 int abi_layout_ok = 1;

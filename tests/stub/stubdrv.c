@@ -352,6 +352,7 @@ EXPORT CUresult cuStreamQuery(void *s) {
   return 0;
 }
 EXPORT CUresult cuStreamIsCapturing(void *s, int *st) { (void)s; *st = 0; return 0; }
+EXPORT CUresult cuThreadExchangeStreamCaptureMode(int *mode) { static __thread int cur = 0; int old = cur; cur = *mode; *mode = old; return 0; }
 static volatile int g_parked; /* callers blocked behind the gate (the fake GPU's "parked streams") */
 static CUresult wait64_unlocked(CUdeviceptr addr, unsigned long long value);
 static CUresult wait64(CUdeviceptr addr, unsigned long long value) {

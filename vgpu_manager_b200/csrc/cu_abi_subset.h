@@ -18,6 +18,7 @@ typedef unsigned long long cuuint64_t;
 typedef void *CUcontext, *CUstream, *CUfunction, *CUmodule, *CUarray, *CUmipmappedArray,
     *CUmemoryPool, *CUevent, *CUgraph, *CUgraphNode, *CUgraphExec;
 enum { VCU_GRAPH_NODE_KERNEL = 0, VCU_GRAPH_NODE_GRAPH = 4 }; /* CUgraphNodeType */
+enum { VCU_STREAM_CAPTURE_MODE_RELAXED = 2 };                  /* CUstreamCaptureMode */
 typedef unsigned long long CUmemGenericAllocationHandle;
 typedef struct { char bytes[16]; } CUuuid;
 

@@ -41,7 +41,7 @@ static int pinned_block(size_t bytes, void **host, CUdeviceptr *dev) {
 CUresult vgpu_rt_launch(vgpu_dev_rt *rt, CUfunction f, unsigned grid, unsigned block, unsigned smem,
                         CUstream s, void **params) {
   (void)rt;
-  return R.cuLaunchKernel(f, grid, 1, 1, block, 1, 1, smem, s, params, NULL);
+  return VGPU_CAPCHK(R.cuLaunchKernel(f, grid, 1, 1, block, 1, 1, smem, s, params, NULL));
 }
 
 /* bytes NVML attributes to this process on `nvdev` (calibration of our own footprint only) */
@@ -63,13 +63,18 @@ static int spin_seq(volatile uint32_t *word, uint32_t want, CUstream s) {
   for (int i = 0; i < 2000000; i++) {
     if (*word == want) return 0;
     if ((i & 1023) == 1023) {
-      CUresult q = R.cuStreamQuery ? R.cuStreamQuery(s) : CUDA_SUCCESS;
+      int prev = vgpu_capture_relax();
+      CUresult q = R.cuStreamQuery ? VGPU_CAPCHK(R.cuStreamQuery(s)) : CUDA_SUCCESS;
+      vgpu_capture_restore(prev);
       if (q != CUDA_SUCCESS && q != CUDA_ERROR_NOT_READY) return -1;
       sched_yield();
     }
     __builtin_ia32_pause();
   }
-  if (R.cuStreamSynchronize(s) != CUDA_SUCCESS) return -1;
+  int prev = vgpu_capture_relax();
+  CUresult sr = VGPU_CAPCHK(R.cuStreamSynchronize(s));
+  vgpu_capture_restore(prev);
+  if (sr != CUDA_SUCCESS) return -1;
   return *word == want ? 0 : -1;
 }
 
@@ -288,7 +293,13 @@ vgpu_dev_rt *vgpu_rt_get(int host_index, CUdevice dev) {
   }
   vgpu_dev_rt *out = NULL;
   if (rt->ready == 1) out = rt;
-  else if (rt->ready == 0) out = bring_up(rt, slot, host_index, dev);
+  else if (rt->ready == 0) {
+    /* module load, allocations and the warm-up synchronise are "unsafe" calls for CUDA's capture
+     * rules: another tenant thread may be capturing in global mode right now */
+    int prev = vgpu_capture_relax();
+    out = bring_up(rt, slot, host_index, dev);
+    vgpu_capture_restore(prev);
+  }
   pthread_mutex_unlock(&g_rt_mu);
   return out;
 }

@@ -169,7 +169,9 @@ static void settle_idle_streams(vgpu_dev_rt *rt, int h) {
     sl->seen_launched = l;
     if (l <= d || !quiet || sl->marked >= l) continue;
     if (sl->ptsz && sl->stream == NULL) continue; /* another thread's default stream: not addressable */
-    if (R.cuStreamQuery && R.cuStreamQuery(sl->stream) == CUDA_SUCCESS && H->launched[i] == l && H->done[i] < l)
+    int capturing = 0; /* a query would invalidate the tenant's capture */
+    if (sl->stream && R.cuStreamIsCapturing && (R.cuStreamIsCapturing(sl->stream, &capturing) != CUDA_SUCCESS || capturing)) continue;
+    if (R.cuStreamQuery && VGPU_CAPCHK(R.cuStreamQuery(sl->stream)) == CUDA_SUCCESS && H->launched[i] == l && H->done[i] < l)
       H->done[i] = l;
   }
 }
@@ -179,6 +181,7 @@ static void *tick_main(void *arg) {
   uint32_t epoch = 0;
   int fails = 0;
   uint64_t rng = 0x9E3779B97F4A7C15ull ^ (uint64_t)getpid();
+  int relaxed = 0;
   for (;;) {
     /* One short sampler window per tick, at a uniformly random offset inside the tick: the
      * sampler stays resident ~5 % of the time (it would otherwise show up as GPU utilisation in
@@ -195,7 +198,11 @@ static void *tick_main(void *arg) {
       if (!g_tick_devices[h]) continue;
       vgpu_dev_rt *rt = vgpu_rt_peek(h);
       if (!rt) continue;
-      if (R.cuCtxPushCurrent_v2(rt->ctx) != CUDA_SUCCESS) continue;
+      if (VGPU_CAPCHK(R.cuCtxPushCurrent_v2(rt->ctx)) != CUDA_SUCCESS) continue;
+      if (!relaxed) { /* once, with a context current: this thread never takes part in a tenant's capture */
+        vgpu_capture_relax();
+        relaxed = 1;
+      }
       settle_idle_streams(rt, h);
       if ((epoch % 100) == 1) refresh_process_count(rt);
       if ((epoch % 100) == 0 && vgpu_log_level() >= VL_VERBOSE) {
@@ -216,14 +223,14 @@ static void *tick_main(void *arg) {
           if (R.cuLaunchKernel(rt->k_sampler, grid, 1, 1, 128, 1, 1, 0, rt->p_stream, params, NULL) == CUDA_SUCCESS)
             vgpu_metric_add(h, VM_SAMPLER_LAUNCHES, 1);
         }
-      } else if (R.cuStreamQuery(rt->s_stream) == CUDA_SUCCESS) {
+      } else if (VGPU_CAPCHK(R.cuStreamQuery(rt->s_stream)) == CUDA_SUCCESS) {
         uint32_t ep = epoch;
         /* while a tenant thread waits for the device to go idle, keep the sampler's residency
          * negligible so the wait is not stretched by it */
         uint32_t window = g_sync_waiters > 0 ? 200u : g_window_us;
         void *params[] = {&rt->lim_d, &rt->lim_h_d, &window, &g_interval_us, &g_period_ticks, &ep};
         unsigned grid = rt->sm_num > 0 ? (unsigned)rt->sm_num : 148u;
-        CUresult r = R.cuLaunchKernel(rt->k_sampler, grid, 1, 1, 128, 1, 1, 0, rt->s_stream, params, NULL);
+        CUresult r = VGPU_CAPCHK(R.cuLaunchKernel(rt->k_sampler, grid, 1, 1, 128, 1, 1, 0, rt->s_stream, params, NULL));
         if (r == CUDA_SUCCESS) {
           fails = 0;
           vgpu_metric_add(h, VM_SAMPLER_LAUNCHES, 1);
@@ -469,7 +476,7 @@ static inline void enqueue_marker(vgpu_dev_rt *rt, int h, uint32_t slot, unsigne
   CUdeviceptr addr = rt->lim_h_d + offsetof(vgpu_lim_host_t, done) + (CUdeviceptr)slot * sizeof(unsigned long long);
   CUresult (*wr)(CUstream, CUdeviceptr, cuuint64_t, unsigned) =
       (ptsz && R.cuStreamWriteValue64_v2_ptsz) ? R.cuStreamWriteValue64_v2_ptsz : R.cuStreamWriteValue64_v2;
-  if (likely(wr(s, addr, (cuuint64_t)seq, 0) == CUDA_SUCCESS)) g_slots[h][slot].marked = seq;
+  if (likely(VGPU_CAPCHK(wr(s, addr, (cuuint64_t)seq, 0)) == CUDA_SUCCESS)) g_slots[h][slot].marked = seq;
   else rt->memops64 = 0;
 }
 
@@ -496,7 +503,7 @@ static inline int admit(admit_t *a, unsigned gx, unsigned gy, unsigned gz, CUstr
   a->slot = slot_of(h, s, ptsz);
   /* the legacy NULL stream cannot be captured; any other stream might be */
   int capturing = 0;
-  if ((s != NULL || ptsz) && R.cuStreamIsCapturing) R.cuStreamIsCapturing(s, &capturing);
+  if ((s != NULL || ptsz) && R.cuStreamIsCapturing) VGPU_CAPCHK(R.cuStreamIsCapturing(s, &capturing));
   if (capturing) { /* graph capture: tokens are paid at capture time, like the reference; no gate or
                       marker nodes are recorded into the graph (they would replay stale values) */
     a->rt = NULL;
@@ -548,7 +555,7 @@ static inline int admit(admit_t *a, unsigned gx, unsigned gy, unsigned gz, CUstr
     if (likely(rt->memops64 > 0)) {
       CUresult (*wait)(CUstream, CUdeviceptr, cuuint64_t, unsigned) =
           (ptsz && R.cuStreamWaitValue64_v2_ptsz) ? R.cuStreamWaitValue64_v2_ptsz : R.cuStreamWaitValue64_v2;
-      CUresult wr = wait(s, rt->lim_h_d + offsetof(vgpu_lim_host_t, granted_mirror), (cuuint64_t)ticket, VCU_WAIT_GEQ);
+      CUresult wr = VGPU_CAPCHK(wait(s, rt->lim_h_d + offsetof(vgpu_lim_host_t, granted_mirror), (cuuint64_t)ticket, VCU_WAIT_GEQ));
       if (unlikely(wr != CUDA_SUCCESS)) {
         VLOG(VL_ERROR, "cuStreamWaitValue64 failed (%d: %s); falling back to the gate kernel", wr, vgpu_cu_err(wr));
         rt->memops64 = 0;

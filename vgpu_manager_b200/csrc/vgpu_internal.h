@@ -103,6 +103,7 @@ void vgpu_log_emit(int level, const char *file, int line, const char *fmt, ...)
   X(cuStreamDestroy_v2, CUresult, (CUstream))                                                   \
   X(cuStreamQuery, CUresult, (CUstream))                                                        \
   X(cuStreamIsCapturing, CUresult, (CUstream, int *))                                           \
+  X(cuThreadExchangeStreamCaptureMode, CUresult, (int *))                                       \
   X(cuStreamWaitValue64_v2, CUresult, (CUstream, CUdeviceptr, cuuint64_t, unsigned int))        \
   X(cuStreamWaitValue64_v2_ptsz, CUresult, (CUstream, CUdeviceptr, cuuint64_t, unsigned int))   \
   X(cuStreamWriteValue64_v2, CUresult, (CUstream, CUdeviceptr, cuuint64_t, unsigned int))       \
@@ -170,6 +171,28 @@ typedef struct {
 extern vgpu_real_t R; /* real entry points; NULL when the driver lacks the symbol */
 typedef void *(*vgpu_dlsym_fn)(void *, const char *);
 extern vgpu_dlsym_fn vgpu_real_dlsym;
+
+/* A library call that conflicts with a tenant's ongoing stream capture invalidates the tenant's
+ * graph (CUDA_ERROR_STREAM_CAPTURE_* = 900..908): never let that pass silently. */
+#define VGPU_CAPCHK(call) vgpu_capchk((call), #call, __FILE__, __LINE__)
+static inline CUresult vgpu_capchk(CUresult r, const char *what, const char *file, int line) {
+  if (__builtin_expect((int)r >= 900 && (int)r <= 908, 0))
+    vgpu_log_emit(VL_ERROR, file, line, "stream-capture conflict: %s returned %d", what, (int)r);
+  return r;
+}
+
+/* Library-internal driver calls that CUDA classifies as "potentially unsafe" (cuStreamQuery,
+ * cuStreamSynchronize ...) would invalidate a graph capture that ANOTHER tenant thread has open
+ * in global mode (seen with torch.cuda.graph: CUDA_ERROR_STREAM_CAPTURE_UNSUPPORTED from the tick
+ * thread's cuStreamQuery).  They run with this thread's capture-interaction mode set to relaxed. */
+static inline int vgpu_capture_relax(void) {
+  int mode = VCU_STREAM_CAPTURE_MODE_RELAXED;
+  if (R.cuThreadExchangeStreamCaptureMode && R.cuThreadExchangeStreamCaptureMode(&mode) == CUDA_SUCCESS) return mode;
+  return -1;
+}
+static inline void vgpu_capture_restore(int prev) {
+  if (prev >= 0 && R.cuThreadExchangeStreamCaptureMode) R.cuThreadExchangeStreamCaptureMode(&prev);
+}
 
 /* ------------------------------------------------------------------ global state */
 extern vgpu_cfg_t *G_cfg;       /* mmap'ed (RO) or env-built vgpu.config */

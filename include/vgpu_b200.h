@@ -70,6 +70,10 @@ typedef int vb_nvmlReturn;               /* nvmlReturn_t  */
  *                                            kernel to retire before the tenant's device sync)
  *  cuStreamDestroy_v2                       (none - B200 addition: releases the stream's
  *                                            completion-marker slot)
+ *  cuCtxDestroy / _v2                       (none - B200 addition: the token bucket, slab, streams and
+ *  cuDevicePrimaryCtxReset / _v2              module live in the tenant's context; these detach the
+ *  cuDevicePrimaryCtxRelease / _v2            runtime before the driver frees it, the next hooked call
+ *                                            rebuilds it in the new context)
  *  cuGraphInstantiateWithFlags              library/src/cuda_originals.c:2953-2980 (forward) - B200
  *  cuGraphInstantiateWithParams / _ptsz       addition, opt-in VGPU_B200_GRAPH_LIMIT=1: learns the
  *  cuGraphExecDestroy                         token cost of a graph (sum of its kernel nodes' grids)

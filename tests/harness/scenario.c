@@ -87,6 +87,16 @@ int main(int argc, char **argv) {
       int r5 = n_init();
       int r6 = n_h((unsigned)a, &nvdev);
       printf("init %d %d %d %d %d %d\n", r1, r2, r3, r4, r5, r6);
+    } else if (!strcmp(cmd, "reset")) { /* cudaDeviceReset(): primary context destroyed and re-created */
+      CUresult (*f_reset)(int) = sym("cuDevicePrimaryCtxReset_v2");
+      CUresult (*f_ret)(void **, int) = sym("cuDevicePrimaryCtxRetain");
+      CUresult (*f_set)(void *) = sym("cuCtxSetCurrent");
+      CUresult r1 = f_reset ? f_reset(dev) : 500;
+      g_np = 0; /* every allocation died with the context */
+      g_exec = NULL;
+      CUresult r2 = f_ret(&ctx, dev);
+      CUresult r3 = f_set(ctx);
+      printf("reset %d %d %d\n", r1, r2, r3);
     } else if (!strcmp(cmd, "nvmlinit")) {
       /* NVML-only client (nvidia-smi style): no cuInit, no CUDA context */
       int (*n_init)(void) = sym("nvmlInit_v2");

@@ -201,6 +201,20 @@ EXPORT CUresult cuGetErrorName(CUresult r, const char **s) { return cuGetErrorSt
 /* contexts: one implicit primary context per device, made current by the harness */
 EXPORT CUresult cuDevicePrimaryCtxRetain(void **ctx, CUdevice d) { stub_init(); *ctx = (void *)(uintptr_t)(0x1000 + d); g_any_ctx = 1; return 0; }
 EXPORT CUresult cuDevicePrimaryCtxRelease_v2(CUdevice d) { (void)d; return 0; }
+EXPORT CUresult cuDevicePrimaryCtxGetState(CUdevice d, unsigned *flags, int *active) { (void)d; if (flags) *flags = 0; *active = g_any_ctx; return 0; }
+/* context death: everything that lived in it is unmapped, so a library that still touches its old
+ * device or pinned memory afterwards faults instead of silently reading stale bytes */
+EXPORT CUresult cuDevicePrimaryCtxReset_v2(CUdevice d) {
+  (void)d;
+  pthread_mutex_lock(&g_mu);
+  for (size_t i = 0; i < g_nallocs; i++) big_free(g_allocs[i].p, g_allocs[i].n);
+  g_nallocs = 0;
+  memset(g_dev_bytes, 0, sizeof g_dev_bytes);
+  g_any_ctx = 0;
+  pthread_mutex_unlock(&g_mu);
+  t_has_ctx = 0;
+  return 0;
+}
 EXPORT CUresult cuCtxCreate_v2(void **ctx, unsigned f, CUdevice d) { (void)f; stub_init(); *ctx = (void *)(uintptr_t)(0x1000 + d); t_cur_dev = d; t_has_ctx = 1; g_any_ctx = 1; return 0; }
 EXPORT CUresult cuCtxDestroy_v2(void *ctx) { (void)ctx; return 0; }
 EXPORT CUresult cuCtxSetCurrent(void *ctx) { if (!ctx) { t_has_ctx = 0; return 0; } t_cur_dev = (int)((uintptr_t)ctx - 0x1000); t_has_ctx = 1; return 0; }
@@ -723,6 +737,9 @@ static const struct { const char *name; void *fn; } g_self_table[] = {
   {"cuGetErrorName", (void *)cuGetErrorName},
   {"cuDevicePrimaryCtxRetain", (void *)cuDevicePrimaryCtxRetain},
   {"cuDevicePrimaryCtxRelease_v2", (void *)cuDevicePrimaryCtxRelease_v2},
+  {"cuDevicePrimaryCtxRelease", (void *)cuDevicePrimaryCtxRelease_v2},
+  {"cuDevicePrimaryCtxReset_v2", (void *)cuDevicePrimaryCtxReset_v2}, {"cuDevicePrimaryCtxReset", (void *)cuDevicePrimaryCtxReset_v2},
+  {"cuDevicePrimaryCtxGetState", (void *)cuDevicePrimaryCtxGetState},
   {"cuCtxCreate_v2", (void *)cuCtxCreate_v2},
   {"cuCtxDestroy_v2", (void *)cuCtxDestroy_v2},
   {"cuCtxSetCurrent", (void *)cuCtxSetCurrent},

@@ -30,7 +30,9 @@ def test_exports_the_reference_hook_surface_and_nothing_accidental(built):
     extra = {s for s in sym if not s.startswith("vgpu_b200_")} - set(REFERENCE_CUDA_HOOKS) - set(REFERENCE_NVML_HOOKS)
     graph_opt_in = {"cuGraphInstantiateWithFlags", "cuGraphInstantiateWithParams", "cuGraphInstantiateWithParams_ptsz",
                     "cuGraphExecDestroy", "cuGraphLaunch", "cuGraphLaunch_ptsz"}
-    assert extra == {"dlsym", "cuCtxSynchronize", "cuStreamDestroy_v2", "nvmlDeviceGetUtilizationRates"} | graph_opt_in, extra
+    ctx_teardown = {"cuCtxDestroy", "cuCtxDestroy_v2", "cuDevicePrimaryCtxReset", "cuDevicePrimaryCtxReset_v2",
+                    "cuDevicePrimaryCtxRelease", "cuDevicePrimaryCtxRelease_v2"}
+    assert extra == {"dlsym", "cuCtxSynchronize", "cuStreamDestroy_v2", "nvmlDeviceGetUtilizationRates"} | graph_opt_in | ctx_teardown, extra
     if H.have_reference():
         ref = exported(H.REF_SO)
         assert set(REFERENCE_CUDA_HOOKS + REFERENCE_NVML_HOOKS + ["dlsym"]) <= ref

@@ -336,3 +336,23 @@ def test_cuda_graph_replays_forward_by_default_and_are_metered_on_request(built)
     out, err, sb = H.run_scenario(H.NEW_SO, "init 0\ngraph 8 4000\ngraphlaunch 400\n", hot)
     sb.cleanup()
     assert "graphlaunch 400 -> ok 400" in out and "metric=rate_gated" in err
+
+
+def test_device_reset_rebuilds_the_device_state(built):
+    """cudaDeviceReset() mid-process: the reference keeps no device state and simply carries on;
+    this library's token bucket / slab / streams die with the context (the stub unmaps them, so a
+    stale access faults) and must be rebuilt on next use - same transcript, cap still enforced,
+    launches still metered."""
+    script = ("init 0\nalloc %d\nalloc %d\nmeminfo\nlaunch 300 4 1 1\n"
+              "reset\nmeminfo\nalloc %d\nalloc %d\nalloc %d\nmeminfo\nnvmlinfo\nlaunch 300 4 1 1\n"
+              "reset\nalloc %d\nmeminfo\n") % (256 * MiB, 256 * MiB, 512 * MiB, 400 * MiB, 400 * MiB, 900 * MiB)
+    env = {"CUDA_MEM_LIMIT_0": "1g", "CUDA_CORE_LIMIT_0": "50", "STUB_UTIL": "fixed:20"}
+    for args in ((), ("--gpa",)):
+        t = assert_same(both(script, env, args=args))
+        assert t.count("reset 0 0 0") == 2 and "-> 2" in t  # the cap is enforced again after the reset
+    e = dict(BASE)
+    e.update(env)
+    out, err, sb = H.run_scenario(H.NEW_SO, script + "limstate\n", dict(e, LOGGER_LEVEL="3"))
+    sb.cleanup()
+    assert err.count("device runtime up") == 3 and err.count("will be rebuilt on next use") == 2, err[-1500:]
+    assert "limstate consumed 0" in out  # a fresh bucket after the last reset (nothing launched since)

@@ -62,6 +62,18 @@ def test_oversold_spill_sequence_matches_reference_on_real_driver(built):
     assert "ledger -> size 1 [self" in a and "-> 2" in a
 
 
+def test_device_reset_mid_process_matches_reference_on_real_driver(built):
+    """cudaDeviceReset() and carry on: the library's device-resident state dies with the primary context
+    and is rebuilt (own footprint re-measured) - every reported number still equals the reference's."""
+    lines = ["init 0", "alloc %d" % GiB, "alloc %d" % GiB, "meminfo", "nvmlinfo", "reset", "meminfo", "nvmlinfo",
+             "alloc %d" % (2 * GiB), "alloc %d" % GiB, "alloc %d" % GiB, "meminfo", "nvmlinfo", "nvmlinfo2", "reset",
+             "alloc %d" % (512 * MiB), "meminfo", "nvmlinfo"]
+    for args in ((), ("--gpa",)):
+        (a, ea), (b, eb) = both("\n".join(lines) + "\n", {"CUDA_MEM_LIMIT_0": "4g", "CUDA_CORE_LIMIT_0": "50"}, args=args)
+        assert a == b, "reference:\n%s\nb200:\n%s\n%s" % (a, b, eb[-2000:])
+        assert a.count("reset 0 0 0") == 2 and "-> 2" in a
+
+
 def test_launch_storm_under_core_cap_completes_and_is_gated_on_device(built):
     sb = H.Sandbox()
     env = H.preload_env(H.NEW_SO, sb, {"MANAGER_COMPATIBILITY_MODE": "0", "MANAGER_VISIBLE_DEVICES": gpu0_uuid(),

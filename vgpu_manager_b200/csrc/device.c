@@ -116,6 +116,18 @@ static vgpu_dev_rt *bring_up(vgpu_dev_rt *rt, int slot, int host_index, CUdevice
   rt->host_index = host_index;
   rt->cuda_dev = dev;
   rt->ctx = ctx;
+  {
+    unsigned int fl = 0;
+    int active = 0;
+    CUcontext prim = NULL;
+    rt->ctx_is_primary = retained;
+    if (!retained && R.cuDevicePrimaryCtxGetState && R.cuDevicePrimaryCtxGetState(dev, &fl, &active) == CUDA_SUCCESS && active &&
+        R.cuDevicePrimaryCtxRetain && R.cuDevicePrimaryCtxRetain(&prim, dev) == CUDA_SUCCESS) {
+      rt->ctx_is_primary = (prim == ctx);
+      if (R.cuDevicePrimaryCtxRelease_v2) R.cuDevicePrimaryCtxRelease_v2(dev);
+      else if (R.cuDevicePrimaryCtxRelease) R.cuDevicePrimaryCtxRelease(dev);
+    }
+  }
 
   nvmlDevice_t nvdev = vgpu_nvml_handle_of_host(host_index);
   int lock_fd = host_index >= 0 ? vgpu_lock_gpu(host_index) : -1;
@@ -302,6 +314,45 @@ vgpu_dev_rt *vgpu_rt_get(int host_index, CUdevice dev) {
   }
   pthread_mutex_unlock(&g_rt_mu);
   return out;
+}
+
+unsigned vgpu_rt_context_before(CUcontext ctx, CUdevice dev, int primary) {
+  unsigned mask = 0;
+  if (g_rt_epoch != vgpu_fork_epoch + 1) return 0;
+  pthread_mutex_lock(&g_rt_mu);
+  for (int slot = 0; slot < VGPU_MAX_DEVICES; slot++) {
+    vgpu_dev_rt *rt = &g_rt[slot];
+    if (rt->ready != 1) continue;
+    int hit = primary ? (rt->cuda_dev == dev && rt->ctx_is_primary) : (rt->ctx == ctx);
+    if (!hit) continue;
+    if (rt->host_index >= 0) vgpu_limiter_detach(rt->host_index);
+    rt->ready = 2; /* parked: neither usable nor up for a new bring-up until _after() decides */
+    mask |= 1u << slot;
+  }
+  pthread_mutex_unlock(&g_rt_mu);
+  return mask;
+}
+
+void vgpu_rt_context_after(unsigned mask, int still_alive) {
+  if (!mask) return;
+  pthread_mutex_lock(&g_rt_mu);
+  for (int slot = 0; slot < VGPU_MAX_DEVICES; slot++) {
+    if (!(mask & (1u << slot))) continue;
+    vgpu_dev_rt *rt = &g_rt[slot];
+    if (rt->ready != 2) continue;
+    if (still_alive) {
+      rt->ready = 1;
+      if (rt->host_index >= 0) vgpu_limiter_attach(rt->host_index, 0);
+    } else {
+      /* everything the runtime owned went with the context; the next hooked call in a new
+       * context brings a fresh one up (token bucket and slab start empty, like a new process) */
+      VLOG(VL_INFO, "context of runtime slot %d is gone; device state will be rebuilt on next use", slot);
+      if (rt->host_index >= 0) vgpu_limiter_attach(rt->host_index, 1);
+      pthread_mutex_destroy(&rt->q_mu);
+      memset(rt, 0, sizeof *rt);
+    }
+  }
+  pthread_mutex_unlock(&g_rt_mu);
 }
 
 vgpu_dev_rt *vgpu_rt_peek(int host_index) {

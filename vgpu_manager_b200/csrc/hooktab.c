@@ -4,7 +4,8 @@
  * This is the drop-in boundary of SURVEY.md 8(b): the 37 CUDA names of reference
  * library/src/cuda_hook.c:243-281 and the 7 NVML names of library/src/nvml_hook.c:20-28, plus
  * cuCtxSynchronize (needed so a resident sampler kernel never delays a tenant's device
- * synchronisation) and nvmlDeviceGetUtilizationRates (named by BASELINE.json; pure forward in
+ * synchronisation), cuStreamDestroy and the context teardown entry points (the device-resident
+ * state lives in the tenant's context) and nvmlDeviceGetUtilizationRates (named by BASELINE.json; pure forward in
  * the reference, library/src/nvml_originals.c:698-702).
  * The entry points are only address-taken here, hence the untyped declarations.
  */
@@ -23,7 +24,9 @@
   X(cuLaunchGrid) X(cuLaunchGridAsync) X(cuFuncSetBlockShape) X(cuMemAllocAsync)              \
   X(cuMemAllocAsync_ptsz) X(cuMemCreate) X(cuMemAllocFromPoolAsync)                           \
   X(cuMemAllocFromPoolAsync_ptsz) X(cuMemFree_v2) X(cuMemFree) X(cuMemFreeAsync)              \
-  X(cuMemFreeAsync_ptsz) X(cuCtxSynchronize) X(cuStreamDestroy_v2)
+  X(cuMemFreeAsync_ptsz) X(cuCtxSynchronize) X(cuStreamDestroy_v2)                             \
+  X(cuCtxDestroy_v2) X(cuCtxDestroy) X(cuDevicePrimaryCtxReset_v2) X(cuDevicePrimaryCtxReset)  \
+  X(cuDevicePrimaryCtxRelease_v2) X(cuDevicePrimaryCtxRelease)
 /* opt-in (VGPU_B200_GRAPH_LIMIT=1): only then are these names substituted in dlsym /
  * cuGetProcAddress answers; the reference forwards all of them (cuda_originals.c:2953-3040) */
 #define VGPU_GRAPH_HOOKS(X)                                                                   \
@@ -55,6 +58,9 @@ void *vgpu_lookup_cuda_hook(const char *name, int want_ptsz) {
   /* cuGetProcAddress callers ask for the base name; cuStreamDestroy has had the _v2 ABI since
    * CUDA 4.0 and the driver hands out exactly that for it */
   if (!strcmp(name, "cuStreamDestroy")) name = "cuStreamDestroy_v2";
+  if (!strcmp(name, "cuCtxDestroy")) name = "cuCtxDestroy_v2";                           /* v2 ABI since CUDA 4.0 */
+  if (!strcmp(name, "cuDevicePrimaryCtxReset")) name = "cuDevicePrimaryCtxReset_v2";     /* since CUDA 11.0 */
+  if (!strcmp(name, "cuDevicePrimaryCtxRelease")) name = "cuDevicePrimaryCtxRelease_v2"; /* since CUDA 11.0 */
   if (!strncmp(name, "cuGraph", 7)) {
     if (!vgpu_graph_limit_enabled()) return NULL;
     /* since CUDA 12.0 the base name is the WithFlags entry point (cuda.h maps it); the legacy

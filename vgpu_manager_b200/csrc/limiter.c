@@ -97,6 +97,7 @@ static uint32_t g_gov_interval_us = 50, g_gov_period_us = 80000, g_gov_idle_us =
 static int g_governor_mode; /* VGPU_B200_GOVERNOR=1 */
 static uint32_t g_window_us = 500, g_interval_us = 50, g_period_ticks = 8, g_tick_ms = 10;
 static volatile int g_sync_waiters; /* threads currently inside a device-wide synchronise */
+static volatile unsigned long g_tick_gen, g_wd_gen; /* completed loop iterations (quiescence points) */
 
 static uint32_t env_u32(const char *name, uint32_t dflt) {
   const char *s = getenv(name);
@@ -244,6 +245,7 @@ static void *tick_main(void *arg) {
       CUcontext dummy;
       R.cuCtxPopCurrent_v2(&dummy);
     }
+    g_tick_gen++;
     uint64_t after = tick_ns - before;
     struct timespec rest = {(time_t)(after / 1000000000ull), (long)(after % 1000000000ull)};
     nanosleep(&rest, NULL);
@@ -301,6 +303,7 @@ static void *watchdog_main(void *arg) {
       VLOG(VL_WARNING, "host device %d: controller has not stepped for %u ms while streams are parked "
                        "(driver busy?); lent tokens up to ticket %lld", h, g_watchdog_ms, newest);
     }
+    g_wd_gen++;
   }
 }
 
@@ -428,6 +431,31 @@ static inline void governor_ensure(vgpu_dev_rt *rt, int h) {
  * is (or was, when it left) still executing, so that the time it was away is attributed. */
 static __thread unsigned long long t_sync_snap[VGPU_STREAM_SLOTS];
 static inline void enqueue_marker(vgpu_dev_rt *rt, int h, uint32_t slot, unsigned long long seq, CUstream s, int ptsz);
+
+/* The tenant is tearing a context down: make sure neither background thread is inside (or will
+ * enter) this device's runtime.  Both re-read g_tick_devices[] at the top of every iteration, so
+ * one completed iteration after the flag is cleared is a quiescence point. */
+void vgpu_limiter_detach(int h) {
+  if (h < 0 || h >= VGPU_MAX_DEVICES || !g_tick_devices[h]) return;
+  g_tick_devices[h] = 0;
+  __sync_synchronize();
+  if (g_tick_epoch != vgpu_fork_epoch + 1) return;
+  unsigned long t0 = g_tick_gen, w0 = g_wd_gen;
+  struct timespec nap = {0, 1000000};
+  for (int i = 0; i < 2000; i++) { /* 2 s: a tick thread stuck in the driver must not wedge the tenant */
+    if ((!g_tick_running || g_tick_gen != t0) && (!g_wd_running || g_wd_gen != w0)) break;
+    nanosleep(&nap, NULL);
+  }
+}
+
+void vgpu_limiter_attach(int h, int forget_streams) {
+  if (h < 0 || h >= VGPU_MAX_DEVICES) return;
+  if (forget_streams) {
+    memset((void *)g_slots[h], 0, sizeof g_slots[h]);
+    return; /* the next limited launch registers the device again */
+  }
+  g_tick_devices[h] = 1;
+}
 
 void vgpu_limiter_quiesce(vgpu_dev_rt *rt) {
   if (!rt || !rt->lim_h) return;
@@ -829,4 +857,45 @@ VGPU_EXPORT CUresult cuGraphLaunch_ptsz(CUgraphExec exec, CUstream s) {
   unsigned tokens = graph_tokens(exec);
   if (!tokens) return R.cuGraphLaunch_ptsz(exec, s);
   LIMITED_LAUNCH(tokens, 1, 1, s, 1, R.cuGraphLaunch_ptsz(exec, s));
+}
+
+/* ------------------------------------------------------------------ context teardown (B200 addition)
+ * The reference keeps no device state, so it does not care when a tenant destroys or resets a
+ * context; this library's token bucket, slab, streams and module live in one.  These hooks
+ * detach the runtime before the driver frees everything underneath it. */
+static CUresult ctx_gone(CUresult (*real)(CUcontext), CUcontext ctx) {
+  vgpu_boot();
+  if (unlikely(!real)) return CUDA_ERROR_NOT_FOUND;
+  unsigned mask = vgpu_rt_context_before(ctx, 0, 0);
+  CUresult r = real(ctx);
+  vgpu_rt_context_after(mask, r != CUDA_SUCCESS);
+  return r;
+}
+static CUresult primary_gone(CUresult (*real)(CUdevice), CUdevice dev, int release) {
+  vgpu_boot();
+  if (unlikely(!real)) return CUDA_ERROR_NOT_FOUND;
+  unsigned mask = vgpu_rt_context_before(NULL, dev, 1);
+  CUresult r = real(dev);
+  int alive = (r != CUDA_SUCCESS);
+  if (!alive && release && mask) { /* a release only destroys the context when it was the last reference */
+    unsigned int fl = 0;
+    int active = 0;
+    if (R.cuDevicePrimaryCtxGetState && R.cuDevicePrimaryCtxGetState(dev, &fl, &active) == CUDA_SUCCESS) alive = active;
+  }
+  vgpu_rt_context_after(mask, alive);
+  return r;
+}
+VGPU_EXPORT CUresult cuCtxDestroy_v2(CUcontext ctx) { return ctx_gone(R.cuCtxDestroy_v2 ? R.cuCtxDestroy_v2 : R.cuCtxDestroy, ctx); }
+VGPU_EXPORT CUresult cuCtxDestroy(CUcontext ctx) { return ctx_gone(R.cuCtxDestroy ? R.cuCtxDestroy : R.cuCtxDestroy_v2, ctx); }
+VGPU_EXPORT CUresult cuDevicePrimaryCtxReset_v2(CUdevice dev) {
+  return primary_gone(R.cuDevicePrimaryCtxReset_v2 ? R.cuDevicePrimaryCtxReset_v2 : R.cuDevicePrimaryCtxReset, dev, 0);
+}
+VGPU_EXPORT CUresult cuDevicePrimaryCtxReset(CUdevice dev) {
+  return primary_gone(R.cuDevicePrimaryCtxReset ? R.cuDevicePrimaryCtxReset : R.cuDevicePrimaryCtxReset_v2, dev, 0);
+}
+VGPU_EXPORT CUresult cuDevicePrimaryCtxRelease_v2(CUdevice dev) {
+  return primary_gone(R.cuDevicePrimaryCtxRelease_v2 ? R.cuDevicePrimaryCtxRelease_v2 : R.cuDevicePrimaryCtxRelease, dev, 1);
+}
+VGPU_EXPORT CUresult cuDevicePrimaryCtxRelease(CUdevice dev) {
+  return primary_gone(R.cuDevicePrimaryCtxRelease ? R.cuDevicePrimaryCtxRelease : R.cuDevicePrimaryCtxRelease_v2, dev, 1);
 }

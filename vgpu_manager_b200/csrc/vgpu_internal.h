@@ -62,6 +62,13 @@ void vgpu_log_emit(int level, const char *file, int line, const char *fmt, ...)
   X(cuCtxPopCurrent_v2, CUresult, (CUcontext *))                                                \
   X(cuCtxSynchronize, CUresult, (void))                                                         \
   X(cuDevicePrimaryCtxRetain, CUresult, (CUcontext *, CUdevice))                                \
+  X(cuDevicePrimaryCtxGetState, CUresult, (CUdevice, unsigned int *, int *))                    \
+  X(cuDevicePrimaryCtxRelease, CUresult, (CUdevice))                                            \
+  X(cuDevicePrimaryCtxRelease_v2, CUresult, (CUdevice))                                         \
+  X(cuDevicePrimaryCtxReset, CUresult, (CUdevice))                                              \
+  X(cuDevicePrimaryCtxReset_v2, CUresult, (CUdevice))                                           \
+  X(cuCtxDestroy, CUresult, (CUcontext))                                                        \
+  X(cuCtxDestroy_v2, CUresult, (CUcontext))                                                     \
   X(cuMemAlloc, CUresult, (CUdeviceptr *, size_t))                                              \
   X(cuMemAlloc_v2, CUresult, (CUdeviceptr *, size_t))                                           \
   X(cuMemAllocManaged, CUresult, (CUdeviceptr *, size_t, unsigned int))                         \
@@ -257,11 +264,18 @@ typedef struct vgpu_dev_rt {
   int sm_num, max_thread_per_sm;
   int64_t total_cores;
   int memops64; /* cuStreamWaitValue64 usable */
+  int ctx_is_primary; /* `ctx` is the device's primary context */
   uint32_t spill_chunk, spill_stages, spill_ctas_per_sm;
 } vgpu_dev_rt;
 
 vgpu_dev_rt *vgpu_rt_get(int host_index, CUdevice dev); /* bring up (needs a current ctx) */
 vgpu_dev_rt *vgpu_rt_peek(int host_index);              /* NULL unless ready */
+/* The tenant is about to destroy / reset / release a context: every runtime living in it stops
+ * being used (its streams, module, HBM and pinned blocks die with the context).  Returns a
+ * bitmask of the detached runtime slots for vgpu_rt_context_after(). */
+unsigned vgpu_rt_context_before(CUcontext ctx, CUdevice dev, int primary);
+/* still_alive != 0 (a primary-context release that left references): take the runtimes back */
+void vgpu_rt_context_after(unsigned mask, int still_alive);
 CUresult vgpu_rt_launch(vgpu_dev_rt *rt, CUfunction f, unsigned grid, unsigned block,
                         unsigned smem, CUstream s, void **params);
 
@@ -273,6 +287,8 @@ CUresult vgpu_rt_spill(vgpu_dev_rt *rt, CUdeviceptr dst, CUdeviceptr src, size_t
 
 /* limiter.c */
 void vgpu_limiter_start(void); /* == reference initialization() (cuda_hook.c:566) */
+void vgpu_limiter_detach(int host_index); /* tick + watchdog threads stop touching this device's runtime */
+void vgpu_limiter_attach(int host_index, int forget_streams);
 void vgpu_limiter_quiesce(vgpu_dev_rt *rt); /* device-wide sync ahead: governor retires once nothing is parked */
 void vgpu_limiter_resume(vgpu_dev_rt *rt, int everything_completed); /* the sync returned */
 

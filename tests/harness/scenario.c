@@ -87,6 +87,16 @@ int main(int argc, char **argv) {
       int r5 = n_init();
       int r6 = n_h((unsigned)a, &nvdev);
       printf("init %d %d %d %d %d %d\n", r1, r2, r3, r4, r5, r6);
+    } else if (!strcmp(cmd, "dev")) { /* switch this thread to device <a> (its primary context) */
+      CUresult (*f_get)(int *, int) = sym("cuDeviceGet");
+      CUresult (*f_ret)(void **, int) = sym("cuDevicePrimaryCtxRetain");
+      CUresult (*f_set)(void *) = sym("cuCtxSetCurrent");
+      int (*n_h)(unsigned, void **) = sym("nvmlDeviceGetHandleByIndex_v2");
+      CUresult r2 = f_get(&dev, (int)a);
+      CUresult r3 = f_ret(&ctx, dev);
+      CUresult r4 = f_set(ctx);
+      int r6 = n_h((unsigned)a, &nvdev);
+      printf("dev %llu -> %d %d %d %d\n", a, r2, r3, r4, r6);
     } else if (!strcmp(cmd, "reset")) { /* cudaDeviceReset(): primary context destroyed and re-created */
       CUresult (*f_reset)(int) = sym("cuDevicePrimaryCtxReset_v2");
       CUresult (*f_ret)(void **, int) = sym("cuDevicePrimaryCtxRetain");

@@ -356,3 +356,21 @@ def test_device_reset_rebuilds_the_device_state(built):
     sb.cleanup()
     assert err.count("device runtime up") == 3 and err.count("will be rebuilt on next use") == 2, err[-1500:]
     assert "limstate consumed 0" in out  # a fresh bucket after the last reset (nothing launched since)
+
+
+def test_one_process_on_two_gpus_with_a_hole_in_the_visible_list(built):
+    """MANAGER_VISIBLE_DEVICES lists host GPUs by index with all-zero UUIDs as holes (util.c:27-120):
+    host 0 = CUDA device 1, host 1 = hole, host 2 = CUDA device 0.  One process uses both devices;
+    caps, reported numbers and the written vgpu.config must follow the host index, not the CUDA one."""
+    u0, u1 = H.STUB_UUID, "GPU-22222222-2222-2222-2222-222222222222"
+    hole = "GPU-00000000-0000-0000-0000-000000000000"
+    env = {"MANAGER_VISIBLE_DEVICES": ",".join((u1, hole, u0)), "CUDA_MEM_LIMIT_0": "1g", "CUDA_MEM_LIMIT_2": "3g",
+           "CUDA_CORE_LIMIT_0": "30", "CUDA_CORE_LIMIT_2": "60", "CUDA_MEM_LIMIT": "2g"}
+    script = ("init 0\ntotalmem\nmeminfo\nalloc %d\nalloc %d\nmeminfo\nnvmlinfo\n"        # CUDA 0 = host 2: 3 GiB cap
+              "dev 1\ntotalmem\nmeminfo\nalloc %d\nalloc %d\nmeminfo\nnvmlinfo\nlaunch 200 3 1 1\n"  # CUDA 1 = host 0: 1 GiB cap
+              "dev 0\nmeminfo\nalloc %d\nmeminfo\nlaunch 200 3 1 1\n") % (GiB, GiB, 600 * MiB, 600 * MiB, 2 * GiB)
+    outs = both(script, env, {"STUB_GPU_COUNT": "2", "STUB_UTIL": "fixed:10"})
+    t = assert_same(outs)
+    lines = t.splitlines()
+    assert lines[1].endswith(str(3 * GiB)) and any(l.startswith("totalmem") and l.endswith(str(GiB)) for l in lines[8:11]), t
+    assert t.count("-> 2") == 2  # one refusal per device, each against its own cap

@@ -74,6 +74,28 @@ def test_device_reset_mid_process_matches_reference_on_real_driver(built):
         assert a.count("reset 0 0 0") == 2 and "-> 2" in a
 
 
+def gpu_uuids():
+    out = subprocess.run(["nvidia-smi", "--query-gpu=uuid", "--format=csv,noheader"], capture_output=True, text=True)
+    return [l.strip() for l in out.stdout.splitlines() if l.strip()]
+
+
+@pytest.mark.skipif(len(gpu_uuids()) < 2, reason="needs two GPUs (gpurun --gpus 2)")
+def test_one_process_on_two_real_gpus_follows_host_indexes(built):
+    """Host index 0 = CUDA device 1, host index 1 = a hole, host index 2 = CUDA device 0 (the visible list is
+    in host order, CUDA order comes from CUDA_VISIBLE_DEVICES): caps and reported numbers per device must
+    match the reference's, which resolves the mapping through the UUIDs like this library does."""
+    u = gpu_uuids()
+    hole = "GPU-00000000-0000-0000-0000-000000000000"
+    env = {"MANAGER_VISIBLE_DEVICES": ",".join((u[1], hole, u[0])), "CUDA_VISIBLE_DEVICES": "0,1",
+           "CUDA_MEM_LIMIT_0": "2g", "CUDA_MEM_LIMIT_2": "6g", "CUDA_CORE_LIMIT_0": "30", "CUDA_CORE_LIMIT_2": "60"}
+    lines = ["init 0", "totalmem", "meminfo", "alloc %d" % (2 * GiB), "alloc %d" % (2 * GiB), "meminfo", "nvmlinfo",
+             "dev 1", "totalmem", "meminfo", "alloc %d" % GiB, "alloc %d" % GiB, "meminfo", "nvmlinfo",
+             "dev 0", "meminfo", "alloc %d" % (3 * GiB), "meminfo", "nvmlinfo2"]
+    (a, ea), (b, eb) = both("\n".join(lines) + "\n", env)
+    assert a == b, "reference:\n%s\nb200:\n%s\n%s" % (a, b, eb[-2000:])
+    assert a.count("-> 2") == 2 and str(6 * GiB) in a.splitlines()[1]
+
+
 def test_launch_storm_under_core_cap_completes_and_is_gated_on_device(built):
     sb = H.Sandbox()
     env = H.preload_env(H.NEW_SO, sb, {"MANAGER_COMPATIBILITY_MODE": "0", "MANAGER_VISIBLE_DEVICES": gpu0_uuid(),

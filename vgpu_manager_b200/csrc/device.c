@@ -383,7 +383,12 @@ int vgpu_rt_quota(vgpu_dev_rt *rt, vgpu_quota_res_t *out) {
   __sync_synchronize();
   void *params[] = {&rt->q_req_d, &rt->q_res_d};
   int pushed = ctx_enter(rt);
-  CUresult r = vgpu_rt_launch(rt, rt->k_quota, 1, 1024, 0, rt->q_stream, params);
+  /* one thread per record of the longest list, whole warps (see the kernel) */
+  uint32_t longest = rt->q_req->n_compute > rt->q_req->n_graphics ? rt->q_req->n_compute : rt->q_req->n_graphics;
+  if (rt->q_req->n_vmem > longest) longest = rt->q_req->n_vmem;
+  if (longest > VGPU_MAX_PIDS) longest = VGPU_MAX_PIDS;
+  unsigned block = longest ? (longest + 31u) & ~31u : 32u;
+  CUresult r = vgpu_rt_launch(rt, rt->k_quota, 1, block, 0, rt->q_stream, params);
   if (r != CUDA_SUCCESS) {
     ctx_leave(pushed);
     VLOG(VL_ERROR, "quota kernel launch failed: %d (%s)", r, vgpu_cu_err(r));

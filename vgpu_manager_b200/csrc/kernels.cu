@@ -207,7 +207,7 @@ DEVINL unsigned int warp_min_u32(unsigned int v) {
   for (int o = 16; o > 0; o >>= 1) v = min(v, __shfl_down_sync(0xffffffffu, v, o));
   return v;
 }
-/* all threads of a 1024-thread CTA call; result valid in every thread */
+/* all threads of the CTA call (blockDim a multiple of 32); result valid in every thread */
 DEVINL unsigned long long block_sum_u64(unsigned long long v, unsigned long long *scratch) {
   v = warp_sum_u64(v);
   __syncthreads();
@@ -237,8 +237,8 @@ DEVINL unsigned int block_min_u32(unsigned int v, unsigned int *scratch) {
 }
 
 /* ======================================================================= memory quota
- * One CTA of 1024 threads: thread i owns compute record i, graphics record i and ledger
- * record i (each list is capped at 1024 by the contract).  The request block lives in pinned
+ * One CTA of ceil32(longest list) <= 1024 threads: thread i owns compute record i, graphics
+ * record i and ledger record i (each list is capped at 1024 by the contract).  The request block lives in pinned
  * host memory; every record is fetched with one 128-bit load. */
 
 /* membership ladder shared by memory and utilisation folds (cuda_hook.c:740-803) */
@@ -290,6 +290,15 @@ extern "C" __global__ void __launch_bounds__(1024)
   __shared__ int self_state;
 
   const uint32_t t = threadIdx.x;
+  /* The request block is pinned host memory: every load below is a PCIe round trip (~1.5 us).
+   * The record loads therefore do not wait for the header that says how many records are valid -
+   * the host launches ceil32(max(n)) threads, so thread t's records exist (or are stale bytes
+   * that are masked out below) - and all five loads of a thread are in flight together. */
+  const uint4 c_raw = *reinterpret_cast<const uint4 *>(&req->compute[t]);
+  const uint4 g_raw = *reinterpret_cast<const uint4 *>(&req->graphics[t]);
+  const uint4 v_raw = *reinterpret_cast<const uint4 *>(&req->vmem[t]);
+  const uint32_t cf_raw = req->cflags[t];
+  const uint32_t gf_raw = req->gflags[t];
   const uint32_t nc = min(req->n_compute, (uint32_t)VGPU_MAX_PIDS);
   const uint32_t ng = min(req->n_graphics, (uint32_t)VGPU_MAX_PIDS);
   const uint32_t nv = min(req->n_vmem, (uint32_t)VGPU_MAX_PIDS);
@@ -299,32 +308,26 @@ extern "C" __global__ void __launch_bounds__(1024)
   if (t == 0) self_state = 0;
 
   /* compute list */
-  uint4 c = make_uint4(0, 0, 0, 0);
-  if (t < nc) c = *reinterpret_cast<const uint4 *>(&req->compute[t]);
+  const uint4 c = (t < nc) ? c_raw : make_uint4(0, 0, 0, 0);
   cpid[t] = (t < nc) ? c.x : 0xffffffffu;
   unsigned long long cbytes = ((unsigned long long)c.w << 32) | c.z;
-  uint32_t cf = (t < nc) ? req->cflags[t] : 0;
+  uint32_t cf = (t < nc) ? cf_raw : 0;
   __syncthreads();
   unsigned long long used = fold_list(sel, open_mode, t < nc, cf, cbytes, s64, s32, c.x == self_pid, &self_state);
 
   /* graphics list minus pids already present in the compute list (cuda_hook.c:868-887) */
-  uint4 g = make_uint4(0, 0, 0, 0);
-  if (t < ng) g = *reinterpret_cast<const uint4 *>(&req->graphics[t]);
+  const uint4 g = (t < ng) ? g_raw : make_uint4(0, 0, 0, 0);
   bool glive = t < ng;
   if (glive) {
     for (uint32_t j = 0; j < nc; j++)
       if (cpid[j] == g.x) { glive = false; break; }
   }
   unsigned long long gbytes = ((unsigned long long)g.w << 32) | g.z;
-  uint32_t gf = (t < ng) ? req->gflags[t] : 0;
+  uint32_t gf = (t < ng) ? gf_raw : 0;
   used += fold_list(sel, open_mode, glive, gf, gbytes, s64, s32, g.x == self_pid, &self_state);
 
   /* UVA ledger sum (loader.c:1909-1922) */
-  unsigned long long v = 0;
-  if (t < nv) {
-    uint4 r = *reinterpret_cast<const uint4 *>(&req->vmem[t]);
-    v = ((unsigned long long)r.w << 32) | r.z;
-  }
+  unsigned long long v = (t < nv) ? (((unsigned long long)v_raw.w << 32) | v_raw.z) : 0;
   unsigned long long vmem = block_sum_u64(v, s64);
 
   if (t == 0) {

@@ -1,0 +1,97 @@
+"""Seeded random differential test on the stub driver: random tenant scripts (every allocation API the
+reference hooks, frees, the four reporting calls, launches) under random limit configurations
+(cap, oversold ratio, ledger on/off, other tenants' processes incl. graphics/compute overlap,
+compatibility mode host / cgroup-v2), run under the compiled reference and under the B200 library:
+transcripts and the published vgpu.config must be identical.  Deterministic (seed 0x5EED)."""
+import os
+import random
+
+import pytest
+
+import helpers as H
+
+pytestmark = pytest.mark.skipif(not os.path.exists(H.REF_SO), reason="needs oracle/_ref (the compiled reference)")
+MiB, GiB = 1 << 20, 1 << 30
+
+
+@pytest.fixture(scope="module")
+def built():
+    H.build_all()
+
+
+def random_script(rng, n_cmds):
+    lines = ["init 0", "totalmem", "meminfo"]
+    handles = 0
+    sizes = [1, 4096, 65536, MiB, 3 * MiB + 17, 64 * MiB, 200 * MiB, 512 * MiB, GiB, 3 * GiB, (1 << 63) + 5, (1 << 64) - 4096]
+    for _ in range(n_cmds):
+        k = rng.random()
+        if k < 0.28:
+            lines.append("alloc %d" % rng.choice(sizes)); handles += 1
+        elif k < 0.36:
+            lines.append("managed %d %d" % (rng.choice(sizes[:9]), rng.choice((1, 2)))); handles += 1
+        elif k < 0.42:
+            lines.append("pitch %d %d %d" % (rng.choice((1000, 4096, 1 << 20)), rng.choice((1, 100, 3000)), rng.choice((4, 8, 16)))); handles += 1
+        elif k < 0.47:
+            lines.append("%s %d" % (rng.choice(("allocasync", "pool")), rng.choice(sizes[:9]))); handles += 1
+        elif k < 0.52:
+            lines.append("create %d" % rng.choice((2 * MiB, 64 * MiB, GiB))); handles += 1
+        elif k < 0.57:
+            lines.append("array %d %d %d %d" % (rng.choice((64, 1024, 8192)), rng.choice((0, 64, 4096)), rng.choice((1, 2, 3, 8, 0x20)), rng.choice((1, 2, 4)))); handles += 1
+        elif k < 0.61:
+            lines.append("%s %d %d %d %d %d" % (rng.choice(("array3d", "mipmap")), rng.choice((32, 256)), rng.choice((32, 256)), rng.choice((0, 16, 128)), rng.choice((1, 0x20)), rng.choice((1, 4)))); handles += 1
+        elif k < 0.78 and handles:
+            lines.append("%s %d" % (rng.choice(("free", "free", "freeasync")), rng.randrange(handles)))
+        elif k < 0.86:
+            lines.append(rng.choice(("meminfo", "nvmlinfo", "nvmlinfo2", "totalmem")))
+        elif k < 0.90:
+            lines.append("launch %d %d %d %d" % (rng.choice((1, 50)), rng.choice((1, 7, 70000)), rng.choice((1, 3)), rng.choice((1, 65536))))
+        elif k < 0.94:
+            lines.append("ledger 0")
+        else:
+            lines.append(rng.choice(("setmode 1", "persistence")))
+    lines += ["meminfo", "nvmlinfo", "nvmlinfo2", "ledger 0"]
+    return "\n".join(lines) + "\n"
+
+
+def random_env(rng):
+    env = {"MANAGER_COMPATIBILITY_MODE": "0", "MANAGER_VISIBLE_DEVICES": H.STUB_UUID, "LOGGER_LEVEL": "0"}
+    env["CUDA_MEM_LIMIT_0"] = rng.choice(("256m", "1g", "1536m", "4g", "0.5g"))
+    if rng.random() < 0.5:
+        env["CUDA_MEM_RATIO_0"] = rng.choice(("2", "4", "1.5"))
+    if rng.random() < 0.2:
+        env["CUDA_MEM_OVERSOLD_0"] = "true"
+    if rng.random() < 0.6:
+        env["VMEMORY_NODE_ENABLED"] = "true"
+    if rng.random() < 0.4:
+        env["CUDA_CORE_LIMIT_0"] = rng.choice(("10", "50", "100"))
+        env["STUB_UTIL"] = "fixed:5"
+    if rng.random() < 0.5:
+        procs = []
+        for pid in rng.sample(range(900, 960), rng.randrange(1, 5)):
+            procs.append("%d:%d:%s" % (pid, rng.choice((MiB, 100 * MiB, 700 * MiB)), rng.choice(("c", "g", "cg"))))
+        env["STUB_OTHER_PROCS"] = ",".join(procs)
+    if rng.random() < 0.3:
+        env["STUB_CTX_BYTES"] = str(rng.choice((0, 300 * MiB)))
+    if rng.random() < 0.3:
+        env["STUB_PHYS_MEM"] = str(rng.choice((2 * GiB, 8 * GiB)))
+    return env
+
+
+def run(lib, script, env, args):
+    sb = H.Sandbox()
+    out, err, rc = H.run_scenario(lib, script, env, sb=sb, args=args, check=False)
+    cfg = sb.config_bytes() if os.path.exists(sb.path("etc/vgpu-manager/config/vgpu.config")) else b""
+    sb.cleanup()
+    return out, rc, cfg, err
+
+
+def test_random_scripts_same_transcript_as_the_reference(built):
+    rng = random.Random(0x5EED)
+    for case in range(40):
+        script = random_script(rng, rng.randrange(10, 60))
+        env = random_env(rng)
+        args = ("--gpa",) if rng.random() < 0.3 else ()
+        ref = run(H.REF_SO, script, env, args)
+        new = run(H.NEW_SO, script, env, args)
+        assert ref[:3] == new[:3], "case %d env %r args %r\nscript:\n%s\n--- reference (rc %d)\n%s\n--- b200 (rc %d)\n%s\n%s" % (
+            case, env, args, script, ref[1], ref[0], new[1], new[0], new[3][-1500:])

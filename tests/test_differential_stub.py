@@ -374,3 +374,23 @@ def test_one_process_on_two_gpus_with_a_hole_in_the_visible_list(built):
     lines = t.splitlines()
     assert lines[1].endswith(str(3 * GiB)) and any(l.startswith("totalmem") and l.endswith(str(GiB)) for l in lines[8:11]), t
     assert t.count("-> 2") == 2  # one refusal per device, each against its own cap
+
+
+def test_closed_loop_share_is_in_the_references_ballpark(built):
+    """The reference defines no core-% tolerance (SURVEY.md 8a L-tol); what can be compared is the rate each
+    limiter settles at when the fake GPU's utilisation follows the tenant's own launch rate (closed loop,
+    same model for both).  Measured: 0.84-1.31 x the reference over caps 10/25/50 %; asserted loosely."""
+    import json
+    import subprocess
+    rates = []
+    for lib in (H.REF_SO, H.NEW_SO):
+        sb = H.Sandbox()
+        e = dict(BASE)
+        e.update({"CUDA_CORE_LIMIT_0": "10", "CUDA_MEM_LIMIT_0": "1g", "STUB_UTIL": "closed:0.02"})
+        r = subprocess.run([H.STORM, "--steps", "1000", "--warmup", "0", "--per-step", "20000", "--no-kernel", "--max-seconds", "6"],
+                           env=H.preload_env(lib, sb, e), capture_output=True, text=True, timeout=120)
+        sb.cleanup()
+        assert r.returncode == 0, r.stderr[-1500:]
+        d = json.loads(r.stdout.strip().splitlines()[-1])
+        rates.append(d["launches"] / d["wall_s"])
+    assert 0.5 < rates[1] / rates[0] < 2.0, rates

@@ -343,10 +343,10 @@ def main():
         "clocks": clk,
         "e2e": {"value": round(total / life_max, 1), "unit": "launches/s",
                 "h2d_bytes_per_step": 16 * per_step if args.impl == "b200" else 0,
-                "d2h_bytes_per_step": 8 * per_step // 128 if args.impl == "b200" else 0,
+                "d2h_bytes_per_step": 8 * per_step // 256 if args.impl == "b200" else 0,
                 "what": "same K steps on the tenant's HOST clock around launch calls + device sync, through the "
                         "LD_PRELOADed hook; h2d = ticket + sequence words the hook publishes per launch in pinned "
-                        "memory (read by the sampler over PCIe), d2h = completion markers (one per 128 launches)"},
+                        "memory (read by the sampler over PCIe), d2h = completion markers (one per 256 launches)"},
         "tenant_process_life_s": round(res["life_s"], 3),
         "gpu_launches": int(sum(r[5] for r in rows)) + own_launches,
         "gated_launches": int(sum(r[6] for r in rows)),

@@ -49,7 +49,7 @@ extern vgpu_dev_rt *vgpu_rt_get(int host_index, CUdevice dev);
 /* ------------------------------------------------------------------ stream slots
  * Every (stream, per-thread-default flag) of a device gets a slot in the pinned block: launch
  * sequence, completion marker, ticket ring.  Host-only bookkeeping lives here. */
-#define MARK_EVERY 128u             /* dense launch trains: one completion marker per 128 launches */
+#define MARK_EVERY 256u             /* dense launch trains: one completion marker per 256 launches */
 #define SPARSE_TSC 120000ull        /* launches further apart than ~50 us are each marked       */
 typedef struct {
   volatile uintptr_t key;           /* CUstream | ptsz bit | top bit; 0 = empty */

@@ -75,7 +75,10 @@ def test_device_reset_mid_process_matches_reference_on_real_driver(built):
 
 
 def gpu_uuids():
-    out = subprocess.run(["nvidia-smi", "--query-gpu=uuid", "--format=csv,noheader"], capture_output=True, text=True)
+    try:  # evaluated at collection time, also on machines without a driver
+        out = subprocess.run(["nvidia-smi", "--query-gpu=uuid", "--format=csv,noheader"], capture_output=True, text=True)
+    except OSError:
+        return []
     return [l.strip() for l in out.stdout.splitlines() if l.strip()]
 
 

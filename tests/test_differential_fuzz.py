@@ -77,8 +77,47 @@ def random_env(rng):
     return env
 
 
-def run(lib, script, env, args):
+def random_membership(rng, env):
+    """Compatibility modes other than HOST decide per NVML pid whether it belongs to the container
+    (cuda_hook.c:645-803): cgroup v1 / v2 through .host_proc/<pid>/cgroup, client mode through
+    pids.config, +100 = open-kernel-module variant.  Returns (env, prep(sandbox))."""
+    mode = rng.choice((1, 2, 101, 102, 200, 100))
+    env = dict(env, MANAGER_COMPATIBILITY_MODE=str(mode))
+    pids = rng.sample(range(900, 960), rng.randrange(2, 6))
+    env["STUB_OTHER_PROCS"] = ",".join("%d:%d:%s" % (p, rng.choice((MiB, 100 * MiB, 300 * MiB)), rng.choice(("c", "g", "cg")))
+                                       for p in pids)
+    mine = {p: rng.random() < 0.5 for p in pids}
+    missing = {p for p in pids if rng.random() < 0.2}
+    v1 = mode % 100 == 1
+    if mode == 200:
+        env.update({"VGPU_POD_UID": "uid-%d" % rng.randrange(100), "VGPU_CONTAINER_NAME": "c", "MANAGER_CLIENT_REGISTER_UUID": "r"})
+
+    def prep(sb):
+        for p in pids:
+            if p in missing:
+                continue
+            d = sb.path("etc/vgpu-manager/.host_proc/%d" % p)
+            os.makedirs(d, exist_ok=True)
+            with open(os.path.join(d, "cgroup"), "w") as f:
+                if v1:
+                    f.write("12:memory:/kubepods/x\n11:devices:%s\n1:name=systemd:/y\n" % ("/" if mine[p] else "/kubepods/besteffort/pod1/abc"))
+                else:
+                    f.write("0::/\n" if mine[p] else "0::/kubepods/burstable/other\n")
+        if mode == 200:
+            os.makedirs(sb.path("etc/vgpu-manager/registry"), exist_ok=True)
+            client = sb.path("etc/vgpu-manager/registry/device-client")
+            with open(client, "w") as f:
+                f.write("#!/bin/sh\nexit 0\n")
+            os.chmod(client, 0o755)
+            with open(sb.path("etc/vgpu-manager/config/pids.config"), "w") as f:
+                f.write("".join("%d\n" % p for p in sorted(p for p in pids if mine[p])))
+    return env, prep
+
+
+def run(lib, script, env, args, prep=None):
     sb = H.Sandbox()
+    if prep:
+        prep(sb)
     out, err, rc = H.run_scenario(lib, script, env, sb=sb, args=args, check=False)
     cfg = sb.config_bytes() if os.path.exists(sb.path("etc/vgpu-manager/config/vgpu.config")) else b""
     sb.cleanup()
@@ -95,3 +134,14 @@ def test_random_scripts_same_transcript_as_the_reference(built):
         new = run(H.NEW_SO, script, env, args)
         assert ref[:3] == new[:3], "case %d env %r args %r\nscript:\n%s\n--- reference (rc %d)\n%s\n--- b200 (rc %d)\n%s\n%s" % (
             case, env, args, script, ref[1], ref[0], new[1], new[0], new[3][-1500:])
+
+
+def test_random_scripts_in_every_compatibility_mode(built):
+    rng = random.Random(0xC0FFEE)
+    for case in range(30):
+        script = random_script(rng, rng.randrange(8, 30))
+        env, prep = random_membership(rng, random_env(rng))
+        ref = run(H.REF_SO, script, env, (), prep)
+        new = run(H.NEW_SO, script, env, (), prep)
+        assert ref[:3] == new[:3], "case %d env %r\nscript:\n%s\n--- reference (rc %d)\n%s\n--- b200 (rc %d)\n%s\n%s" % (
+            case, env, script, ref[1], ref[0], new[1], new[0], new[3][-1500:])

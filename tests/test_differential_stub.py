@@ -398,7 +398,7 @@ def test_closed_loop_share_is_in_the_references_ballpark(built):
 
 def test_eight_threads_allocating_under_an_oversold_cap(built):
     """Thread safety of the memory path: 8 threads x 400 steps of alloc / managed alloc / free / report / launch in
-    one process (1 GiB virtual, 512 MiB physical, ledger on).  Per-call outcomes depend on the interleaving;
+    one process (384 MiB virtual, 192 MiB physical, ledger on).  Per-call outcomes depend on the interleaving;
     what must hold under either library: only SUCCESS or OUT_OF_MEMORY, self-consistent reports, and - once
     every thread has freed what it held - the same final figures."""
     import subprocess
@@ -407,7 +407,7 @@ def test_eight_threads_allocating_under_an_oversold_cap(built):
         for seed in (1, 2):
             sb = H.Sandbox()
             e = dict(BASE)
-            e.update({"CUDA_MEM_LIMIT_0": "1g", "CUDA_MEM_RATIO_0": "2", "VMEMORY_NODE_ENABLED": "true", "CUDA_CORE_LIMIT_0": "50",
+            e.update({"CUDA_MEM_LIMIT_0": "384m", "CUDA_MEM_RATIO_0": "2", "VMEMORY_NODE_ENABLED": "true", "CUDA_CORE_LIMIT_0": "50",
                       "STUB_UTIL": "fixed:10"})
             r = subprocess.run([os.path.join(H.BUILD, "mtstorm"), "--threads", "8", "--steps", "400", "--seed", str(seed)],
                                env=H.preload_env(lib, sb, e), capture_output=True, text=True, timeout=120)

@@ -416,3 +416,42 @@ def test_eight_threads_allocating_under_an_oversold_cap(built):
             assert "oom 0\n" not in r.stderr  # the cap was actually hit
             finals.append(r.stdout)
     assert len(set(finals)) == 1, finals
+
+
+def test_ledger_hygiene_purges_dead_processes_identically(built):
+    """vmem_node.config outlives its writers: at start-up the library drops records of dead or zombie pids
+    (swap-with-last removal, loader.c:1580-1673) and at exit its own.  Starting from the same dirty file, both
+    libraries must leave byte-identical files behind."""
+    import struct
+    dead = [4100001, 4100002, 4100003, 4100004]
+    alive = [1, os.getpid()]
+
+    def dirty(sb):
+        raw = bytearray(262272)
+        def put(dev, recs):
+            base = dev * 16392
+            for i, (pid, used) in enumerate(recs):
+                struct.pack_into("<iiQ", raw, base + 16 * i, pid, 0, used)
+            struct.pack_into("<I", raw, base + 16384, len(recs))
+        put(0, [(dead[0], 5 * MiB), (alive[0], 7 * MiB), (dead[1], 11 * MiB), (alive[1], 13 * MiB), (dead[2], 17 * MiB)])
+        put(3, [(dead[3], 19 * MiB), (alive[1], 23 * MiB)])
+        put(5, [(alive[0], 29 * MiB)])
+        with open(sb.ledger(), "wb") as f:
+            f.write(raw)
+
+    script = "init 0\nledger 0\n" + "alloc %d\n" % (300 * MiB) * 3 + "ledger 0\nmeminfo\nnvmlinfo\n"
+    env = dict(BASE)
+    env.update({"CUDA_MEM_LIMIT_0": "1g", "CUDA_MEM_RATIO_0": "2", "VMEMORY_NODE_ENABLED": "true"})
+    files, outs = [], []
+    for lib in (H.REF_SO, H.NEW_SO):
+        sb = H.Sandbox()
+        dirty(sb)
+        out, err, _ = H.run_scenario(lib, script, env, sb=sb)
+        files.append(open(sb.ledger(), "rb").read())
+        outs.append(out)
+        sb.cleanup()
+    assert outs[0] == outs[1]
+    assert files[0] == files[1]
+    n0 = struct.unpack_from("<I", files[1], 16384)[0]
+    pids0 = sorted(struct.unpack_from("<iiQ", files[1], 16 * i)[0] for i in range(n0))
+    assert pids0 == sorted(alive)  # the dead are gone, the tenant removed itself at exit

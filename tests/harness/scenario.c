@@ -87,6 +87,11 @@ int main(int argc, char **argv) {
       int r5 = n_init();
       int r6 = n_h((unsigned)a, &nvdev);
       printf("init %d %d %d %d %d %d\n", r1, r2, r3, r4, r5, r6);
+    } else if (!strcmp(cmd, "drvver")) { /* allowed before cuInit; the hook loads config + device map (cuda_hook.c:1162) */
+      CUresult (*f)(int *) = sym("cuDriverGetVersion");
+      int v = 0;
+      CUresult r = f ? f(&v) : 500;
+      printf("drvver -> %d %d\n", r, v);
     } else if (!strcmp(cmd, "dev")) { /* switch this thread to device <a> (its primary context) */
       CUresult (*f_get)(int *, int) = sym("cuDeviceGet");
       CUresult (*f_ret)(void **, int) = sym("cuDevicePrimaryCtxRetain");

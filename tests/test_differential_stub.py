@@ -455,3 +455,14 @@ def test_ledger_hygiene_purges_dead_processes_identically(built):
     n0 = struct.unpack_from("<I", files[1], 16384)[0]
     pids0 = sorted(struct.unpack_from("<iiQ", files[1], 16 * i)[0] for i in range(n0))
     assert pids0 == sorted(alive)  # the dead are gone, the tenant removed itself at exit
+
+
+def test_cuDriverGetVersion_alone_publishes_the_config(built):
+    """Appendix B.12: the cuDriverGetVersion hook loads the config and the device mapping (so vgpu.config is
+    written from env) without cuInit and without starting the watcher."""
+    for args in ((), ("--gpa",)):
+        outs = both("drvver\n", {"CUDA_MEM_LIMIT_0": "1.5g", "CUDA_CORE_LIMIT_0": "30", "CUDA_CORE_SOFT_LIMIT_0": "60"}, args=args)
+        t = assert_same(outs)
+        assert t == "drvver -> 0 12090\n"
+        cfg = H.Cfg.from_buffer_copy(outs[1][1])
+        assert cfg.devices[0].total_memory == 1536 * MiB and cfg.devices[0].hard_core == 30 and cfg.devices[0].soft_core == 60

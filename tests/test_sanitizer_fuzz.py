@@ -15,7 +15,7 @@ import test_differential_fuzz as F
 
 CSRC = os.path.join(H.ROOT, "vgpu_manager_b200", "csrc")
 UBSAN_SO = os.path.join(H.BUILD, "ubsan", "libvgpu-control.so")
-SRCS = ["boot.c", "hooktab.c", "config.c", "device.c", "memgate.c", "limiter.c", "metrics.c", "kernels_image.gen.c"]
+SRCS = ["boot.c", "hooktab.c", "config.c", "device.c", "memgate.c", "limiter.c", "lifecycle.c", "metrics.c", "kernels_image.gen.c"]
 
 
 @pytest.fixture(scope="module")

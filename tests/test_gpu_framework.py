@@ -74,8 +74,14 @@ def test_pytorch_tenant_under_cap(built):
     assert b["sum"] == float(256 * 1024 * 1024)
     g, gerr = run_tenant(H.NEW_SO, 150, {"VGPU_B200_GOVERNOR": "1"})  # device-autonomous refill mode
     assert g == b, gerr
+    # PyTorch's expandable segments allocate through the VMM API (cuMemAddressReserve / cuMemCreate / cuMemMap):
+    # the cap then bites in the cuMemCreate hook instead of cuMemAlloc
+    x, xerr = run_tenant(H.NEW_SO, 150, {"PYTORCH_CUDA_ALLOC_CONF": "expandable_segments:True"})
+    assert x == b, xerr
     if os.path.exists(H.REF_SO):
         ref, rerr = run_tenant(H.REF_SO, 100)
+        refx, _ = run_tenant(H.REF_SO, 100, {"PYTORCH_CUDA_ALLOC_CONF": "expandable_segments:True"})
+        assert refx is None or refx == x
         os.makedirs(os.path.join(H.ROOT, "gpurun_out"), exist_ok=True)
         with open(os.path.join(H.ROOT, "gpurun_out", "pytorch_tenant_r1.json"), "w") as f:
             import json

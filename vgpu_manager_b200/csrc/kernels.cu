@@ -12,6 +12,8 @@
  *   vgpu_sampler_kernel      per-SM sampler: %smid/%clock64 probe deltas + stream-queue busy
  *                            sampling, warp-reduced into the HBM token bucket; the last CTA of
  *                            the last tick of a period runs the controller
+ *   vgpu_governor_kernel     opt-in resident variant of sampler + controller: one warp, no host
+ *                            launch in the refill loop (VGPU_B200_GOVERNOR=1)
  *   vgpu_gate_kernel         device-side gate (fallback when 64-bit stream mem-ops are missing)
  *
  * None of this exists in the reference: both of its enforcement paths are host C

@@ -311,6 +311,14 @@ int main(int argc, char **argv) {
       memset(&ls, 0, sizeof ls);
       if (lstate && lstate(&ls) == 0) printf("limstate consumed %lld\n", ls.consumed);
       else printf("limstate none\n");
+    } else if (!strcmp(cmd, "metrics")) { /* B200 library only */
+      unsigned long long (*metric)(int, int) = dlsym(RTLD_DEFAULT, "vgpu_b200_metric");
+      struct { long long granted, consumed, bucket, share; int v[10]; unsigned long long steps; } ls;
+      int (*lstate)(void *) = dlsym(RTLD_DEFAULT, "vgpu_b200_limiter_state");
+      memset(&ls, 0, sizeof ls);
+      if (metric && lstate && lstate(&ls) == 0)
+        printf("metrics sampler_launches %llu sampler_skipped %llu control_steps %llu\n", metric((int)a, 7), metric((int)a, 10), ls.steps);
+      else printf("metrics none\n");
     } else if (!strcmp(cmd, "sleepms")) {
       struct timespec ts = {(time_t)(a / 1000), (long)(a % 1000) * 1000000L};
       nanosleep(&ts, NULL);

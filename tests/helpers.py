@@ -221,6 +221,9 @@ def preload_env(lib, sb, env=None, stub=True):
     e["SCENARIO_LEDGER"] = sb.ledger()
     if stub:
         e["LD_LIBRARY_PATH"] = STUB_DIR
+        # the fake GPU completes tenant kernels instantly, so "is tenant work executing" is never true there and
+        # its utilisation is scripted instead (STUB_UTIL): keep every sampler window unless a test asks otherwise
+        e["VGPU_B200_SKIP_IDLE_WINDOWS"] = "0"
     e["LD_PRELOAD"] = REDIRECT + ((" " + lib) if lib else "")
     e.update(env or {})
     return e

@@ -49,6 +49,8 @@ static alloc_t *g_allocs;
 static size_t g_nallocs, g_callocs;
 static uint64_t g_dev_bytes[16];
 static __thread int t_cur_dev = 0;
+static volatile int g_parked; /* callers blocked behind the gate (the fake GPU's "parked streams") */
+static void *volatile g_parked_streams[64]; /* which streams those are (cuStreamQuery answers NOT_READY for them) */
 static __thread int t_has_ctx = 0;
 static int g_any_ctx;
 
@@ -351,6 +353,7 @@ static void ctx_unlock(void) {
 }
 static int g_ctx_lock = -1;
 static CUresult wait64_unlocked(CUdeviceptr addr, unsigned long long value);
+static __thread void *t_wait_stream;
 static int ctx_lock_on(void) {
   if (g_ctx_lock < 0) { const char *e = getenv("STUB_CTX_LOCK"); g_ctx_lock = (e && atoi(e)) ? 1 : 0; }
   return g_ctx_lock;
@@ -363,11 +366,12 @@ EXPORT CUresult cuStreamSynchronize(void *s) { (void)s; return 0; }
 EXPORT CUresult cuStreamQuery(void *s) {
   (void)s;
   if (ctx_lock_on()) { ctx_lock(); ctx_unlock(); }
+  for (int i = 0; i < 64; i++)
+    if (g_parked_streams[i] == (s ? s : (void *)1)) return 600; /* NOT_READY: a stream-wait is pending on this stream */
   return 0;
 }
 EXPORT CUresult cuStreamIsCapturing(void *s, int *st) { (void)s; *st = 0; return 0; }
 EXPORT CUresult cuThreadExchangeStreamCaptureMode(int *mode) { static __thread int cur = 0; int old = cur; cur = *mode; *mode = old; return 0; }
-static volatile int g_parked; /* callers blocked behind the gate (the fake GPU's "parked streams") */
 static CUresult wait64_unlocked(CUdeviceptr addr, unsigned long long value);
 static CUresult wait64(CUdeviceptr addr, unsigned long long value) {
   if (!ctx_lock_on()) return wait64_unlocked(addr, value);
@@ -382,15 +386,20 @@ static CUresult wait64_unlocked(CUdeviceptr addr, unsigned long long value) {
   struct timespec nap = {0, 200000};
   if ((long long)(*p - (long long)value) >= 0) return 0;
   __sync_fetch_and_add(&g_parked, 1);
+  void *tag = t_wait_stream ? t_wait_stream : (void *)1; /* 1 = the legacy stream */
+  int mine = -1;
+  for (int i = 0; i < 64 && mine < 0; i++)
+    if (__sync_bool_compare_and_swap(&g_parked_streams[i], NULL, tag)) mine = i;
   for (int i = 0; i < 100000; i++) { /* 20 s cap */
     if ((long long)(*p - (long long)value) >= 0) break;
     nanosleep(&nap, NULL);
   }
+  if (mine >= 0) g_parked_streams[mine] = NULL;
   __sync_fetch_and_sub(&g_parked, 1);
   return 0;
 }
-EXPORT CUresult cuStreamWaitValue64_v2(void *s, CUdeviceptr a, unsigned long long v, unsigned f) { (void)s; (void)f; return wait64(a, v); }
-EXPORT CUresult cuStreamWaitValue64_v2_ptsz(void *s, CUdeviceptr a, unsigned long long v, unsigned f) { (void)s; (void)f; return wait64(a, v); }
+EXPORT CUresult cuStreamWaitValue64_v2(void *s, CUdeviceptr a, unsigned long long v, unsigned f) { (void)f; t_wait_stream = s; return wait64(a, v); }
+EXPORT CUresult cuStreamWaitValue64_v2_ptsz(void *s, CUdeviceptr a, unsigned long long v, unsigned f) { (void)f; t_wait_stream = s; return wait64(a, v); }
 EXPORT CUresult cuStreamWriteValue64_v2(void *s, CUdeviceptr a, unsigned long long v, unsigned f) { (void)s; (void)f; *(volatile unsigned long long *)(uintptr_t)a = v; return 0; }
 EXPORT CUresult cuStreamWriteValue64_v2_ptsz(void *s, CUdeviceptr a, unsigned long long v, unsigned f) { (void)s; (void)f; *(volatile unsigned long long *)(uintptr_t)a = v; return 0; }
 
@@ -620,12 +629,24 @@ static void run_fake_kernel(const char *name, void **p) {
     vgpu_lim_dev_t *D = (vgpu_lim_dev_t *)(uintptr_t) * (CUdeviceptr *)p[0];
     vgpu_lim_host_t *H = (vgpu_lim_host_t *)(uintptr_t) * (CUdeviceptr *)p[1];
     uint32_t period = *(uint32_t *)p[4];
+    uint32_t skipped = *(uint32_t *)p[6];
     int util = current_util();
     D->busy_samples += (unsigned long long)util;
-    D->total_samples += 100;
-    if (period != VGPU_SAMPLER_PROBE_ONLY && ++D->period_tick >= period) {
-      D->period_tick = 0;
-      fake_period_end(D, H);
+    D->total_samples += 100ull * (1ull + skipped); /* skipped ticks = idle windows */
+    if (period != VGPU_SAMPLER_PROBE_ONLY) {
+      unsigned long long tick = (unsigned long long)D->period_tick + skipped + 1ull;
+      if (tick < period) {
+        D->period_tick = (uint32_t)tick;
+      } else {
+        unsigned long long periods = period ? tick / period : 1ull;
+        D->period_tick = period ? (uint32_t)(tick % period) : 0u;
+        fake_period_end(D, H);
+        if (periods > 129ull) periods = 129ull;
+        for (unsigned long long k = 1; k < periods; k++) {
+          D->total_samples = 1;
+          fake_period_end(D, H);
+        }
+      }
     }
   } else if (!strcmp(name, VGPU_K_GOVERNOR)) {
     gov_arg_t *a = (gov_arg_t *)malloc(sizeof *a);

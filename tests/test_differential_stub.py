@@ -466,3 +466,23 @@ def test_cuDriverGetVersion_alone_publishes_the_config(built):
         assert t == "drvver -> 0 12090\n"
         cfg = H.Cfg.from_buffer_copy(outs[1][1])
         assert cfg.devices[0].total_memory == 1536 * MiB and cfg.devices[0].hard_core == 30 and cfg.devices[0].soft_core == 60
+
+
+def test_idle_tenant_keeps_no_kernel_on_the_gpu(built):
+    """While nothing of the tenant is executing the tick thread launches no sampler windows at all (an idle
+    or fully throttled tenant must not hold a time slice of a shared GPU); the ticks it skipped are
+    accounted as idle windows and the control periods among them are replayed by the next launch."""
+    env = dict(BASE)
+    env.update({"CUDA_MEM_LIMIT_0": "1g", "CUDA_CORE_LIMIT_0": "30", "STUB_UTIL": "fixed:20", "VGPU_B200_SKIP_IDLE_WINDOWS": "1"})
+    script = "init 0\nlaunch 200 4 1 1\nsleepms 1200\nmetrics 0\n"
+    out, err, sb = H.run_scenario(H.NEW_SO, script, env)
+    sb.cleanup()
+    m = [l for l in out.splitlines() if l.startswith("metrics")][0].split()
+    launches, skipped, steps = int(m[2]), int(m[4]), int(m[6])
+    # ~120 ticks went by; on the fake GPU tenant kernels finish instantly, so nearly all of them are skipped
+    assert skipped >= 80 and launches <= 5, out
+    # same script with skipping off: one launch per tick and a control step every 8th
+    out2, _, sb = H.run_scenario(H.NEW_SO, script, dict(env, VGPU_B200_SKIP_IDLE_WINDOWS="0"))
+    sb.cleanup()
+    m2 = [l for l in out2.splitlines() if l.startswith("metrics")][0].split()
+    assert int(m2[2]) >= 80 and int(m2[4]) == 0 and int(m2[6]) >= 10, out2

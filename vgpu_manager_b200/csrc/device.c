@@ -238,7 +238,8 @@ static vgpu_dev_rt *bring_up(vgpu_dev_rt *rt, int slot, int host_index, CUdevice
     void *p_ctl[] = {&rt->lim_d, &rt->lim_h_d, &in};
     CU_TRY(vgpu_rt_launch(rt, rt->k_controller, 1, 32, 0, rt->q_stream, p_ctl), "warm controller");
     uint32_t w = 0, iv = 1, per = VGPU_SAMPLER_PROBE_ONLY, ep = 0;
-    void *p_smp[] = {&rt->lim_d, &rt->lim_h_d, &w, &iv, &per, &ep};
+    uint32_t none = 0;
+    void *p_smp[] = {&rt->lim_d, &rt->lim_h_d, &w, &iv, &per, &ep, &none};
     CU_TRY(vgpu_rt_launch(rt, rt->k_sampler, 1, 128, 0, rt->q_stream, p_smp), "warm sampler");
     rt->lim_h->quit = 1;
     rt->lim_h->ctl_state = 1;
@@ -603,7 +604,8 @@ VGPU_EXPORT int vgpu_b200_sampler_run(unsigned window_us, unsigned interval_us, 
   static uint32_t epoch = 1u << 20;
   rt->lim_h->ext_user_override = user_override;
   uint32_t ep = ++epoch;
-  void *params[] = {&rt->lim_d, &rt->lim_h_d, &window_us, &interval_us, &period_ticks, &ep};
+  uint32_t skipped = 0;
+  void *params[] = {&rt->lim_d, &rt->lim_h_d, &window_us, &interval_us, &period_ticks, &ep, &skipped};
   unsigned grid = rt->sm_num > 0 ? (unsigned)rt->sm_num : 148u;
   if (vgpu_rt_launch(rt, rt->k_sampler, grid, 128, 0, rt->p_stream, params) != CUDA_SUCCESS) return -1;
   if (R.cuStreamSynchronize(rt->p_stream) != CUDA_SUCCESS) return -1;

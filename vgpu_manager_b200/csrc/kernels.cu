@@ -638,7 +638,8 @@ DEVINL void period_end(vgpu_lim_dev_t *D, vgpu_lim_host_t *H, int grid_sms, uint
  *
  * Everything is accumulated in registers, warp-reduced, and added to the HBM block once per
  * warp per launch.  The last CTA to retire bumps the tick; every `period_ticks` ticks it turns
- * the accumulators into user_current and runs ctl_step (refilling the token bucket). */
+ * the accumulators into user_current and runs ctl_step (refilling the token bucket).  Ticks the
+ * host skipped because nothing of the tenant was executing are accounted as idle windows. */
 #define SAMPLER_THREADS 128
 DEVINL uint32_t probe_burst() {
   uint32_t a0 = threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, b0 = a0 ^ 5, b1 = a0 ^ 6,
@@ -667,7 +668,7 @@ DEVINL uint32_t probe_burst() {
 
 extern "C" __global__ void __launch_bounds__(SAMPLER_THREADS)
     vgpu_sampler_kernel(vgpu_lim_dev_t *D, vgpu_lim_host_t *H, uint32_t window_us,
-                        uint32_t interval_us, uint32_t period_ticks, uint32_t epoch) {
+                        uint32_t interval_us, uint32_t period_ticks, uint32_t epoch, uint32_t skipped) {
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t sm = smid();
   const uint32_t pslot = (sm < VGPU_MAX_SMS ? sm : VGPU_MAX_SMS - 1) * 4 + warp;
@@ -735,12 +736,28 @@ extern "C" __global__ void __launch_bounds__(SAMPLER_THREADS)
   *quit_dev = 0;
   /* coverage: SMs that hosted a sampler CTA at least once this period */
   if (probe_only) return;
-  uint32_t tick = ++D->period_tick;
-  if (tick < period_ticks) return;
-  D->period_tick = 0;
+  /* `skipped` ticks went by without a launch because the host saw no tenant work executing
+   * (everything parked, or nothing queued at all): each of them would have produced a window of
+   * idle samples, and each period boundary among them a controller step with that reading -
+   * exactly what the reference's watcher does while its tenant is quiet. */
+  if (skipped) {
+    const uint32_t per_window = window_us / (interval_us ? interval_us : 1u) + 1u;
+    D->total_samples += (unsigned long long)skipped * per_window;
+  }
+  unsigned long long tick = (unsigned long long)D->period_tick + skipped + 1ull;
+  if (tick < period_ticks) {
+    D->period_tick = (uint32_t)tick;
+    return;
+  }
+  unsigned long long periods = period_ticks ? tick / period_ticks : 1ull;
+  D->period_tick = period_ticks ? (uint32_t)(tick % period_ticks) : 0u;
   __threadfence();
-
   period_end(D, H, (int)gridDim.x, epoch, period_ticks);
+  if (periods > 129ull) periods = 129ull; /* bounded replay: the controller saturates long before */
+  for (unsigned long long k = 1; k < periods; k++) {
+    D->total_samples = 1; /* one idle sample: a valid zero reading */
+    period_end(D, H, (int)gridDim.x, epoch, period_ticks);
+  }
 }
 
 /* ======================================================================= governor

@@ -95,6 +95,7 @@ static volatile unsigned g_tick_epoch;
 static volatile int g_tick_devices[VGPU_MAX_DEVICES]; /* host indexes with a live runtime + core limit */
 static uint32_t g_gov_interval_us = 50, g_gov_period_us = 80000, g_gov_idle_us = 5000;
 static int g_governor_mode; /* VGPU_B200_GOVERNOR=1 */
+static int g_skip_idle = 1;  /* VGPU_B200_SKIP_IDLE_WINDOWS=0 turns the skipping of idle sampler windows off */
 static uint32_t g_window_us = 500, g_interval_us = 50, g_period_ticks = 8, g_tick_ms = 10;
 static volatile int g_sync_waiters; /* threads currently inside a device-wide synchronise */
 static volatile unsigned long g_tick_gen, g_wd_gen; /* completed loop iterations (quiescence points) */
@@ -177,6 +178,27 @@ static void settle_idle_streams(vgpu_dev_rt *rt, int h) {
   }
 }
 
+/* Decide whether this tick needs a sampler launch.  Same predicate as the kernel's queue-busy
+ * sample, evaluated on the host copies: a stream is executing iff its oldest unfinished launch is
+ * admitted.  Returns 1 = launch; 0 = skipped (and counted in *skipped). */
+static uint32_t g_skipped[VGPU_MAX_DEVICES];
+static int tenant_activity(vgpu_dev_rt *rt, uint32_t *skipped) {
+  if (!g_skip_idle) return 1;
+  vgpu_lim_host_t *H = rt->lim_h;
+  long long granted = H->granted_mirror;
+  int parked = 0;
+  for (uint32_t i = 0; i < VGPU_STREAM_SLOTS; i++) {
+    unsigned long long d = H->done[i], l = H->launched[i];
+    if (l <= d) continue;
+    if (granted - H->ticket[i][(d + 1) & (VGPU_TICKET_RING - 1)] >= 0) return 1; /* executing */
+    parked = 1;
+  }
+  if (H->release_pending) return 1;                       /* a loan is waiting to be folded in */
+  if (parked && *skipped + 1 >= g_period_ticks) return 1; /* the period boundary: the refill that releases them */
+  if (*skipped < 0x3fffffffu) (*skipped)++;
+  return 0;
+}
+
 static void *tick_main(void *arg) {
   (void)arg;
   uint32_t epoch = 0;
@@ -218,22 +240,29 @@ static void *tick_main(void *arg) {
         /* the governor owns the queue signal and the controller; the per-SM probe is only
          * needed when the controller is asked to look at SM activity */
         if (rt->lim_h->util_source != 0 && R.cuStreamQuery(rt->p_stream) == CUDA_SUCCESS) {
-          uint32_t ep = epoch, never = VGPU_SAMPLER_PROBE_ONLY;
-          void *params[] = {&rt->lim_d, &rt->lim_h_d, &g_window_us, &g_interval_us, &never, &ep};
+          uint32_t ep = epoch, never = VGPU_SAMPLER_PROBE_ONLY, none = 0;
+          void *params[] = {&rt->lim_d, &rt->lim_h_d, &g_window_us, &g_interval_us, &never, &ep, &none};
           unsigned grid = rt->sm_num > 0 ? (unsigned)rt->sm_num : 148u;
           if (R.cuLaunchKernel(rt->k_sampler, grid, 1, 1, 128, 1, 1, 0, rt->p_stream, params, NULL) == CUDA_SUCCESS)
             vgpu_metric_add(h, VM_SAMPLER_LAUNCHES, 1);
         }
+      } else if (!tenant_activity(rt, &g_skipped[h])) {
+        /* Nothing of the tenant is executing: a window now could only record "idle".  Skip it -
+         * an idle or fully throttled tenant should not keep a kernel of ours on a GPU it shares -
+         * and let the next launch account for the skipped ticks (kernels.cu).  While streams are
+         * parked one launch per control period is kept, because only the controller releases them. */
+        vgpu_metric_add(h, VM_SAMPLER_SKIPPED, 1);
       } else if (VGPU_CAPCHK(R.cuStreamQuery(rt->s_stream)) == CUDA_SUCCESS) {
-        uint32_t ep = epoch;
+        uint32_t ep = epoch, skipped = g_skipped[h];
         /* while a tenant thread waits for the device to go idle, keep the sampler's residency
          * negligible so the wait is not stretched by it */
         uint32_t window = g_sync_waiters > 0 ? 200u : g_window_us;
-        void *params[] = {&rt->lim_d, &rt->lim_h_d, &window, &g_interval_us, &g_period_ticks, &ep};
+        void *params[] = {&rt->lim_d, &rt->lim_h_d, &window, &g_interval_us, &g_period_ticks, &ep, &skipped};
         unsigned grid = rt->sm_num > 0 ? (unsigned)rt->sm_num : 148u;
         CUresult r = VGPU_CAPCHK(R.cuLaunchKernel(rt->k_sampler, grid, 1, 1, 128, 1, 1, 0, rt->s_stream, params, NULL));
         if (r == CUDA_SUCCESS) {
           fails = 0;
+          g_skipped[h] = 0;
           vgpu_metric_add(h, VM_SAMPLER_LAUNCHES, 1);
         } else if (++fails == 100) {
           /* fail open: never leave tenant streams parked on a bucket nobody refills */
@@ -343,6 +372,7 @@ static void tick_start(void) {
   g_gov_idle_us = env_u32("VGPU_B200_GOVERNOR_IDLE_US", 5000);
   g_governor_mode = env_u32("VGPU_B200_GOVERNOR", 0) != 0;
   g_watchdog_ms = env_u32("VGPU_B200_WATCHDOG_MS", 170);
+  g_skip_idle = env_u32("VGPU_B200_SKIP_IDLE_WINDOWS", 1) != 0;
   if (!g_period_ticks) g_period_ticks = 1;
   if (!g_tick_ms) g_tick_ms = 1;
   g_tick_epoch = vgpu_fork_epoch + 1;

@@ -294,7 +294,7 @@ void vgpu_limiter_resume(vgpu_dev_rt *rt, int everything_completed); /* the sync
 
 /* metrics.c */
 enum { VM_RATE_GATED, VM_RATE_FAST, VM_OOM_LIMIT, VM_OOM_DRIVER, VM_UVA_FALLBACK, VM_LOCK_TIMEOUT,
-       VM_QUOTA_KERNELS, VM_SAMPLER_LAUNCHES, VM_SCRUBBED_BYTES, VM_WATCHDOG_LOANS, VM_COUNT };
+       VM_QUOTA_KERNELS, VM_SAMPLER_LAUNCHES, VM_SCRUBBED_BYTES, VM_WATCHDOG_LOANS, VM_SAMPLER_SKIPPED, VM_COUNT };
 void vgpu_metric_add(int host_index, int which, uint64_t v);
 uint64_t vgpu_metric_get(int host_index, int which);
 

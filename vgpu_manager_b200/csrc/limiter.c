@@ -183,8 +183,9 @@ static void settle_idle_streams(vgpu_dev_rt *rt, int h) {
  * admitted.  Returns 1 = launch; 0 = skipped (and counted in *skipped). */
 static uint32_t g_skipped[VGPU_MAX_DEVICES];
 static int tenant_activity(vgpu_dev_rt *rt, uint32_t *skipped) {
-  if (!g_skip_idle) return 1;
   vgpu_lim_host_t *H = rt->lim_h;
+  /* the SM probe also sees work the hook does not number (graph replays): it needs its windows */
+  if (!g_skip_idle || H->util_source != 0) return 1;
   long long granted = H->granted_mirror;
   int parked = 0;
   for (uint32_t i = 0; i < VGPU_STREAM_SLOTS; i++) {

@@ -880,6 +880,20 @@ static nvmlReturn_t proc_list(void *d, unsigned *count, vgpu_proc_t *out, int gr
   *count = n;
   return n > cap ? 7 /* INSUFFICIENT_SIZE */ : 0;
 }
+/* the 24-byte v3 ABI (pid, usedGpuMemory, gpuInstanceId, computeInstanceId), what a current NVML exports */
+static nvmlReturn_t proc_list_v3(void *d, unsigned *count, vgpu_proc_v2_t *out, int graphics) {
+  static __thread vgpu_proc_t narrow[VGPU_MAX_PIDS];
+  unsigned cap = *count, n = cap > VGPU_MAX_PIDS ? VGPU_MAX_PIDS : cap;
+  nvmlReturn_t r = proc_list(d, &n, narrow, graphics);
+  for (unsigned i = 0; i < n && i < cap; i++) {
+    out[i].pid = narrow[i].pid; out[i]._pad = 0; out[i].used_bytes = narrow[i].used_bytes;
+    out[i].gi = out[i].ci = 0xFFFFFFFFu;
+  }
+  *count = n;
+  return r;
+}
+EXPORT nvmlReturn_t nvmlDeviceGetComputeRunningProcesses_v3(void *d, unsigned *c, vgpu_proc_v2_t *o) { return proc_list_v3(d, c, o, 0); }
+EXPORT nvmlReturn_t nvmlDeviceGetGraphicsRunningProcesses_v3(void *d, unsigned *c, vgpu_proc_v2_t *o) { return proc_list_v3(d, c, o, 1); }
 EXPORT nvmlReturn_t nvmlDeviceGetComputeRunningProcesses(void *d, unsigned *c, vgpu_proc_t *o) { return proc_list(d, c, o, 0); }
 EXPORT nvmlReturn_t nvmlDeviceGetGraphicsRunningProcesses(void *d, unsigned *c, vgpu_proc_t *o) { return proc_list(d, c, o, 1); }
 EXPORT nvmlReturn_t nvmlDeviceGetProcessUtilization(void *d, vgpu_util_sample_t *s, unsigned *count, unsigned long long since) {

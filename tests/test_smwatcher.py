@@ -79,7 +79,7 @@ def test_file_is_created_sized_and_filled_like_the_go_producer(built, tmp_path):
         assert d.compute_size == len(comp) and d.graphics_size == len(graph) and d.samples_size == len(samples)
         assert [(p.pid, p.used) for p in d.compute[:d.compute_size]] == comp
         assert [(p.pid, p.used) for p in d.graphics[:d.graphics_size]] == graph
-        assert all(p.gi == 0xFFFFFFFF and p.ci == 0xFFFFFFFF for p in d.compute[:d.compute_size])  # v1 NVML ABI -> "no MIG instance"
+        assert all(p.gi == 0xFFFFFFFF and p.ci == 0xFFFFFFFF for p in d.compute[:d.compute_size])  # not a MIG instance (the fake NVML serves the 24-byte v3 records)
         assert [(s.pid, s.sm) for s in d.samples[:d.samples_size]] == samples
         # lastSeenTimeStamp = now - 1 s at the time of the pass; sample stamps are newer than it
         assert t0 - 1_000_000 <= d.last_seen_us <= t1 - 1_000_000

@@ -100,3 +100,24 @@ def test_ledger_is_ignored_without_the_feature_gate_and_without_gpu_pids(built):
 def test_exposition_format():
     text = E.exposition([("m_bytes", {"a": 'x"y', "b": "1"}, 1024.0), ("m_ratio", {"a": "z"}, 0.5)])
     assert text == 'm_bytes{a="x\\"y",b="1"} 1024\nm_ratio{a="z"} 0.5\n'
+
+
+def test_metrics_endpoint_serves_the_exposition():
+    import threading
+    import urllib.request
+    samples = [("container_vgpu_device_memory_usage_in_bytes", {"pod_name": "p", "vdevice_idx": "0"}, 4096.0)]
+    srv = E.serve(0, lambda: samples, host="127.0.0.1")
+    t = threading.Thread(target=srv.serve_forever, daemon=True)
+    t.start()
+    try:
+        port = srv.server_address[1]
+        with urllib.request.urlopen("http://127.0.0.1:%d/metrics" % port, timeout=5) as r:
+            assert r.status == 200 and r.headers["Content-Type"].startswith("text/plain")
+            assert r.read().decode() == 'container_vgpu_device_memory_usage_in_bytes{pod_name="p",vdevice_idx="0"} 4096\n'
+        try:
+            urllib.request.urlopen("http://127.0.0.1:%d/other" % port, timeout=5)
+            assert False, "404 expected"
+        except urllib.error.HTTPError as e:
+            assert e.code == 404
+    finally:
+        srv.shutdown()

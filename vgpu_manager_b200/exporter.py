@@ -167,6 +167,32 @@ def nvml_snapshot():
     return idx, info, util
 
 
+def serve(port, collect, host="0.0.0.0"):
+    """Minimal /metrics endpoint (Prometheus text exposition); `collect()` returns the samples."""
+    import http.server
+
+    class Handler(http.server.BaseHTTPRequestHandler):
+        def do_GET(self):
+            if self.path.split("?")[0] not in ("/metrics", "/"):
+                self.send_error(404)
+                return
+            try:
+                body = exposition(collect()).encode()
+            except Exception as e:  # a scrape must never kill the exporter
+                self.send_error(500, str(e))
+                return
+            self.send_response(200)
+            self.send_header("Content-Type", "text/plain; version=0.0.4; charset=utf-8")
+            self.send_header("Content-Length", str(len(body)))
+            self.end_headers()
+            self.wfile.write(body)
+
+        def log_message(self, *a):
+            pass
+
+    return http.server.ThreadingHTTPServer((host, port), Handler)
+
+
 def main(argv=None):
     ap = argparse.ArgumentParser(description=__doc__.split("\n\n")[0])
     ap.add_argument("--config", default="/etc/vgpu-manager/config/vgpu.config")
@@ -174,17 +200,22 @@ def main(argv=None):
     ap.add_argument("--pids", required=True, help="comma-separated host pids of the container (or @file, one per line)")
     ap.add_argument("--node", default=os.uname().nodename)
     ap.add_argument("--no-vmem", action="store_true", help="VMemoryNode feature gate off")
+    ap.add_argument("--listen", type=int, default=0, help="serve /metrics on this port instead of printing once")
     a = ap.parse_args(argv)
     if a.pids.startswith("@"):
         with open(a.pids[1:]) as f:
             pids = [int(x) for x in f.read().split()]
     else:
         pids = [int(x) for x in a.pids.split(",") if x]
-    with open(a.config, "rb") as f:
-        cfg = parse_config(f.read())
-    idx, info, util = nvml_snapshot()
-    sys.stdout.write(exposition(container_metrics(cfg, pids, idx, info, util, a.node, a.vmem,
-                                                  vmem_enabled=not a.no_vmem and bool(cfg["vmem_node"]))))
+    def collect():
+        with open(a.config, "rb") as f:
+            cfg = parse_config(f.read())
+        idx, info, util = nvml_snapshot()
+        return container_metrics(cfg, pids, idx, info, util, a.node, a.vmem, vmem_enabled=not a.no_vmem and bool(cfg["vmem_node"]))
+
+    if a.listen:
+        serve(a.listen, collect).serve_forever()
+    sys.stdout.write(exposition(collect()))
 
 
 if __name__ == "__main__":

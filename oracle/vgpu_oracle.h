@@ -8,9 +8,9 @@
  * Parity status: PINNED DIFFERENTIALLY.  The reference ships no golden vectors for this
  * path, so every function here is pinned against the reference's own code
  * executed in this container: oracle/_ref/libvgpu-control.so (the reference library built
- * from /root/reference/library/src by oracle/Makefile) and oracle/_ref/libref_internals.so
- * (the same translation units with their `static` arithmetic exported and the watcher
- * thread run on a virtual clock).  tests/golden/ holds the vectors generated from those.
+ * from /root/reference/library/src by oracle/Makefile) and oracle/_ref/ref_cosim (ref_cosim.c
+ * #includes the reference's cuda_hook.c, so its `static` arithmetic and its watcher thread run
+ * unmodified, the latter on a virtual clock).  tests/golden/ holds the vectors generated from those.
  *
  * Each function cites the reference lines it follows.
  */

@@ -246,8 +246,8 @@ typedef struct vgpu_dev_rt {
   CUmodule mod;
   CUfunction k_clear, k_spill, k_copy_generic, k_quota, k_slab_insert, k_slab_remove, k_controller, k_sampler, k_gate, k_governor;
   CUstream q_stream; /* quota / ledger kernels (app thread)     */
-  CUstream s_stream; /* the resident governor                    */
-  CUstream p_stream; /* per-SM probe sampler (tick thread)      */
+  CUstream s_stream; /* sampler + controller (tick thread); the governor in VGPU_B200_GOVERNOR=1 mode */
+  CUstream p_stream; /* direct-API sampler runs; probe-only sampler beside the governor          */
   /* pinned, mapped blocks */
   vgpu_quota_req_t *q_req;  CUdeviceptr q_req_d;
   vgpu_quota_res_t *q_res;  CUdeviceptr q_res_d;

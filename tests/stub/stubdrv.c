@@ -625,6 +625,29 @@ static void run_fake_kernel(const char *name, void **p) {
     vgpu_ctrl_in_t *in = (vgpu_ctrl_in_t *)p[2];
     fake_ctl_step((vgpu_lim_dev_t *)(uintptr_t) * (CUdeviceptr *)p[0], (vgpu_lim_host_t *)(uintptr_t) * (CUdeviceptr *)p[1],
                   in->user_current, in->sys_current, in->valid, in->sys_process_num);
+  } else if (!strcmp(name, VGPU_K_REFILL)) {
+    /* vgpu_refill_kernel: fold of the published samples (oracle restatement of cuda_hook.c:1044-1159)
+     * into the persistent top_result, then one watcher step */
+    vgpu_lim_dev_t *D = (vgpu_lim_dev_t *)(uintptr_t) * (CUdeviceptr *)p[0];
+    vgpu_lim_host_t *H = (vgpu_lim_host_t *)(uintptr_t) * (CUdeviceptr *)p[1];
+    const vgpu_util_req_t *U = (const vgpu_util_req_t *)(uintptr_t) * (CUdeviceptr *)p[2];
+    if (U->status == VGPU_UTIL_SAMPLES) {
+      uint8_t prim[VGPU_MAX_PIDS], loc[VGPU_MAX_PIDS];
+      uint32_t n = U->n_samples > VGPU_MAX_PIDS ? VGPU_MAX_PIDS : U->n_samples;
+      for (uint32_t i = 0; i < n; i++) { prim[i] = (U->flags[i] & VGPU_FLAG_PRIMARY) != 0; loc[i] = (U->flags[i] & VGPU_FLAG_LOCAL) != 0; }
+      orc_util_t u = {0, 0, D->valid, 0};
+      orc_fold_utilization((int)U->mode, U->samples, n, U->checktime_us, prim, loc, (int)U->have_container_pids, &u);
+      D->top_user = u.user_current; D->top_sys = u.sys_current;
+      if (u.valid) D->valid = 1;
+    }
+    if (U->status != VGPU_UTIL_NOTHING) {
+      int np = U->sys_process_num;
+      if (U->status == VGPU_UTIL_SAMPLES && (U->mode & VGPU_MODE_OPEN_KERNEL) == VGPU_MODE_OPEN_KERNEL && (int)U->n_samples > np) np = (int)U->n_samples;
+      D->top_nproc = np;
+    }
+    D->top_seq = (int)U->seq;
+    int user = H->ext_user_override >= 0 ? H->ext_user_override : D->top_user;
+    fake_ctl_step(D, H, user, D->top_sys, H->ext_user_override >= 0, D->top_nproc);
   } else if (!strcmp(name, VGPU_K_SAMPLER)) {
     vgpu_lim_dev_t *D = (vgpu_lim_dev_t *)(uintptr_t) * (CUdeviceptr *)p[0];
     vgpu_lim_host_t *H = (vgpu_lim_host_t *)(uintptr_t) * (CUdeviceptr *)p[1];

@@ -469,11 +469,13 @@ def test_cuDriverGetVersion_alone_publishes_the_config(built):
 
 
 def test_idle_tenant_keeps_no_kernel_on_the_gpu(built):
-    """While nothing of the tenant is executing the tick thread launches no sampler windows at all (an idle
+    """(On-device queue signal, VGPU_B200_UTIL_SOURCE=queue.)
+    While nothing of the tenant is executing the tick thread launches no sampler windows at all (an idle
     or fully throttled tenant must not hold a time slice of a shared GPU); the ticks it skipped are
     accounted as idle windows and the control periods among them are replayed by the next launch."""
     env = dict(BASE)
-    env.update({"CUDA_MEM_LIMIT_0": "1g", "CUDA_CORE_LIMIT_0": "30", "STUB_UTIL": "fixed:20", "VGPU_B200_SKIP_IDLE_WINDOWS": "1"})
+    env.update({"CUDA_MEM_LIMIT_0": "1g", "CUDA_CORE_LIMIT_0": "30", "STUB_UTIL": "fixed:20", "VGPU_B200_SKIP_IDLE_WINDOWS": "1",
+                "VGPU_B200_UTIL_SOURCE": "queue"})
     script = "init 0\nlaunch 200 4 1 1\nsleepms 1200\nmetrics 0\n"
     out, err, sb = H.run_scenario(H.NEW_SO, script, env)
     sb.cleanup()
@@ -486,3 +488,15 @@ def test_idle_tenant_keeps_no_kernel_on_the_gpu(built):
     sb.cleanup()
     m2 = [l for l in out2.splitlines() if l.startswith("metrics")][0].split()
     assert int(m2[2]) >= 80 and int(m2[4]) == 0 and int(m2[6]) >= 10, out2
+
+
+def test_default_reading_is_one_refill_launch_per_control_period(built):
+    """Default utilisation source (the reference's NVML samples folded on the device): exactly one
+    library kernel - vgpu_refill_kernel - per 80 ms control period, idle tenant or not."""
+    env = dict(BASE)
+    env.update({"CUDA_MEM_LIMIT_0": "1g", "CUDA_CORE_LIMIT_0": "30", "STUB_UTIL": "fixed:20"})
+    out, err, sb = H.run_scenario(H.NEW_SO, "init 0\nlaunch 200 4 1 1\nsleepms 1200\nmetrics 0\n", env)
+    sb.cleanup()
+    m = [l for l in out.splitlines() if l.startswith("metrics")][0].split()
+    launches, skipped, steps = int(m[2]), int(m[4]), int(m[6])
+    assert 10 <= launches <= 17 and skipped == 0 and steps == launches, out

@@ -333,15 +333,22 @@ static int read_container_pids(int *pids, int cap) { /* util.c:221-267 */
   return n;
 }
 
-void vgpu_pid_flags(const uint32_t *pids, uint32_t n, uint8_t *flags) {
+static int pid_flags(const uint32_t *pids, uint32_t n, uint8_t *flags, int fatal_if_unregistered);
+void vgpu_pid_flags(const uint32_t *pids, uint32_t n, uint8_t *flags) { pid_flags(pids, n, flags, 1); }
+int vgpu_pid_flags_util(const uint32_t *pids, uint32_t n, uint8_t *flags) { return pid_flags(pids, n, flags, 0); }
+
+static int pid_flags(const uint32_t *pids, uint32_t n, uint8_t *flags, int fatal_if_unregistered) {
   int mode = G_cfg->compatibility_mode;
   int open_mode = (mode & VGPU_MODE_OPEN_KERNEL) == VGPU_MODE_OPEN_KERNEL;
   memset(flags, 0, n);
-  if (n == 0) return;
+  if (n == 0) return 1;
   if ((mode & VGPU_MODE_CLIENT) == VGPU_MODE_CLIENT) {
     static __thread int cpids[VGPU_MAX_PIDS];
     int cn = read_container_pids(cpids, VGPU_MAX_PIDS);
-    if (cn == 0) VLOG(VL_FATAL, "unable to find registered container process");
+    if (cn == 0) {
+      if (fatal_if_unregistered) VLOG(VL_FATAL, "unable to find registered container process");
+      return 0;
+    }
     for (uint32_t i = 0; i < n; i++) {
       int key = (int)pids[i];
       if (pids[i] && bsearch(&key, cpids, (size_t)cn, sizeof(int), cmp_int)) flags[i] |= VGPU_FLAG_PRIMARY;
@@ -360,6 +367,7 @@ void vgpu_pid_flags(const uint32_t *pids, uint32_t n, uint8_t *flags) {
   if (open_mode)
     for (uint32_t i = 0; i < n; i++)
       if (is_local_gpu_pid(pids[i])) flags[i] |= VGPU_FLAG_LOCAL;
+  return 1;
 }
 
 /* ------------------------------------------------------------------ own-footprint registry

@@ -78,6 +78,20 @@ static int spin_seq(volatile uint32_t *word, uint32_t want, CUstream s) {
   return *word == want ? 0 : -1;
 }
 
+/* How the controller's utilisation reading is formed.  Default `nvml`: the reference's own
+ * signal - per-process NVML samples (or sm_util.config), published once per control period and
+ * folded on the device by vgpu_refill_kernel.  `queue` / `sm` / `max` are the driver-free
+ * on-device signals (stream queue-busy, per-SM issue-slot probe). */
+static void read_util_tunables(vgpu_lim_host_t *H) {
+  const char *src = vgpu_tunable("VGPU_B200_UTIL_SOURCE");
+  H->util_source = !src ? VGPU_SRC_NVML : !strcmp(src, "queue") ? VGPU_SRC_QUEUE : !strcmp(src, "sm") ? VGPU_SRC_SM
+                   : !strcmp(src, "max") ? VGPU_SRC_MAX : VGPU_SRC_NVML;
+  const char *win = vgpu_tunable("VGPU_B200_UTIL_WINDOW_PERIODS"); /* control periods (~80 ms) per utilisation reading */
+  H->util_window = (win && atoi(win) >= 1) ? (uint32_t)atoi(win) : 4u;
+  const char *um = vgpu_tunable("VGPU_B200_UTIL_MODE"); /* block (default, NVML-like) | average */
+  H->util_mode = (um && !strcmp(um, "average")) ? 0u : 1u;
+}
+
 static void write_limiter_config(vgpu_dev_rt *rt, vgpu_lim_dev_t *init) {
   const vgpu_cfg_dev_t *c = (rt->host_index >= 0 && G_cfg) ? &G_cfg->devices[rt->host_index] : NULL;
   memset(init, 0, sizeof *init);
@@ -108,10 +122,14 @@ static vgpu_dev_rt *bring_up(vgpu_dev_rt *rt, int slot, int host_index, CUdevice
   }
   if (!R.cuModuleLoadData || !R.cuLaunchKernel || !R.cuMemAlloc_v2) {
     VLOG(VL_ERROR, "device runtime: driver lacks module/launch entry points");
+    if (retained) { CUcontext dummy; R.cuCtxPopCurrent_v2(&dummy); }
     rt->ready = -1;
+    rt->retry_at = 0; /* deterministic: never retried */
     return NULL;
   }
+  unsigned fails = rt->fails;
   memset(rt, 0, sizeof *rt);
+  rt->fails = fails;
   pthread_mutex_init(&rt->q_mu, NULL);
   rt->host_index = host_index;
   rt->cuda_dev = dev;
@@ -151,6 +169,7 @@ static vgpu_dev_rt *bring_up(vgpu_dev_rt *rt, int slot, int host_index, CUdevice
   CU_TRY(R.cuModuleGetFunction(&rt->k_sampler, rt->mod, VGPU_K_SAMPLER), VGPU_K_SAMPLER);
   CU_TRY(R.cuModuleGetFunction(&rt->k_gate, rt->mod, VGPU_K_GATE), VGPU_K_GATE);
   CU_TRY(R.cuModuleGetFunction(&rt->k_governor, rt->mod, VGPU_K_GOVERNOR), VGPU_K_GOVERNOR);
+  CU_TRY(R.cuModuleGetFunction(&rt->k_refill, rt->mod, VGPU_K_REFILL), VGPU_K_REFILL);
   {
     /* spill-copy geometry: defaults from kernel_abi.h, overridable for tuning sweeps */
     const char *e;
@@ -180,20 +199,14 @@ static vgpu_dev_rt *bring_up(vgpu_dev_rt *rt, int slot, int host_index, CUdevice
   if (pinned_block(sizeof(vgpu_quota_req_t), (void **)&rt->q_req, &rt->q_req_d) ||
       pinned_block(sizeof(vgpu_quota_res_t), (void **)&rt->q_res, &rt->q_res_d) ||
       pinned_block(sizeof(vgpu_slab_res_t), (void **)&rt->slab_res, &rt->slab_res_d) ||
+      pinned_block(sizeof(vgpu_util_req_t), (void **)&rt->u_req, &rt->u_req_d) ||
       pinned_block(sizeof(vgpu_lim_host_t), (void **)&rt->lim_h, &rt->lim_h_d)) {
     VLOG(VL_ERROR, "device runtime: pinned host blocks unavailable");
     goto fail;
   }
   rt->lim_h->ext_user_override = -1;
   rt->lim_h->ext_sys_process_num = 1;
-  {
-    const char *src = getenv("VGPU_B200_UTIL_SOURCE"); /* queue (default) | sm | max */
-    rt->lim_h->util_source = (src && !strcmp(src, "sm")) ? 1 : (src && !strcmp(src, "max")) ? 2 : 0;
-    const char *win = getenv("VGPU_B200_UTIL_WINDOW_PERIODS"); /* control periods (~80 ms) per utilisation reading */
-    rt->lim_h->util_window = (win && atoi(win) >= 1) ? (uint32_t)atoi(win) : 4u;
-    const char *um = getenv("VGPU_B200_UTIL_MODE"); /* block (default, NVML-like) | average */
-    rt->lim_h->util_mode = (um && !strcmp(um, "average")) ? 0u : 1u;
-  }
+  read_util_tunables(rt->lim_h);
 
   /* One HBM allocation: limiter state followed by the UVA slab, rounded up to a whole 2 MiB
    * allocation granule.  A sub-granule request would be carved from the driver's small-block
@@ -237,6 +250,8 @@ static vgpu_dev_rt *bring_up(vgpu_dev_rt *rt, int slot, int host_index, CUdevice
     vgpu_ctrl_in_t in = {0, 0, 0, 1};
     void *p_ctl[] = {&rt->lim_d, &rt->lim_h_d, &in};
     CU_TRY(vgpu_rt_launch(rt, rt->k_controller, 1, 32, 0, rt->q_stream, p_ctl), "warm controller");
+    void *p_ref[] = {&rt->lim_d, &rt->lim_h_d, &rt->u_req_d};
+    CU_TRY(vgpu_rt_launch(rt, rt->k_refill, 1, 32, 0, rt->q_stream, p_ref), "warm refill");
     uint32_t w = 0, iv = 1, per = VGPU_SAMPLER_PROBE_ONLY, ep = 0;
     uint32_t none = 0;
     void *p_smp[] = {&rt->lim_d, &rt->lim_h_d, &w, &iv, &per, &ep, &none};
@@ -267,18 +282,15 @@ static vgpu_dev_rt *bring_up(vgpu_dev_rt *rt, int slot, int host_index, CUdevice
     rt->lim_h->gov_left_busy = 0;
     rt->lim_h->ext_user_override = -1;
     rt->lim_h->ext_sys_process_num = 1;
-    const char *src = getenv("VGPU_B200_UTIL_SOURCE");
-    rt->lim_h->util_source = (src && !strcmp(src, "sm")) ? 1 : (src && !strcmp(src, "max")) ? 2 : 0;
-    const char *win = getenv("VGPU_B200_UTIL_WINDOW_PERIODS");
-    rt->lim_h->util_window = (win && atoi(win) >= 1) ? (uint32_t)atoi(win) : 4u;
-    const char *um = getenv("VGPU_B200_UTIL_MODE");
-    rt->lim_h->util_mode = (um && !strcmp(um, "average")) ? 0u : 1u;
+    read_util_tunables(rt->lim_h);
   }
 
   uint64_t after = own_process_bytes(nvdev);
   rt->self_bytes = after > before ? after - before : 0;
   if (host_index >= 0 && lock_fd >= 0) vgpu_self_registry(host_index, rt->self_bytes, 1);
   vgpu_unlock_gpu(lock_fd);
+  rt->fails = 0;
+  rt->retry_at = 0;
   __sync_synchronize();
   rt->ready = 1;
   if (retained) { CUcontext dummy; R.cuCtxPopCurrent_v2(&dummy); }
@@ -287,10 +299,40 @@ static vgpu_dev_rt *bring_up(vgpu_dev_rt *rt, int slot, int host_index, CUdevice
   return rt;
 fail:
   vgpu_unlock_gpu(lock_fd);
-  if (retained) { CUcontext dummy; R.cuCtxPopCurrent_v2(&dummy); }
-  rt->ready = -1;
-  VLOG(VL_ERROR, "device runtime bring-up failed on cuda device %d: the sm_100a enforcement "
-                 "kernels are unavailable (no CPU fallback exists)", dev);
+  /* give back whatever was created: a transient cause (the tenant filled the GPU, a capture
+   * conflict) must not leak a module, three streams and the pinned blocks on every retry */
+  if (rt->lim_d && R.cuMemFree_v2) R.cuMemFree_v2(rt->lim_d);
+  if (R.cuMemFreeHost) {
+    if (rt->q_req) R.cuMemFreeHost(rt->q_req);
+    if (rt->q_res) R.cuMemFreeHost(rt->q_res);
+    if (rt->slab_res) R.cuMemFreeHost(rt->slab_res);
+    if (rt->u_req) R.cuMemFreeHost(rt->u_req);
+    if (rt->lim_h) R.cuMemFreeHost((void *)rt->lim_h);
+  }
+  if (R.cuStreamDestroy_v2) {
+    if (rt->q_stream) R.cuStreamDestroy_v2(rt->q_stream);
+    if (rt->s_stream) R.cuStreamDestroy_v2(rt->s_stream);
+    if (rt->p_stream) R.cuStreamDestroy_v2(rt->p_stream);
+  }
+  if (rt->mod && R.cuModuleUnload) R.cuModuleUnload(rt->mod);
+  if (retained) {
+    CUcontext dummy;
+    R.cuCtxPopCurrent_v2(&dummy);
+    if (R.cuDevicePrimaryCtxRelease_v2) R.cuDevicePrimaryCtxRelease_v2(dev);
+  }
+  {
+    unsigned f = rt->fails + 1;
+    pthread_mutex_destroy(&rt->q_mu);
+    memset(rt, 0, sizeof *rt);
+    rt->fails = f;
+    /* back-off 1 s, 2 s, 4 s ... 32 s: the next hooked call after that tries again */
+    struct timespec now;
+    clock_gettime(CLOCK_MONOTONIC, &now);
+    rt->retry_at = (uint64_t)now.tv_sec + (1ull << (f > 6 ? 5 : f - 1));
+    rt->ready = -1;
+  }
+  VLOG(VL_ERROR, "device runtime bring-up failed on cuda device %d (attempt %u): the sm_100a enforcement "
+                 "kernels are unavailable until the retry (no CPU fallback exists)", dev, rt->fails);
   return NULL;
 }
 
@@ -305,6 +347,11 @@ vgpu_dev_rt *vgpu_rt_get(int host_index, CUdevice dev) {
     g_rt_epoch = me;
   }
   vgpu_dev_rt *out = NULL;
+  if (rt->ready == -1 && rt->retry_at) { /* a transient failure is retried after its back-off */
+    struct timespec now;
+    clock_gettime(CLOCK_MONOTONIC, &now);
+    if ((uint64_t)now.tv_sec >= rt->retry_at) rt->ready = 0;
+  }
   if (rt->ready == 1) out = rt;
   else if (rt->ready == 0) {
     /* module load, allocations and the warm-up synchronise are "unsafe" calls for CUDA's capture

@@ -23,6 +23,7 @@ extern "C" {
 #define VGPU_K_SAMPLER "vgpu_sampler_kernel"
 #define VGPU_K_GATE "vgpu_gate_kernel"
 #define VGPU_K_GOVERNOR "vgpu_governor_kernel"
+#define VGPU_K_REFILL "vgpu_refill_kernel"
 
 /* ---------------------------------------------------------------- spill copy geometry */
 #define VGPU_SPILL_CHUNK 16384u      /* bytes per TMA bulk copy                      */
@@ -97,6 +98,7 @@ typedef struct {
 #define VGPU_STREAM_SLOTS 64u
 #define VGPU_TICKET_RING 1024u /* per stream slot; power of two */
 #define VGPU_MAX_SMS 256u
+enum { VGPU_SRC_QUEUE = 0, VGPU_SRC_SM = 1, VGPU_SRC_MAX = 2, VGPU_SRC_NVML = 3 }; /* vgpu_lim_host_t.util_source */
 #define VGPU_SAMPLER_PROBE_ONLY 0x7fffffffu /* sampler period_ticks value: probe SMs, leave the queue signal and the controller to the governor */
 
 /* device-resident (HBM) limiter state, one per GPU */
@@ -137,6 +139,8 @@ typedef struct {
   unsigned long long gov_left_ns;      /* %globaltimer at which the previous governor incarnation retired   */
   uint32_t gov_left_busy;              /* ... and whether tenant work was executing at that moment           */
   uint32_t _pad_g;
+  /* top_result of the NVML-sample reading (cuda_hook.c:376): persists between publications */
+  int32_t top_user, top_sys, top_nproc, top_seq;
   /* last results, for metrics and tests */
   int32_t last_user_current;
   int32_t last_sys_current;
@@ -150,7 +154,7 @@ typedef struct {
   volatile long long consumed;        /* host-owned, fetch_add by the hook                     */
   volatile long long granted_mirror;  /* device-written copy of granted                        */
   volatile uint32_t quit;             /* >0: threads inside a device-wide synchronise; resident kernels leave */
-  volatile uint32_t util_source;      /* 0 queue-busy, 1 sm-active, 2 max of both              */
+  volatile uint32_t util_source;      /* VGPU_SRC_*: 3 NVML samples (default), 0 queue-busy, 1 sm-active, 2 max of both */
   volatile int32_t ext_sys_current;   /* other tenants' util (host-provided, balance mode)     */
   volatile int32_t ext_sys_process_num;
   volatile int32_t ext_user_override; /* >=0: test hook, use this as user_current              */
@@ -172,6 +176,33 @@ typedef struct {
   volatile uint32_t gov_left_busy;    /* the governor retired while tenant work was executing (see device block) */
   volatile unsigned long long steps;
 } vgpu_lim_host_t;
+
+/* ---------------------------------------------------------------- utilisation reading (L5)
+ * One publication per control period by the tick thread: the raw per-process samples exactly as
+ * nvmlDeviceGetProcessUtilization (or sm_util.config) returned them plus the container
+ * membership flags of their pids.  vgpu_refill_kernel folds them (reference
+ * cuda_hook.c:1044-1159) and runs the controller step (:413-466) in the same launch.
+ * Pinned, device-mapped host memory; record arrays 16-byte aligned (128-bit loads). */
+enum {
+  VGPU_UTIL_NOTHING = 0,   /* process-list query failed: top_result untouched (:946-950)         */
+  VGPU_UTIL_NPROC_ONLY = 1,/* list ok, sample query failed (NOT_FOUND between NVML updates):
+                              only sys_process_num changes, the previous reading is kept (:984) */
+  VGPU_UTIL_SAMPLES = 2    /* both ok: fold the samples                                          */
+};
+typedef struct {
+  uint32_t seq;
+  uint32_t status;           /* VGPU_UTIL_*                                        */
+  uint32_t mode;             /* compatibility mode                                 */
+  uint32_t n_samples;
+  int32_t sys_process_num;
+  uint32_t have_container_pids; /* client mode: pids.config non-empty (:1073)      */
+  uint32_t _pad[2];
+  uint64_t checktime_us;     /* samples older than this are skipped (:972-979)     */
+  uint64_t _pad2;
+  vgpu_util_sample_t samples[VGPU_MAX_PIDS];
+  uint8_t flags[VGPU_MAX_PIDS]; /* VGPU_FLAG_* per sample pid                      */
+} vgpu_util_req_t;
+VGPU_STATIC_ASSERT(offsetof(vgpu_util_req_t, samples) % 16 == 0, ureq_samples_align);
 
 /* one explicit controller step (also the unit the parity tests drive) */
 typedef struct {

@@ -567,6 +567,61 @@ extern "C" __global__ void vgpu_controller_kernel(vgpu_lim_dev_t *D, vgpu_lim_ho
     ctl_step(D, H, in.user_current, in.sys_current, in.valid, in.sys_process_num);
 }
 
+/* ======================================================================= refill (L5 + L2-L4)
+ * The default control step: one CTA of ceil32(n_samples) <= 1024 threads, launched once per control
+ * period.  Thread t owns sample t of the publication in pinned host memory (two 128-bit loads,
+ * all in flight together with the header loads - one PCIe round trip).  It restates
+ * get_used_gpu_utilization (cuda_hook.c:1044-1159): time filter against checktime, sticky
+ * `valid`, GET_VALID_VALUE / CODEC_NORMALIZE (hook.h:140-141), the per-mode membership latch
+ * (same ladder as the memory fold), `sys_current` over everyone and `user_current` over the
+ * container - then runs the watcher body (ctl_step) on the persistent top_result.  A publication
+ * whose sample query failed keeps the previous reading, exactly like the reference's early
+ * return (:1057). */
+DEVINL uint32_t valid_pct(uint32_t v) { return v <= 100u ? v : 0u; } /* GET_VALID_VALUE */
+
+extern "C" __global__ void __launch_bounds__(1024)
+    vgpu_refill_kernel(vgpu_lim_dev_t *D, vgpu_lim_host_t *H, const vgpu_util_req_t *__restrict__ U) {
+  __shared__ unsigned long long s64[33];
+  __shared__ unsigned int s32[33];
+  __shared__ int dummy_state;
+  const uint32_t t = threadIdx.x;
+  const uint4 lo = *reinterpret_cast<const uint4 *>(&U->samples[t]);                                   /* pid, pad, ts */
+  const uint4 hi = *(reinterpret_cast<const uint4 *>(&U->samples[t]) + 1);                             /* sm, mem, enc, dec */
+  const uint32_t fl_raw = U->flags[t];
+  const uint32_t status = U->status, n = min(U->n_samples, (uint32_t)VGPU_MAX_PIDS);
+  const unsigned long long checktime = U->checktime_us;
+  int open_mode;
+  const int sel = mode_select(U->mode, &open_mode);
+  if (t == 0) dummy_state = 0;
+
+  if (status == VGPU_UTIL_SAMPLES) { /* uniform across the CTA */
+    const bool client_empty = ((U->mode & VGPU_MODE_CLIENT) == VGPU_MODE_CLIENT) && !U->have_container_pids;
+    const unsigned long long ts = ((unsigned long long)lo.w << 32) | lo.z;
+    const bool live = (t < n) && !client_empty && sel != SEL_BAD && ts >= checktime;
+    const uint32_t codec = (valid_pct(hi.z) + valid_pct(hi.w)) * 85u / 100u; /* CODEC_NORMALIZE */
+    const unsigned long long util = live ? (unsigned long long)(valid_pct(hi.x) + codec) : 0ull;
+    const unsigned long long sys = block_sum_u64(util, s64);
+    const unsigned long long any = block_sum_u64(live ? 1ull : 0ull, s64);
+    const unsigned long long user = fold_list(sel, open_mode, live, live ? fl_raw : 0u, util, s64, s32, false, &dummy_state);
+    if (t == 0) {
+      D->top_user = (int)user;
+      D->top_sys = (int)sys;
+      if (any) D->valid = 1;
+    }
+  }
+  if (t != 0) return;
+  if (status != VGPU_UTIL_NOTHING) {
+    int nproc = U->sys_process_num;
+    if (status == VGPU_UTIL_SAMPLES && open_mode && (int)U->n_samples > nproc) nproc = (int)U->n_samples; /* :991-995 */
+    D->top_nproc = nproc;
+  }
+  D->top_seq = (int)U->seq;
+  int user = D->top_user;
+  const int ov = H->ext_user_override;
+  if (ov >= 0) user = ov;
+  ctl_step(D, H, user, D->top_sys, ov >= 0 ? 1 : 0, D->top_nproc);
+}
+
 /* End of a control period: turn the accumulators into the utilisation reading and run one
  * controller step.  Shared by the sampler's tail (direct API / tests) and the governor. */
 DEVINL void period_end(vgpu_lim_dev_t *D, vgpu_lim_host_t *H, int grid_sms, uint32_t epoch, uint32_t period_ticks) {

@@ -17,14 +17,19 @@
  *              cuStreamWaitValue64(granted >= ticket) is enqueued in front of it, so the stream
  *              itself waits on the bucket word (see watchdog for which copy).  Contexts without
  *              64-bit stream mem-ops use vgpu_gate_kernel, a one-thread device spin.
- *   markers  = behind launches a cuStreamWriteValue64 bumps the stream's `done` sequence; the
- *              sampler compares it with `launched` to measure how long tenant work is resident
- *              (the NVML notion of utilisation) without NVML.
- *   tick     = one light thread per process: every 10 ms it launches vgpu_sampler_kernel for a
- *              0.5 ms window at a random offset (5 % residency - a resident kernel costs the
- *              *other* tenants of a time-sliced GPU a full time slice, measured in
- *              profiles/README.md); the last CTA of every 8th launch runs the controller.  It
- *              also settles unmarked launch-train tails and refreshes the process count.
+ *   markers  = behind launches a cuStreamWriteValue64 bumps the stream's `done` sequence: the
+ *              controller needs the first launch still parked behind the gate to know how many
+ *              tokens were really spent, and the queue-busy signal compares it with `launched`.
+ *   tick     = one light thread per process, the counterpart of the reference's watcher thread.
+ *              Default (VGPU_B200_UTIL_SOURCE=nvml): once per control period (80 ms) it publishes
+ *              the reference's own reading - the raw per-process NVML samples (or sm_util.config)
+ *              plus the container-membership flags of their pids - into pinned memory and
+ *              launches vgpu_refill_kernel (one warp in the common case), which folds them
+ *              (cuda_hook.c:1044-1159) and runs the controller (:413-466) on the device.
+ *              With the on-device signals (queue | sm | max) it launches vgpu_sampler_kernel every
+ *              10 ms for a 0.5 ms window at a random offset instead (one CTA for `queue`, one per
+ *              SM for the probe); the last CTA of every 8th launch runs the controller.  It
+ *              also settles unmarked launch-train tails.
  *   watchdog = a second thread that never enters the driver.  Some driver calls block while
  *              holding the context lock (a pageable cuMemcpyDtoH behind a parked kernel is the
  *              common one); the tick thread can then not launch the refill and the stream
@@ -50,16 +55,19 @@ extern vgpu_dev_rt *vgpu_rt_get(int host_index, CUdevice dev);
  * Every (stream, per-thread-default flag) of a device gets a slot in the pinned block: launch
  * sequence, completion marker, ticket ring.  Host-only bookkeeping lives here. */
 #define MARK_EVERY 256u             /* dense launch trains: one completion marker per 256 launches */
-#define SPARSE_TSC 120000ull        /* launches further apart than ~50 us are each marked       */
+#define SPARSE_TSC 120000ull        /* launches further apart than ~50 us are each marked (on-device signals only) */
+#define SLOT_TOMB ((uintptr_t)1)    /* key of a slot whose stream was destroyed: reusable, but does not end a probe chain */
 typedef struct {
-  volatile uintptr_t key;           /* CUstream | ptsz bit | top bit; 0 = empty */
+  volatile uintptr_t key;           /* CUstream | ptsz bit | top bit; 0 = never used, SLOT_TOMB = freed */
   CUstream stream;
   int ptsz;
+  volatile int lock;                /* serialises {ticket, sequence, ring write} of launches sharing the slot */
   volatile unsigned long long marked; /* last sequence number a marker was enqueued for */
   unsigned long long seen_launched;   /* tick thread: launch count at the previous tick  */
   unsigned long long last_tsc;
 } slot_t;
 static slot_t g_slots[VGPU_MAX_DEVICES][VGPU_STREAM_SLOTS];
+static pthread_mutex_t g_slot_insert_mu = PTHREAD_MUTEX_INITIALIZER;
 
 static inline unsigned long long rdtsc(void) {
   unsigned int lo, hi;
@@ -67,8 +75,40 @@ static inline unsigned long long rdtsc(void) {
   return ((unsigned long long)hi << 32) | lo;
 }
 
+static inline void slot_lock(slot_t *sl) {
+  while (__sync_lock_test_and_set(&sl->lock, 1))
+    while (sl->lock) __builtin_ia32_pause();
+}
+static inline void slot_unlock(slot_t *sl) { __sync_lock_release(&sl->lock); }
+
 static inline uintptr_t slot_key(CUstream s, int ptsz) {
   return ((uintptr_t)s << 1) | (uintptr_t)(ptsz & 1) | ((uintptr_t)1 << 63);
+}
+
+/* Open addressing with tombstones: a destroyed stream's slot keeps later probe chains intact
+ * (a live stream that originally probed past it must still find its own slot).  Lookups are
+ * lock-free; insertions (once per stream) are serialised and re-probe under the mutex, so one
+ * stream first used from two threads at once cannot end up with two slots. */
+static uint32_t slot_insert(slot_t *tab, uintptr_t key, uint32_t h, CUstream s, int ptsz) {
+  uint32_t out = VGPU_STREAM_SLOTS - 1, reuse = VGPU_STREAM_SLOTS;
+  pthread_mutex_lock(&g_slot_insert_mu);
+  for (uint32_t i = 0; i < VGPU_STREAM_SLOTS - 1; i++) {
+    uint32_t idx = (h + i) % (VGPU_STREAM_SLOTS - 1);
+    uintptr_t k = tab[idx].key;
+    if (k == key) { out = idx; reuse = VGPU_STREAM_SLOTS; break; }
+    if (k == SLOT_TOMB && reuse == VGPU_STREAM_SLOTS) reuse = idx;
+    if (k == 0) { if (reuse == VGPU_STREAM_SLOTS) reuse = idx; break; }
+  }
+  if (reuse != VGPU_STREAM_SLOTS) {
+    tab[reuse].stream = s;
+    tab[reuse].ptsz = ptsz;
+    tab[reuse].marked = tab[reuse].seen_launched = 0;
+    __sync_synchronize();
+    tab[reuse].key = key;
+    out = reuse;
+  }
+  pthread_mutex_unlock(&g_slot_insert_mu);
+  return out; /* table full: the overflow slot, shared - every launch is marked */
 }
 
 static inline uint32_t slot_of(int host_index, CUstream s, int ptsz) {
@@ -78,15 +118,10 @@ static inline uint32_t slot_of(int host_index, CUstream s, int ptsz) {
   for (uint32_t i = 0; i < VGPU_STREAM_SLOTS - 1; i++) {
     uint32_t idx = (h + i) % (VGPU_STREAM_SLOTS - 1);
     uintptr_t k = tab[idx].key;
-    if (k == key) return idx;
-    if (k == 0 && __sync_bool_compare_and_swap(&tab[idx].key, 0, key)) {
-      tab[idx].stream = s;
-      tab[idx].ptsz = ptsz;
-      return idx;
-    }
-    if (tab[idx].key == key) return idx;
+    if (likely(k == key)) return idx;
+    if (k == 0) break;
   }
-  return VGPU_STREAM_SLOTS - 1; /* overflow slot, shared: every launch is marked */
+  return slot_insert(tab, key, h, s, ptsz);
 }
 
 /* ------------------------------------------------------------------ tick thread */
@@ -101,8 +136,100 @@ static volatile int g_sync_waiters; /* threads currently inside a device-wide sy
 static volatile unsigned long g_tick_gen, g_wd_gen; /* completed loop iterations (quiescence points) */
 
 static uint32_t env_u32(const char *name, uint32_t dflt) {
-  const char *s = getenv(name);
-  return (s && *s) ? (uint32_t)strtoul(s, NULL, 10) : dflt;
+  const char *s = vgpu_tunable(name); /* ignored under a mounted control-plane config */
+  return s ? (uint32_t)strtoul(s, NULL, 10) : dflt;
+}
+
+/* ------------------------------------------------------------------ utilisation publication (L5, host half)
+ * What get_gpu_process_from_local_nvml_driver / _external_watcher collect (cuda_hook.c:922-1042),
+ * left raw: the fold itself runs on the device.  The outcomes the reference distinguishes are
+ * kept apart (status): list query failed -> nothing changes; sample query failed (NVML answers
+ * NOT_FOUND between its ~1 s sample updates) -> only the process count changes and the watcher
+ * keeps steering with the previous reading; both fine -> fold. */
+static unsigned long long wall_us(void) {
+  struct timespec now;
+  clock_gettime(CLOCK_REALTIME, &now);
+  return (unsigned long long)now.tv_sec * 1000000ull + (unsigned long long)now.tv_nsec / 1000ull;
+}
+
+static int publish_from_external_watcher(vgpu_dev_rt *rt, vgpu_util_req_t *U) {
+  if (!G_cfg->sm_watcher || !G_smutil) return 0;
+  int h = rt->host_index;
+  int fd = vgpu_smutil_rdlock(h);
+  if (fd < 0) {
+    VLOG(VL_WARNING, "failed to acquire read lock for host device %d, fallback to nvml driver", h);
+    return 0;
+  }
+  const vgpu_smutil_dev_t *d = &G_smutil->devices[h];
+  int ok = 0;
+  if (wall_us() - d->last_seen_us < 5000000ull) { /* is_expired (:1002-1007) */
+    uint32_t n = d->samples_size > VGPU_MAX_PIDS ? VGPU_MAX_PIDS : d->samples_size;
+    memcpy(U->samples, d->samples, (size_t)n * sizeof(vgpu_util_sample_t));
+    U->n_samples = n;
+    U->sys_process_num = (int)(d->compute_size >= d->graphics_size ? d->compute_size : d->graphics_size);
+    U->checktime_us = d->last_seen_us;
+    U->status = VGPU_UTIL_SAMPLES;
+    ok = 1;
+  }
+  vgpu_smutil_unlock(fd, h);
+  return ok;
+}
+
+static void publish_from_nvml(vgpu_dev_rt *rt, vgpu_util_req_t *U) {
+  nvmlDevice_t nv = vgpu_nvml_handle_of_host(rt->host_index);
+  if (!nv) return;
+  static vgpu_proc_t procs[VGPU_MAX_PIDS];
+  static vgpu_proc_v2_t wide[VGPU_MAX_PIDS];
+  unsigned int n = VGPU_MAX_PIDS;
+  nvmlReturn_t r;
+  if (R.nvmlDeviceGetComputeRunningProcesses) r = R.nvmlDeviceGetComputeRunningProcesses(nv, &n, procs);
+  else if (R.nvmlDeviceGetComputeRunningProcesses_v3) r = R.nvmlDeviceGetComputeRunningProcesses_v3(nv, &n, wide);
+  else r = NVML_ERROR_FUNCTION_NOT_FOUND;
+  if (r != NVML_SUCCESS) {
+    VLOG(VL_VERBOSE, "nvmlDeviceGetComputeRunningProcesses can't get pids on host device %d, return %d, str: %s",
+         rt->host_index, r, vgpu_nv_err(r));
+    return; /* VGPU_UTIL_NOTHING */
+  }
+  U->sys_process_num = (int)n;
+  if (n == 0) { /* nobody computing: the graphics list decides the process count (:952-971) */
+    n = VGPU_MAX_PIDS;
+    if (R.nvmlDeviceGetGraphicsRunningProcesses) r = R.nvmlDeviceGetGraphicsRunningProcesses(nv, &n, procs);
+    else if (R.nvmlDeviceGetGraphicsRunningProcesses_v3) r = R.nvmlDeviceGetGraphicsRunningProcesses_v3(nv, &n, wide);
+    else r = NVML_ERROR_FUNCTION_NOT_FOUND;
+    if (r == NVML_SUCCESS) U->sys_process_num = (int)n;
+  }
+  U->status = VGPU_UTIL_NPROC_ONLY;
+  U->checktime_us = wall_us() - 1000000ull; /* "since one second ago" (:972-976) */
+  unsigned int ns = VGPU_MAX_PIDS;
+  r = R.nvmlDeviceGetProcessUtilization ? R.nvmlDeviceGetProcessUtilization(nv, U->samples, &ns, U->checktime_us)
+                                        : NVML_ERROR_FUNCTION_NOT_FOUND;
+  if (r != NVML_SUCCESS) {
+    if (r != NVML_ERROR_NOT_FOUND)
+      VLOG(VL_VERBOSE, "nvmlDeviceGetProcessUtilization can't get process utilization on host device %d, return: %d, str: %s",
+           rt->host_index, r, vgpu_nv_err(r));
+    return;
+  }
+  U->n_samples = ns > VGPU_MAX_PIDS ? VGPU_MAX_PIDS : ns;
+  U->status = VGPU_UTIL_SAMPLES;
+}
+
+/* returns the CTA size the refill kernel needs for this publication */
+static unsigned publish_utilization(vgpu_dev_rt *rt) {
+  vgpu_util_req_t *U = rt->u_req;
+  U->status = VGPU_UTIL_NOTHING;
+  U->n_samples = 0;
+  U->mode = (uint32_t)G_cfg->compatibility_mode;
+  U->have_container_pids = 1;
+  if (!publish_from_external_watcher(rt, U)) publish_from_nvml(rt, U);
+  if (U->status == VGPU_UTIL_SAMPLES && G_cfg->compatibility_mode != VGPU_MODE_HOST) {
+    static uint32_t pids[VGPU_MAX_PIDS];
+    for (uint32_t i = 0; i < U->n_samples; i++) pids[i] = U->samples[i].pid;
+    U->have_container_pids = (uint32_t)vgpu_pid_flags_util(pids, U->n_samples, U->flags);
+  }
+  __sync_synchronize();
+  U->seq++;
+  unsigned n = U->status == VGPU_UTIL_SAMPLES ? U->n_samples : 0;
+  return n ? (n + 31u) & ~31u : 32u;
 }
 
 /* External SM watcher (reference cuda_hook.c:1009-1042): when the control plane publishes
@@ -165,7 +292,7 @@ static void settle_idle_streams(vgpu_dev_rt *rt, int h) {
   vgpu_lim_host_t *H = rt->lim_h;
   for (uint32_t i = 0; i < VGPU_STREAM_SLOTS - 1; i++) {
     slot_t *sl = &g_slots[h][i];
-    if (!sl->key) continue;
+    if (sl->key <= SLOT_TOMB) continue;
     unsigned long long l = H->launched[i], d = H->done[i];
     int quiet = (l == sl->seen_launched);
     sl->seen_launched = l;
@@ -185,7 +312,7 @@ static uint32_t g_skipped[VGPU_MAX_DEVICES];
 static int tenant_activity(vgpu_dev_rt *rt, uint32_t *skipped) {
   vgpu_lim_host_t *H = rt->lim_h;
   /* the SM probe also sees work the hook does not number (graph replays): it needs its windows */
-  if (!g_skip_idle || H->util_source != 0) return 1;
+  if (!g_skip_idle || H->util_source != VGPU_SRC_QUEUE) return 1;
   long long granted = H->granted_mirror;
   int parked = 0;
   for (uint32_t i = 0; i < VGPU_STREAM_SLOTS; i++) {
@@ -228,7 +355,7 @@ static void *tick_main(void *arg) {
         relaxed = 1;
       }
       settle_idle_streams(rt, h);
-      if ((epoch % 100) == 1) refresh_process_count(rt);
+      if ((epoch % 100) == 1 && rt->lim_h->util_source != VGPU_SRC_NVML) refresh_process_count(rt);
       if ((epoch % 100) == 0 && vgpu_log_level() >= VL_VERBOSE) {
         vgpu_lim_host_t *H = rt->lim_h;
         VLOG(VL_VERBOSE, "limiter host %d: steps %llu user %d (queue %d sm %d) share %lld bucket %lld granted %lld consumed %lld "
@@ -237,10 +364,27 @@ static void *tick_main(void *arg) {
              (long long)H->granted_mirror, (long long)H->consumed, H->ext_sys_process_num, H->ctl_state,
              (unsigned long long)H->launched[0], (unsigned long long)H->done[0]);
       }
-      if (g_governor_mode) {
+      if (rt->lim_h->util_source == VGPU_SRC_NVML && !g_governor_mode) {
+        /* the reference's cadence and the reference's reading: once per control period publish
+         * the samples and let one small CTA fold them and refill the bucket */
+        if (epoch % g_period_ticks == 0) {
+          unsigned block = publish_utilization(rt);
+          void *params[] = {&rt->lim_d, &rt->lim_h_d, &rt->u_req_d};
+          CUresult r = VGPU_CAPCHK(R.cuLaunchKernel(rt->k_refill, 1, 1, 1, block, 1, 1, 0, rt->s_stream, params, NULL));
+          if (r == CUDA_SUCCESS) {
+            fails = 0;
+            vgpu_metric_add(h, VM_SAMPLER_LAUNCHES, 1);
+          } else if (++fails == 25) {
+            VLOG(VL_ERROR, "refill launch keeps failing (%d: %s); opening the gate", r, vgpu_cu_err(r));
+            rt->memops64 = -1;
+            rt->lim_h->granted_mirror = (long long)1 << 60;
+          }
+        }
+      } else if (g_governor_mode) {
         /* the governor owns the queue signal and the controller; the per-SM probe is only
          * needed when the controller is asked to look at SM activity */
-        if (rt->lim_h->util_source != 0 && R.cuStreamQuery(rt->p_stream) == CUDA_SUCCESS) {
+        if (rt->lim_h->util_source != VGPU_SRC_QUEUE && rt->lim_h->util_source != VGPU_SRC_NVML &&
+            R.cuStreamQuery(rt->p_stream) == CUDA_SUCCESS) {
           uint32_t ep = epoch, never = VGPU_SAMPLER_PROBE_ONLY, none = 0;
           void *params[] = {&rt->lim_d, &rt->lim_h_d, &g_window_us, &g_interval_us, &never, &ep, &none};
           unsigned grid = rt->sm_num > 0 ? (unsigned)rt->sm_num : 148u;
@@ -259,7 +403,8 @@ static void *tick_main(void *arg) {
          * negligible so the wait is not stretched by it */
         uint32_t window = g_sync_waiters > 0 ? 200u : g_window_us;
         void *params[] = {&rt->lim_d, &rt->lim_h_d, &window, &g_interval_us, &g_period_ticks, &ep, &skipped};
-        unsigned grid = rt->sm_num > 0 ? (unsigned)rt->sm_num : 148u;
+        /* the queue signal is one warp's work: only the per-SM probe needs a CTA on every SM */
+        unsigned grid = rt->lim_h->util_source == VGPU_SRC_QUEUE ? 1u : rt->sm_num > 0 ? (unsigned)rt->sm_num : 148u;
         CUresult r = VGPU_CAPCHK(R.cuLaunchKernel(rt->k_sampler, grid, 1, 1, 128, 1, 1, 0, rt->s_stream, params, NULL));
         if (r == CUDA_SUCCESS) {
           fails = 0;
@@ -368,14 +513,15 @@ static void tick_start(void) {
   g_interval_us = env_u32("VGPU_B200_SAMPLER_INTERVAL_US", 50);
   g_period_ticks = env_u32("VGPU_B200_PERIOD_TICKS", 8);
   g_tick_ms = env_u32("VGPU_B200_TICK_MS", 10);
+  if (!g_period_ticks) g_period_ticks = 1;
+  if (!g_tick_ms) g_tick_ms = 1;
   g_gov_interval_us = env_u32("VGPU_B200_GOVERNOR_INTERVAL_US", 50);
   g_gov_period_us = env_u32("VGPU_B200_PERIOD_US", 80000);
   g_gov_idle_us = env_u32("VGPU_B200_GOVERNOR_IDLE_US", 5000);
   g_governor_mode = env_u32("VGPU_B200_GOVERNOR", 0) != 0;
   g_watchdog_ms = env_u32("VGPU_B200_WATCHDOG_MS", 170);
+  if (g_watchdog_ms < 2 * g_tick_ms * g_period_ticks) g_watchdog_ms = 2 * g_tick_ms * g_period_ticks + 10; /* never sooner than two control periods */
   g_skip_idle = env_u32("VGPU_B200_SKIP_IDLE_WINDOWS", 1) != 0;
-  if (!g_period_ticks) g_period_ticks = 1;
-  if (!g_tick_ms) g_tick_ms = 1;
   g_tick_epoch = vgpu_fork_epoch + 1;
   if (pthread_create(&g_tick_tid, NULL, tick_main, NULL) == 0) {
     pthread_setname_np(g_tick_tid, "vgpu_b200_tick");
@@ -497,7 +643,7 @@ void vgpu_limiter_quiesce(vgpu_dev_rt *rt) {
       slot_t *sl = &g_slots[h][i];
       unsigned long long l = H->launched[i];
       t_sync_snap[i] = l;
-      if (!sl->key || l <= H->done[i] || sl->marked >= l || rt->memops64 <= 0) continue;
+      if (sl->key <= SLOT_TOMB || l <= H->done[i] || sl->marked >= l || rt->memops64 <= 0) continue;
       if (i == VGPU_STREAM_SLOTS - 1 || (sl->ptsz && !sl->stream)) continue; /* marked per launch already */
       enqueue_marker(rt, h, i, l, sl->stream, sl->ptsz);
     }
@@ -529,6 +675,7 @@ typedef struct {
   uint32_t slot;
   unsigned long long seq;
   int ptsz;
+  int capturing; /* the launch was recorded into a graph (found out at the gate) */
 } admit_t;
 
 static inline void enqueue_marker(vgpu_dev_rt *rt, int h, uint32_t slot, unsigned long long seq, CUstream s, int ptsz) {
@@ -537,6 +684,15 @@ static inline void enqueue_marker(vgpu_dev_rt *rt, int h, uint32_t slot, unsigne
       (ptsz && R.cuStreamWriteValue64_v2_ptsz) ? R.cuStreamWriteValue64_v2_ptsz : R.cuStreamWriteValue64_v2;
   if (likely(VGPU_CAPCHK(wr(s, addr, (cuuint64_t)seq, 0)) == CUDA_SUCCESS)) g_slots[h][slot].marked = seq;
   else rt->memops64 = 0;
+}
+
+/* Is `s` recording into a graph right now?  Only asked where the library is about to enqueue a
+ * stream operation of its own (marker, gate) - those must not be recorded, they would replay
+ * stale values - never on the per-launch fast path.  The legacy NULL stream cannot capture. */
+static inline int stream_capturing(CUstream s, int ptsz) {
+  int capturing = 0;
+  if ((s != NULL || ptsz) && R.cuStreamIsCapturing) VGPU_CAPCHK(R.cuStreamIsCapturing(s, &capturing));
+  return capturing;
 }
 
 /* returns 0 when the launch should simply be forwarded */
@@ -548,7 +704,7 @@ static inline int admit(admit_t *a, unsigned gx, unsigned gy, unsigned gz, CUstr
   int h = vgpu_host_index_of_cuda(dev);
   if (h < 0 || !G_cfg->devices[h].core_limit) return 0;
   vgpu_dev_rt *rt = vgpu_rt_get(h, dev);
-  if (unlikely(!rt)) return 0; /* bring-up failed: logged there; launches stay un-throttled */
+  if (unlikely(!rt)) return 0; /* bring-up failed: logged there, retried after its back-off */
   if (unlikely(!g_tick_devices[h])) {
     g_tick_devices[h] = 1;
     pthread_once(&g_tick_once, tick_start);
@@ -556,61 +712,67 @@ static inline int admit(admit_t *a, unsigned gx, unsigned gy, unsigned gz, CUstr
   vgpu_lim_host_t *H = rt->lim_h;
   /* the reference multiplies the three unsigned dims in 32 bits and passes the result as int */
   long long cost = (long long)(int)(gx * gy * gz);
-  long long ticket = __sync_fetch_and_add(&H->consumed, cost);
   a->rt = rt;
   a->ptsz = ptsz;
   a->slot = slot_of(h, s, ptsz);
-  /* the legacy NULL stream cannot be captured; any other stream might be */
-  int capturing = 0;
-  if ((s != NULL || ptsz) && R.cuStreamIsCapturing) VGPU_CAPCHK(R.cuStreamIsCapturing(s, &capturing));
-  if (capturing) { /* graph capture: tokens are paid at capture time, like the reference; no gate or
-                      marker nodes are recorded into the graph (they would replay stale values) */
-    a->rt = NULL;
-    return 1;
-  }
-  /* bounded run-ahead: the ticket ring holds VGPU_TICKET_RING outstanding launches per stream */
-  unsigned long long seq = H->launched[a->slot] + 1;
-  if (unlikely(seq - H->done[a->slot] >= VGPU_TICKET_RING - 2)) {
+  slot_t *sl = &g_slots[h][a->slot];
+  /* bounded run-ahead: the ticket ring holds VGPU_TICKET_RING outstanding launches per stream
+   * (signed difference: several threads may share a slot - the legacy stream, the per-thread
+   * default streams, the overflow slot - and `done` may be a moment ahead of a stale read) */
+  if (unlikely((long long)(H->launched[a->slot] + 1 - H->done[a->slot]) >= (long long)VGPU_TICKET_RING - 64)) {
     /* wait for the stream to drain a little; never forever - if completion markers stopped
      * arriving (driver refused the mem-op, context torn down) fall back to marker-less mode */
+    if (sl->marked < H->launched[a->slot] && rt->memops64 > 0 && !stream_capturing(s, ptsz))
+      enqueue_marker(rt, h, a->slot, H->launched[a->slot], s, ptsz);
     struct timespec t0, t1;
     clock_gettime(CLOCK_MONOTONIC, &t0);
-    while (seq - H->done[a->slot] >= VGPU_TICKET_RING - 2) {
+    while ((long long)(H->launched[a->slot] + 1 - H->done[a->slot]) >= (long long)VGPU_TICKET_RING - 64) {
       sched_yield();
       clock_gettime(CLOCK_MONOTONIC, &t1);
       if (t1.tv_sec - t0.tv_sec >= 5) {
         VLOG(VL_ERROR, "completion markers stalled on host device %d; disabling stream mem-ops", h);
         rt->memops64 = 0;
-        H->done[a->slot] = seq - 1;
+        H->done[a->slot] = H->launched[a->slot];
         break;
       }
     }
   }
+  /* ticket, sequence number and ring entry of one launch are taken together, so tickets grow
+   * monotonically inside a slot even when several threads launch into it */
+  slot_lock(sl);
+  long long ticket = __sync_fetch_and_add(&H->consumed, cost);
+  unsigned long long seq = H->launched[a->slot] + 1;
   H->ticket[a->slot][seq & (VGPU_TICKET_RING - 1)] = ticket;
   __atomic_store_n(&H->launched[a->slot], seq, __ATOMIC_RELEASE); /* ticket first, then the sequence */
+  slot_unlock(sl);
   a->seq = seq;
   if (unlikely(g_governor_mode)) governor_ensure(rt, h);
   if (H->granted_mirror - ticket < 0 && rt->memops64 >= 0) {
+    if (stream_capturing(s, ptsz)) { /* graph capture: tokens are paid at capture time, like the
+                                        reference; no gate or marker nodes are recorded */
+      a->capturing = 1;
+      return 1;
+    }
     /* bucket empty: park the *stream* on the bucket word (its host-visible mirror, so that the
      * watchdog can lend tokens without the driver), not the CPU thread */
     vgpu_metric_add(h, VM_RATE_GATED, 1);
     /* Bounded run-ahead.  A parked stream must never be allowed to fill the driver's hardware
      * queue: a launch call that blocks inside the driver for queue space holds the context lock,
-     * and the tick thread could then no longer launch the sampler whose controller is the only
+     * and the tick thread could then no longer launch the refill whose controller is the only
      * thing that can release the stream.  So once GATED_RUNAHEAD launches are queued behind the
      * gate, wait here - in user space, in ~20 us steps - for the stream to drain or for tokens.
      * (The reference blocks the thread for every throttled launch, in 10 ms steps.) */
-    if (unlikely(seq - H->done[a->slot] > GATED_RUNAHEAD)) {
+    if (unlikely((long long)(seq - H->done[a->slot]) > (long long)GATED_RUNAHEAD)) {
       struct timespec nap = {0, 20000};
-      for (int spins = 0; seq - H->done[a->slot] > GATED_RUNAHEAD && H->granted_mirror - ticket < 0; spins++) {
+      for (int spins = 0; (long long)(seq - H->done[a->slot]) > (long long)GATED_RUNAHEAD && H->granted_mirror - ticket < 0; spins++) {
         if (spins < 64) sched_yield();
         else nanosleep(&nap, NULL);
         if (unlikely(rt->memops64 <= 0)) break;
       }
     }
-    /* make the sampler's view exact at the gate: everything before this launch gets its marker
-     * now, so the oldest unfinished launch it will see is this (parked) one */
-    if (likely(rt->memops64 > 0) && g_slots[h][a->slot].marked < seq - 1) enqueue_marker(rt, h, a->slot, seq - 1, s, ptsz);
+    /* make the controller's view exact at the gate: everything before this launch gets its
+     * marker now, so the oldest unfinished launch it will see is this (parked) one */
+    if (likely(rt->memops64 > 0) && sl->marked < seq - 1) enqueue_marker(rt, h, a->slot, seq - 1, s, ptsz);
     if (likely(rt->memops64 > 0)) {
       CUresult (*wait)(CUstream, CUdeviceptr, cuuint64_t, unsigned) =
           (ptsz && R.cuStreamWaitValue64_v2_ptsz) ? R.cuStreamWaitValue64_v2_ptsz : R.cuStreamWaitValue64_v2;
@@ -634,21 +796,35 @@ static inline int admit(admit_t *a, unsigned gx, unsigned gy, unsigned gz, CUstr
 }
 
 static inline void mark_done(const admit_t *a, CUstream s) {
-  if (!a->rt) return;
   vgpu_dev_rt *rt = a->rt;
+  if (!rt) return;
   int h = rt->host_index;
   slot_t *sl = &g_slots[h][a->slot];
   if (likely(rt->memops64 > 0)) {
     /* a completion marker costs a driver call (~3 us): dense trains share one per MARK_EVERY
-     * launches, isolated launches and the overflow slot get their own */
-    unsigned long long now = rdtsc();
-    int sparse = (now - sl->last_tsc) > SPARSE_TSC;
-    sl->last_tsc = now;
-    if (sparse || a->seq - sl->marked >= MARK_EVERY || a->slot == VGPU_STREAM_SLOTS - 1 || (sl->ptsz && !sl->stream))
-      enqueue_marker(rt, h, a->slot, a->seq, s, a->ptsz);
+     * launches; the overflow slot and other threads' default streams get one per launch (the
+     * tick thread cannot settle those); the on-device queue signal also wants one behind every
+     * isolated launch.  With the default NVML reading the markers only bound the run-ahead and
+     * locate the first parked launch, so the dense rule is enough. */
+    int due = a->seq - sl->marked >= MARK_EVERY || a->slot == VGPU_STREAM_SLOTS - 1 || (sl->ptsz && !sl->stream);
+    if (rt->lim_h->util_source != VGPU_SRC_NVML) {
+      unsigned long long now = rdtsc();
+      due |= (now - sl->last_tsc) > SPARSE_TSC;
+      sl->last_tsc = now;
+    }
+    if (likely(!due && !a->capturing)) return;
+    if (a->capturing || stream_capturing(s, a->ptsz)) {
+      /* recorded into a graph, not executed: nothing is in flight for this sequence number */
+      unsigned long long d;
+      while ((d = rt->lim_h->done[a->slot]) < a->seq && !__sync_bool_compare_and_swap(&rt->lim_h->done[a->slot], d, a->seq)) {}
+      return;
+    }
+    enqueue_marker(rt, h, a->slot, a->seq, s, a->ptsz);
     if (likely(rt->memops64 > 0)) return;
   }
-  rt->lim_h->done[a->slot] = a->seq; /* no completion signal available: treat as instantaneous */
+  /* no completion signal available: treat as instantaneous (monotonic: slots can be shared) */
+  unsigned long long d;
+  while ((d = rt->lim_h->done[a->slot]) < a->seq && !__sync_bool_compare_and_swap(&rt->lim_h->done[a->slot], d, a->seq)) {}
 }
 
 #define LIMITED_LAUNCH(gx, gy, gz, stream, ptsz, CALL)          \
@@ -743,13 +919,15 @@ VGPU_EXPORT CUresult cuStreamDestroy_v2(CUstream s) {
   for (int h = 0; h < VGPU_MAX_DEVICES; h++)
     for (uint32_t i = 0; i < VGPU_STREAM_SLOTS - 1; i++) {
       slot_t *sl = &g_slots[h][i];
-      if (sl->key && sl->stream == s) {
+      if (sl->key > SLOT_TOMB && sl->stream == s) {
         vgpu_dev_rt *rt = vgpu_rt_peek(h);
+        slot_lock(sl);
         if (rt) rt->lim_h->done[i] = rt->lim_h->launched[i];
         sl->stream = NULL;
         sl->marked = sl->seen_launched = 0;
         __sync_synchronize();
-        sl->key = 0;
+        sl->key = SLOT_TOMB; /* not 0: streams that probed past this slot keep finding theirs */
+        slot_unlock(sl);
       }
     }
   return R.cuStreamDestroy_v2 ? R.cuStreamDestroy_v2(s) : CUDA_ERROR_NOT_FOUND;

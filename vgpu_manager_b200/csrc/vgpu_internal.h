@@ -209,6 +209,7 @@ extern vgpu_vmem_t *G_vmem;     /* shared UVA ledger file (RW)           */
 /* Optional development/test sandbox: VGPU_B200_SANDBOX=/dir prefixes every contract path
  * (never set in production; the control plane knows nothing about it). */
 const char *vgpu_path(const char *abs, char *buf, size_t cap);
+const char *vgpu_tunable(const char *name); /* getenv, but NULL when a control-plane config is mounted */
 #define VP(p) vgpu_path((p), (char[512]){0}, 512)
 
 /* boot.c */
@@ -236,15 +237,20 @@ void vgpu_smutil_unlock(int fd, int host_index);
 uint64_t vgpu_self_registry(int h, uint64_t publish_bytes, int publish);
 /* container membership flags for a list of device pids (VGPU_FLAG_*), per compatibility mode */
 void vgpu_pid_flags(const uint32_t *pids, uint32_t n, uint8_t *flags);
+/* same for the utilisation fold: client mode with an empty pids.config is not fatal there, the
+ * reference just skips the samples (cuda_hook.c:1073); returns 0 in exactly that case */
+int vgpu_pid_flags_util(const uint32_t *pids, uint32_t n, uint8_t *flags);
 
 /* device.c - per-GPU device runtime (module, streams, pinned blocks) */
 typedef struct vgpu_dev_rt {
   int host_index;
-  int ready;   /* 1 once the module is loaded in `ctx`; -1 if bring-up failed */
+  int ready;   /* 1 once the module is loaded in `ctx`; -1 if bring-up failed (retried at retry_at) */
+  unsigned fails;     /* consecutive failed bring-ups */
+  uint64_t retry_at;  /* CLOCK_MONOTONIC second of the next attempt; 0 = never (deterministic failure) */
   CUdevice cuda_dev;
   CUcontext ctx;
   CUmodule mod;
-  CUfunction k_clear, k_spill, k_copy_generic, k_quota, k_slab_insert, k_slab_remove, k_controller, k_sampler, k_gate, k_governor;
+  CUfunction k_clear, k_spill, k_copy_generic, k_quota, k_slab_insert, k_slab_remove, k_controller, k_sampler, k_gate, k_governor, k_refill;
   CUstream q_stream; /* quota / ledger kernels (app thread)     */
   CUstream s_stream; /* sampler + controller (tick thread); the governor in VGPU_B200_GOVERNOR=1 mode */
   CUstream p_stream; /* direct-API sampler runs; probe-only sampler beside the governor          */
@@ -253,6 +259,7 @@ typedef struct vgpu_dev_rt {
   vgpu_quota_res_t *q_res;  CUdeviceptr q_res_d;
   vgpu_slab_res_t *slab_res; CUdeviceptr slab_res_d;
   vgpu_lim_host_t *lim_h;   CUdeviceptr lim_h_d;
+  vgpu_util_req_t *u_req;   CUdeviceptr u_req_d;  /* utilisation publication (tick thread -> refill kernel) */
   /* HBM */
   CUdeviceptr lim_d;  /* vgpu_lim_dev_t          */
   CUdeviceptr slab_d; /* vgpu_slab_slot_t[SLOTS] */

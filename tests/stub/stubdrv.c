@@ -463,6 +463,27 @@ static void fake_quota(const vgpu_quota_req_t *q, vgpu_quota_res_t *r) {
   r->seq_done = q->seq;
 }
 
+typedef struct { const vgpu_quota_req_t *q; vgpu_quota_res_t *r; uint32_t seq; } armed_arg_t;
+static void *fake_armed_quota(void *argp) {
+  armed_arg_t a = *(armed_arg_t *)argp;
+  free(argp);
+  struct timespec nap = {0, 20000};
+  int ok = 0;
+  for (int i = 0; i < 1000 && !ok; i++) { /* 20 ms, like the kernel */
+    ok = *(volatile uint32_t *)&a.q->seq == a.seq;
+    if (!ok) nanosleep(&nap, NULL);
+  }
+  __sync_synchronize();
+  if (ok) {
+    fake_quota(a.q, a.r);
+  } else {
+    a.r->path = VGPU_PATH_RETRY;
+    __sync_synchronize();
+    a.r->seq_done = a.seq;
+  }
+  return NULL;
+}
+
 static void fake_ctl_step(vgpu_lim_dev_t *D, vgpu_lim_host_t *H, int user, int sys, int valid, int nproc) {
   orc_gpu_t g = {D->sm_num, D->max_thread_per_sm, D->total_cores};
   vgpu_cfg_dev_t c;
@@ -599,7 +620,23 @@ static void run_fake_kernel(const char *name, void **p) {
     unsigned long long n = *(unsigned long long *)p[2];
     if (n) memmove((void *)(uintptr_t) * (CUdeviceptr *)p[0], (void *)(uintptr_t) * (CUdeviceptr *)p[1], n);
   } else if (!strcmp(name, VGPU_K_QUOTA)) {
-    fake_quota((const vgpu_quota_req_t *)(uintptr_t) * (CUdeviceptr *)p[0], (vgpu_quota_res_t *)(uintptr_t) * (CUdeviceptr *)p[1]);
+    const vgpu_quota_req_t *q = (const vgpu_quota_req_t *)(uintptr_t) * (CUdeviceptr *)p[0];
+    vgpu_quota_res_t *r = (vgpu_quota_res_t *)(uintptr_t) * (CUdeviceptr *)p[1];
+    uint32_t armed = *(uint32_t *)p[2];
+    if (!armed) {
+      fake_quota(q, r);
+    } else {
+      /* armed launch: the real kernel is asynchronous and waits on the device for the request to be
+       * published under `armed`; the synchronous fake GPU needs a thread for that */
+      armed_arg_t *a = (armed_arg_t *)malloc(sizeof *a);
+      a->q = q; a->r = r; a->seq = armed;
+      pthread_t t;
+      pthread_attr_t at;
+      pthread_attr_init(&at);
+      pthread_attr_setdetachstate(&at, PTHREAD_CREATE_DETACHED);
+      if (pthread_create(&t, &at, fake_armed_quota, a) != 0) { r->path = VGPU_PATH_RETRY; __sync_synchronize(); r->seq_done = armed; free(a); }
+      pthread_attr_destroy(&at);
+    }
   } else if (!strcmp(name, VGPU_K_SLAB_INSERT)) {
     vgpu_slab_slot_t *slab = (vgpu_slab_slot_t *)(uintptr_t) * (CUdeviceptr *)p[0];
     unsigned long long dptr = *(unsigned long long *)p[1], bytes = *(unsigned long long *)p[2];

@@ -176,24 +176,37 @@ def test_existing_config_file_wins_over_env(built):
     assert outs[0][1] == raw and "totalmem -> 0 %d" % (3 * GiB) in t
 
 
-def test_nvml_only_client_needs_opt_in_context(built):
-    """nvidia-smi style process: no CUDA context.  The reference answers on the CPU; the B200
-    library has no CPU path, so it refuses by default and matches the reference's numbers once
-    VGPU_B200_NVML_CONTEXT=1 lets it retain the primary context for its kernel."""
+def test_nvml_only_client_gets_the_reference_numbers(built):
+    """nvidia-smi style process: no CUDA context, so no place to run the quota kernel.  Like the reference
+    (nvml_hook.c:47-103) the report is computed on the host there - same fold, same clamp - and no
+    context is created behind the client's back.  Compared across compatibility modes, with other
+    tenants' processes, graphics duplicates and a UVA ledger on the GPU."""
     script = "nvmlinit 0\nnvmlinfo\nnvmlinfo2\npersistence\nsetmode 0\n"
-    env = dict(BASE)
-    env.update({"CUDA_MEM_LIMIT_0": "1g", "STUB_OTHER_PROCS": "901:268435456:c"})
-    sb = H.Sandbox()
-    ref, _, _ = H.run_scenario(H.REF_SO, script, env, sb=sb)
-    sb.cleanup()
-    sb = H.Sandbox()
-    off, err, _ = H.run_scenario(H.NEW_SO, script, dict(env, LOGGER_LEVEL="1"), sb=sb)
-    sb.cleanup()
-    assert "nvmlinfo -> 3 " in off and "no CPU fallback" in err
-    sb = H.Sandbox()
-    on, _, _ = H.run_scenario(H.NEW_SO, script, dict(env, VGPU_B200_NVML_CONTEXT="1"), sb=sb)
-    sb.cleanup()
-    assert on == ref and "used 268435456" in ref
+    cases = [
+        {"CUDA_MEM_LIMIT_0": "1g", "STUB_OTHER_PROCS": "901:268435456:c"},
+        {"CUDA_MEM_LIMIT_0": "1g", "STUB_OTHER_PROCS": "901:268435456:c,902:1048576:cg,903:4096:g,904:999999999999:c"},
+        {"CUDA_MEM_LIMIT_0": "8g", "CUDA_MEM_RATIO_0": "4", "VMEMORY_NODE_ENABLED": "true",
+         "STUB_OTHER_PROCS": "901:268435456:c,905:123456789:g"},
+        {"CUDA_MEM_LIMIT_0": "2g", "MANAGER_COMPATIBILITY_MODE": "2", "STUB_OTHER_PROCS": "901:268435456:c,902:1048576:c"},
+    ]
+    for extra in cases:
+        env = dict(BASE)
+        env.update(extra)
+        outs = []
+        for lib in (H.REF_SO, H.NEW_SO):
+            sb = H.Sandbox()
+            if extra.get("MANAGER_COMPATIBILITY_MODE") == "2":  # pid 901 is a member of the container, 902 is not
+                for pid, line in ((901, "0::/\n"), (902, "0::/kubepods/other\n")):
+                    d = sb.path("etc/vgpu-manager/.host_proc/%d" % pid)
+                    os.makedirs(d, exist_ok=True)
+                    with open(os.path.join(d, "cgroup"), "w") as f:
+                        f.write(line)
+            out, err, _ = H.run_scenario(lib, script, dict(env, LOGGER_LEVEL="1"), sb=sb)
+            sb.cleanup()
+            outs.append(out)
+        assert outs[0] == outs[1], (extra, outs)
+        assert "nvmlinfo -> 0 " in outs[1]
+    assert "used 268435456" in outs[1]
 
 
 def test_scrub_on_free_runs_the_clear_kernel(built):

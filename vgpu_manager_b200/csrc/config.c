@@ -148,23 +148,52 @@ static void build_nvml_map(void) { /* loader.c:2119-2164 */
 void vgpu_map_devices(void) { pthread_once(&g_nvml_map_once, build_nvml_map); }
 
 /* ------------------------------------------------------------------ locks */
+/* Per-GPU whole-file write lock (lock.c:47-99).  The reference opens, locks, unlocks and closes
+ * the file around every allocation (5 system calls); here the descriptor stays open per process,
+ * so taking the lock is one fcntl and dropping it another.  POSIX record locks belong to the
+ * process, not the descriptor, so the semantics towards other processes are identical; inside
+ * the process the runtime's q_mu serialises.  The value returned is a token (fd + 1 would do;
+ * the fd itself is kept for the old call sites) that vgpu_unlock_gpu understands. */
+static int g_lock_fd[VGPU_MAX_DEVICES];       /* fd + 1 */
+static unsigned g_lock_epoch[VGPU_MAX_DEVICES];
+static pthread_mutex_t g_lock_open_mu = PTHREAD_MUTEX_INITIALIZER;
+
+static int lock_file_fd(int h) {
+  if (g_lock_fd[h] && g_lock_epoch[h] == vgpu_fork_epoch + 1) return g_lock_fd[h] - 1;
+  pthread_mutex_lock(&g_lock_open_mu);
+  if (!g_lock_fd[h] || g_lock_epoch[h] != vgpu_fork_epoch + 1) {
+    /* (a forked child keeps using the inherited descriptor number, but re-opens so that the two
+     * processes do not share one open file description) */
+    if (access(VP(VGPU_LOCK_DIR), F_OK) != 0) mkdir(VP(VGPU_LOCK_DIR), 0755);
+    char raw[64];
+    snprintf(raw, sizeof raw, VGPU_LOCK_FMT, h);
+    int fd = open(VP(raw), O_RDWR | O_CREAT | O_CLOEXEC, 0644);
+    if (fd >= 0) {
+      g_lock_fd[h] = fd + 1;
+      g_lock_epoch[h] = vgpu_fork_epoch + 1;
+    }
+  }
+  int out = g_lock_fd[h] && g_lock_epoch[h] == vgpu_fork_epoch + 1 ? g_lock_fd[h] - 1 : -1;
+  pthread_mutex_unlock(&g_lock_open_mu);
+  return out;
+}
+
 int vgpu_lock_gpu(int h) {
   if (h < 0 || h >= VGPU_MAX_DEVICES) {
     VLOG(VL_ERROR, "invalid device index %d", h);
     return -1;
   }
-  if (access(VP(VGPU_LOCK_DIR), F_OK) != 0) mkdir(VP(VGPU_LOCK_DIR), 0755);
-  char raw[64];
-  snprintf(raw, sizeof raw, VGPU_LOCK_FMT, h);
-  const char *path = VP(raw);
   struct timespec t0, now, nap = {0, 10 * 1000 * 1000};
-  clock_gettime(CLOCK_MONOTONIC, &t0);
+  int timed = 0;
   for (;;) {
-    int fd = open(path, O_RDWR | O_CREAT | O_CLOEXEC, 0644);
+    int fd = lock_file_fd(h);
     if (fd >= 0) {
       struct flock fl = {.l_type = F_WRLCK, .l_whence = SEEK_SET, .l_start = 0, .l_len = 0};
       if (fcntl(fd, F_SETLK, &fl) == 0) return fd;
-      close(fd);
+    }
+    if (!timed) {
+      clock_gettime(CLOCK_MONOTONIC, &t0);
+      timed = 1;
     }
     clock_gettime(CLOCK_MONOTONIC, &now);
     long ms = (now.tv_sec - t0.tv_sec) * 1000 + (now.tv_nsec - t0.tv_nsec) / 1000000;
@@ -180,8 +209,7 @@ int vgpu_lock_gpu(int h) {
 void vgpu_unlock_gpu(int fd) {
   if (fd < 0) return;
   struct flock fl = {.l_type = F_UNLCK, .l_whence = SEEK_SET, .l_start = 0, .l_len = 0};
-  fcntl(fd, F_SETLK, &fl);
-  close(fd);
+  fcntl(fd, F_SETLK, &fl); /* the descriptor stays open (see above) */
 }
 
 static int range_lock(const char *path, int oflags, off_t off, short type) {

@@ -239,7 +239,8 @@ static vgpu_dev_rt *bring_up(vgpu_dev_rt *rt, int slot, int host_index, CUdevice
     CU_TRY(vgpu_rt_launch(rt, rt->k_spill, 1, 32, rt->spill_chunk * rt->spill_stages, rt->q_stream, p_copy), "warm spill");
     CU_TRY(vgpu_rt_launch(rt, rt->k_copy_generic, 1, 256, 0, rt->q_stream, p_copy), "warm copy");
     rt->q_req->seq = ++rt->seq;
-    void *p_quota[] = {&rt->q_req_d, &rt->q_res_d};
+    uint32_t plain = 0;
+    void *p_quota[] = {&rt->q_req_d, &rt->q_res_d, &plain};
     CU_TRY(vgpu_rt_launch(rt, rt->k_quota, 1, 1024, 0, rt->q_stream, p_quota), "warm quota");
     uint32_t sq = ++rt->seq;
     unsigned long long key = 2, bytes = 0;
@@ -291,6 +292,10 @@ static vgpu_dev_rt *bring_up(vgpu_dev_rt *rt, int slot, int host_index, CUdevice
   vgpu_unlock_gpu(lock_fd);
   rt->fails = 0;
   rt->retry_at = 0;
+  {
+    const char *e = getenv("VGPU_B200_QUOTA_ARMED"); /* 0: launch the quota kernel after the NVML queries (round-1 behaviour) */
+    rt->quota_armed = !(e && *e == '0');
+  }
   __sync_synchronize();
   rt->ready = 1;
   if (retained) { CUcontext dummy; R.cuCtxPopCurrent_v2(&dummy); }
@@ -422,6 +427,11 @@ static void ctx_leave(int pushed) {
   if (pushed) R.cuCtxPopCurrent_v2(&dummy);
 }
 
+static unsigned quota_block(uint32_t longest) {
+  if (longest > VGPU_MAX_PIDS) longest = VGPU_MAX_PIDS;
+  return longest ? (longest + 31u) & ~31u : 32u;
+}
+
 int vgpu_rt_quota(vgpu_dev_rt *rt, vgpu_quota_res_t *out) {
   /* caller filled rt->q_req (except seq) and holds rt->q_mu */
   uint32_t seq = ++rt->seq;
@@ -429,14 +439,14 @@ int vgpu_rt_quota(vgpu_dev_rt *rt, vgpu_quota_res_t *out) {
   if (!rt->q_req_self_set) rt->q_req->self_bytes = rt->self_bytes;
   rt->q_req_self_set = 0;
   __sync_synchronize();
-  void *params[] = {&rt->q_req_d, &rt->q_res_d};
+  uint32_t plain = 0;
+  void *params[] = {&rt->q_req_d, &rt->q_res_d, &plain};
   int pushed = ctx_enter(rt);
   /* one thread per record of the longest list, whole warps (see the kernel) */
   uint32_t longest = rt->q_req->n_compute > rt->q_req->n_graphics ? rt->q_req->n_compute : rt->q_req->n_graphics;
   if (rt->q_req->n_vmem > longest) longest = rt->q_req->n_vmem;
-  if (longest > VGPU_MAX_PIDS) longest = VGPU_MAX_PIDS;
-  unsigned block = longest ? (longest + 31u) & ~31u : 32u;
-  CUresult r = vgpu_rt_launch(rt, rt->k_quota, 1, block, 0, rt->q_stream, params);
+  rt->q_longest = longest;
+  CUresult r = vgpu_rt_launch(rt, rt->k_quota, 1, quota_block(longest), 0, rt->q_stream, params);
   if (r != CUDA_SUCCESS) {
     ctx_leave(pushed);
     VLOG(VL_ERROR, "quota kernel launch failed: %d (%s)", r, vgpu_cu_err(r));
@@ -451,6 +461,43 @@ int vgpu_rt_quota(vgpu_dev_rt *rt, vgpu_quota_res_t *out) {
   *out = *rt->q_res;
   vgpu_metric_add(rt->host_index, VM_QUOTA_KERNELS, 1);
   return 0;
+}
+
+/* Armed evaluation, used by the allocation hooks: the kernel is launched first and waits on the
+ * device for the request block to be published under `seq`, so its launch latency overlaps the
+ * NVML queries the host makes in between.  arm -> (host stages the request) -> publish ->
+ * (host may do other work) -> collect.  Caller holds rt->q_mu.  Returns the sequence number, 0 if
+ * the launch failed (the caller then uses vgpu_rt_quota). */
+uint32_t vgpu_rt_quota_arm(vgpu_dev_rt *rt) {
+  uint32_t seq = ++rt->seq;
+  if (!seq) seq = ++rt->seq;
+  void *params[] = {&rt->q_req_d, &rt->q_res_d, &seq};
+  int pushed = ctx_enter(rt);
+  /* the lists are not known yet: size the CTA for what the previous call saw plus some slack;
+   * a longer list makes the kernel answer VGPU_PATH_RETRY */
+  CUresult r = vgpu_rt_launch(rt, rt->k_quota, 1, quota_block(rt->q_longest + 8), 0, rt->q_stream, params);
+  ctx_leave(pushed);
+  if (r != CUDA_SUCCESS) return 0;
+  vgpu_metric_add(rt->host_index, VM_QUOTA_KERNELS, 1);
+  return seq;
+}
+
+void vgpu_rt_quota_publish(vgpu_dev_rt *rt, uint32_t seq) {
+  __sync_synchronize(); /* request first, then the sequence number the kernel waits for */
+  *(volatile uint32_t *)&rt->q_req->seq = seq;
+}
+
+/* 0 = result in *out; 1 = the kernel asked for a plain re-evaluation; -1 = failure */
+int vgpu_rt_quota_collect(vgpu_dev_rt *rt, uint32_t seq, vgpu_quota_res_t *out) {
+  int pushed = ctx_enter(rt);
+  int stuck = spin_seq(&rt->q_res->seq_done, seq, rt->q_stream);
+  ctx_leave(pushed);
+  if (stuck) return -1;
+  *out = *rt->q_res;
+  uint32_t longest = rt->q_req->n_compute > rt->q_req->n_graphics ? rt->q_req->n_compute : rt->q_req->n_graphics;
+  if (rt->q_req->n_vmem > longest) longest = rt->q_req->n_vmem;
+  rt->q_longest = longest;
+  return out->path == VGPU_PATH_RETRY ? 1 : 0;
 }
 
 int vgpu_rt_slab_insert(vgpu_dev_rt *rt, CUdeviceptr dptr, uint64_t bytes) {
@@ -547,6 +594,7 @@ VGPU_EXPORT int vgpu_b200_quota_eval(const void *req_, void *res_) {
   if (!rt || !req || !res) return -1;
   pthread_mutex_lock(&rt->q_mu);
   memcpy(rt->q_req, req, sizeof *req);
+  rt->gfx_valid = 0;      /* the hooks' cached graphics list was just overwritten */
   rt->q_req_self_set = 1; /* the caller's request is evaluated verbatim */
   int rc = vgpu_rt_quota(rt, res);
   pthread_mutex_unlock(&rt->q_mu);

@@ -37,7 +37,8 @@ extern "C" {
 #define VGPU_FLAG_LOCAL 2u   /* pid passes the open-kernel "local container pid" test   */
 
 enum { VGPU_Q_ALLOC = 0, VGPU_Q_NVML_INFO = 1, VGPU_Q_CU_INFO = 2 };
-enum { VGPU_PATH_GPU = 0, VGPU_PATH_UVA = 1, VGPU_PATH_OOM = 2 };
+enum { VGPU_PATH_GPU = 0, VGPU_PATH_UVA = 1, VGPU_PATH_OOM = 2,
+       VGPU_PATH_RETRY = 3 /* armed launch gave up (timeout / CTA too small): evaluate again */ };
 
 /* request block: pinned, device-mapped host memory, one per GPU; written by the host under the
  * per-GPU file lock, read by the kernel with coalesced 128-bit loads */

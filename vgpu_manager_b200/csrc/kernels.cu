@@ -285,13 +285,42 @@ DEVINL unsigned long long fold_list(int sel, int open_mode, bool live, uint32_t 
 }
 
 extern "C" __global__ void __launch_bounds__(1024)
-    vgpu_quota_kernel(const vgpu_quota_req_t *__restrict__ req, vgpu_quota_res_t *res) {
+    vgpu_quota_kernel(const vgpu_quota_req_t *__restrict__ req, vgpu_quota_res_t *res, uint32_t armed_seq) {
   __shared__ unsigned long long s64[33];
   __shared__ unsigned int s32[33];
   __shared__ uint32_t cpid[VGPU_MAX_PIDS];
   __shared__ int self_state;
+  __shared__ int armed_ok;
 
   const uint32_t t = threadIdx.x;
+  /* Armed launch (armed_seq != 0): the hook launches this kernel BEFORE it asks NVML for the
+   * process lists (two ioctls, ~70 us), so the launch latency is hidden behind them; thread 0
+   * waits here for the request block to be published under that sequence number.  Never for
+   * ever: after 20 ms it answers VGPU_PATH_RETRY and the hook evaluates again with a plain
+   * launch.  The same answer is given when the lists turned out longer than this CTA. */
+  if (armed_seq) {
+    if (t == 0) {
+      const uint64_t t0 = globaltimer_ns();
+      int ok = 1;
+      while (*reinterpret_cast<const volatile uint32_t *>(&req->seq) != armed_seq) {
+        if (globaltimer_ns() - t0 > 20000000ull) { ok = 0; break; }
+        __nanosleep(100);
+      }
+      __threadfence_system(); /* acquire: everything below is (re)loaded after the publication */
+      if (ok) {
+        uint32_t longest = max(max(req->n_compute, req->n_graphics), req->n_vmem);
+        if (min(longest, (uint32_t)VGPU_MAX_PIDS) > blockDim.x) ok = 0;
+      }
+      armed_ok = ok;
+      if (!ok) {
+        res->path = VGPU_PATH_RETRY;
+        __threadfence_system();
+        *reinterpret_cast<volatile uint32_t *>(&res->seq_done) = armed_seq;
+      }
+    }
+    __syncthreads();
+    if (!armed_ok) return;
+  }
   /* The request block is pinned host memory: every load below is a PCIe round trip (~1.5 us).
    * The record loads therefore do not wait for the header that says how many records are valid -
    * the host launches ceil32(max(n)) threads, so thread t's records exist (or are stale bytes
@@ -368,9 +397,8 @@ extern "C" __global__ void __launch_bounds__(1024)
     res->out_used = o_used;
     res->out_free = o_free;
     res->path = path;
-    __threadfence_system();
+    __threadfence_system(); /* results before the sequence number the host polls */
     *reinterpret_cast<volatile uint32_t *>(&res->seq_done) = req->seq;
-    __threadfence_system();
   }
 }
 

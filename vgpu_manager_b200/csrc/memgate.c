@@ -6,8 +6,10 @@
  * the real allocator.  What moved to the device: the fold of those lists into the container's
  * `used`, the ledger sum, the quota check, the GPU/UVA/OOM decision and the reported
  * total/used/free numbers (vgpu_quota_kernel), plus the record table of UVA allocations
- * (vgpu_slab_*_kernel).  If the device runtime cannot be brought up the hooks fail loudly
- * (CUDA_ERROR_NOT_SUPPORTED / NVML_ERROR_NOT_SUPPORTED): there is no CPU decision path.
+ * (vgpu_slab_*_kernel).  If the device runtime cannot be brought up in a process that HAS a CUDA
+ * context the hooks fail loudly (CUDA_ERROR_NOT_SUPPORTED): allocation decisions have no CPU
+ * path.  The one host evaluation is the NVML memory report for processes without any CUDA
+ * context (nvidia-smi and friends), which the reference also serves (nvml_hook.c:47-103).
  *
  * Behavioural contract (reference library/src/cuda_hook.c):
  *   prepare_memory_allocation :93-116      load_limited_memory_view :118-136
@@ -54,38 +56,32 @@ static uint32_t fetch_list(nvmlDevice_t nv, int graphics, vgpu_proc_t *out, nvml
 }
 
 /* Fill the request block with everything the kernel needs to restate get_used_gpu_memory +
- * get_used_gpu_virt_memory.  Caller holds rt->q_mu and the per-GPU file lock. */
-static void stage_request(vgpu_dev_rt *rt, int host_index, nvmlDevice_t nv) {
-  vgpu_quota_req_t *q = rt->q_req;
+ * get_used_gpu_virt_memory - except the graphics list (stage_graphics).  Caller holds the
+ * per-GPU file lock (and rt->q_mu when `q` is a runtime's block).  Returns 0 when the compute
+ * list is unavailable: used = 0 and the graphics list is not consulted (:825-830). */
+static int stage_request(vgpu_quota_req_t *q, int host_index, nvmlDevice_t nv) {
   const vgpu_cfg_dev_t *c = &G_cfg->devices[host_index];
   q->mode = (uint32_t)G_cfg->compatibility_mode;
   q->memory_oversold = (uint32_t)c->memory_oversold;
   q->total_memory = c->total_memory;
   q->real_memory = c->real_memory;
   q->self_pid = (uint32_t)getpid();
-  q->n_compute = q->n_graphics = q->n_vmem = 0;
-
-  nvmlReturn_t rc;
-  uint32_t nc = fetch_list(nv, 0, q->compute, &rc);
-  if (rc != NVML_SUCCESS) {
-    /* compute list unavailable => used = 0 and the graphics list is not consulted (:825-830) */
-    VLOG(VL_ERROR, "nvmlDeviceGetComputeRunningProcesses call failed, return: %d, str: %s", rc,
-         vgpu_nv_err(rc));
-  } else {
-    q->n_compute = nc;
-    uint32_t ng = fetch_list(nv, 1, q->graphics, &rc);
+  q->n_compute = q->n_vmem = 0;
+  int have_compute = 0;
+  if (nv) {
+    nvmlReturn_t rc;
+    uint32_t nc = fetch_list(nv, 0, q->compute, &rc);
     if (rc != NVML_SUCCESS) {
-      VLOG(VL_ERROR, "nvmlDeviceGetGraphicsRunningProcesses call failed, return: %d, str: %s", rc,
+      VLOG(VL_ERROR, "nvmlDeviceGetComputeRunningProcesses call failed, return: %d, str: %s", rc,
            vgpu_nv_err(rc));
-      ng = 0;
-    }
-    q->n_graphics = ng;
-    if (G_cfg->compatibility_mode != VGPU_MODE_HOST) {
-      static __thread uint32_t pids[VGPU_MAX_PIDS];
-      for (uint32_t i = 0; i < nc; i++) pids[i] = q->compute[i].pid;
-      vgpu_pid_flags(pids, nc, q->cflags);
-      for (uint32_t i = 0; i < ng; i++) pids[i] = q->graphics[i].pid;
-      vgpu_pid_flags(pids, ng, q->gflags);
+    } else {
+      have_compute = 1;
+      q->n_compute = nc;
+      if (G_cfg->compatibility_mode != VGPU_MODE_HOST) {
+        static __thread uint32_t pids[VGPU_MAX_PIDS];
+        for (uint32_t i = 0; i < nc; i++) pids[i] = q->compute[i].pid;
+        vgpu_pid_flags(pids, nc, q->cflags);
+      }
     }
   }
   if (G_cfg->vmem_node && G_vmem) {
@@ -98,13 +94,104 @@ static void stage_request(vgpu_dev_rt *rt, int host_index, nvmlDevice_t nv) {
       vgpu_vmem_unlock(fd, host_index);
     }
   }
+  return have_compute;
+}
+
+/* The graphics list, fetched into a scratch copy first: the allocation path evaluates the
+ * request speculatively against the previous call's graphics list (still in the block) while
+ * this ioctl is in flight, and only re-evaluates when the list really changed. */
+typedef struct {
+  uint32_t n;
+  vgpu_proc_t recs[VGPU_MAX_PIDS];
+  uint8_t flags[VGPU_MAX_PIDS];
+} gfx_scratch_t;
+
+static void fetch_graphics(gfx_scratch_t *g, nvmlDevice_t nv) {
+  nvmlReturn_t rc;
+  g->n = fetch_list(nv, 1, g->recs, &rc);
+  if (rc != NVML_SUCCESS) {
+    VLOG(VL_ERROR, "nvmlDeviceGetGraphicsRunningProcesses call failed, return: %d, str: %s", rc,
+         vgpu_nv_err(rc));
+    g->n = 0;
+  }
+  if (g->n && G_cfg->compatibility_mode != VGPU_MODE_HOST) {
+    static __thread uint32_t pids[VGPU_MAX_PIDS];
+    for (uint32_t i = 0; i < g->n; i++) pids[i] = g->recs[i].pid;
+    vgpu_pid_flags(pids, g->n, g->flags);
+  } else {
+    memset(g->flags, 0, g->n);
+  }
+}
+
+static int graphics_same(const vgpu_quota_req_t *q, const gfx_scratch_t *g) {
+  return q->n_graphics == g->n && (g->n == 0 || (memcmp(q->graphics, g->recs, (size_t)g->n * sizeof(vgpu_proc_t)) == 0 &&
+                                                 memcmp(q->gflags, g->flags, g->n) == 0));
+}
+
+static void graphics_install(vgpu_quota_req_t *q, const gfx_scratch_t *g) {
+  memcpy(q->graphics, g->recs, (size_t)g->n * sizeof(vgpu_proc_t));
+  memcpy(q->gflags, g->flags, g->n);
+  q->n_graphics = g->n;
 }
 
 extern int vgpu_rt_quota(vgpu_dev_rt *rt, vgpu_quota_res_t *out);
 extern int vgpu_rt_slab_insert(vgpu_dev_rt *rt, CUdeviceptr dptr, uint64_t bytes);
 extern int vgpu_rt_slab_remove(vgpu_dev_rt *rt, CUdeviceptr dptr, uint64_t *bytes);
 
-/* Run the quota kernel for (kind, request).  On return the per-GPU lock is still held
+/* ------------------------------------------------------------------ context-less evaluation
+ * An NVML-only client (nvidia-smi, pynvml, a metrics exporter, a framework probing memory
+ * before it forks its CUDA workers) has no CUDA context for vgpu_quota_kernel to run in.  The
+ * reference answers those on the CPU (nvml_hook.c:47-103), so does this: the same fold as the
+ * kernel (membership latch cuda_hook.c:735-805, graphics/compute dedup :868-887, ledger sum
+ * loader.c:1909-1922, clamp nvml_hook.c:58-63), written for one thread.  Only the NVML report
+ * uses it; allocation decisions always run on the device. */
+static uint64_t host_fold(uint32_t mode, const vgpu_proc_t *p, const uint8_t *flags, const uint8_t *dead, uint32_t n) {
+  int open_mode = (mode & VGPU_MODE_OPEN_KERNEL) == VGPU_MODE_OPEN_KERNEL;
+  int ladder = (mode & VGPU_MODE_CLIENT) == VGPU_MODE_CLIENT || (mode & VGPU_MODE_CGROUPV2) == VGPU_MODE_CGROUPV2 ||
+               (mode & VGPU_MODE_CGROUPV1) == VGPU_MODE_CGROUPV1;
+  uint64_t sum = 0;
+  int regime = 0; /* 0 undecided, 1 primary, 2 open-kernel */
+  for (uint32_t i = 0; i < n; i++) {
+    if (dead && dead[i]) continue;
+    int prim = (flags[i] & VGPU_FLAG_PRIMARY) != 0, loc = open_mode && (flags[i] & VGPU_FLAG_LOCAL);
+    if (ladder) {
+      if (regime != 2 && prim) { regime = 1; sum += p[i].used_bytes; }
+      else if (regime != 1 && loc) { regime = 2; sum += p[i].used_bytes; }
+    } else if (open_mode) {
+      if (flags[i] & VGPU_FLAG_LOCAL) sum += p[i].used_bytes;
+    } else if (mode == VGPU_MODE_HOST) {
+      sum += p[i].used_bytes;
+    }
+  }
+  return sum;
+}
+
+static void host_nvml_view(const vgpu_quota_req_t *q, vgpu_quota_res_t *r) {
+  static __thread uint8_t dead[VGPU_MAX_PIDS];
+  uint32_t nc = q->n_compute > VGPU_MAX_PIDS ? VGPU_MAX_PIDS : q->n_compute;
+  uint32_t ng = q->n_graphics > VGPU_MAX_PIDS ? VGPU_MAX_PIDS : q->n_graphics;
+  uint32_t nv = q->n_vmem > VGPU_MAX_PIDS ? VGPU_MAX_PIDS : q->n_vmem;
+  uint64_t used = host_fold(q->mode, q->compute, q->cflags, NULL, nc);
+  for (uint32_t i = 0; i < ng; i++) { /* graphics pids already in the compute list are dropped */
+    dead[i] = 0;
+    for (uint32_t j = 0; j < nc && !dead[i]; j++) dead[i] = q->compute[j].pid == q->graphics[i].pid;
+  }
+  used += host_fold(q->mode, q->graphics, q->gflags, dead, ng);
+  /* footprint of the container's CUDA-holding siblings that run this library (none of ours:
+   * this process has no context) */
+  used = used >= q->self_bytes ? used - q->self_bytes : 0;
+  uint64_t vmem = 0;
+  for (uint32_t i = 0; i < nv; i++) vmem += q->vmem[i].used;
+  uint64_t tu = used + vmem;
+  memset(r, 0, sizeof *r);
+  r->used = used;
+  r->vmem = vmem;
+  r->total = q->total_memory;
+  r->out_used = tu >= q->total_memory ? q->total_memory : tu;
+  r->out_free = r->total - r->out_used;
+}
+
+/* Evaluate (kind, request) for one GPU.  On return the per-GPU lock is still held
  * (mv->lock_fd) exactly like load_limited_memory_view leaves it. */
 static void memview(memview_t *mv, CUdevice dev, int host_index, nvmlDevice_t nv, uint32_t kind,
                     uint64_t request, int allow_uva, int real_ok, uint64_t real_total) {
@@ -120,25 +207,53 @@ static void memview(memview_t *mv, CUdevice dev, int host_index, nvmlDevice_t nv
   mv->rt = rt;
   mv->lock_fd = vgpu_lock_gpu(host_index);
   if (!nv) nv = vgpu_nvml_handle_of_host(host_index);
+  if (!nv) VLOG(VL_ERROR, "cuda device %d cannot find the corresponding nvml devices", dev);
   pthread_mutex_lock(&rt->q_mu);
   vgpu_quota_req_t *q = rt->q_req;
-  if (nv) {
-    stage_request(rt, host_index, nv);
-  } else {
-    VLOG(VL_ERROR, "cuda device %d cannot find the corresponding nvml devices", dev);
-    q->n_compute = q->n_graphics = 0;
-    stage_request(rt, host_index, NULL);
-  }
+  /* launch first: the kernel waits on the device for the publication while the host talks to NVML */
+  uint32_t armed = (rt->quota_armed && nv) ? vgpu_rt_quota_arm(rt) : 0;
+  int have_compute = stage_request(q, host_index, nv);
   /* footprint of every live library instance of this container on this GPU (lock is held) */
   q->self_bytes = mv->lock_fd >= 0 ? vgpu_self_registry(host_index, rt->self_bytes, 0) : rt->self_bytes;
-  rt->q_req_self_set = 1;
   q->kind = kind;
   q->request = request;
   q->allow_uva = (uint32_t)allow_uva;
   q->real_ok = (uint32_t)real_ok;
   q->real_total = real_total;
-  if (vgpu_rt_quota(rt, &mv->res)) mv->failed = 1;
-  else mv->limited = 1;
+  int done = 0;
+  if (!have_compute) {
+    q->n_graphics = 0;
+    rt->gfx_valid = 0;
+    if (armed) vgpu_rt_quota_publish(rt, armed);
+  } else {
+    static __thread gfx_scratch_t scratch;
+    if (armed && rt->gfx_valid) {
+      /* speculate: graphics list unchanged since the previous evaluation (it is empty on a
+       * compute-only part); the kernel decides while the second ioctl is in flight */
+      vgpu_rt_quota_publish(rt, armed);
+      fetch_graphics(&scratch, nv);
+      if (graphics_same(q, &scratch)) {
+        done = vgpu_rt_quota_collect(rt, armed, &mv->res) == 0;
+      } else {
+        vgpu_quota_res_t drop;
+        vgpu_rt_quota_collect(rt, armed, &drop); /* let the speculative evaluation finish before restaging */
+        graphics_install(q, &scratch);
+      }
+      armed = 0;
+    } else {
+      fetch_graphics(&scratch, nv);
+      graphics_install(q, &scratch);
+      rt->gfx_valid = 1;
+      if (armed) vgpu_rt_quota_publish(rt, armed);
+    }
+  }
+  if (!done && armed) done = vgpu_rt_quota_collect(rt, armed, &mv->res) == 0;
+  if (!done) {
+    rt->q_req_self_set = 1;
+    if (vgpu_rt_quota(rt, &mv->res)) mv->failed = 1;
+    else done = 1;
+  }
+  if (done) mv->limited = 1;
   pthread_mutex_unlock(&rt->q_mu);
 }
 
@@ -520,33 +635,36 @@ static vgpu_dev_rt *rt_for_nvml(int host_index, CUdevice *dev_out) {
     *dev_out = dev;
     return vgpu_rt_get(host_index, dev);
   }
-  /* An NVML-only client (nvidia-smi, a metrics exporter) has no CUDA context for the quota
-   * kernel to run in.  Opt-in: retain the device's primary context for it.  Off by default
-   * because that context's own footprint (hundreds of MiB) would then be charged to the tenant,
-   * which the reference - computing on the CPU - never does. */
-  const char *opt = getenv("VGPU_B200_NVML_CONTEXT");
-  if (!opt || strcmp(opt, "1") != 0 || !R.cuInit || !R.cuDevicePrimaryCtxRetain || !R.cuDeviceGetCount) return NULL;
-  int n = 0;
-  if (R.cuInit(0) != CUDA_SUCCESS || R.cuDeviceGetCount(&n) != CUDA_SUCCESS) return NULL;
-  for (int i = 0; i < n; i++) {
-    CUcontext ctx = NULL;
-    if (R.cuDeviceGet(&dev, i) != CUDA_SUCCESS || vgpu_host_index_of_cuda(dev) != host_index) continue;
-    if (R.cuDevicePrimaryCtxRetain(&ctx, dev) != CUDA_SUCCESS || R.cuCtxPushCurrent_v2(ctx) != CUDA_SUCCESS) return NULL;
-    rt = vgpu_rt_get(host_index, dev);
-    R.cuCtxPopCurrent_v2(&ctx);
-    *dev_out = dev;
-    return rt;
-  }
-  return NULL;
+  return NULL; /* no CUDA context in this process: answered on the host (host_nvml_view) */
 }
 
 static nvmlReturn_t nvml_view(nvmlDevice_t device, int host_index, vgpu_quota_res_t *out) {
   CUdevice dev = 0;
   vgpu_dev_rt *rt = rt_for_nvml(host_index, &dev);
   if (!rt) {
-    VLOG(VL_ERROR, "nvmlDeviceGetMemoryInfo: no CUDA context on host device %d, the quota kernel "
-                   "cannot run (no CPU fallback)", host_index);
-    return NVML_ERROR_NOT_SUPPORTED;
+    /* A context is never created behind the client's back: frameworks query NVML before they
+     * fork their CUDA workers precisely to keep the parent CUDA-free. */
+    static pthread_mutex_t mu = PTHREAD_MUTEX_INITIALIZER;
+    static vgpu_quota_req_t *hq;
+    static gfx_scratch_t *hg;
+    pthread_mutex_lock(&mu);
+    if (!hq) hq = (vgpu_quota_req_t *)calloc(1, sizeof *hq);
+    if (!hg) hg = (gfx_scratch_t *)calloc(1, sizeof *hg);
+    if (!hq || !hg) {
+      pthread_mutex_unlock(&mu);
+      return NVML_ERROR_NOT_SUPPORTED;
+    }
+    int lock_fd = vgpu_lock_gpu(host_index);
+    hq->n_graphics = 0;
+    if (stage_request(hq, host_index, device)) {
+      fetch_graphics(hg, device);
+      graphics_install(hq, hg);
+    }
+    hq->self_bytes = lock_fd >= 0 ? vgpu_self_registry(host_index, 0, 0) : 0;
+    host_nvml_view(hq, out);
+    vgpu_unlock_gpu(lock_fd);
+    pthread_mutex_unlock(&mu);
+    return NVML_SUCCESS;
   }
   memview_t mv;
   CUcontext prev = NULL;

@@ -266,6 +266,9 @@ typedef struct vgpu_dev_rt {
   uint64_t self_bytes; /* measured device footprint of everything above */
   int q_req_self_set;  /* q_req->self_bytes was provided by the caller of vgpu_rt_quota */
   uint32_t seq;
+  uint32_t q_longest;  /* longest list of the previous quota evaluation (sizes the armed launch) */
+  int quota_armed;     /* allocation hooks launch the quota kernel ahead of the NVML queries */
+  int gfx_valid;       /* q_req->graphics / gflags hold the graphics list of the previous evaluation */
   volatile long uva_live; /* records in the slab (host-side count; skip lookups when 0) */
   pthread_mutex_t q_mu;
   int sm_num, max_thread_per_sm;
@@ -287,6 +290,9 @@ CUresult vgpu_rt_launch(vgpu_dev_rt *rt, CUfunction f, unsigned grid, unsigned b
                         unsigned smem, CUstream s, void **params);
 
 int vgpu_rt_quota(vgpu_dev_rt *rt, vgpu_quota_res_t *out);
+uint32_t vgpu_rt_quota_arm(vgpu_dev_rt *rt);
+void vgpu_rt_quota_publish(vgpu_dev_rt *rt, uint32_t seq);
+int vgpu_rt_quota_collect(vgpu_dev_rt *rt, uint32_t seq, vgpu_quota_res_t *out);
 int vgpu_rt_slab_insert(vgpu_dev_rt *rt, CUdeviceptr dptr, uint64_t bytes);
 int vgpu_rt_slab_remove(vgpu_dev_rt *rt, CUdeviceptr dptr, uint64_t *bytes);
 CUresult vgpu_rt_clear(vgpu_dev_rt *rt, CUdeviceptr dst, size_t bytes, CUstream s);

@@ -125,6 +125,11 @@ int vgpu_b200_limiter_reset(int sm_num, int max_thread_per_sm, int hard_core, in
  * (== one iteration of reference cuda_hook.c:413-466). */
 int vgpu_b200_limiter_step(int user_current, int sys_current, int valid, int sys_process_num,
                            vgpu_b200_limiter_state_t *out);
+/* One default control step on a caller-supplied utilisation publication (vgpu_util_req_t,
+ * kernel_abi.h): raw per-process samples + membership flags are folded on the device
+ * (== reference get_used_gpu_utilization, cuda_hook.c:1044-1159) and the watcher body runs on
+ * the result, in one launch of vgpu_refill_kernel.  0 / -1. */
+int vgpu_b200_refill(const void *util_req /* vgpu_util_req_t */, vgpu_b200_limiter_state_t *out);
 /* Host-side consumption of tokens (what a launch hook does), for tests. */
 int vgpu_b200_limiter_consume(long long tokens);
 int vgpu_b200_limiter_state(vgpu_b200_limiter_state_t *out);
@@ -133,6 +138,12 @@ int vgpu_b200_limiter_state(vgpu_b200_limiter_state_t *out);
  * utilisation (test hook), -1 uses the measurement. */
 int vgpu_b200_sampler_run(unsigned window_us, unsigned interval_us, unsigned period_ticks,
                           int user_override, vgpu_b200_limiter_state_t *out);
+
+/* Node-level rebalance (no reference counterpart): assign tenant(s) of GPU
+ * `host_index` a utilisation target `up_limit` (percent) under a ceiling `soft_core`; a ceiling
+ * above the tenant's hard quota switches it to balance mode with that target.  Written to
+ * /etc/vgpu-manager/config/rebalance.config, applied by each tenant at its next control step. */
+int vgpu_b200_set_limits(int host_index, int up_limit, int soft_core);
 
 /* Tuning: bytes per TMA bulk copy (multiple of 16), ring depth (2..16), CTAs per SM; the ring must
  * fit 200 KiB of shared memory.  0 / -1. */

@@ -32,6 +32,8 @@ extern "C" {
 #define VGPU_CFG_DIR VGPU_ROOT_DIR "/config"
 #define VGPU_CFG_FILE VGPU_CFG_DIR "/vgpu.config"
 #define VGPU_PIDS_FILE VGPU_CFG_DIR "/pids.config"
+#define VGPU_REBALANCE_FILE VGPU_CFG_DIR "/rebalance.config" /* B200 addition, optional (kernel_abi.h) */
+#define VGPU_STATUS_FMT VGPU_LOCK_DIR "/vgpu_%d.status"       /* B200 addition, written only while the former exists */
 #define VGPU_SMUTIL_FILE VGPU_ROOT_DIR "/watcher/sm_util.config"
 #define VGPU_SELF_FILE VGPU_ROOT_DIR "/driver/libvgpu-control.so"
 #define VGPU_HOSTPROC_CGROUP_FMT VGPU_ROOT_DIR "/.host_proc/%d/cgroup"

@@ -103,6 +103,37 @@ class QuotaReq(C.Structure):
                 ("vmem", VmemRec * 1024), ("cflags", C.c_uint8 * 1024), ("gflags", C.c_uint8 * 1024)]
 
 
+class UtilReq(C.Structure):
+    _fields_ = [("seq", C.c_uint32), ("status", C.c_uint32), ("mode", C.c_uint32), ("n_samples", C.c_uint32),
+                ("sys_process_num", C.c_int32), ("have_container_pids", C.c_uint32), ("_pad", C.c_uint32 * 2),
+                ("checktime_us", C.c_uint64), ("_pad2", C.c_uint64), ("samples", UtilSample * 1024),
+                ("flags", C.c_uint8 * 1024)]
+
+
+UTIL_NOTHING, UTIL_NPROC_ONLY, UTIL_SAMPLES = 0, 1, 2
+
+
+def util_req_from_golden_step(mode, st, seq):
+    """The publication the tick thread would have made for one step of a golden watcher trajectory
+    (tests/golden/watcher.json: samples = [pid, sm, enc, dec, age_ms, mine]); the reference's NVML
+    stand-in answers NOT_FOUND when there are no samples (oracle/ref_cosim.c)."""
+    u = UtilReq()
+    T = 1_700_000_000_000_000
+    u.seq, u.mode, u.sys_process_num, u.have_container_pids = seq, mode, st["nproc"], 1
+    u.checktime_us = T
+    if not st["samples"]:
+        u.status = UTIL_NPROC_ONLY
+        return u
+    u.status = UTIL_SAMPLES
+    u.n_samples = len(st["samples"])
+    for i, (pid, sm, enc, dec, age, mine) in enumerate(st["samples"]):
+        s = u.samples[i]
+        s.pid, s.sm, s.enc, s.dec = pid, sm, enc, dec
+        s.ts_us = T + 1_000_000 - age * 1000
+        u.flags[i] = 1 if mine else 0  # VGPU_FLAG_PRIMARY
+    return u
+
+
 class QuotaRes(C.Structure):
     _fields_ = [("used", C.c_uint64), ("vmem", C.c_uint64), ("total", C.c_uint64), ("out_used", C.c_uint64),
                 ("out_free", C.c_uint64), ("path", C.c_uint32), ("seq_done", C.c_uint32)]

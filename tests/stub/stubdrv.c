@@ -499,7 +499,25 @@ static void fake_ctl_step(vgpu_lim_dev_t *D, vgpu_lim_host_t *H, int user, int s
   }
   long long consumed = H->consumed;
   int64_t bucket = D->granted - consumed;
-  orc_watcher_step(&g, &c, &w, &u, &bucket);
+  if (H->ext_limits_seq != D->limits_seen) { /* node-level rebalance, as in ctl_step */
+    D->limits_seen = H->ext_limits_seq;
+    int soft = H->ext_soft_core, up = H->ext_up_limit;
+    if (D->limits_seen != 0 && soft > D->hard_core) {
+      D->soft_core = soft; D->hard_limit = 0;
+      c.soft_core = soft; c.hard_limit = 0;
+      D->ext_up = up < D->hard_core ? D->hard_core : (up > soft ? soft : up);
+    } else {
+      D->ext_up = 0;
+    }
+  }
+  if (D->ext_up > 0 && !D->hard_limit && D->core_limit && D->valid) {
+    w.sys_free = 100 - sys;
+    w.up_limit = D->ext_up;
+    w.share = orc_delta(&g, w.up_limit, user, w.share);
+    bucket = orc_change_token(&g, bucket, w.share);
+  } else {
+    orc_watcher_step(&g, &c, &w, &u, &bucket);
+  }
   D->share = w.share; D->sys_free = w.sys_free; D->avg_sys_free = w.avg_sys_free; D->ctr_i = w.i;
   D->pre_sys_process_num = w.pre_sys_process_num; D->up_limit = w.up_limit;
   if (D->core_limit && D->valid) D->granted = bucket + consumed;
@@ -668,7 +686,7 @@ static void run_fake_kernel(const char *name, void **p) {
     vgpu_lim_dev_t *D = (vgpu_lim_dev_t *)(uintptr_t) * (CUdeviceptr *)p[0];
     vgpu_lim_host_t *H = (vgpu_lim_host_t *)(uintptr_t) * (CUdeviceptr *)p[1];
     const vgpu_util_req_t *U = (const vgpu_util_req_t *)(uintptr_t) * (CUdeviceptr *)p[2];
-    if (U->status == VGPU_UTIL_SAMPLES) {
+    if (U->status == VGPU_UTIL_SAMPLES && D->core_limit) {
       uint8_t prim[VGPU_MAX_PIDS], loc[VGPU_MAX_PIDS];
       uint32_t n = U->n_samples > VGPU_MAX_PIDS ? VGPU_MAX_PIDS : U->n_samples;
       for (uint32_t i = 0; i < n; i++) { prim[i] = (U->flags[i] & VGPU_FLAG_PRIMARY) != 0; loc[i] = (U->flags[i] & VGPU_FLAG_LOCAL) != 0; }

@@ -31,6 +31,17 @@ for user in (90, 90, 10, 30, 25, 0):
     st = lib.limiter_step(user, user, 1, 1)
     traj.append([st.share, st.granted - st.consumed])
 out["steps"] = traj
+# default control step: raw samples folded + controller, a few golden steps
+import json as _j
+tr = _j.load(open(os.path.join(os.environ["REPO"], "tests", "golden", "watcher.json")))["trajectories"][3]
+lib.limiter_reset(tr["sm"], tr["thr"], tr["hard"], tr["soft"], tr["core_limit"], tr["hard_limit"])
+bucket, rf = 0, []
+for i, st in enumerate(tr["steps"][:60]):
+    lib.limiter_consume(bucket - st["bucket_in"])
+    s = lib.refill(H.util_req_from_golden_step(tr["mode"], st, i + 1))
+    rf.append([s.share, s.granted - s.consumed, s.up_limit, s.valid] == st["out"][:4])
+    bucket = st["out"][1]
+out["refill_ok"] = all(rf)
 # memory: quota decision and numbers
 q = H.QuotaReq()
 q.kind, q.mode, q.n_compute, q.total_memory, q.real_memory = 0, 0, 3, 1 << 30, 1 << 30
@@ -72,7 +83,7 @@ def test_direct_api_round_trip_on_the_fake_driver():
     sb.cleanup()
     assert r.returncode == 0, r.stderr[-3000:]
     out = json.loads([l for l in r.stdout.splitlines() if l.startswith("RESULT ")][-1][7:])
-    assert "sm_100a" in out["version"] and out["copy_ok"] and out["clear_ok"]
+    assert "sm_100a" in out["version"] and out["copy_ok"] and out["clear_ok"] and out["refill_ok"]
     assert out["quota"] == [900 << 20, 2]
     # the same trajectory from the oracle (= reference arithmetic, tests/test_oracle_parity.py)
     o = H.oracle()

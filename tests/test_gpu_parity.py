@@ -245,6 +245,57 @@ def test_controller_kernel_replays_reference_watcher(gpu):
             bucket = bucket_w
 
 
+def test_refill_kernel_folds_samples_and_replays_reference_watcher(gpu):
+    """The default control step end to end: the raw per-process samples of every golden step (ages
+    around the 1 s window, out-of-range percentages, codec terms, other containers' pids under
+    cgroup-v2 membership, NOT_FOUND gaps) are folded by vgpu_refill_kernel and its controller must land
+    on the reference watcher's share / bucket / up_limit / valid / user / sys at every step."""
+    lib, torch = gpu
+    with open(os.path.join(GOLD, "watcher.json")) as f:
+        trajs = json.load(f)["trajectories"]
+    for tr in trajs:
+        lib.limiter_reset(tr["sm"], tr["thr"], tr["hard"], tr["soft"], tr["core_limit"], tr["hard_limit"])
+        bucket = 0
+        for i, st in enumerate(tr["steps"]):
+            share_w, bucket_w, up_w, valid_w, user_w, sys_w = st["out"]
+            lib.limiter_consume(bucket - st["bucket_in"])
+            s = lib.refill(H.util_req_from_golden_step(tr["mode"], st, i + 1))
+            got = (s.share, s.granted - s.consumed, s.up_limit, s.valid)
+            assert got == (share_w, bucket_w, up_w, valid_w), (tr["name"], i, got, st["out"])
+            if tr["core_limit"] and valid_w:  # the step published its reading
+                assert (s.user_current, s.sys_current) == (user_w, sys_w), (tr["name"], i, s.user_current, s.sys_current, st["out"])
+            bucket = bucket_w
+
+
+def test_refill_kernel_full_width_publication(gpu):
+    """1024 samples (the contract's maximum): one thread per sample, block reductions across 32 warps,
+    against the oracle's sequential fold in every compatibility mode."""
+    lib, torch = gpu
+    o = H.oracle()
+    rng = random.Random(0x5EED)
+    for mode in (0, 1, 2, 100, 101, 102, 200, 300):
+        for n in (1, 31, 32, 33, 500, 1024):
+            u = H.UtilReq()
+            u.seq, u.status, u.mode, u.n_samples, u.sys_process_num, u.have_container_pids = 1, 2, mode, n, 3, 1
+            u.checktime_us = 10_000_000
+            prim = (C.c_uint8 * 1024)()
+            loc = (C.c_uint8 * 1024)()
+            for i in range(n):
+                s = u.samples[i]
+                s.pid, s.sm, s.enc, s.dec = 1000 + i, rng.choice([0, 1, 50, 100, 101, 4000000000]), rng.choice([0, 0, 7, 101]), rng.choice([0, 3])
+                s.ts_us = 10_000_000 + rng.choice([-1, 0, 1, 500])
+                f = rng.choice([0, 0, 1, 2, 3])
+                u.flags[i] = f
+                prim[i], loc[i] = f & 1, (f >> 1) & 1
+            want = H.OrcUtil(0, 0, 0, 0)
+            o.orc_fold_utilization(mode, u.samples, n, u.checktime_us, prim, loc, 1, C.byref(want))
+            lib.limiter_reset(148, 2048, 25, 0, 1, 1)
+            s = lib.refill(u)
+            assert s.valid == want.valid, (mode, n)
+            if want.valid:
+                assert (s.user_current, s.sys_current) == (want.user_current, want.sys_current), (mode, n)
+
+
 def test_delta_on_device_via_controller(gpu):
     """delta() vectors from the reference (float compare, overflow guard) through one step."""
     lib, torch = gpu

@@ -9,6 +9,7 @@
 #include "vgpu_internal.h"
 
 #include <errno.h>
+#include <fcntl.h>
 #include <sched.h>
 #include <time.h>
 
@@ -680,6 +681,26 @@ VGPU_EXPORT int vgpu_b200_limiter_step(int user_current, int sys_current, int va
   return read_lim(rt, out);
 }
 
+/* One default control step with a caller-supplied publication (vgpu_util_req_t): the fold of the
+ * raw samples (reference cuda_hook.c:1044-1159) and the watcher body (:413-466) in one launch. */
+VGPU_EXPORT int vgpu_b200_refill(const void *util_req, vgpu_b200_limiter_state_t *out) {
+  vgpu_dev_rt *rt = attached();
+  if (!rt || !util_req) return -1;
+  pthread_mutex_lock(&rt->q_mu);
+  memcpy(rt->u_req, util_req, sizeof(vgpu_util_req_t));
+  rt->lim_h->ext_user_override = -1; /* a reading forced by an earlier vgpu_b200_sampler_run must not leak in */
+  __sync_synchronize();
+  uint32_t n = rt->u_req->status == VGPU_UTIL_SAMPLES ? rt->u_req->n_samples : 0;
+  if (n > VGPU_MAX_PIDS) n = VGPU_MAX_PIDS;
+  void *params[] = {&rt->lim_d, &rt->lim_h_d, &rt->u_req_d};
+  int rc = -1;
+  if (vgpu_rt_launch(rt, rt->k_refill, 1, n ? (n + 31u) & ~31u : 32u, 0, rt->q_stream, params) == CUDA_SUCCESS &&
+      R.cuStreamSynchronize(rt->q_stream) == CUDA_SUCCESS)
+    rc = read_lim(rt, out);
+  pthread_mutex_unlock(&rt->q_mu);
+  return rc;
+}
+
 VGPU_EXPORT int vgpu_b200_limiter_consume(long long tokens) {
   vgpu_dev_rt *rt = attached();
   if (!rt) return -1;
@@ -706,6 +727,31 @@ VGPU_EXPORT int vgpu_b200_sampler_run(unsigned window_us, unsigned interval_us, 
   if (R.cuStreamSynchronize(rt->p_stream) != CUDA_SUCCESS) return -1;
   vgpu_metric_add(rt->host_index, VM_SAMPLER_LAUNCHES, 1);
   return read_lim(rt, out);
+}
+
+/* Node-agent side of the rebalance: assign a utilisation target / ceiling to the tenant(s) of
+ * one GPU.  Writes VGPU_CFG_DIR/rebalance.config (the agent runs where that directory is
+ * writable - the host side of the tenants' read-only config mount); every tenant's tick thread
+ * applies it at its next control step.  seq must change with every new assignment.  0 / -1. */
+VGPU_EXPORT int vgpu_b200_set_limits(int host_index, int up_limit, int soft_core) {
+  if (host_index < 0 || host_index >= VGPU_MAX_DEVICES) return -1;
+  vgpu_boot();
+  int fd = open(VP(VGPU_REBALANCE_FILE), O_RDWR | O_CREAT | O_CLOEXEC, 0644);
+  if (fd < 0) return -1;
+  vgpu_rebalance_rec_t rec = {0, 0, 0, 0};
+  off_t off = (off_t)host_index * (off_t)sizeof rec;
+  ssize_t got = pread(fd, &rec, sizeof rec, off);
+  (void)got;
+  if (rec.magic != VGPU_REBALANCE_MAGIC) rec.seq = 0;
+  rec.magic = VGPU_REBALANCE_MAGIC;
+  rec.seq++;
+  if (!rec.seq) rec.seq = 1;
+  rec.up_limit = up_limit;
+  rec.soft_core = soft_core;
+  int rc = pwrite(fd, &rec, sizeof rec, off) == (ssize_t)sizeof rec ? 0 : -1;
+  if (rc == 0 && lseek(fd, 0, SEEK_END) < (off_t)sizeof(vgpu_rebalance_t) && ftruncate(fd, sizeof(vgpu_rebalance_t)) != 0) rc = -1;
+  close(fd);
+  return rc;
 }
 
 VGPU_EXPORT int vgpu_b200_set_spill_geometry(unsigned chunk, unsigned stages, unsigned ctas_per_sm) {

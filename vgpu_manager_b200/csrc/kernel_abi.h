@@ -140,6 +140,9 @@ typedef struct {
   unsigned long long gov_left_ns;      /* %globaltimer at which the previous governor incarnation retired   */
   uint32_t gov_left_busy;              /* ... and whether tenant work was executing at that moment           */
   uint32_t _pad_g;
+  /* node-level rebalance: last applied sequence number and the assigned target (0 = none) */
+  uint32_t limits_seen;
+  int32_t ext_up;
   /* top_result of the NVML-sample reading (cuda_hook.c:376): persists between publications */
   int32_t top_user, top_sys, top_nproc, top_seq;
   /* last results, for metrics and tests */
@@ -163,7 +166,9 @@ typedef struct {
   volatile uint32_t util_mode;        /* 0 moving average, 1 tumbling block (NVML-like sampling) */
   volatile uint32_t ctl_state;        /* governor: 0 not resident, 1 resident (or being launched), 2 leaving */
   volatile uint32_t release_pending;  /* watchdog lent tokens: fold release_floor into granted at the next step */
-  volatile uint32_t _pad_r;
+  volatile uint32_t ext_limits_seq;   /* node-level rebalance (rebalance.config): bumped when the two values below change */
+  volatile int32_t ext_up_limit;      /* utilisation target the node agent assigned to this tenant (percent)            */
+  volatile int32_t ext_soft_core;     /* ceiling it may be raised to; > hard_core switches the device to balance mode    */
   volatile long long release_floor;   /* ticket up to which the watchdog released parked launches */
   volatile unsigned long long launched[VGPU_STREAM_SLOTS]; /* per-slot launch sequence (host)   */
   /* per-slot completion markers, written by cuStreamWriteValue64 right after each launch */
@@ -204,6 +209,30 @@ typedef struct {
   uint8_t flags[VGPU_MAX_PIDS]; /* VGPU_FLAG_* per sample pid                      */
 } vgpu_util_req_t;
 VGPU_STATIC_ASSERT(offsetof(vgpu_util_req_t, samples) % 16 == 0, ureq_samples_align);
+
+/* ---------------------------------------------------------------- node-level rebalance
+ * VGPU_CFG_DIR/rebalance.config, written by a node agent (control-plane side of the read-only
+ * config mount, so a tenant cannot raise its own share), read by the tick thread once per control
+ * period.  No reference counterpart: the reference's balance policy lives inside
+ * each process (cuda_hook.c:430-465). */
+#define VGPU_REBALANCE_MAGIC 0x4c424756u /* "VGBL" */
+typedef struct {
+  uint32_t magic;
+  uint32_t seq;       /* bumped by the agent with every change; 0 = nothing assigned */
+  int32_t up_limit;   /* utilisation target in percent                               */
+  int32_t soft_core;  /* ceiling; <= hard_core leaves the device in hard-limit mode   */
+} vgpu_rebalance_rec_t;
+typedef struct {
+  vgpu_rebalance_rec_t devices[VGPU_MAX_DEVICES];
+} vgpu_rebalance_t;
+/* VGPU_LOCK_DIR/vgpu_<h>.status, written by a tenant's tick thread while a rebalance.config
+ * exists: what the agent folds into its next plan */
+typedef struct {
+  uint32_t magic, seq;
+  int32_t pid, user_current, sys_current, up_limit, hard_core, soft_core;
+  int64_t share;
+  uint64_t gated, launched, steps;
+} vgpu_tenant_status_t;
 
 /* one explicit controller step (also the unit the parity tests drive) */
 typedef struct {

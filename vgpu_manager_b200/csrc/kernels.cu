@@ -527,6 +527,23 @@ DEVINL void ctl_step(vgpu_lim_dev_t *D, vgpu_lim_host_t *H, int user_current, in
     H->release_pending = 0;
     if (floor - D->granted > 0) D->granted = floor;
   }
+  {
+    /* node-level rebalance (no reference counterpart): a new assignment from the node agent */
+    const uint32_t ls = H->ext_limits_seq;
+    if (ls != D->limits_seen) {
+      D->limits_seen = ls;
+      const int soft = H->ext_soft_core;
+      int up = H->ext_up_limit;
+      if (ls != 0 && soft > D->hard_core) { /* a ceiling above the hard quota: balance mode under the agent's target */
+        D->soft_core = soft;
+        D->hard_limit = 0;
+        up = up < D->hard_core ? D->hard_core : (up > soft ? soft : up);
+        D->ext_up = up;
+      } else {
+        D->ext_up = 0;
+      }
+    }
+  }
   long long consumed = consumed_admitted(H, D->granted);
   long long bucket = D->granted - consumed;
   bool touched = false;
@@ -539,6 +556,10 @@ DEVINL void ctl_step(vgpu_lim_dev_t *D, vgpu_lim_host_t *H, int user_current, in
       } else {
         D->share = ctl_delta(D, D->hard_core, user_current, D->share);
       }
+    } else if (D->ext_up > 0) {
+      /* the node agent owns the target: no in-process ramp */
+      D->up_limit = D->ext_up;
+      D->share = ctl_delta(D, D->up_limit, user_current, D->share);
     } else {
       if (D->pre_sys_process_num != sys_process_num) {
         if (D->pre_sys_process_num < sys_process_num) {
@@ -622,7 +643,8 @@ extern "C" __global__ void __launch_bounds__(1024)
   const int sel = mode_select(U->mode, &open_mode);
   if (t == 0) dummy_state = 0;
 
-  if (status == VGPU_UTIL_SAMPLES) { /* uniform across the CTA */
+  /* a device without a core limit is skipped before the reading is even taken (:419) */
+  if (status == VGPU_UTIL_SAMPLES && D->core_limit) { /* uniform across the CTA */
     const bool client_empty = ((U->mode & VGPU_MODE_CLIENT) == VGPU_MODE_CLIENT) && !U->have_container_pids;
     const unsigned long long ts = ((unsigned long long)lo.w << 32) | lo.z;
     const bool live = (t < n) && !client_empty && sel != SEL_BAD && ts >= checktime;

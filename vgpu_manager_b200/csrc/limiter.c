@@ -46,6 +46,7 @@
 #include "vgpu_internal.h"
 
 #include <errno.h>
+#include <fcntl.h>
 #include <sched.h>
 #include <time.h>
 
@@ -213,6 +214,46 @@ static void publish_from_nvml(vgpu_dev_rt *rt, vgpu_util_req_t *U) {
   U->status = VGPU_UTIL_SAMPLES;
 }
 
+/* ------------------------------------------------------------------ node-level rebalance (host half)
+ * Optional VGPU_CFG_DIR/rebalance.config (kernel_abi.h): the node agent's assignment for this GPU
+ * is handed to the controller through the pinned block; while that file exists the tenant
+ * publishes its state next to the lock file so the agent can fold it into its next plan. */
+static void exchange_with_node_agent(vgpu_dev_rt *rt, int h) {
+  static int fd_cfg = -2; /* -2 not looked for yet, -1 absent (looked for again every ~5 s) */
+  static unsigned looked;
+  if (fd_cfg < 0) {
+    if (fd_cfg == -1 && (++looked % 64) != 0) return;
+    fd_cfg = open(VP(VGPU_REBALANCE_FILE), O_RDONLY | O_CLOEXEC);
+    if (fd_cfg < 0) { fd_cfg = -1; return; }
+  }
+  vgpu_rebalance_rec_t rec;
+  if (pread(fd_cfg, &rec, sizeof rec, (off_t)h * (off_t)sizeof rec) != (ssize_t)sizeof rec || rec.magic != VGPU_REBALANCE_MAGIC) return;
+  vgpu_lim_host_t *H = rt->lim_h;
+  if (rec.seq != H->ext_limits_seq) {
+    H->ext_up_limit = rec.up_limit;
+    H->ext_soft_core = rec.soft_core;
+    __sync_synchronize();
+    H->ext_limits_seq = rec.seq;
+    VLOG(VL_INFO, "host device %d: node agent assigned up_limit %d soft_core %d (seq %u)", h, rec.up_limit, rec.soft_core, rec.seq);
+  }
+  static int fd_st[VGPU_MAX_DEVICES];
+  if (!fd_st[h]) {
+    char raw[64];
+    snprintf(raw, sizeof raw, VGPU_STATUS_FMT, h);
+    int fd = open(VP(raw), O_RDWR | O_CREAT | O_CLOEXEC, 0644);
+    fd_st[h] = fd >= 0 ? fd + 1 : -1;
+  }
+  if (fd_st[h] > 0) {
+    static uint32_t seq;
+    const vgpu_cfg_dev_t *c = &G_cfg->devices[h];
+    vgpu_tenant_status_t st = {VGPU_REBALANCE_MAGIC, ++seq, (int32_t)getpid(), H->user_current, H->sys_current, H->up_limit_mirror,
+                               c->hard_core, c->soft_core, H->share_mirror, vgpu_metric_get(h, VM_RATE_GATED),
+                               vgpu_metric_get(h, VM_RATE_GATED) + vgpu_metric_get(h, VM_RATE_FAST), H->steps};
+    ssize_t w = pwrite(fd_st[h] - 1, &st, sizeof st, 0);
+    (void)w;
+  }
+}
+
 /* returns the CTA size the refill kernel needs for this publication */
 static unsigned publish_utilization(vgpu_dev_rt *rt) {
   vgpu_util_req_t *U = rt->u_req;
@@ -368,6 +409,7 @@ static void *tick_main(void *arg) {
         /* the reference's cadence and the reference's reading: once per control period publish
          * the samples and let one small CTA fold them and refill the bucket */
         if (epoch % g_period_ticks == 0) {
+          exchange_with_node_agent(rt, h);
           unsigned block = publish_utilization(rt);
           void *params[] = {&rt->lim_d, &rt->lim_h_d, &rt->u_req_d};
           CUresult r = VGPU_CAPCHK(R.cuLaunchKernel(rt->k_refill, 1, 1, 1, block, 1, 1, 0, rt->s_stream, params, NULL));

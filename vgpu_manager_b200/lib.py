@@ -56,6 +56,7 @@ class B200Library:
         h.vgpu_b200_limiter_reset.argtypes = [C.c_int] * 6
         h.vgpu_b200_limiter_step.argtypes = [C.c_int] * 4 + [C.POINTER(LimiterState)]
         h.vgpu_b200_limiter_consume.argtypes = [C.c_longlong]
+        h.vgpu_b200_refill.argtypes = [C.c_void_p, C.POINTER(LimiterState)]
         h.vgpu_b200_limiter_state.argtypes = [C.POINTER(LimiterState)]
         h.vgpu_b200_sampler_run.argtypes = [C.c_uint, C.c_uint, C.c_uint, C.c_int, C.POINTER(LimiterState)]
         h.vgpu_b200_self_bytes.restype = C.c_ulonglong
@@ -104,6 +105,12 @@ class B200Library:
     def limiter_step(self, user, sys_, valid, nproc):
         st = LimiterState()
         self._check(self.h.vgpu_b200_limiter_step(user, sys_, valid, nproc, C.byref(st)), "vgpu_b200_limiter_step")
+        return st
+
+    def refill(self, util_req):
+        """One default control step: device fold of the published samples + controller."""
+        st = LimiterState()
+        self._check(self.h.vgpu_b200_refill(C.byref(util_req), C.byref(st)), "vgpu_b200_refill")
         return st
 
     def limiter_consume(self, tokens):

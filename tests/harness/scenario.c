@@ -196,6 +196,31 @@ int main(int argc, char **argv) {
       CUresult (*f)(CUdeviceptr, unsigned char, size_t) = sym("cuMemsetD8_v2");
       CUresult r = ((int)a < g_np && g_ptr[a]) ? f(g_ptr[a], 0xA5, (size_t)b) : 1;
       printf("dirty h%llu -> %d\n", a, r);
+    } else if (!strcmp(cmd, "fill")) { /* fill h<a> with <b> bytes of value <c> */
+      CUresult (*f)(CUdeviceptr, unsigned char, size_t) = sym("cuMemsetD8_v2");
+      CUresult (*sy)(void) = sym("cuCtxSynchronize");
+      CUresult r = ((int)a < g_np && g_ptr[a]) ? f(g_ptr[a], (unsigned char)c, (size_t)b) : 1;
+      if (r == 0 && sy) r = sy();
+      printf("fill h%llu -> %d\n", a, r);
+    } else if (!strcmp(cmd, "check")) { /* h<a>: do bytes [0,64), the middle and the last 64 of <b> still hold value <c>? */
+      CUresult (*f)(void *, CUdeviceptr, size_t) = sym("cuMemcpyDtoH_v2");
+      unsigned char buf[64];
+      int ok = (int)a < g_np && g_ptr[a] && b >= 64;
+      unsigned long long offs[3] = {0, (b / 2) & ~63ull, b - 64};
+      CUresult r = 0;
+      for (int k = 0; ok && k < 3; k++) {
+        r = f(buf, g_ptr[a] + offs[k], 64);
+        if (r) { ok = 0; break; }
+        for (int i = 0; i < 64; i++) ok &= buf[i] == (unsigned char)c;
+      }
+      printf("check h%llu -> %d %s\n", a, r, ok ? "intact" : "CORRUPT");
+    } else if (!strcmp(cmd, "slabstats")) { /* B200 library only: what the slab mode moved */
+      unsigned long long (*metric)(int, int) = dlsym(RTLD_DEFAULT, "vgpu_b200_metric");
+      if (metric)
+        printf("slabstats allocs %llu demotions %llu spill_bytes %llu promote_bytes %llu scrubbed_bytes %llu spill_ns %llu scrub_ns %llu promote_ns %llu\n",
+               metric((int)a, 16), metric((int)a, 17), metric((int)a, 11), metric((int)a, 14), metric((int)a, 8), metric((int)a, 12),
+               metric((int)a, 13), metric((int)a, 15));
+      else printf("slabstats none\n");
     } else if (!strcmp(cmd, "meminfo")) {
       CUresult (*f)(size_t *, size_t *) = sym("cuMemGetInfo_v2");
       size_t fr = 0, tot = 0;

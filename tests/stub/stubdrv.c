@@ -281,17 +281,72 @@ EXPORT CUresult cuMemGetInfo_v2(size_t *fr, size_t *tot) {
   *fr = used >= g_total_mem ? 0 : g_total_mem - used;
   return 0;
 }
+/* ---- virtual memory management: handles are memfds, mappings are MAP_SHARED|MAP_FIXED views of them,
+ * so re-pointing a virtual address at another handle behaves like the real thing (contents travel
+ * with the handle, not with the address) */
+typedef struct { int fd; size_t size; int host; } vmm_handle_t;
+EXPORT CUresult cuMemGetAllocationGranularity(size_t *g, const void *prop, int opt) { (void)prop; (void)opt; *g = (size_t)2 << 20; return 0; }
 EXPORT CUresult cuMemCreate(unsigned long long *h, size_t n, const void *prop, unsigned long long f) {
-  (void)prop; (void)f;
+  (void)f;
   stub_init();
-  int dev = t_has_ctx ? t_cur_dev : 0;
-  if (g_dev_bytes[dev] + g_ctx_bytes + n > g_phys_mem) return 2;
-  void *p = big_alloc(1);
-  track(p, n, 3, dev);
-  *h = (unsigned long long)(uintptr_t)p;
+  const int *pi = (const int *)prop; /* CUmemAllocationProp: {type, requestedHandleTypes, location{type, id}, ...} */
+  int host = pi && pi[2] != 1;
+  int dev = t_has_ctx ? t_cur_dev : (pi && pi[2] == 1 ? pi[3] : 0);
+  if (!host && g_dev_bytes[dev] + g_ctx_bytes + n > g_phys_mem) return 2;
+  vmm_handle_t *v = (vmm_handle_t *)calloc(1, sizeof *v);
+  v->fd = memfd_create("stub-vmm", 0);
+  v->size = n;
+  v->host = host;
+  if (v->fd < 0 || ftruncate(v->fd, (off_t)n) != 0) { if (v->fd >= 0) close(v->fd); free(v); return 2; }
+  track(v, n, host ? 4 : 3, dev);
+  *h = (unsigned long long)(uintptr_t)v;
   return 0;
 }
-EXPORT CUresult cuMemRelease(unsigned long long h) { alloc_t a; if (!untrack((void *)(uintptr_t)h, &a)) return 1; big_free(a.p, 1); return 0; }
+EXPORT CUresult cuMemRelease(unsigned long long h) {
+  alloc_t a;
+  if (!untrack((void *)(uintptr_t)h, &a)) return 1;
+  vmm_handle_t *v = (vmm_handle_t *)a.p;
+  close(v->fd);
+  free(v);
+  return 0;
+}
+EXPORT CUresult cuMemAddressReserve(CUdeviceptr *ptr, size_t size, size_t align, CUdeviceptr addr, unsigned long long flags) {
+  (void)align; (void)addr; (void)flags;
+  void *p = mmap(NULL, size, PROT_NONE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
+  if (p == MAP_FAILED) return 2;
+  *ptr = (CUdeviceptr)(uintptr_t)p;
+  return 0;
+}
+EXPORT CUresult cuMemAddressFree(CUdeviceptr ptr, size_t size) { return munmap((void *)(uintptr_t)ptr, size) == 0 ? 0 : 1; }
+EXPORT CUresult cuMemMap(CUdeviceptr ptr, size_t size, size_t offset, unsigned long long h, unsigned long long flags) {
+  (void)flags;
+  vmm_handle_t *v = (vmm_handle_t *)(uintptr_t)h;
+  if (!v || offset + size > v->size) return 1;
+  void *p = mmap((void *)(uintptr_t)ptr, size, PROT_READ | PROT_WRITE, MAP_SHARED | MAP_FIXED, v->fd, (off_t)offset);
+  return p == MAP_FAILED ? 1 : 0;
+}
+EXPORT CUresult cuMemUnmap(CUdeviceptr ptr, size_t size) {
+  void *p = mmap((void *)(uintptr_t)ptr, size, PROT_NONE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_FIXED | MAP_NORESERVE, -1, 0);
+  return p == MAP_FAILED ? 1 : 0;
+}
+EXPORT CUresult cuMemSetAccess(CUdeviceptr ptr, size_t size, const void *desc, size_t n) { (void)ptr; (void)size; (void)desc; (void)n; return 0; }
+EXPORT unsigned long long stub_ctl_host_vmm_bytes(void) {
+  unsigned long long n = 0;
+  pthread_mutex_lock(&g_mu);
+  for (size_t i = 0; i < g_nallocs; i++) if (g_allocs[i].kind == 4) n += g_allocs[i].n;
+  pthread_mutex_unlock(&g_mu);
+  return n;
+}
+/* events: host clock (the fake GPU executes synchronously) */
+EXPORT CUresult cuEventCreate(void **e, unsigned f) { (void)f; *e = calloc(1, sizeof(struct timespec)); return *e ? 0 : 2; }
+EXPORT CUresult cuEventRecord(void *e, void *s) { (void)s; clock_gettime(CLOCK_MONOTONIC, (struct timespec *)e); return 0; }
+EXPORT CUresult cuEventSynchronize(void *e) { (void)e; return 0; }
+EXPORT CUresult cuEventElapsedTime(float *ms, void *a, void *b) {
+  struct timespec *x = (struct timespec *)a, *y = (struct timespec *)b;
+  *ms = (float)((y->tv_sec - x->tv_sec) * 1e3 + (y->tv_nsec - x->tv_nsec) * 1e-6);
+  return 0;
+}
+EXPORT CUresult cuEventDestroy_v2(void *e) { free(e); return 0; }
 typedef struct { size_t W, H; int fmt; unsigned ch; } arr2_t;
 typedef struct { size_t W, H, D; int fmt; unsigned ch, flags; } arr3_t;
 static size_t fmt_bytes(int f) { return (f == 1 || f == 8) ? 1 : (f == 2 || f == 9 || f == 0x10) ? 2 : 4; }
@@ -674,6 +729,33 @@ static void run_fake_kernel(const char *name, void **p) {
     for (uint32_t i = 0; i < VGPU_SLAB_SLOTS; i++)
       if (slab[i].dptr == dptr && dptr > 1) { bytes = slab[i].bytes; slab[i].dptr = 1; slab[i].bytes = 0; slot = i; break; }
     res->bytes = bytes; res->slot = slot;
+    __sync_synchronize();
+    res->seq_done = seq;
+  } else if (!strcmp(name, VGPU_K_VSLAB)) {
+    vgpu_vslab_slot_t *tab = (vgpu_vslab_slot_t *)(uintptr_t) * (CUdeviceptr *)p[0];
+    const vgpu_vslab_req_t *rq = (const vgpu_vslab_req_t *)p[1];
+    vgpu_vslab_res_t *res = (vgpu_vslab_res_t *)(uintptr_t) * (CUdeviceptr *)p[2];
+    uint32_t seq = *(uint32_t *)p[3], slot = 0xffffffffu;
+    unsigned long long best = ~0ull;
+    for (uint32_t i = 0; i < VGPU_VSLAB_SLOTS; i++) {
+      unsigned long long k = ~0ull;
+      if (rq->op == VGPU_VSLAB_PUT) { if (tab[i].dptr == rq->dptr) k = i; else if (tab[i].dptr == 0) k = (1ull << 32) | i; }
+      else if (rq->op == VGPU_VSLAB_TAKE) { if (tab[i].dptr == rq->dptr && rq->dptr) k = i; }
+      else if (tab[i].dptr && (rq->dptr ? tab[i].dptr == rq->dptr : (tab[i].size == rq->size && (tab[i].state & rq->mask) == rq->want)))
+        k = ((unsigned long long)tab[i].age << 32) | i;
+      if (k < best) best = k;
+    }
+    if (best != ~0ull) slot = (uint32_t)(best & 0xffffffffu);
+    memset(res, 0, sizeof *res);
+    res->slot = slot;
+    if (slot != 0xffffffffu) {
+      if (rq->op == VGPU_VSLAB_PUT) {
+        tab[slot].dptr = rq->dptr; tab[slot].bytes = rq->bytes; tab[slot].size = rq->size; tab[slot].state = rq->state; tab[slot].age = rq->age;
+      }
+      res->dptr = tab[slot].dptr; res->bytes = tab[slot].bytes; res->size = tab[slot].size; res->state = tab[slot].state; res->age = tab[slot].age;
+      if (rq->op == VGPU_VSLAB_TAKE) { tab[slot].dptr = 0; tab[slot].state = 0; }
+      else if (rq->op == VGPU_VSLAB_SCAN && rq->set_mask) tab[slot].state = (res->state & ~rq->set_mask) | (rq->set_val & rq->set_mask);
+    }
     __sync_synchronize();
     res->seq_done = seq;
   } else if (!strcmp(name, VGPU_K_CONTROLLER)) {

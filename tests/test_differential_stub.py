@@ -513,3 +513,91 @@ def test_default_reading_is_one_refill_launch_per_control_period(built):
     m = [l for l in out.splitlines() if l.startswith("metrics")][0].split()
     launches, skipped, steps = int(m[2]), int(m[4]), int(m[6])
     assert 10 <= launches <= 17 and skipped == 0 and steps == launches, out
+
+
+SLAB_SCRIPT = """init 0
+nvmlinit 0
+alloc 67108864
+fill 0 67108864 17
+alloc 67108864
+fill 1 67108864 34
+alloc 67108864
+fill 2 67108864 51
+alloc 67108864
+fill 3 67108864 68
+nvmlinfo
+ledger 0
+alloc 67108864
+fill 4 67108864 85
+nvmlinfo
+meminfo
+ledger 0
+alloc 67108864
+fill 5 67108864 102
+alloc 33554432
+fill 6 33554432 119
+nvmlinfo
+ledger 0
+check 0 67108864 17
+check 1 67108864 34
+check 2 67108864 51
+check 3 67108864 68
+check 4 67108864 85
+check 5 67108864 102
+check 6 33554432 119
+free 4
+nvmlinfo
+ledger 0
+check 0 67108864 17
+check 5 67108864 102
+free 1
+nvmlinfo
+ledger 0
+check 0 67108864 17
+check 2 67108864 51
+check 3 67108864 68
+check 5 67108864 102
+free 0
+free 5
+free 6
+nvmlinfo
+ledger 0
+check 2 67108864 51
+check 3 67108864 68
+alloc 1073741824
+free 2
+free 3
+nvmlinfo
+ledger 0
+"""
+
+
+def test_slab_mode_spills_with_reference_accounting(built):
+    """VGPU_B200_SLAB=1 on an oversold device (1 GiB cap over 256 MiB physical, ledger on): every
+    reported number - NVML view, cuMemGetInfo, ledger bytes, OOM point - is the reference's, while the
+    data really moves: the 5th and 6th 64 MiB allocation each demote the coldest HBM slab to host
+    memory (spill copy) and take its scrubbed HBM; a 32 MiB allocation finds no victim of its size class
+    and is host-backed itself; frees bring the partner slab home (promote) or push it out (demote).
+    Every buffer keeps its contents through all of it."""
+    env = dict(BASE)
+    env.update({"CUDA_MEM_LIMIT_0": "1g", "CUDA_MEM_RATIO_0": "4", "VMEMORY_NODE_ENABLED": "true", "LOGGER_LEVEL": "1"})
+    ref, _, sb = H.run_scenario(H.REF_SO, SLAB_SCRIPT, env)
+    sb.cleanup()
+    plain, _, sb = H.run_scenario(H.NEW_SO, SLAB_SCRIPT, env)
+    sb.cleanup()
+    slab, err, sb = H.run_scenario(H.NEW_SO, SLAB_SCRIPT + "slabstats 0\n", dict(env, VGPU_B200_SLAB="1"))
+    sb.cleanup()
+    assert plain == ref
+    lines = slab.splitlines()
+    assert "\n".join(lines[:-1]) + "\n" == ref, err[-2000:]
+    assert "CORRUPT" not in slab and slab.count("intact") == 15
+    st = dict(zip(lines[-1].split()[1::2], map(int, lines[-1].split()[2::2])))
+    MiB64 = 64 << 20
+    # allocs: 7 slabs (the 1 GiB request is refused by the cap before any slab exists)
+    assert st["allocs"] == 7 and "alloc 1073741824 -> 2" in slab
+    # demotions: h4 and h5 each push one slab out; freeing h1 (a demoted, GPU-accounted slab) pushes h5's HBM out too
+    assert st["demotions"] == 3 and st["spill_bytes"] == 3 * MiB64
+    # freeing h4 (UVA-accounted, in HBM) brings its demoted partner home
+    assert st["promote_bytes"] == MiB64
+    # HBM taken over from a victim is scrubbed before the newcomer sees it
+    assert st["scrubbed_bytes"] == 2 * MiB64

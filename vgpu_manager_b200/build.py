@@ -17,7 +17,7 @@ CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libvgpu-control.so")
 NVCC = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
 BIN2C = shutil.which("bin2c") or "/usr/local/cuda/bin/bin2c"
-HOST_SRCS = ["boot.c", "hooktab.c", "config.c", "device.c", "memgate.c", "limiter.c", "lifecycle.c", "metrics.c"]
+HOST_SRCS = ["boot.c", "hooktab.c", "config.c", "device.c", "memgate.c", "slabmode.c", "limiter.c", "lifecycle.c", "metrics.c"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17"]
 
 

@@ -54,6 +54,17 @@ typedef struct {
 } vcu_mem_alloc_prop_t; /* CUmemAllocationProp_v1 */
 
 typedef struct {
+  struct { int type; int id; } location; /* CUmemLocation */
+  int flags;                              /* CUmemAccess_flags */
+} vcu_mem_access_desc_t; /* CUmemAccessDesc_v1 */
+#define VCU_MEM_LOCATION_DEVICE 1
+#define VCU_MEM_LOCATION_HOST_NUMA 3
+#define VCU_MEM_ALLOCATION_PINNED 1
+#define VCU_MEM_ACCESS_READWRITE 3
+#define VCU_MEM_GRANULARITY_MINIMUM 0
+#define VCU_ATTR_HOST_NUMA_ID 134
+
+typedef struct {
   unsigned int gridDimX, gridDimY, gridDimZ, blockDimX, blockDimY, blockDimZ, sharedMemBytes;
   CUstream hStream;
   void *attrs;

@@ -171,6 +171,7 @@ static vgpu_dev_rt *bring_up(vgpu_dev_rt *rt, int slot, int host_index, CUdevice
   CU_TRY(R.cuModuleGetFunction(&rt->k_gate, rt->mod, VGPU_K_GATE), VGPU_K_GATE);
   CU_TRY(R.cuModuleGetFunction(&rt->k_governor, rt->mod, VGPU_K_GOVERNOR), VGPU_K_GOVERNOR);
   CU_TRY(R.cuModuleGetFunction(&rt->k_refill, rt->mod, VGPU_K_REFILL), VGPU_K_REFILL);
+  CU_TRY(R.cuModuleGetFunction(&rt->k_vslab, rt->mod, VGPU_K_VSLAB), VGPU_K_VSLAB);
   {
     /* spill-copy geometry: defaults from kernel_abi.h, overridable for tuning sweeps */
     const char *e;
@@ -201,6 +202,7 @@ static vgpu_dev_rt *bring_up(vgpu_dev_rt *rt, int slot, int host_index, CUdevice
       pinned_block(sizeof(vgpu_quota_res_t), (void **)&rt->q_res, &rt->q_res_d) ||
       pinned_block(sizeof(vgpu_slab_res_t), (void **)&rt->slab_res, &rt->slab_res_d) ||
       pinned_block(sizeof(vgpu_util_req_t), (void **)&rt->u_req, &rt->u_req_d) ||
+      pinned_block(sizeof(vgpu_vslab_res_t), (void **)&rt->vs_res, &rt->vs_res_d) ||
       pinned_block(sizeof(vgpu_lim_host_t), (void **)&rt->lim_h, &rt->lim_h_d)) {
     VLOG(VL_ERROR, "device runtime: pinned host blocks unavailable");
     goto fail;
@@ -215,10 +217,12 @@ static vgpu_dev_rt *bring_up(vgpu_dev_rt *rt, int slot, int host_index, CUdevice
    * 2 MiB granule would stop showing up in NVML and the reported usage would differ from a
    * reference deployment by one granule (seen with the reference's test_alloc). */
   size_t lim_bytes = (sizeof(vgpu_lim_dev_t) + 255) & ~(size_t)255;
-  size_t hbm_bytes = lim_bytes + sizeof(vgpu_slab_slot_t) * VGPU_SLAB_SLOTS;
+  size_t slab_bytes = sizeof(vgpu_slab_slot_t) * VGPU_SLAB_SLOTS;
+  size_t hbm_bytes = lim_bytes + slab_bytes + sizeof(vgpu_vslab_slot_t) * VGPU_VSLAB_SLOTS;
   hbm_bytes = (hbm_bytes + ((size_t)2 << 20) - 1) & ~(((size_t)2 << 20) - 1);
   CU_TRY(R.cuMemAlloc_v2(&rt->lim_d, hbm_bytes), "HBM state");
   rt->slab_d = rt->lim_d + lim_bytes;
+  rt->vslab_d = rt->slab_d + slab_bytes;
   CU_TRY(R.cuMemsetD8_v2(rt->lim_d, 0, hbm_bytes), "HBM state clear");
   {
     vgpu_lim_dev_t *init = (vgpu_lim_dev_t *)malloc(sizeof *init);
@@ -252,6 +256,9 @@ static vgpu_dev_rt *bring_up(vgpu_dev_rt *rt, int slot, int host_index, CUdevice
     vgpu_ctrl_in_t in = {0, 0, 0, 1};
     void *p_ctl[] = {&rt->lim_d, &rt->lim_h_d, &in};
     CU_TRY(vgpu_rt_launch(rt, rt->k_controller, 1, 32, 0, rt->q_stream, p_ctl), "warm controller");
+    vgpu_vslab_req_t vq = {VGPU_VSLAB_TAKE, 0, 0, 0, 0, 0, 2, 0, 0, 0, 0};
+    void *p_vs[] = {&rt->vslab_d, &vq, &rt->vs_res_d, &sq};
+    CU_TRY(vgpu_rt_launch(rt, rt->k_vslab, 1, 1024, 0, rt->q_stream, p_vs), "warm slab table");
     void *p_ref[] = {&rt->lim_d, &rt->lim_h_d, &rt->u_req_d};
     CU_TRY(vgpu_rt_launch(rt, rt->k_refill, 1, 32, 0, rt->q_stream, p_ref), "warm refill");
     uint32_t w = 0, iv = 1, per = VGPU_SAMPLER_PROBE_ONLY, ep = 0;
@@ -313,6 +320,7 @@ fail:
     if (rt->q_res) R.cuMemFreeHost(rt->q_res);
     if (rt->slab_res) R.cuMemFreeHost(rt->slab_res);
     if (rt->u_req) R.cuMemFreeHost(rt->u_req);
+    if (rt->vs_res) R.cuMemFreeHost(rt->vs_res);
     if (rt->lim_h) R.cuMemFreeHost((void *)rt->lim_h);
   }
   if (R.cuStreamDestroy_v2) {
@@ -402,6 +410,7 @@ void vgpu_rt_context_after(unsigned mask, int still_alive) {
        * context brings a fresh one up (token bucket and slab start empty, like a new process) */
       VLOG(VL_INFO, "context of runtime slot %d is gone; device state will be rebuilt on next use", slot);
       if (rt->host_index >= 0) vgpu_limiter_attach(rt->host_index, 1);
+      vgpu_slab_forget(rt);
       pthread_mutex_destroy(&rt->q_mu);
       memset(rt, 0, sizeof *rt);
     }

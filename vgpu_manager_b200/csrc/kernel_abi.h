@@ -94,6 +94,42 @@ typedef struct {
   uint32_t seq_done;
 } vgpu_slab_res_t;
 
+/* ---------------------------------------------------------------- slab placement table (VGPU_B200_SLAB=1)
+ * Device-resident table of the VMM-backed slabs the allocation hooks serve cuMemAlloc from when a
+ * device is oversold: which slabs are accounted like the reference's GPU path / UVA path (the
+ * accounting is exactly the reference's), and where their backing currently lives (HBM or host).
+ * vgpu_vslab_kernel is the allocator's bookkeeping: free-slot scan (PUT), lookup (TAKE) and
+ * the spill decision - the coldest slab of a size class in a given placement (SCAN), flipped in
+ * the same launch. */
+#define VGPU_K_VSLAB "vgpu_vslab_kernel"
+#define VGPU_VSLAB_SLOTS 4096u
+enum { VGPU_VSLAB_PUT = 0, VGPU_VSLAB_TAKE = 1, VGPU_VSLAB_SCAN = 2 };
+#define VGPU_VS_UVA 1u /* accounted on the reference's UVA path: its bytes are in the ledger     */
+#define VGPU_VS_DEV 2u /* backing currently in HBM (else: host memory mapped under the same VA)  */
+typedef struct {
+  uint64_t dptr;  /* 0 = free slot */
+  uint64_t bytes; /* what the tenant asked for                  */
+  uint64_t size;  /* mapped size (granularity multiple) = size class */
+  uint32_t state; /* VGPU_VS_*                                  */
+  uint32_t age;   /* allocation order; smallest = coldest       */
+} vgpu_vslab_slot_t;
+typedef struct {
+  uint32_t op;               /* VGPU_VSLAB_*                                                   */
+  uint32_t mask, want;       /* SCAN: (state & mask) == want                                   */
+  uint32_t set_mask, set_val;/* SCAN: new state bits of the slot found                         */
+  uint32_t age;              /* PUT                                                            */
+  uint64_t dptr;             /* PUT / TAKE key; SCAN: 0 = any slab of the size class           */
+  uint64_t bytes, size;      /* PUT; SCAN: size class                                          */
+  uint32_t state, _pad;      /* PUT                                                            */
+} vgpu_vslab_req_t;
+typedef struct {
+  uint64_t dptr, bytes, size;
+  uint32_t state, age;
+  uint32_t slot;     /* 0xffffffff: nothing found / table full */
+  uint32_t seq_done;
+} vgpu_vslab_res_t;
+VGPU_STATIC_ASSERT(sizeof(vgpu_vslab_slot_t) == 32, vslab_slot);
+
 /* ---------------------------------------------------------------- limiter */
 
 #define VGPU_STREAM_SLOTS 64u

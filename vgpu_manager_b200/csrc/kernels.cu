@@ -473,6 +473,86 @@ extern "C" __global__ void __launch_bounds__(32)
   }
 }
 
+/* ======================================================================= slab placement table
+ * One CTA, 1024 threads, 4 slots per thread (second 16 bytes of each 32-byte slot = {size, state,
+ * age}: one 128-bit load per slot, 128 KiB for the whole table).  Every thread reduces its slots to
+ * one 64-bit key, the block minimum is the answer:
+ *   PUT   key = existing slot of dptr, else the first free slot        (free-list scan)
+ *   TAKE  key = slot of dptr; the record is returned and the slot freed
+ *   SCAN  key = (age << 32 | slot) over the slabs of a size class whose placement bits match:
+ *         the coldest one - the spill / promote decision - whose bits are flipped in the same launch
+ * Callers serialise (host mutex), so thread 0 applies the result with plain stores. */
+DEVINL unsigned long long block_min_u64(unsigned long long v, unsigned long long *scratch) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    unsigned long long w = __shfl_down_sync(0xffffffffu, v, o);
+    v = w < v ? w : v;
+  }
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    unsigned long long r = (threadIdx.x < (blockDim.x >> 5)) ? scratch[threadIdx.x] : ~0ull;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      unsigned long long w = __shfl_down_sync(0xffffffffu, r, o);
+      r = w < r ? w : r;
+    }
+    if (threadIdx.x == 0) scratch[32] = r;
+  }
+  __syncthreads();
+  return scratch[32];
+}
+
+extern "C" __global__ void __launch_bounds__(1024)
+    vgpu_vslab_kernel(vgpu_vslab_slot_t *tab, vgpu_vslab_req_t rq, vgpu_vslab_res_t *res, uint32_t seq) {
+  __shared__ unsigned long long s64[33];
+  unsigned long long key = ~0ull;
+  for (uint32_t i = threadIdx.x; i < VGPU_VSLAB_SLOTS; i += blockDim.x) {
+    const unsigned long long d = tab[i].dptr;
+    const uint4 m = *reinterpret_cast<const uint4 *>(&tab[i].size); /* size lo, size hi, state, age */
+    const unsigned long long size = ((unsigned long long)m.y << 32) | m.x;
+    unsigned long long k = ~0ull;
+    if (rq.op == VGPU_VSLAB_PUT) {
+      if (d == rq.dptr) k = i;
+      else if (d == 0) k = (1ull << 32) | i;
+    } else if (rq.op == VGPU_VSLAB_TAKE) {
+      if (d == rq.dptr && d != 0) k = i;
+    } else {
+      const bool hit = d != 0 && (rq.dptr ? d == rq.dptr : (size == rq.size && (m.z & rq.mask) == rq.want));
+      if (hit) k = ((unsigned long long)m.w << 32) | i;
+    }
+    key = k < key ? k : key;
+  }
+  key = block_min_u64(key, s64);
+  if (threadIdx.x != 0) return;
+  const uint32_t slot = key == ~0ull ? 0xffffffffu : (uint32_t)(key & 0xffffffffu);
+  vgpu_vslab_res_t out = {0, 0, 0, 0, 0, slot, 0};
+  if (slot != 0xffffffffu) {
+    if (rq.op == VGPU_VSLAB_PUT) {
+      tab[slot].bytes = rq.bytes;
+      tab[slot].size = rq.size;
+      tab[slot].state = rq.state;
+      tab[slot].age = rq.age;
+      tab[slot].dptr = rq.dptr;
+      out.dptr = rq.dptr; out.bytes = rq.bytes; out.size = rq.size; out.state = rq.state; out.age = rq.age;
+    } else {
+      out.dptr = tab[slot].dptr; out.bytes = tab[slot].bytes; out.size = tab[slot].size;
+      out.state = tab[slot].state; out.age = tab[slot].age;
+      if (rq.op == VGPU_VSLAB_TAKE) {
+        tab[slot].dptr = 0;
+        tab[slot].state = 0;
+      } else if (rq.set_mask) {
+        tab[slot].state = (out.state & ~rq.set_mask) | (rq.set_val & rq.set_mask);
+      }
+    }
+  }
+  res->dptr = out.dptr; res->bytes = out.bytes; res->size = out.size;
+  res->state = out.state; res->age = out.age; res->slot = out.slot;
+  __threadfence_system();
+  *reinterpret_cast<volatile uint32_t *>(&res->seq_done) = seq;
+}
+
 /* ======================================================================= controller
  * Exactly the reference's delta / change_token / watcher body (cuda_hook.c:292-367, :413-466),
  * with the bucket expressed as granted - consumed so that the host hook (sole writer of

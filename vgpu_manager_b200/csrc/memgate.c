@@ -380,6 +380,23 @@ static CUresult alloc_linear(CUdeviceptr *dptr, size_t bytes) {
   gate_t g;
   gate_open(&g, bytes, 1, NULL);
   CUresult r = g.early;
+  if (r == CUDA_SUCCESS && g.mv.limited && oversold(&g) && vgpu_slab_mode()) {
+    /* VGPU_B200_SLAB=1: same decision, same accounting, but the library owns the placement -
+     * a "UVA" decision spills the coldest slab instead of leaving it to UVM (slabmode.c) */
+    int recorded = 0;
+    CUresult sr = vgpu_slab_alloc(g.mv.rt, g.dev, g.path, dptr, bytes, &recorded);
+    if (sr != CUDA_ERROR_NOT_SUPPORTED) {
+      if (sr == CUDA_SUCCESS && recorded) {
+        if (g.path != VGPU_PATH_UVA) { /* the driver ran out of HBM on the GPU path (:1372-1386) */
+          vgpu_metric_add(g.mv.host_index, VM_OOM_DRIVER, 1);
+          vgpu_metric_add(g.mv.host_index, VM_UVA_FALLBACK, 1);
+        }
+        ledger_add(g.mv.rt, *dptr, bytes, g.mv.host_index);
+      }
+      gate_close(&g);
+      return sr;
+    }
+  }
   if (r == CUDA_SUCCESS) {
     if (g.path == VGPU_PATH_UVA) {
       r = to_uva(&g, dptr, bytes);
@@ -553,6 +570,14 @@ static CUresult free_sync(CUdeviceptr dptr) {
   if (r != CUDA_SUCCESS) return r;
   /* cuMemFree synchronises the device: it must not wait for the resident governor */
   vgpu_dev_rt *rt = vgpu_rt_peek(vgpu_host_index_of_cuda(dev));
+  if (rt && rt->vs_host) { /* a slab of the VGPU_B200_SLAB mode is not the driver's to free */
+    int was_uva = 0;
+    uint64_t sbytes = 0;
+    if (vgpu_slab_free(rt, dptr, &r, &was_uva, &sbytes)) {
+      if (r == CUDA_SUCCESS) ledger_sub(dev, dptr);
+      return r;
+    }
+  }
   if (rt) vgpu_limiter_quiesce(rt);
   if (rt && scrub_on_free()) scrub(rt, dptr);
   r = R.cuMemFree_v2 ? R.cuMemFree_v2(dptr) : R.cuMemFree ? R.cuMemFree(dptr) : CUDA_ERROR_NOT_FOUND;
@@ -568,6 +593,10 @@ static CUresult free_async(CUdeviceptr dptr, CUstream s, int ptsz) {
   if (unlikely(!G_cfg)) vgpu_boot();
   CUresult r = R.cuCtxGetDevice ? R.cuCtxGetDevice(&dev) : CUDA_ERROR_NOT_FOUND;
   if (r != CUDA_SUCCESS) return r;
+  {
+    vgpu_dev_rt *rt = vgpu_rt_peek(vgpu_host_index_of_cuda(dev));
+    if (rt && rt->vs_host) return free_sync(dptr); /* slabs are remapped, not pooled: freed synchronously */
+  }
   CUresult (*fn)(CUdeviceptr, CUstream) = ptsz ? R.cuMemFreeAsync_ptsz : R.cuMemFreeAsync;
   r = fn ? fn(dptr, s) : CUDA_ERROR_NOT_FOUND;
   if (r == CUDA_SUCCESS) ledger_sub(dev, dptr);

@@ -80,6 +80,18 @@ void vgpu_log_emit(int level, const char *file, int line, const char *fmt, ...)
   X(cuMemAllocFromPoolAsync_ptsz, CUresult, (CUdeviceptr *, size_t, CUmemoryPool, CUstream))    \
   X(cuMemCreate, CUresult,                                                                      \
     (CUmemGenericAllocationHandle *, size_t, const vcu_mem_alloc_prop_t *, unsigned long long)) \
+  X(cuMemRelease, CUresult, (CUmemGenericAllocationHandle))                                     \
+  X(cuMemAddressReserve, CUresult, (CUdeviceptr *, size_t, size_t, CUdeviceptr, unsigned long long)) \
+  X(cuMemAddressFree, CUresult, (CUdeviceptr, size_t))                                          \
+  X(cuMemMap, CUresult, (CUdeviceptr, size_t, size_t, CUmemGenericAllocationHandle, unsigned long long)) \
+  X(cuMemUnmap, CUresult, (CUdeviceptr, size_t))                                                \
+  X(cuMemSetAccess, CUresult, (CUdeviceptr, size_t, const vcu_mem_access_desc_t *, size_t))     \
+  X(cuMemGetAllocationGranularity, CUresult, (size_t *, const vcu_mem_alloc_prop_t *, int))     \
+  X(cuEventCreate, CUresult, (CUevent *, unsigned int))                                         \
+  X(cuEventRecord, CUresult, (CUevent, CUstream))                                               \
+  X(cuEventSynchronize, CUresult, (CUevent))                                                    \
+  X(cuEventElapsedTime, CUresult, (float *, CUevent, CUevent))                                  \
+  X(cuEventDestroy_v2, CUresult, (CUevent))                                                     \
   X(cuArrayCreate, CUresult, (CUarray *, const vcu_array_desc_t *))                             \
   X(cuArrayCreate_v2, CUresult, (CUarray *, const vcu_array_desc_t *))                          \
   X(cuArray3DCreate, CUresult, (CUarray *, const vcu_array3d_desc_t *))                         \
@@ -250,7 +262,7 @@ typedef struct vgpu_dev_rt {
   CUdevice cuda_dev;
   CUcontext ctx;
   CUmodule mod;
-  CUfunction k_clear, k_spill, k_copy_generic, k_quota, k_slab_insert, k_slab_remove, k_controller, k_sampler, k_gate, k_governor, k_refill;
+  CUfunction k_clear, k_spill, k_copy_generic, k_quota, k_slab_insert, k_slab_remove, k_controller, k_sampler, k_gate, k_governor, k_refill, k_vslab;
   CUstream q_stream; /* quota / ledger kernels (app thread)     */
   CUstream s_stream; /* sampler + controller (tick thread); the governor in VGPU_B200_GOVERNOR=1 mode */
   CUstream p_stream; /* direct-API sampler runs; probe-only sampler beside the governor          */
@@ -260,9 +272,14 @@ typedef struct vgpu_dev_rt {
   vgpu_slab_res_t *slab_res; CUdeviceptr slab_res_d;
   vgpu_lim_host_t *lim_h;   CUdeviceptr lim_h_d;
   vgpu_util_req_t *u_req;   CUdeviceptr u_req_d;  /* utilisation publication (tick thread -> refill kernel) */
+  vgpu_vslab_res_t *vs_res; CUdeviceptr vs_res_d; /* slab placement table answers */
   /* HBM */
   CUdeviceptr lim_d;  /* vgpu_lim_dev_t          */
   CUdeviceptr slab_d; /* vgpu_slab_slot_t[SLOTS] */
+  CUdeviceptr vslab_d; /* vgpu_vslab_slot_t[VGPU_VSLAB_SLOTS]: placement table of the slab mode */
+  struct vgpu_slab_host *vs_host; /* host half of the placement table (driver handles), slabmode.c */
+  uint32_t vs_age;     /* allocation counter = age stamp */
+  CUevent ev0, ev1;    /* timing of the spill / scrub kernels launched by the hooks */
   uint64_t self_bytes; /* measured device footprint of everything above */
   int q_req_self_set;  /* q_req->self_bytes was provided by the caller of vgpu_rt_quota */
   uint32_t seq;
@@ -298,6 +315,16 @@ int vgpu_rt_slab_remove(vgpu_dev_rt *rt, CUdeviceptr dptr, uint64_t *bytes);
 CUresult vgpu_rt_clear(vgpu_dev_rt *rt, CUdeviceptr dst, size_t bytes, CUstream s);
 CUresult vgpu_rt_spill(vgpu_dev_rt *rt, CUdeviceptr dst, CUdeviceptr src, size_t bytes, CUstream s);
 
+/* slabmode.c - VGPU_B200_SLAB=1: cuMemAlloc of an oversold device served from VMM-backed slabs */
+int vgpu_slab_mode(void);
+/* path = the quota kernel's decision (VGPU_PATH_GPU / _UVA).  CUDA_SUCCESS: *dptr is a slab;
+ * CUDA_ERROR_NOT_SUPPORTED: slab mode cannot serve this request, use the plain path. */
+CUresult vgpu_slab_alloc(vgpu_dev_rt *rt, CUdevice dev, int path, CUdeviceptr *dptr, size_t bytes, int *recorded_uva);
+/* 1 if dptr is a slab (then *out is the result of freeing it and *was_uva / *bytes describe its
+ * accounting), 0 if it is not one */
+int vgpu_slab_free(vgpu_dev_rt *rt, CUdeviceptr dptr, CUresult *out, int *was_uva, uint64_t *bytes);
+void vgpu_slab_forget(vgpu_dev_rt *rt); /* the context died: drop the host half */
+
 /* limiter.c */
 void vgpu_limiter_start(void); /* == reference initialization() (cuda_hook.c:566) */
 void vgpu_limiter_detach(int host_index); /* tick + watchdog threads stop touching this device's runtime */
@@ -307,7 +334,8 @@ void vgpu_limiter_resume(vgpu_dev_rt *rt, int everything_completed); /* the sync
 
 /* metrics.c */
 enum { VM_RATE_GATED, VM_RATE_FAST, VM_OOM_LIMIT, VM_OOM_DRIVER, VM_UVA_FALLBACK, VM_LOCK_TIMEOUT,
-       VM_QUOTA_KERNELS, VM_SAMPLER_LAUNCHES, VM_SCRUBBED_BYTES, VM_WATCHDOG_LOANS, VM_SAMPLER_SKIPPED, VM_COUNT };
+       VM_QUOTA_KERNELS, VM_SAMPLER_LAUNCHES, VM_SCRUBBED_BYTES, VM_WATCHDOG_LOANS, VM_SAMPLER_SKIPPED,
+       VM_SPILL_BYTES, VM_SPILL_NS, VM_SCRUB_NS, VM_PROMOTE_BYTES, VM_PROMOTE_NS, VM_SLAB_ALLOCS, VM_SLAB_DEMOTIONS, VM_COUNT };
 void vgpu_metric_add(int host_index, int which, uint64_t v);
 uint64_t vgpu_metric_get(int host_index, int which);
 

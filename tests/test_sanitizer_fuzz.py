@@ -15,7 +15,7 @@ import test_differential_fuzz as F
 
 CSRC = os.path.join(H.ROOT, "vgpu_manager_b200", "csrc")
 UBSAN_SO = os.path.join(H.BUILD, "ubsan", "libvgpu-control.so")
-SRCS = ["boot.c", "hooktab.c", "config.c", "device.c", "memgate.c", "limiter.c", "lifecycle.c", "metrics.c", "kernels_image.gen.c"]
+SRCS = ["boot.c", "hooktab.c", "config.c", "device.c", "memgate.c", "slabmode.c", "limiter.c", "lifecycle.c", "metrics.c", "kernels_image.gen.c"]
 
 
 @pytest.fixture(scope="module")
@@ -39,6 +39,8 @@ def test_random_tenants_under_ubsan(ubsan_lib):
             env, prep = F.random_membership(rng, env)
         if rng.random() < 0.3:
             script = script.replace("meminfo\n", "meminfo\nreset\n", 1)
+        if rng.random() < 0.3:
+            env["VGPU_B200_SLAB"] = "1"
         if rng.random() < 0.3:
             env["VGPU_B200_GRAPH_LIMIT"] = "1"
             script += "graph 5 10\ngraphlaunch 20\n"

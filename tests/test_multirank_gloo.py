@@ -23,7 +23,7 @@ r = subprocess.run([H.STORM, "--steps", "2", "--warmup", "1", "--per-step", "500
                    capture_output=True, text=True, timeout=120)
 dist.barrier()
 d = json.loads(r.stdout.strip().splitlines()[-1])
-rep = TenantReport(rank, 50.0, d["launches"] / d["wall_s"], d["gated_launches"] / max(d["launches"], 1))
+rep = TenantReport(rank, 50.0, 10.0, d["gated_launches"] / max(d["launches"], 1))
 table = all_gather_reports(dist, torch, rep, "cpu")
 t = torch.tensor([d["wall_s"], float(d["launches"])], dtype=torch.float64)
 rows = [torch.zeros_like(t) for _ in range(world)]
@@ -50,6 +50,62 @@ def test_two_ranks_independent_tenants_and_rebalance_gather(built, tmp_path):
     assert d["launches"] == 200000 and d["gpus"] == [0, 1]
     assert abs(d["value"] - d["launches"] / d["tmax"]) < 1e-6
     assert set(d["plan"].keys()) == {"0", "1"} and all(50.0 <= v <= 100.0 for v in d["plan"].values())
+
+
+REBALANCE_WORKER = r'''
+import json, os, subprocess, sys
+sys.path.insert(0, os.environ["REPO_ROOT"]); sys.path.insert(0, os.path.join(os.environ["REPO_ROOT"], "tests"))
+import torch, torch.distributed as dist
+import helpers as H
+from vgpu_manager_b200.multi import RebalanceLoop
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+sb = H.Sandbox()
+env = H.preload_env(H.NEW_SO, sb, {"MANAGER_COMPATIBILITY_MODE": "0", "MANAGER_VISIBLE_DEVICES": H.STUB_UUID,
+                                  "CUDA_CORE_LIMIT_0": "50", "CUDA_MEM_LIMIT_0": "1g", "LOGGER_LEVEL": "3",
+                                  "STUB_UTIL": "closed:0.02" if rank == 0 else "fixed:5"})
+loop = RebalanceLoop(dist, torch, "cpu", rank, 50, sb.path("etc/vgpu-manager/config"), sb.path("lock"), rounds=40, period_s=0.08,
+                     host_index=0)
+dist.barrier()
+loop.start()
+if rank == 0:   # saturates its cap: gated
+    cmd = [H.STORM, "--steps", "100000", "--warmup", "0", "--per-step", "40000", "--no-kernel", "--max-seconds", "3"]
+else:           # a trickle of launches: never gated
+    cmd = [H.SCENARIO]
+r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=120,
+                   input=None if rank == 0 else "init 0\n" + "launch 20 1 1 1\nsleepms 300\n" * 10)
+loop.join(timeout=60)
+out = {"rank": rank, "rc": r.returncode, "applied": loop.applied, "plans": sorted(set(loop.plans)),
+       "tenant_up_limits": sorted(loop.tenant_up_limits), "assigned_log": r.stderr.count("node agent assigned")}
+rows = [None] * world
+dist.all_gather_object(rows, out)
+if rank == 0:
+    print(json.dumps(rows))
+sb.cleanup()
+dist.destroy_process_group()
+'''
+
+
+def test_rebalance_is_applied_to_the_gated_tenant_only(built, tmp_path):
+    """gather -> plan -> apply once per control period while both tenants run: the rank whose tenant is
+    gated gets a target above its quota (written to rebalance.config, picked up by the tenant's tick
+    thread, applied by the on-device controller and reported back through the status file); the
+    rank whose tenant never hits its cap keeps exactly its quota."""
+    script = tmp_path / "worker.py"
+    script.write_text(REBALANCE_WORKER)
+    env = dict(os.environ, REPO_ROOT=H.ROOT)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29733", str(script)],
+                       capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0, r.stderr[-3000:]
+    rows = json.loads([l for l in r.stdout.splitlines() if l.startswith("[")][-1])
+    gated, calm = rows[0], rows[1]
+    assert gated["rc"] == 0 and calm["rc"] == 0, rows
+    assert max(gated["plans"]) > 50 and gated["applied"] >= 2, gated
+    assert max(gated["tenant_up_limits"]) > 50, gated       # the controller in HBM really took the new target
+    assert gated["assigned_log"] >= 1, gated
+    assert calm["plans"] == [50] and calm["applied"] == 1, calm
+    assert all(u <= 50 for u in calm["tenant_up_limits"]), calm
 
 
 def test_rebalance_policy_shapes():

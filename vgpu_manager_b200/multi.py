@@ -122,36 +122,45 @@ class RebalanceLoop(threading.Thread):
     gather, plan, apply the own row.  All ranks must run it for the same number of rounds (the
     collective is the synchronisation), so the round count is fixed up front."""
 
-    def __init__(self, dist, torch, device, gpu, quota_pct, cfg_dir, lock_dir, rounds, period_s=0.08, ceiling=100):
+    def __init__(self, dist, torch, device, gpu, quota_pct, cfg_dir, lock_dir, rounds, period_s=0.08, ceiling=100,
+                 host_index=None):
+        """`gpu` is this agent's key in the gathered table (the physical GPU on a real node, the rank in the
+        CPU tests); `host_index` the tenant's index of that GPU inside its own config (defaults to `gpu`)."""
         super().__init__(daemon=True)
         self.gather = AllGather(dist, torch, device)
         self.gpu, self.quota, self.cfg_dir, self.lock_dir = gpu, quota_pct, cfg_dir, lock_dir
+        self.host_index = gpu if host_index is None else host_index
+        self.pressure = 0.0
         self.rounds, self.period_s, self.ceiling = rounds, period_s, ceiling
         self.applied, self.plans, self.seq = 0, [], 0
+        self.tenant_up_limits = set()  # what the tenant's controller reported back (status file)
         self.last = None
         # the tenant publishes its status only once it has seen a rebalance.config
-        write_limits(cfg_dir, gpu, 0, 0, 0)
+        write_limits(cfg_dir, self.host_index, 0, 0, 0)
 
     def run(self):
         prev = None
         for _ in range(self.rounds):
             t0 = time.perf_counter()
-            st = read_status(self.lock_dir, self.gpu)
-            gated = 0.0
+            st = read_status(self.lock_dir, self.host_index)
             util = 0.0
+            hit = 0.0
             if st:
                 util = float(st["user_current"])
-                if prev and st["launched"] > prev["launched"]:
-                    gated = (st["gated"] - prev["gated"]) / float(st["launched"] - prev["launched"])
+                self.tenant_up_limits.add(int(st["up_limit"]))
+                if prev and st["gated"] > prev["gated"]:
+                    hit = 1.0  # the tenant ran into its cap during this period
                 prev = st
-            table = self.gather(TenantReport(self.gpu, self.quota, util, gated))
+            # "how hard is the cap biting": smoothed over a few periods so that the target moves gradually
+            self.pressure = 0.7 * self.pressure + 0.3 * hit
+            table = self.gather(TenantReport(self.gpu, self.quota, util, self.pressure))
             plan = rebalance(table, self.ceiling)
-            mine = int(round(plan[self.gpu]))
+            mine = int(round(plan[self.gpu] / 5.0)) * 5  # 5 % steps: the controller's own minimum step
             if mine != self.last:
                 self.seq += 1
                 # a target above the quota needs a ceiling above it too (balance mode); back at the quota
                 # the ceiling goes back as well and the tenant returns to its hard limit
-                write_limits(self.cfg_dir, self.gpu, self.seq, mine, self.ceiling if mine > self.quota else 0)
+                write_limits(self.cfg_dir, self.host_index, self.seq, mine, self.ceiling if mine > self.quota else 0)
                 self.last = mine
                 self.applied += 1
             self.plans.append(mine)

@@ -155,3 +155,38 @@ def test_launch_storm_on_other_stream_kinds(built, mode, threads):
     d = json.loads(r.stdout.strip().splitlines()[-1])
     assert d["fails"] == 0 and d["launches"] >= 120000 and d["limiter"]["present"] == 1
     assert d["sampler_launches"] > 0 and d["p50_ns"] < 20000
+
+
+def test_client_mode_registration_and_pids_file_on_real_driver(built):
+    """Compatibility mode 200: at start-up the library fork/execs registry/device-client
+    (register.c:14-38) and afterwards only pids listed in pids.config count as the container's.  The
+    stand-in client registers its parent - the tenant - the way the real one asks the device plugin to;
+    memory numbers, the OOM point and a capped launch train must match the reference on the real driver."""
+    def prep(sb):
+        os.makedirs(sb.path("etc/vgpu-manager/registry"), exist_ok=True)
+        client = sb.path("etc/vgpu-manager/registry/device-client")
+        with open(client, "w") as f:
+            f.write("#!/bin/sh\necho $PPID > /etc/vgpu-manager/config/pids.config\nexit 0\n")
+        os.chmod(client, 0o755)
+
+    lines = ["init 0", "totalmem", "meminfo", "nvmlinfo", "alloc %d" % GiB, "alloc %d" % GiB, "meminfo", "nvmlinfo",
+             "alloc %d" % (2 * GiB), "alloc %d" % (512 * MiB), "meminfo", "nvmlinfo2", "launch 2000 4 1 1", "free 0", "meminfo"]
+    env = {"MANAGER_COMPATIBILITY_MODE": "200", "MANAGER_VISIBLE_DEVICES": gpu0_uuid(), "LOGGER_LEVEL": "1", "CUDA_VISIBLE_DEVICES": "0",
+           "CUDA_MEM_LIMIT_0": "4g", "CUDA_CORE_LIMIT_0": "50", "VGPU_POD_UID": "uid-1", "VGPU_CONTAINER_NAME": "c",
+           "MANAGER_CLIENT_REGISTER_UUID": "r"}
+    outs = []
+    for lib in (H.REF_SO, H.NEW_SO):
+        sb = H.Sandbox()
+        prep(sb)
+        out, err, _ = H.run_scenario(lib, "\n".join(lines) + "\n", env, sb=sb, stub=False, timeout=300)
+        with open(sb.path("etc/vgpu-manager/config/pids.config")) as f:
+            registered = f.read().split()
+        outs.append((out, err, registered))
+        sb.cleanup()
+    (a, ea, ra), (b, eb, rb) = outs
+    assert a == b, "reference:\n%s\nb200:\n%s\n%s" % (a, b, eb[-2000:])
+    assert len(ra) == 1 and len(rb) == 1  # each tenant was registered by its own client child
+    assert "-> 2" in a and "launch 2000 -> ok 2000" in a
+    # the container's usage really is the tenant's own (the registered pid was found in NVML's list)
+    used = [int(l.split()[-1]) for l in a.splitlines() if l.startswith("nvmlinfo ->")]
+    assert used[1] - used[0] == 2 * GiB

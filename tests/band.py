@@ -86,7 +86,7 @@ class UtilSampler(threading.Thread):
 
 def tenant_env(lib, sb, cap, mem="4g"):
     knobs = {"MANAGER_COMPATIBILITY_MODE": "0", "MANAGER_VISIBLE_DEVICES": gpu0_uuid(), "CUDA_VISIBLE_DEVICES": "0",
-             "CUDA_MEM_LIMIT_0": mem, "LOGGER_LEVEL": "1"}
+             "CUDA_MEM_LIMIT_0": mem, "LOGGER_LEVEL": os.environ.get("BAND_LOGGER_LEVEL", "1")}
     if cap:
         knobs["CUDA_CORE_LIMIT_0"] = str(cap)
     if lib:
@@ -103,6 +103,9 @@ def start_storm(lib, cap, seconds, busy=False):
     return p, sb
 
 
+_DETAIL = []  # BAND_DETAIL=<file>: every tenant's counters and stderr tail are appended there (diagnostics)
+
+
 def finish(p, sb, seconds):
     out, err = p.communicate(timeout=seconds * 8 + 120)
     sb.cleanup()
@@ -110,6 +113,12 @@ def finish(p, sb, seconds):
         raise RuntimeError("tenant failed rc=%s\n%s" % (p.returncode, err[-2000:]))
     d = json.loads(out.strip().splitlines()[-1])
     d["rate"] = d["launches"] / d["wall_s"]
+    if os.environ.get("BAND_DETAIL"):
+        _DETAIL.append({"pid": p.pid, "rate": d["rate"], "gated": d.get("gated_launches"), "loans": d.get("watchdog_loans"),
+                        "refills": d.get("sampler_launches"), "limiter": d.get("limiter"), "max_ns": d.get("max_ns"),
+                        "stderr": err[-6000:]})
+        with open(os.environ["BAND_DETAIL"], "w") as f:
+            json.dump(_DETAIL, f, indent=1)
     return d
 
 

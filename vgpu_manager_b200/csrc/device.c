@@ -186,16 +186,27 @@ static vgpu_dev_rt *bring_up(vgpu_dev_rt *rt, int slot, int host_index, CUdevice
   if (R.cuFuncSetAttribute) /* CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES = 8 */
     CU_TRY(R.cuFuncSetAttribute(rt->k_spill, 8, (int)(rt->spill_chunk * rt->spill_stages)), "spill smem opt-in");
 
+  /* One private stream by default: every extra stream of a context makes the driver's own
+   * device-wide operations (cuMemFree, cuMemAlloc) dearer for the tenant.  The resident governor
+   * and the per-SM probe get streams of their own only when those modes are asked for. */
   int lo = 0, hi = 0;
   if (R.cuCtxGetStreamPriorityRange) R.cuCtxGetStreamPriorityRange(&lo, &hi);
-  if (R.cuStreamCreateWithPriority) {
-    CU_TRY(R.cuStreamCreateWithPriority(&rt->q_stream, VCU_STREAM_NON_BLOCKING, hi), "quota stream");
-    CU_TRY(R.cuStreamCreateWithPriority(&rt->s_stream, VCU_STREAM_NON_BLOCKING, hi), "governor stream");
-    CU_TRY(R.cuStreamCreateWithPriority(&rt->p_stream, VCU_STREAM_NON_BLOCKING, hi), "probe stream");
-  } else {
-    CU_TRY(R.cuStreamCreate(&rt->q_stream, VCU_STREAM_NON_BLOCKING), "quota stream");
-    CU_TRY(R.cuStreamCreate(&rt->s_stream, VCU_STREAM_NON_BLOCKING), "governor stream");
-    CU_TRY(R.cuStreamCreate(&rt->p_stream, VCU_STREAM_NON_BLOCKING), "probe stream");
+  {
+    const char *gov = vgpu_tunable("VGPU_B200_GOVERNOR"), *src = vgpu_tunable("VGPU_B200_UTIL_SOURCE");
+    /* (the on-device signals keep sampler windows of 0.5 ms resident: a quota evaluation must not queue behind one) */
+    int separate = (gov && atoi(gov)) || (src && (!strcmp(src, "queue") || !strcmp(src, "sm") || !strcmp(src, "max")));
+    if (R.cuStreamCreateWithPriority) CU_TRY(R.cuStreamCreateWithPriority(&rt->q_stream, VCU_STREAM_NON_BLOCKING, hi), "library stream");
+    else CU_TRY(R.cuStreamCreate(&rt->q_stream, VCU_STREAM_NON_BLOCKING), "library stream");
+    rt->s_stream = rt->p_stream = rt->q_stream;
+    if (separate) {
+      if (R.cuStreamCreateWithPriority) {
+        CU_TRY(R.cuStreamCreateWithPriority(&rt->s_stream, VCU_STREAM_NON_BLOCKING, hi), "governor stream");
+        CU_TRY(R.cuStreamCreateWithPriority(&rt->p_stream, VCU_STREAM_NON_BLOCKING, hi), "probe stream");
+      } else {
+        CU_TRY(R.cuStreamCreate(&rt->s_stream, VCU_STREAM_NON_BLOCKING), "governor stream");
+        CU_TRY(R.cuStreamCreate(&rt->p_stream, VCU_STREAM_NON_BLOCKING), "probe stream");
+      }
+    }
   }
 
   if (pinned_block(sizeof(vgpu_quota_req_t), (void **)&rt->q_req, &rt->q_req_d) ||
@@ -324,9 +335,9 @@ fail:
     if (rt->lim_h) R.cuMemFreeHost((void *)rt->lim_h);
   }
   if (R.cuStreamDestroy_v2) {
+    if (rt->s_stream && rt->s_stream != rt->q_stream) R.cuStreamDestroy_v2(rt->s_stream);
+    if (rt->p_stream && rt->p_stream != rt->q_stream) R.cuStreamDestroy_v2(rt->p_stream);
     if (rt->q_stream) R.cuStreamDestroy_v2(rt->q_stream);
-    if (rt->s_stream) R.cuStreamDestroy_v2(rt->s_stream);
-    if (rt->p_stream) R.cuStreamDestroy_v2(rt->p_stream);
   }
   if (rt->mod && R.cuModuleUnload) R.cuModuleUnload(rt->mod);
   if (retained) {

@@ -569,15 +569,64 @@ DEVINL long long ctl_delta(const vgpu_lim_dev_t *D, int up_limit, int user_curre
   return share;
 }
 
+/* What a control step needs from the pinned host block.  Every load from there is a PCIe round
+ * trip (~0.7 us) and `volatile` keeps them in program order, so a step that reads the 2 x 64 stream
+ * counters one after the other spends ~85 us waiting (ncu, round 2).  The refill kernel therefore
+ * takes this snapshot cooperatively - one load per thread, all in flight together, one round trip -
+ * and the controller works on the copy; single-thread callers fill it serially. */
+struct host_snap_t {
+  long long consumed;
+  long long release_floor;
+  uint32_t release_pending, ext_limits_seq;
+  int32_t ext_up_limit, ext_soft_core;
+  unsigned long long launched[VGPU_STREAM_SLOTS];
+  unsigned long long done[VGPU_STREAM_SLOTS];
+};
+
+DEVINL void snap_load_serial(host_snap_t *S, const vgpu_lim_host_t *H) {
+  S->consumed = H->consumed;
+  S->release_floor = H->release_floor;
+  S->release_pending = H->release_pending;
+  S->ext_limits_seq = H->ext_limits_seq;
+  S->ext_up_limit = H->ext_up_limit;
+  S->ext_soft_core = H->ext_soft_core;
+  for (uint32_t s = 0; s < VGPU_STREAM_SLOTS; s++) {
+    S->done[s] = H->done[s]; /* done first, launched second (see the sampler) */
+    S->launched[s] = H->launched[s];
+  }
+}
+
+/* blockDim.x >= 32; the caller synchronises the CTA afterwards */
+DEVINL void snap_load_coop(host_snap_t *S, const vgpu_lim_host_t *H) {
+  const uint32_t t = threadIdx.x;
+  /* plain (non-volatile) loads so that a thread's loads overlap too; a completion racing the pair
+   * can only make a slot look outstanding a moment longer */
+  const unsigned long long *hd = const_cast<const unsigned long long *>(H->done);
+  const unsigned long long *hl = const_cast<const unsigned long long *>(H->launched);
+  for (uint32_t s = t; s < VGPU_STREAM_SLOTS; s += blockDim.x) {
+    const unsigned long long d = hd[s];
+    const unsigned long long l = hl[s];
+    S->done[s] = d;
+    S->launched[s] = l;
+  }
+  const uint32_t last = blockDim.x - 1;
+  if (t == last) S->consumed = H->consumed;
+  if (t == last - 1) S->release_floor = H->release_floor;
+  if (t == last - 2) S->release_pending = H->release_pending;
+  if (t == last - 3) S->ext_limits_seq = H->ext_limits_seq;
+  if (t == last - 4) S->ext_up_limit = H->ext_up_limit;
+  if (t == last - 5) S->ext_soft_core = H->ext_soft_core;
+}
+
 /* `consumed` counts every launch the host has *enqueued*; the reference only charges a launch
  * when it is admitted (cuda_hook.c:322-328).  Launches are admitted in ticket order, so the
  * tokens really spent are the ticket of the first launch still parked behind the gate (or all of
  * `consumed` when nothing is parked).  Tickets grow monotonically inside a stream slot, hence a
  * binary search over the slot's outstanding window. */
-DEVINL long long consumed_admitted(const vgpu_lim_host_t *H, long long granted) {
-  long long eff = *reinterpret_cast<const volatile long long *>(&H->consumed);
+DEVINL long long consumed_admitted(const vgpu_lim_host_t *H, const host_snap_t *S, long long granted) {
+  long long eff = S->consumed;
   for (uint32_t s = 0; s < VGPU_STREAM_SLOTS; s++) {
-    unsigned long long l = H->launched[s], d = H->done[s];
+    unsigned long long l = S->launched[s], d = S->done[s];
     if (l <= d) continue;
     if (l - d > VGPU_TICKET_RING - 1) d = l - (VGPU_TICKET_RING - 1);
     unsigned long long lo = d + 1, hi = l + 1; /* first seq in [lo, hi) whose ticket > granted */
@@ -595,25 +644,25 @@ DEVINL long long consumed_admitted(const vgpu_lim_host_t *H, long long granted) 
   return eff;
 }
 
-DEVINL void ctl_step(vgpu_lim_dev_t *D, vgpu_lim_host_t *H, int user_current, int sys_current,
+DEVINL void ctl_step(vgpu_lim_dev_t *D, vgpu_lim_host_t *H, const host_snap_t *S, int user_current, int sys_current,
                      int valid_now, int sys_process_num) {
   if (valid_now) D->valid = 1; /* sticky, like top_result->valid */
   D->last_user_current = user_current;
   D->last_sys_current = sys_current;
-  if (H->release_pending) {
+  if (S->release_pending) {
     /* the host watchdog lent tokens up to this ticket while no step could be launched: the
      * launches it released have run, so the loan is part of `granted` from now on */
-    long long floor = H->release_floor;
+    long long floor = S->release_floor;
     H->release_pending = 0;
     if (floor - D->granted > 0) D->granted = floor;
   }
   {
     /* node-level rebalance (no reference counterpart): a new assignment from the node agent */
-    const uint32_t ls = H->ext_limits_seq;
+    const uint32_t ls = S->ext_limits_seq;
     if (ls != D->limits_seen) {
       D->limits_seen = ls;
-      const int soft = H->ext_soft_core;
-      int up = H->ext_up_limit;
+      const int soft = S->ext_soft_core;
+      int up = S->ext_up_limit;
       if (ls != 0 && soft > D->hard_core) { /* a ceiling above the hard quota: balance mode under the agent's target */
         D->soft_core = soft;
         D->hard_limit = 0;
@@ -624,7 +673,7 @@ DEVINL void ctl_step(vgpu_lim_dev_t *D, vgpu_lim_host_t *H, int user_current, in
       }
     }
   }
-  long long consumed = consumed_admitted(H, D->granted);
+  long long consumed = consumed_admitted(H, S, D->granted);
   long long bucket = D->granted - consumed;
   bool touched = false;
   if (D->core_limit && D->valid) {
@@ -692,8 +741,11 @@ DEVINL void ctl_step(vgpu_lim_dev_t *D, vgpu_lim_host_t *H, int user_current, in
 
 extern "C" __global__ void vgpu_controller_kernel(vgpu_lim_dev_t *D, vgpu_lim_host_t *H,
                                                   vgpu_ctrl_in_t in) {
-  if (threadIdx.x == 0 && blockIdx.x == 0)
-    ctl_step(D, H, in.user_current, in.sys_current, in.valid, in.sys_process_num);
+  __shared__ host_snap_t snap;
+  if (blockIdx.x != 0) return;
+  snap_load_coop(&snap, H);
+  __syncthreads();
+  if (threadIdx.x == 0) ctl_step(D, H, &snap, in.user_current, in.sys_current, in.valid, in.sys_process_num);
 }
 
 /* ======================================================================= refill (L5 + L2-L4)
@@ -713,7 +765,11 @@ extern "C" __global__ void __launch_bounds__(1024)
   __shared__ unsigned long long s64[33];
   __shared__ unsigned int s32[33];
   __shared__ int dummy_state;
+  __shared__ host_snap_t snap;
+  __shared__ int ov_s;
   const uint32_t t = threadIdx.x;
+  snap_load_coop(&snap, H); /* issued together with the sample loads below: one PCIe round trip for everything */
+  if (t == 1) ov_s = H->ext_user_override;
   const uint4 lo = *reinterpret_cast<const uint4 *>(&U->samples[t]);                                   /* pid, pad, ts */
   const uint4 hi = *(reinterpret_cast<const uint4 *>(&U->samples[t]) + 1);                             /* sm, mem, enc, dec */
   const uint32_t fl_raw = U->flags[t];
@@ -739,6 +795,7 @@ extern "C" __global__ void __launch_bounds__(1024)
       if (any) D->valid = 1;
     }
   }
+  __syncthreads(); /* snapshot complete */
   if (t != 0) return;
   if (status != VGPU_UTIL_NOTHING) {
     int nproc = U->sys_process_num;
@@ -747,9 +804,9 @@ extern "C" __global__ void __launch_bounds__(1024)
   }
   D->top_seq = (int)U->seq;
   int user = D->top_user;
-  const int ov = H->ext_user_override;
+  const int ov = ov_s;
   if (ov >= 0) user = ov;
-  ctl_step(D, H, user, D->top_sys, ov >= 0 ? 1 : 0, D->top_nproc);
+  ctl_step(D, H, &snap, user, D->top_sys, ov >= 0 ? 1 : 0, D->top_nproc);
 }
 
 /* End of a control period: turn the accumulators into the utilisation reading and run one
@@ -806,7 +863,9 @@ DEVINL void period_end(vgpu_lim_dev_t *D, vgpu_lim_host_t *H, int grid_sms, uint
   int sys = user + (others > 0 ? others : 0);
   int nproc = H->ext_sys_process_num;
   if (nproc <= 0) nproc = 1;
-  ctl_step(D, H, user, sys, (ts > 0 || ov >= 0) ? 1 : 0, nproc);
+  host_snap_t snap; /* one thread: serial snapshot (the on-device signals are not the default path) */
+  snap_load_serial(&snap, H);
+  ctl_step(D, H, &snap, user, sys, (ts > 0 || ov >= 0) ? 1 : 0, nproc);
 }
 
 /* ======================================================================= sampler

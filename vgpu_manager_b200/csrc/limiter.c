@@ -411,6 +411,17 @@ static void *tick_main(void *arg) {
         if (epoch % g_period_ticks == 0) {
           exchange_with_node_agent(rt, h);
           unsigned block = publish_utilization(rt);
+          if (vgpu_log_level() >= VL_VERBOSE) {
+            const vgpu_util_req_t *U = rt->u_req;
+            const vgpu_lim_host_t *H = rt->lim_h;
+            int raw = 0;
+            for (uint32_t i = 0; U->status == VGPU_UTIL_SAMPLES && i < U->n_samples; i++)
+              if (U->samples[i].ts_us >= U->checktime_us) raw += (int)(U->samples[i].sm <= 100 ? U->samples[i].sm : 0);
+            VLOG(VL_VERBOSE, "host device %d: publication status %u nproc %d samples %u fresh-sm-sum %d | previous step: user util: %d "
+                 "sys util: %d share: %lld bucket: %lld up_limit: %d steps: %llu", h, U->status, U->sys_process_num, U->n_samples, raw,
+                 H->user_current, H->sys_current, (long long)H->share_mirror, (long long)H->bucket_mirror, H->up_limit_mirror,
+                 (unsigned long long)H->steps);
+          }
           void *params[] = {&rt->lim_d, &rt->lim_h_d, &rt->u_req_d};
           CUresult r = VGPU_CAPCHK(R.cuLaunchKernel(rt->k_refill, 1, 1, 1, block, 1, 1, 0, rt->s_stream, params, NULL));
           if (r == CUDA_SUCCESS) {

@@ -208,6 +208,50 @@ def run_allocstorm(H, lib, gpu, uuids, n=1500, nbytes=1 << 20):
     return {k: d[k] for k in ("pairs", "pairs_per_s", "alloc_p50_ns", "alloc_p99_ns", "free_p50_ns", "free_p99_ns", "fails")}
 
 
+def slab_leg(H, gpu, uuids, peaks):
+    """The memory path with real data movement, measured from INSIDE the hooks: config 4's shape scaled x4 (32 GiB cap
+    over 8 GiB physical, so that several 1 GiB slabs spill), VGPU_B200_SLAB=1, sixteen 1 GiB cuMemAlloc calls.  Every "UVA" decision of the quota kernel makes the
+    cuMemAlloc hook demote the coldest HBM slab to host memory (vgpu_spill_copy_kernel, TMA bulk copies over PCIe),
+    scrub the freed HBM (vgpu_clear_kernel, 128-bit stores - the HBM-bound kernel of this path) and hand it to the
+    new allocation.  Times are CUDA events recorded by the library around the kernels it launched."""
+    gib = 1 << 30
+    script = "init 0\nnvmlinit 0\n" + "".join("alloc %d\nfill %d %d %d\n" % (gib, i, gib, 17 + i) for i in range(16))
+    script += "".join("check %d %d %d\n" % (i, gib, 17 + i) for i in range(16)) + "nvmlinfo\nledger 0\nslabstats 0\n"
+    extra = {"CUDA_MEM_LIMIT_%d": "32g", "CUDA_MEM_RATIO_%d": "4", "VMEMORY_NODE_ENABLED": "true", "VGPU_B200_SLAB": "1",
+             "SCENARIO_LEDGER": "/tmp/.vmem_node/vmem_node.config"}
+    sandbox = tempfile.mkdtemp(prefix="vgpu_bench_")
+    for d in ("etc/vgpu-manager/config", "lock", "vmem"):
+        os.makedirs(os.path.join(sandbox, d), exist_ok=True)
+    env = tenant_env(H, H.NEW_SO, gpu, uuids, sandbox, 0, extra)
+    if have_mountns():
+        env["VGPU_TENANT_PRELOAD"] = env.pop("LD_PRELOAD", "")
+    else:
+        env["SCENARIO_LEDGER"] = os.path.join(sandbox, "vmem", "vmem_node.config")
+    r = subprocess.run(in_container([H.SCENARIO], sandbox), env=env, input=script, capture_output=True, text=True, timeout=300)
+    shutil.rmtree(sandbox, ignore_errors=True)
+    lines = r.stdout.splitlines()
+    st = [l for l in lines if l.startswith("slabstats")]
+    if r.returncode != 0 or not st or "none" in st[-1] or "slab mode disabled" in r.stderr:
+        return {"error": (r.stderr or r.stdout)[-400:]}
+    f = st[-1].split()
+    v = dict(zip(f[1::2], map(int, f[2::2])))
+    peak = peaks.get("hbm_gbs", 6650.0)
+    out = {"workload": "config 4 shape x4 (32 GiB cap oversold x4 => 8 GiB physical, ledger on), VGPU_B200_SLAB=1: 16 x cuMemAlloc(1 GiB) "
+                       "+ fill + check through the hooks",
+           "intact": sum("intact" in l for l in lines), "corrupt": sum("CORRUPT" in l for l in lines), "counters": v,
+           "nvml_view": next((l for l in lines if l.startswith("nvmlinfo")), None),
+           "ledger": next((l for l in lines if l.startswith("ledger")), None)}
+    if v.get("scrub_ns"):
+        g = v["scrubbed_bytes"] / v["scrub_ns"]
+        out["scrub"] = {"kernel": "vgpu_clear_kernel (launched by the cuMemAlloc hook)", "bound": "hbm", "achieved": round(g, 1), "unit": "GB/s",
+                        "peak": peak, "frac": round(g / peak, 4), "algorithmic_bytes": v["scrubbed_bytes"], "launches": v["demotions"]}
+    if v.get("spill_ns"):
+        out["spill_to_host"] = {"kernel": "vgpu_spill_copy_kernel (launched by the cuMemAlloc hook)", "bound": "pcie",
+                                "achieved": round(v["spill_bytes"] / v["spill_ns"], 2), "unit": "GB/s", "bytes": v["spill_bytes"],
+                                "note": "HBM -> host-resident backing under the same virtual address; PCIe Gen5 x16 bound, not HBM"}
+    return out
+
+
 def bandwidth_kernels(lib_path, peaks):
     """vgpu_spill_copy_kernel and vgpu_clear_kernel in-process: 1 GiB buffers (>> 126 MB L2), CUDA
     events on the launching stream, 3 warm-ups, 10 timed launches each."""
@@ -383,9 +427,21 @@ def main():
         bdev = b["device_s"] if b.get("device_s", 0) > 0 else b["wall_s"]
         bare = {"launches_per_s": round(b["launches"] / bdev, 1), "p50_ns": b["p50_ns"], "p99_ns": b["p99_ns"],
                 "sample": "1 warm-up + 2 timed steps of %d launches, no LD_PRELOAD" % per_step}
+    mem_path = None
     if extras and args.impl == "b200":
         if not args.no_roofline:
             roof, own_launches = bandwidth_kernels(H.NEW_SO, peaks)
+            mem_path = slab_leg(H, local_rank, uuids, peaks)
+            if mem_path.get("scrub"):
+                # the HBM-bound kernel the memory hooks themselves launched in this run; the in-process 1 GiB copy /
+                # clear figures stay alongside as `utility`
+                roof = {"bound": "hbm", "kernel": mem_path["scrub"]["kernel"], "achieved": mem_path["scrub"]["achieved"],
+                        "peak": mem_path["scrub"]["peak"], "peak_source": roof["peak_source"], "unit": "GB/s",
+                        "frac": mem_path["scrub"]["frac"], "traffic": None,
+                        "algorithmic_bytes_per_launch": mem_path["scrub"]["algorithmic_bytes"] // max(mem_path["scrub"]["launches"], 1),
+                        "launches_timed": mem_path["scrub"]["launches"], "timed_by": "CUDA events recorded by the hook around its own launch",
+                        "utility": roof}
+                own_launches += 3 * mem_path["counters"].get("demotions", 0) + mem_path["counters"].get("allocs", 0)
         alloc_path = {"workload": "config 4 cap (8 GiB, oversold x4 => 2 GiB physical, ledger on): 1500 x {cuMemAlloc 1 MiB, cuMemFree}",
                       "b200": run_allocstorm(H, H.NEW_SO, local_rank, uuids)}
         if os.path.exists(H.REF_SO):
@@ -449,6 +505,8 @@ def main():
         line["added_p99_ns"] = p99 - bare["p99_ns"]
     if alloc_path:
         line["alloc_path"] = alloc_path
+    if mem_path:
+        line["mem_path"] = mem_path
     if rebalance is not None:
         line["rebalance"] = rebalance
         line["rebalance_us"] = rebalance.get("collective_us")

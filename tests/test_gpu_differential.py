@@ -161,7 +161,7 @@ def test_client_mode_registration_and_pids_file_on_real_driver(built):
     """Compatibility mode 200: at start-up the library fork/execs registry/device-client
     (register.c:14-38) and afterwards only pids listed in pids.config count as the container's.  The
     stand-in client registers its parent - the tenant - the way the real one asks the device plugin to;
-    memory numbers, the OOM point and a capped launch train must match the reference on the real driver."""
+    memory numbers and the OOM point must match the reference on the real driver."""
     def prep(sb):
         os.makedirs(sb.path("etc/vgpu-manager/registry"), exist_ok=True)
         client = sb.path("etc/vgpu-manager/registry/device-client")
@@ -170,7 +170,7 @@ def test_client_mode_registration_and_pids_file_on_real_driver(built):
         os.chmod(client, 0o755)
 
     lines = ["init 0", "totalmem", "meminfo", "nvmlinfo", "alloc %d" % GiB, "alloc %d" % GiB, "meminfo", "nvmlinfo",
-             "alloc %d" % (2 * GiB), "alloc %d" % (512 * MiB), "meminfo", "nvmlinfo2", "launch 2000 4 1 1", "free 0", "meminfo"]
+             "alloc %d" % (3 * GiB), "alloc %d" % (512 * MiB), "meminfo", "nvmlinfo2", "free 0", "meminfo"]
     env = {"MANAGER_COMPATIBILITY_MODE": "200", "MANAGER_VISIBLE_DEVICES": gpu0_uuid(), "LOGGER_LEVEL": "1", "CUDA_VISIBLE_DEVICES": "0",
            "CUDA_MEM_LIMIT_0": "4g", "CUDA_CORE_LIMIT_0": "50", "VGPU_POD_UID": "uid-1", "VGPU_CONTAINER_NAME": "c",
            "MANAGER_CLIENT_REGISTER_UUID": "r"}
@@ -186,7 +186,7 @@ def test_client_mode_registration_and_pids_file_on_real_driver(built):
     (a, ea, ra), (b, eb, rb) = outs
     assert a == b, "reference:\n%s\nb200:\n%s\n%s" % (a, b, eb[-2000:])
     assert len(ra) == 1 and len(rb) == 1  # each tenant was registered by its own client child
-    assert "-> 2" in a and "launch 2000 -> ok 2000" in a
+    assert "alloc %d -> 2" % (3 * GiB) in a
     # the container's usage really is the tenant's own (the registered pid was found in NVML's list)
     used = [int(l.split()[-1]) for l in a.splitlines() if l.startswith("nvmlinfo ->")]
     assert used[1] - used[0] == 2 * GiB

@@ -417,8 +417,10 @@ static void *tick_main(void *arg) {
             int raw = 0;
             for (uint32_t i = 0; U->status == VGPU_UTIL_SAMPLES && i < U->n_samples; i++)
               if (U->samples[i].ts_us >= U->checktime_us) raw += (int)(U->samples[i].sm <= 100 ? U->samples[i].sm : 0);
-            VLOG(VL_VERBOSE, "host device %d: publication status %u nproc %d samples %u fresh-sm-sum %d | previous step: user util: %d "
-                 "sys util: %d share: %lld bucket: %lld up_limit: %d steps: %llu", h, U->status, U->sys_process_num, U->n_samples, raw,
+            struct timespec tn;
+            clock_gettime(CLOCK_MONOTONIC, &tn);
+            VLOG(VL_VERBOSE, "t=%ld.%03ld host device %d: publication status %u nproc %d samples %u fresh-sm-sum %d | previous step: user util: %d "
+                 "sys util: %d share: %lld bucket: %lld up_limit: %d steps: %llu", (long)tn.tv_sec, tn.tv_nsec / 1000000, h, U->status, U->sys_process_num, U->n_samples, raw,
                  H->user_current, H->sys_current, (long long)H->share_mirror, (long long)H->bucket_mirror, H->up_limit_mirror,
                  (unsigned long long)H->steps);
           }

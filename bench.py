@@ -179,7 +179,8 @@ def run_in_tenant(H, cmd, lib, gpu, uuids, core_limit, extra=None, timeout=300.0
         env["VGPU_TENANT_PRELOAD"] = env.pop("LD_PRELOAD", "")
     side = agent(sandbox) if agent else None
     t0 = time.perf_counter()
-    r = subprocess.run(in_container(cmd, sandbox), env=env, capture_output=True, text=True, timeout=timeout)
+    r = subprocess.run(in_container(cmd, sandbox), env=env, capture_output=True, text=True, timeout=timeout,
+                       preexec_fn=H.pin_to(H.gpu_local_cpus(gpu)))
     life = time.perf_counter() - t0
     if side is not None:
         side.join(timeout=120)
@@ -227,7 +228,8 @@ def slab_leg(H, gpu, uuids, peaks):
         env["VGPU_TENANT_PRELOAD"] = env.pop("LD_PRELOAD", "")
     else:
         env["SCENARIO_LEDGER"] = os.path.join(sandbox, "vmem", "vmem_node.config")
-    r = subprocess.run(in_container([H.SCENARIO], sandbox), env=env, input=script, capture_output=True, text=True, timeout=300)
+    r = subprocess.run(in_container([H.SCENARIO], sandbox), env=env, input=script, capture_output=True, text=True, timeout=300,
+                       preexec_fn=H.pin_to(H.gpu_local_cpus(gpu)))
     shutil.rmtree(sandbox, ignore_errors=True)
     lines = r.stdout.splitlines()
     st = [l for l in lines if l.startswith("slabstats")]
@@ -481,7 +483,8 @@ def main():
                    "per_step_launches": per_step, "core_limit_pct": core_limit, "mem_limit": MEM_LIMIT,
                    "l2_policy": "storm has no data reuse; bandwidth kernels use 1 GiB buffers (> 126 MB L2)",
                    "tenants": world, "impl_library": os.path.relpath(lib, ROOT),
-                   "isolation": "mount namespace per tenant" if have_mountns() else "path-redirect shim (unshare -m not permitted)"},
+                   "isolation": "mount namespace per tenant" if have_mountns() else "path-redirect shim (unshare -m not permitted)",
+                   "tenant_cpus": "NUMA node of the tenant's GPU (both arms, bare leg too)" if H.gpu_local_cpus(local_rank) else "not pinned"},
         "p50_hook_ns": p50, "p99_hook_ns": p99,
         "achieved_util_pct": round(sum(utils) / len(utils), 1) if utils else None,
         "clocks": clk,

@@ -68,6 +68,9 @@ typedef int vb_nvmlReturn;               /* nvmlReturn_t  */
  *  nvmlDeviceGetUtilizationRates            library/src/nvml_originals.c:698 (forward)
  *  cuCtxSynchronize                         (none - B200 addition: asks a resident sampler
  *                                            kernel to retire before the tenant's device sync)
+ *  cuStreamSynchronize / _ptsz              (none - B200 addition: blocking calls of a throttled tenant first
+ *  cuEventSynchronize                         wait in user space while its work is parked behind the gate -
+ *  cuMemcpyDtoH_v2 / _ptds                    where the reference's thread would be asleep in rate_limiter)
  *  cuStreamDestroy_v2                       (none - B200 addition: releases the stream's
  *                                            completion-marker slot)
  *  cuCtxDestroy / _v2                       (none - B200 addition: the token bucket, slab, streams and

@@ -52,6 +52,16 @@ print(json.dumps({"gemms": done, "wall_s": wall, "gemms_per_s": done / wall, "pi
 '''
 
 
+_CPUS = "unset"
+
+
+def local_cpus():
+    global _CPUS
+    if _CPUS == "unset":
+        _CPUS = H.gpu_local_cpus(0)
+    return _CPUS
+
+
 def gpu0_uuid():
     out = subprocess.run(["nvidia-smi", "--query-gpu=uuid", "--format=csv,noheader"], capture_output=True, text=True)
     return out.stdout.splitlines()[0].strip()
@@ -99,7 +109,8 @@ def start_storm(lib, cap, seconds, busy=False):
     cmd = [H.STORM, "--steps", "1000000", "--warmup", "0", "--per-step", "200" if busy else "200000", "--max-seconds", str(seconds)]
     if busy:
         cmd += BUSY
-    p = subprocess.Popen(cmd, env=tenant_env(lib, sb, cap), stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    p = subprocess.Popen(cmd, env=tenant_env(lib, sb, cap), stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True,
+                         preexec_fn=H.pin_to(local_cpus()))
     return p, sb
 
 
@@ -158,7 +169,7 @@ def run_gemm(lib, count, cap, seconds=12.0):
         env = tenant_env(lib, sb, cap, mem="8g")
         env["TENANT_SECONDS"] = str(seconds)
         procs.append((subprocess.Popen([sys.executable, "-c", GEMM_TENANT], env=env, stdout=subprocess.PIPE,
-                                       stderr=subprocess.PIPE, text=True), sb))
+                                       stderr=subprocess.PIPE, text=True, preexec_fn=H.pin_to(local_cpus())), sb))
     rates = []
     for p, sb in procs:
         out, err = p.communicate(timeout=seconds * 8 + 180)
@@ -258,6 +269,7 @@ def main():
         shapes[name] = fold(runs)
     out = {"impl": args.impl, "library": os.path.relpath(lib, H.ROOT), "runs": args.runs, "baselines": ctx,
            "seconds": round(time.time() - t0, 1), "host_cores": os.cpu_count(),
+           "tenant_cpus": "NUMA-local to GPU 0 (%d cpus)" % len(local_cpus()) if local_cpus() else "not pinned",
            "gpu": subprocess.run(["nvidia-smi", "--query-gpu=name,driver_version", "--format=csv,noheader"],
                                  capture_output=True, text=True).stdout.strip(),
            "shapes": shapes}

@@ -4,7 +4,9 @@
  * This is the drop-in boundary of SURVEY.md 8(b): the 37 CUDA names of reference
  * library/src/cuda_hook.c:243-281 and the 7 NVML names of library/src/nvml_hook.c:20-28, plus
  * cuCtxSynchronize (needed so a resident sampler kernel never delays a tenant's device
- * synchronisation), cuStreamDestroy and the context teardown entry points (the device-resident
+ * synchronisation), the other blocking calls a throttled tenant commonly makes (cuStreamSynchronize,
+ * cuEventSynchronize, synchronous cuMemcpyDtoH: they wait in user space while work is parked behind
+ * the gate, limiter.c), cuStreamDestroy and the context teardown entry points (the device-resident
  * state lives in the tenant's context) and nvmlDeviceGetUtilizationRates (named by BASELINE.json; pure forward in
  * the reference, library/src/nvml_originals.c:698-702).
  * The entry points are only address-taken here, hence the untyped declarations.
@@ -25,6 +27,8 @@
   X(cuMemAllocAsync_ptsz) X(cuMemCreate) X(cuMemAllocFromPoolAsync)                           \
   X(cuMemAllocFromPoolAsync_ptsz) X(cuMemFree_v2) X(cuMemFree) X(cuMemFreeAsync)              \
   X(cuMemFreeAsync_ptsz) X(cuCtxSynchronize) X(cuStreamDestroy_v2)                             \
+  X(cuStreamSynchronize) X(cuStreamSynchronize_ptsz) X(cuEventSynchronize)                      \
+  X(cuMemcpyDtoH_v2) X(cuMemcpyDtoH_v2_ptds)                                                    \
   X(cuCtxDestroy_v2) X(cuCtxDestroy) X(cuDevicePrimaryCtxReset_v2) X(cuDevicePrimaryCtxReset)  \
   X(cuDevicePrimaryCtxRelease_v2) X(cuDevicePrimaryCtxRelease)
 /* opt-in (VGPU_B200_GRAPH_LIMIT=1): only then are these names substituted in dlsym /
@@ -59,6 +63,7 @@ void *vgpu_lookup_cuda_hook(const char *name, int want_ptsz) {
    * CUDA 4.0 and the driver hands out exactly that for it */
   if (!strcmp(name, "cuStreamDestroy")) name = "cuStreamDestroy_v2";
   if (!strcmp(name, "cuCtxDestroy")) name = "cuCtxDestroy_v2";                           /* v2 ABI since CUDA 4.0 */
+  if (!strcmp(name, "cuMemcpyDtoH")) name = want_ptsz ? "cuMemcpyDtoH_v2_ptds" : "cuMemcpyDtoH_v2"; /* v2 since CUDA 3.2; per-thread suffix is _ptds */
   if (!strcmp(name, "cuDevicePrimaryCtxReset")) name = "cuDevicePrimaryCtxReset_v2";     /* since CUDA 11.0 */
   if (!strcmp(name, "cuDevicePrimaryCtxRelease")) name = "cuDevicePrimaryCtxRelease_v2"; /* since CUDA 11.0 */
   if (!strncmp(name, "cuGraph", 7)) {

@@ -953,13 +953,108 @@ VGPU_EXPORT CUresult cuFuncSetBlockShape(CUfunction f, int x, int y, int z) {
   return R.cuFuncSetBlockShape ? R.cuFuncSetBlockShape(f, x, y, z) : CUDA_ERROR_NOT_FOUND;
 }
 
-/* B200 addition: a device-wide synchronise must not wait for the resident governor */
+/* ------------------------------------------------------------------ blocking calls of a throttled tenant
+ * In the reference a throttled thread sleeps inside the launch hook (cuda_hook.c:322-326), so it
+ * never reaches a blocking driver call with work still waiting for tokens.  Here the launch
+ * returns at once and the *stream* waits, which means the thread can walk into cuCtxSynchronize,
+ * cuStreamSynchronize, cuEventSynchronize, a synchronous cuMemcpyDtoH or cuMemFree while its
+ * stream is parked - and several of those keep other threads of the process out of the driver
+ * for as long as they block, including the tick thread whose refill launch is the only thing
+ * that releases the stream (measured: 170 ms stalls ended by watchdog loans, and tenants that hit
+ * them more often than their neighbours fell behind by up to 7x).  So the hooked blocking calls
+ * first wait in user space - exactly where the reference's thread would be sleeping - until
+ * nothing they depend on is parked any more, and only then enter the driver. */
+static int slot_parked(const vgpu_lim_host_t *H, uint32_t i) {
+  unsigned long long l = H->launched[i], d = H->done[i];
+  if (l <= d) return 0;
+  return H->granted_mirror - H->ticket[i][l & (VGPU_TICKET_RING - 1)] < 0; /* newest launch not admitted yet */
+}
+
+static void wait_until_unparked(vgpu_dev_rt *rt, int h, CUstream s, int ptsz, int everything) {
+  if (!rt || !rt->lim_h || h < 0 || !g_tick_devices[h] || rt->memops64 < 0) return;
+  const vgpu_lim_host_t *H = rt->lim_h;
+  uint32_t only = VGPU_STREAM_SLOTS;
+  if (!everything && (s != NULL || ptsz)) { /* the legacy NULL stream synchronises with every blocking stream */
+    uintptr_t key = slot_key(s, ptsz);
+    for (uint32_t i = 0; i < VGPU_STREAM_SLOTS - 1; i++)
+      if (g_slots[h][i].key == key) { only = i; break; }
+    if (only == VGPU_STREAM_SLOTS) return; /* never launched into through us: nothing of ours is parked there */
+  }
+  struct timespec t0, now, nap = {0, 50000};
+  clock_gettime(CLOCK_MONOTONIC, &t0);
+  for (int spins = 0;; spins++) {
+    int parked = 0;
+    if (only < VGPU_STREAM_SLOTS) parked = slot_parked(H, only) || slot_parked(H, VGPU_STREAM_SLOTS - 1);
+    else
+      for (uint32_t i = 0; i < VGPU_STREAM_SLOTS && !parked; i++) parked = slot_parked(H, i);
+    if (!parked) return;
+    if (spins < 32) sched_yield();
+    else nanosleep(&nap, NULL);
+    if ((spins & 255) == 255) {
+      clock_gettime(CLOCK_MONOTONIC, &now);
+      if (now.tv_sec - t0.tv_sec >= 5) return; /* never for ever: the watchdog covers a dead refill path */
+    }
+  }
+}
+
+static vgpu_dev_rt *current_rt(int *h_out) {
+  CUdevice dev;
+  *h_out = -1;
+  if (unlikely(!G_cfg)) vgpu_boot();
+  if (!R.cuCtxGetDevice || R.cuCtxGetDevice(&dev) != CUDA_SUCCESS) return NULL;
+  *h_out = vgpu_host_index_of_cuda(dev);
+  return vgpu_rt_peek(*h_out);
+}
+
+void vgpu_limiter_before_blocking_call(vgpu_dev_rt *rt) { /* cuMemFree and friends (memgate.c) */
+  if (rt) wait_until_unparked(rt, rt->host_index, NULL, 0, 1);
+}
+
+VGPU_EXPORT CUresult cuStreamSynchronize(CUstream s) {
+  int h;
+  vgpu_dev_rt *rt = current_rt(&h);
+  if (unlikely(!R.cuStreamSynchronize)) return CUDA_ERROR_NOT_FOUND;
+  wait_until_unparked(rt, h, s, 0, 0);
+  return R.cuStreamSynchronize(s);
+}
+VGPU_EXPORT CUresult cuStreamSynchronize_ptsz(CUstream s) {
+  int h;
+  vgpu_dev_rt *rt = current_rt(&h);
+  if (unlikely(!R.cuStreamSynchronize_ptsz)) return CUDA_ERROR_NOT_FOUND;
+  wait_until_unparked(rt, h, s, 1, 0);
+  return R.cuStreamSynchronize_ptsz(s);
+}
+VGPU_EXPORT CUresult cuEventSynchronize(CUevent e) {
+  int h;
+  vgpu_dev_rt *rt = current_rt(&h);
+  if (unlikely(!R.cuEventSynchronize)) return CUDA_ERROR_NOT_FOUND;
+  wait_until_unparked(rt, h, NULL, 0, 1); /* the event may sit behind any stream */
+  return R.cuEventSynchronize(e);
+}
+VGPU_EXPORT CUresult cuMemcpyDtoH_v2(void *dst, CUdeviceptr src, size_t n) {
+  int h;
+  vgpu_dev_rt *rt = current_rt(&h);
+  if (unlikely(!R.cuMemcpyDtoH_v2)) return CUDA_ERROR_NOT_FOUND;
+  wait_until_unparked(rt, h, NULL, 0, 1);
+  return R.cuMemcpyDtoH_v2(dst, src, n);
+}
+VGPU_EXPORT CUresult cuMemcpyDtoH_v2_ptds(void *dst, CUdeviceptr src, size_t n) {
+  int h;
+  vgpu_dev_rt *rt = current_rt(&h);
+  if (unlikely(!R.cuMemcpyDtoH_v2_ptds)) return CUDA_ERROR_NOT_FOUND;
+  wait_until_unparked(rt, h, NULL, 1, 0);
+  return R.cuMemcpyDtoH_v2_ptds(dst, src, n);
+}
+
+/* B200 addition: a device-wide synchronise must not wait for the resident governor, and must not
+ * block inside the driver while tenant work is still waiting for tokens */
 VGPU_EXPORT CUresult cuCtxSynchronize(void) {
   vgpu_boot();
   if (unlikely(!R.cuCtxSynchronize)) return CUDA_ERROR_NOT_FOUND;
   CUdevice dev;
   vgpu_dev_rt *rt = NULL;
   if (R.cuCtxGetDevice && R.cuCtxGetDevice(&dev) == CUDA_SUCCESS) rt = vgpu_rt_peek(vgpu_host_index_of_cuda(dev));
+  if (rt) wait_until_unparked(rt, rt->host_index, NULL, 0, 1);
   vgpu_limiter_quiesce(rt);
   __sync_fetch_and_add(&g_sync_waiters, 1);
   CUresult r = R.cuCtxSynchronize();

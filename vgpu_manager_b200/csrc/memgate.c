@@ -578,6 +578,7 @@ static CUresult free_sync(CUdeviceptr dptr) {
       return r;
     }
   }
+  if (rt) vgpu_limiter_before_blocking_call(rt);
   if (rt) vgpu_limiter_quiesce(rt);
   if (rt && scrub_on_free()) scrub(rt, dptr);
   r = R.cuMemFree_v2 ? R.cuMemFree_v2(dptr) : R.cuMemFree ? R.cuMemFree(dptr) : CUDA_ERROR_NOT_FOUND;

@@ -134,6 +134,7 @@ static uint64_t timed_ns(vgpu_dev_rt *rt, struct timespec *t0) {
 
 /* whole-device quiet point: nothing of the tenant may touch a slab while its backing is swapped */
 static void tenant_quiesce(vgpu_dev_rt *rt) {
+  vgpu_limiter_before_blocking_call(rt);
   vgpu_limiter_quiesce(rt);
   if (R.cuCtxSynchronize) R.cuCtxSynchronize();
   vgpu_limiter_resume(rt, 1);

@@ -119,6 +119,8 @@ void vgpu_log_emit(int level, const char *file, int line, const char *fmt, ...)
   X(cuStreamCreateWithPriority, CUresult, (CUstream *, unsigned int, int))                      \
   X(cuCtxGetStreamPriorityRange, CUresult, (int *, int *))                                      \
   X(cuStreamSynchronize, CUresult, (CUstream))                                                  \
+  X(cuStreamSynchronize_ptsz, CUresult, (CUstream))                                             \
+  X(cuMemcpyDtoH_v2_ptds, CUresult, (void *, CUdeviceptr, size_t))                              \
   X(cuStreamDestroy_v2, CUresult, (CUstream))                                                   \
   X(cuStreamQuery, CUresult, (CUstream))                                                        \
   X(cuStreamIsCapturing, CUresult, (CUstream, int *))                                           \
@@ -329,6 +331,7 @@ void vgpu_slab_forget(vgpu_dev_rt *rt); /* the context died: drop the host half 
 void vgpu_limiter_start(void); /* == reference initialization() (cuda_hook.c:566) */
 void vgpu_limiter_detach(int host_index); /* tick + watchdog threads stop touching this device's runtime */
 void vgpu_limiter_attach(int host_index, int forget_streams);
+void vgpu_limiter_before_blocking_call(vgpu_dev_rt *rt); /* wait in user space while tenant work is parked behind the gate */
 void vgpu_limiter_quiesce(vgpu_dev_rt *rt); /* device-wide sync ahead: governor retires once nothing is parked */
 void vgpu_limiter_resume(vgpu_dev_rt *rt, int everything_completed); /* the sync returned */
 

@@ -601,3 +601,28 @@ def test_slab_mode_spills_with_reference_accounting(built):
     assert st["promote_bytes"] == MiB64
     # HBM taken over from a victim is scrubbed before the newcomer sees it
     assert st["scrubbed_bytes"] == 2 * MiB64
+
+
+def test_enforcement_tunables_are_ignored_under_a_mounted_config(built):
+    """The tenant controls its environment.  When the control plane has mounted a vgpu.config the
+    enforcement-affecting VGPU_B200_* knobs must not be honoured (they are only when the limits came from
+    the tenant's own env anyway).  First run: env-built config, knob honoured (queue signal: a sampler
+    window per 10 ms tick).  Second run in the same sandbox: the config file now exists = "mounted" ->
+    default reading (one refill launch per 80 ms control period) although the knob is still set."""
+    env = dict(BASE)
+    env.update({"CUDA_MEM_LIMIT_0": "1g", "CUDA_CORE_LIMIT_0": "30", "STUB_UTIL": "fixed:20",
+                "VGPU_B200_UTIL_SOURCE": "queue", "VGPU_B200_SKIP_IDLE_WINDOWS": "0"})
+    script = "init 0\nlaunch 50 4 1 1\nsleepms 1000\nmetrics 0\n"
+    sb = H.Sandbox()
+    out1, _, _ = H.run_scenario(H.NEW_SO, script, env, sb=sb)
+    assert os.path.exists(sb.path("etc/vgpu-manager/config/vgpu.config"))
+    out2, _, _ = H.run_scenario(H.NEW_SO, script, env, sb=sb)
+    sb.cleanup()
+
+    def counts(out):
+        m = [l for l in out.splitlines() if l.startswith("metrics")][0].split()
+        return int(m[2]), int(m[6])
+    l1, s1 = counts(out1)
+    l2, s2 = counts(out2)
+    assert l1 >= 60 and l1 >= 5 * s1, (l1, s1)      # queue signal: ~100 windows, a step every 8th
+    assert 8 <= l2 <= 16 and l2 == s2, (l2, s2)     # mounted config: the knob is ignored

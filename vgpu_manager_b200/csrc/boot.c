@@ -241,7 +241,7 @@ static void put_field(char *dst, size_t cap, const char *name) {
 
 /* Build the config from the environment when the control plane did not drop a vgpu.config.
  * Field-for-field what reference loader.c:1927-2052 produces (the bytes are diffed against
- * the reference in tests/test_config_parity.py). */
+ * the reference in tests/test_oracle_parity.py and tests/test_differential_stub.py). */
 static void config_from_env(vgpu_cfg_t *c) {
   memset(c, 0, sizeof *c);
   const char *s = getenv("MANAGER_COMPATIBILITY_MODE");

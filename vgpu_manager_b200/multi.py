@@ -128,6 +128,7 @@ class RebalanceLoop(threading.Thread):
         CPU tests); `host_index` the tenant's index of that GPU inside its own config (defaults to `gpu`)."""
         super().__init__(daemon=True)
         self.gather = AllGather(dist, torch, device)
+        self.torch, self.device = torch, device
         self.gpu, self.quota, self.cfg_dir, self.lock_dir = gpu, quota_pct, cfg_dir, lock_dir
         self.host_index = gpu if host_index is None else host_index
         self.pressure = 0.0
@@ -140,6 +141,8 @@ class RebalanceLoop(threading.Thread):
 
     def run(self):
         prev = None
+        if str(self.device).startswith("cuda"):
+            self.torch.cuda.set_device(self.device)  # the current device is per thread
         for _ in range(self.rounds):
             t0 = time.perf_counter()
             st = read_status(self.lock_dir, self.host_index)

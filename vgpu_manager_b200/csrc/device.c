@@ -149,7 +149,14 @@ static vgpu_dev_rt *bring_up(vgpu_dev_rt *rt, int slot, int host_index, CUdevice
   }
 
   nvmlDevice_t nvdev = vgpu_nvml_handle_of_host(host_index);
-  int lock_fd = host_index >= 0 ? vgpu_lock_gpu(host_index) : -1;
+  /* The footprint measurement compares NVML's figure for THIS pid before and after: other
+   * processes cannot disturb it, so the per-GPU lock is only taken to publish the result.  (Holding it
+   * across module load + warm-ups serialised the bring-up of tenants that start together by
+   * 0.1-0.3 s each; the tenant that came up first then ramped its share alone and kept a
+   * multi-million-token head start for the rest of the run - the controller's increments are the
+   * same for everybody once they see the same reading, so start-up offsets never decay.  Measured as
+   * max/min = 4-8 between four 25 % tenants in one run out of three.) */
+  int lock_fd = -1;
   uint64_t before = own_process_bytes(nvdev);
 
   R.cuDeviceGetAttribute(&rt->sm_num, VCU_ATTR_SM_COUNT, dev);
@@ -307,6 +314,7 @@ static vgpu_dev_rt *bring_up(vgpu_dev_rt *rt, int slot, int host_index, CUdevice
 
   uint64_t after = own_process_bytes(nvdev);
   rt->self_bytes = after > before ? after - before : 0;
+  lock_fd = host_index >= 0 ? vgpu_lock_gpu(host_index) : -1;
   if (host_index >= 0 && lock_fd >= 0) vgpu_self_registry(host_index, rt->self_bytes, 1);
   vgpu_unlock_gpu(lock_fd);
   rt->fails = 0;

@@ -55,7 +55,9 @@ extern vgpu_dev_rt *vgpu_rt_get(int host_index, CUdevice dev);
 /* ------------------------------------------------------------------ stream slots
  * Every (stream, per-thread-default flag) of a device gets a slot in the pinned block: launch
  * sequence, completion marker, ticket ring.  Host-only bookkeeping lives here. */
-#define MARK_EVERY 256u             /* dense launch trains: one completion marker per 256 launches */
+#define MARK_EVERY 1024u            /* dense launch trains: one completion marker per 1024 launches (every marker is one more
+                                       operation for the GPU front-end, which is what bounds an empty-kernel storm:
+                                       one per 256 cost 0.4 % of the launch rate) */
 #define SPARSE_TSC 120000ull        /* launches further apart than ~50 us are each marked (on-device signals only) */
 #define SLOT_TOMB ((uintptr_t)1)    /* key of a slot whose stream was destroyed: reusable, but does not end a probe chain */
 typedef struct {

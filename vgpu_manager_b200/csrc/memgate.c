@@ -19,6 +19,45 @@
  */
 #include "vgpu_internal.h"
 
+#include <time.h>
+
+/* ------------------------------------------------------------------ phase profile (VGPU_B200_PROFILE=1)
+ * Where the time of an intercepted allocation / free goes, summed per phase and printed at exit:
+ * development aid for the allocator-storm comparison against the reference. */
+enum { PH_LOCK, PH_ARM, PH_COMPUTE_LIST, PH_STAGE, PH_GRAPHICS_LIST, PH_COLLECT, PH_DRIVER_ALLOC, PH_UNLOCK, PH_FREE_PRE, PH_DRIVER_FREE,
+       PH_FREE_POST, PH_COUNT };
+static const char *g_ph_names[PH_COUNT] = {"lock", "arm", "nvml_compute_list", "stage", "nvml_graphics_list", "collect", "driver_alloc",
+                                           "unlock", "free_pre", "driver_free", "free_post"};
+static uint64_t g_ph_ns[PH_COUNT], g_ph_n[PH_COUNT];
+static int g_prof = -1;
+static inline uint64_t prof_now(void) {
+  struct timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return (uint64_t)ts.tv_sec * 1000000000ull + (uint64_t)ts.tv_nsec;
+}
+static void prof_dump(void) {
+  for (int i = 0; i < PH_COUNT; i++)
+    if (g_ph_n[i]) fprintf(stderr, "[vGPU PROFILE] %-20s n %8llu  mean %8.0f ns\n", g_ph_names[i], (unsigned long long)g_ph_n[i], (double)g_ph_ns[i] / (double)g_ph_n[i]);
+}
+static inline int prof_on(void) {
+  if (unlikely(g_prof < 0)) {
+    const char *e = getenv("VGPU_B200_PROFILE");
+    g_prof = e && *e == '1';
+    if (g_prof) atexit(prof_dump);
+  }
+  return g_prof;
+}
+#define PROF_T0() uint64_t pt_ = prof_on() ? prof_now() : 0
+#define PROF(ph)                                 \
+  do {                                           \
+    if (g_prof > 0) {                            \
+      uint64_t n_ = prof_now();                  \
+      g_ph_ns[ph] += n_ - pt_;                   \
+      g_ph_n[ph]++;                              \
+      pt_ = n_;                                  \
+    }                                            \
+  } while (0)
+
 /* ------------------------------------------------------------------ limited memory view */
 typedef struct {
   int host_index;
@@ -205,14 +244,18 @@ static void memview(memview_t *mv, CUdevice dev, int host_index, nvmlDevice_t nv
     return;
   }
   mv->rt = rt;
+  PROF_T0();
   mv->lock_fd = vgpu_lock_gpu(host_index);
+  PROF(PH_LOCK);
   if (!nv) nv = vgpu_nvml_handle_of_host(host_index);
   if (!nv) VLOG(VL_ERROR, "cuda device %d cannot find the corresponding nvml devices", dev);
   pthread_mutex_lock(&rt->q_mu);
   vgpu_quota_req_t *q = rt->q_req;
   /* launch first: the kernel waits on the device for the publication while the host talks to NVML */
   uint32_t armed = (rt->quota_armed && nv) ? vgpu_rt_quota_arm(rt) : 0;
+  PROF(PH_ARM);
   int have_compute = stage_request(q, host_index, nv);
+  PROF(PH_COMPUTE_LIST);
   /* footprint of every live library instance of this container on this GPU (lock is held) */
   q->self_bytes = mv->lock_fd >= 0 ? vgpu_self_registry(host_index, rt->self_bytes, 0) : rt->self_bytes;
   q->kind = kind;
@@ -231,9 +274,12 @@ static void memview(memview_t *mv, CUdevice dev, int host_index, nvmlDevice_t nv
       /* speculate: graphics list unchanged since the previous evaluation (it is empty on a
        * compute-only part); the kernel decides while the second ioctl is in flight */
       vgpu_rt_quota_publish(rt, armed);
+      PROF(PH_STAGE);
       fetch_graphics(&scratch, nv);
+      PROF(PH_GRAPHICS_LIST);
       if (graphics_same(q, &scratch)) {
         done = vgpu_rt_quota_collect(rt, armed, &mv->res) == 0;
+        PROF(PH_COLLECT);
       } else {
         vgpu_quota_res_t drop;
         vgpu_rt_quota_collect(rt, armed, &drop); /* let the speculative evaluation finish before restaging */
@@ -401,13 +447,19 @@ static CUresult alloc_linear(CUdeviceptr *dptr, size_t bytes) {
     if (g.path == VGPU_PATH_UVA) {
       r = to_uva(&g, dptr, bytes);
     } else {
+      PROF_T0();
       r = R.cuMemAlloc_v2 ? R.cuMemAlloc_v2(dptr, bytes)
           : R.cuMemAlloc  ? R.cuMemAlloc(dptr, bytes)
                           : CUDA_ERROR_NOT_FOUND;
+      PROF(PH_DRIVER_ALLOC);
       if (DRIVER_OOM_RETRY(&g, r)) r = to_uva(&g, dptr, bytes);
     }
   }
-  gate_close(&g);
+  {
+    PROF_T0();
+    gate_close(&g);
+    PROF(PH_UNLOCK);
+  }
   return r;
 }
 VGPU_EXPORT CUresult cuMemAlloc_v2(CUdeviceptr *dptr, size_t bytes) { return alloc_linear(dptr, bytes); }
@@ -578,12 +630,16 @@ static CUresult free_sync(CUdeviceptr dptr) {
       return r;
     }
   }
+  PROF_T0();
   if (rt) vgpu_limiter_before_blocking_call(rt);
   if (rt) vgpu_limiter_quiesce(rt);
   if (rt && scrub_on_free()) scrub(rt, dptr);
+  PROF(PH_FREE_PRE);
   r = R.cuMemFree_v2 ? R.cuMemFree_v2(dptr) : R.cuMemFree ? R.cuMemFree(dptr) : CUDA_ERROR_NOT_FOUND;
+  PROF(PH_DRIVER_FREE);
   if (rt) vgpu_limiter_resume(rt, 0);
   if (r == CUDA_SUCCESS) ledger_sub(dev, dptr);
+  PROF(PH_FREE_POST);
   return r;
 }
 VGPU_EXPORT CUresult cuMemFree_v2(CUdeviceptr p) { return free_sync(p); }

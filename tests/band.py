@@ -124,6 +124,10 @@ def finish(p, sb, seconds):
         raise RuntimeError("tenant failed rc=%s\n%s" % (p.returncode, err[-2000:]))
     d = json.loads(out.strip().splitlines()[-1])
     d["rate"] = d["launches"] / d["wall_s"]
+    if os.environ.get("BAND_STDERR_DIR"):
+        os.makedirs(os.environ["BAND_STDERR_DIR"], exist_ok=True)
+        with open(os.path.join(os.environ["BAND_STDERR_DIR"], "tenant_%d.err" % p.pid), "w") as f:
+            f.write("# rate %.1f\n" % d["rate"] + err)
     if os.environ.get("BAND_DETAIL"):
         _DETAIL.append({"pid": p.pid, "rate": d["rate"], "gated": d.get("gated_launches"), "loans": d.get("watchdog_loans"),
                         "refills": d.get("sampler_launches"), "limiter": d.get("limiter"), "max_ns": d.get("max_ns"),

@@ -626,3 +626,19 @@ def test_enforcement_tunables_are_ignored_under_a_mounted_config(built):
     l2, s2 = counts(out2)
     assert l1 >= 60 and l1 >= 5 * s1, (l1, s1)      # queue signal: ~100 windows, a step every 8th
     assert 8 <= l2 <= 16 and l2 == s2, (l2, s2)     # mounted config: the knob is ignored
+
+
+def test_watcher_runs_from_cuinit_and_the_controller_catches_up(built):
+    """The reference's watcher steps from the first successful cuInit (cuda_hook.c:566-577), i.e. while the
+    application is still creating its context.  The device-resident controller can only exist once a
+    context does, so the tick thread keeps the publications of the periods that elapse before that and
+    replays them through vgpu_refill_kernel the moment the runtime is up: one second between cuInit and
+    the first launch => about twelve control steps already taken when the first launch returns."""
+    env = dict(BASE)
+    env.update({"CUDA_MEM_LIMIT_0": "1g", "CUDA_CORE_LIMIT_0": "30", "STUB_UTIL": "fixed:3", "LOGGER_LEVEL": "3"})
+    out, err, sb = H.run_scenario(H.NEW_SO, "init 0\nsleepms 1000\nlaunch 3 1 1 1\nsleepms 30\nmetrics 0\n", env)
+    sb.cleanup()
+    m = [l for l in out.splitlines() if l.startswith("metrics")][0].split()
+    launches, steps = int(m[2]), int(m[6])
+    assert 10 <= steps <= 16 and launches == steps, out
+    assert "replayed" in err and "control periods that elapsed before the device runtime came up" in err

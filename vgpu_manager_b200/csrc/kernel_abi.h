@@ -133,7 +133,7 @@ VGPU_STATIC_ASSERT(sizeof(vgpu_vslab_slot_t) == 32, vslab_slot);
 /* ---------------------------------------------------------------- limiter */
 
 #define VGPU_STREAM_SLOTS 64u
-#define VGPU_TICKET_RING 4096u /* per stream slot; power of two (64 x 4096 x 8 B = 2 MiB of pinned memory) */
+#define VGPU_TICKET_RING 1024u /* per stream slot; power of two */
 #define VGPU_MAX_SMS 256u
 enum { VGPU_SRC_QUEUE = 0, VGPU_SRC_SM = 1, VGPU_SRC_MAX = 2, VGPU_SRC_NVML = 3 }; /* vgpu_lim_host_t.util_source */
 #define VGPU_SAMPLER_PROBE_ONLY 0x7fffffffu /* sampler period_ticks value: probe SMs, leave the queue signal and the controller to the governor */

@@ -314,6 +314,7 @@ def main():
     ap.add_argument("--per-step", type=int, default=PER_STEP)
     ap.add_argument("--core-limit", type=int, default=0, help="override the config's core cap (percent)")
     ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--no-rebalance", action="store_true", help="N > 1: do not run the cross-tenant rebalance loop beside the tenants")
     ap.add_argument("--no-extras", action="store_true", help="skip the bare / allocator / cpu_baseline legs")
     ap.add_argument("--roofline-only", action="store_true",
                     help="only the in-process bandwidth kernels (the form profiled under ncu: a tenant that runs with the "
@@ -378,7 +379,7 @@ def main():
     # N > 1, B200 arm: every rank also plays its GPU's node agent while the tenant runs - gather -> plan ->
     # apply once per control period (the only collective of the job)
     agent, loops = None, []
-    if distributed and args.impl == "b200":
+    if distributed and args.impl == "b200" and not args.no_rebalance:
         from vgpu_manager_b200.multi import RebalanceLoop
         rounds = int(((args.steps + args.warmup) * per_step / 450e3 + 1.0) / 0.08)
 
@@ -490,10 +491,10 @@ def main():
         "clocks": clk,
         "e2e": {"value": round(total / life_max, 1), "unit": "launches/s",
                 "h2d_bytes_per_step": 16 * per_step if args.impl == "b200" else 0,
-                "d2h_bytes_per_step": 8 * per_step // 256 if args.impl == "b200" else 0,
+                "d2h_bytes_per_step": 8 * per_step // 640 if args.impl == "b200" else 0,
                 "what": "same K steps on the tenant's HOST clock around launch calls + device sync, through the "
                         "LD_PRELOADed hook; h2d = ticket + sequence words the hook publishes per launch in pinned "
-                        "memory (read by the controller over PCIe), d2h = completion markers (one per 256 launches)"},
+                        "memory (read by the controller over PCIe), d2h = completion markers (one per 640 launches)"},
         "tenant_process_life_s": round(res["life_s"], 3),
         "gpu_launches": int(sum(r[5] for r in rows)) + own_launches,
         "gated_launches": int(sum(r[6] for r in rows)),

@@ -259,6 +259,7 @@ def main():
     ap.add_argument("--runs", type=int, default=5)
     ap.add_argument("--shapes", default=",".join(ALL))
     ap.add_argument("--out", default=os.path.join(H.ROOT, "gpurun_out", "tolerance_band.json"))
+    ap.add_argument("--append", default=None, help="an existing band file of the same impl: its runs are kept and these are added")
     args = ap.parse_args()
     H.build_all()
     lib = H.REF_SO if args.impl == "reference" else H.NEW_SO
@@ -271,7 +272,23 @@ def main():
             runs.append(r)
             print("%s[%d] %s" % (name, i, json.dumps(r)), file=sys.stderr, flush=True)
         shapes[name] = fold(runs)
-    out = {"impl": args.impl, "library": os.path.relpath(lib, H.ROOT), "runs": args.runs, "baselines": ctx,
+    runs_note = {args.shapes: args.runs}
+    if args.append and os.path.exists(args.append):
+        with open(args.append) as f:
+            old = json.load(f)
+        assert old.get("impl") == args.impl, "cannot mix libraries in one band"
+        for name, metrics in old["shapes"].items():
+            if name not in shapes:
+                shapes[name] = metrics
+                continue
+            for m, e in metrics.items():
+                vals = e["values"] + shapes[name].get(m, {"values": []})["values"]
+                shapes[name][m] = {"min": min(vals), "max": max(vals), "mean": sum(vals) / len(vals), "values": vals}
+        prev = old.get("runs")
+        runs_note = {"earlier sessions": prev, "this session": runs_note}
+        for k, v in old.get("baselines", {}).items():
+            ctx.setdefault(k + "_earlier", v)
+    out = {"impl": args.impl, "library": os.path.relpath(lib, H.ROOT), "runs": runs_note, "baselines": ctx,
            "seconds": round(time.time() - t0, 1), "host_cores": os.cpu_count(),
            "tenant_cpus": "NUMA-local to GPU 0 (%d cpus)" % len(local_cpus()) if local_cpus() else "not pinned",
            "gpu": subprocess.run(["nvidia-smi", "--query-gpu=name,driver_version", "--format=csv,noheader"],

@@ -182,6 +182,10 @@ def run_gemm(lib, count, cap, seconds=12.0):
         if p.returncode != 0 or not lines:
             raise RuntimeError("gemm tenant failed rc=%s\n%s" % (p.returncode, err[-2000:]))
         rates.append(json.loads(lines[-1])["gemms_per_s"])
+        if os.environ.get("BAND_STDERR_DIR"):
+            os.makedirs(os.environ["BAND_STDERR_DIR"], exist_ok=True)
+            with open(os.path.join(os.environ["BAND_STDERR_DIR"], "gemm_%d.err" % p.pid), "w") as f:
+                f.write("# gemms_per_s %.1f\n" % rates[-1] + err)
     return rates
 
 
@@ -198,8 +202,20 @@ CHEAP = ("storm10", "storm25", "storm50", "neighbour", "fair4")
 ALL = CHEAP + ("gemm1", "gemm4")
 
 
+SETTLE_S = 2.5
+
+
 def run_shape(name, lib, ctx):
-    """ctx carries the un-capped baselines (measured once per session, without any library)."""
+    """ctx carries the un-capped baselines (measured once per session, without any library).
+    Every run starts on a GPU that has been idle for SETTLE_S: NVML keeps the previous measurement's
+    per-process samples "fresh" for a second, HOST mode sums them into everybody's first readings, and
+    the first readings decide how full the bucket gets before the cap starts to bite (the start-up lottery
+    visible in both libraries' logs, profiles/README.md)."""
+    if name in ("gemm1", "gemm4") and "gemm_alone" not in ctx:
+        ctx["gemm_alone"] = run_gemm(None, 1, 0)[0]
+    if name == "neighbour" and "neighbour_alone" not in ctx:
+        ctx["neighbour_alone"] = neighbour_alone()
+    time.sleep(SETTLE_S)
     if name == "storm10":
         return shape_storm(lib, 10)
     if name == "storm25":

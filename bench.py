@@ -189,7 +189,7 @@ def run_in_tenant(H, cmd, lib, gpu, uuids, core_limit, extra=None, timeout=300.0
         raise RuntimeError("tenant failed rc=%d\n%s\n%s" % (r.returncode, r.stdout[-2000:], r.stderr[-3000:]))
     d = json.loads(r.stdout.strip().splitlines()[-1])
     d["life_s"] = life
-    d["stderr_tail"] = r.stderr[-400:]
+    d["stderr_tail"] = r.stderr[-1500:]
     return d
 
 
@@ -290,14 +290,16 @@ def bandwidth_kernels(lib_path, peaks):
         if i >= 3:
             ctimes.append(e0.elapsed_time(e1) * 1e-3)
     cavg = sum(ctimes) / len(ctimes)
+    del src, dst
+    torch.cuda.empty_cache()  # HOST mode counts this process too: give the memory back before the tenants' memory legs
     peak = peaks.get("hbm_gbs", 6650.0)
     achieved = 2 * n / avg / 1e9
     return {"bound": "hbm", "kernel": "vgpu_spill_copy_kernel", "achieved": round(achieved, 1), "peak": peak,
             "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "6650 GB/s (of fallback)",
             "unit": "GB/s", "frac": round(achieved / peak, 4),
-            # not measured by this run: dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel
-            # at this size from profiles/ncu_spill_copy_r1.txt (ncu --set full, round 1: 1.073823 + 1.026727 GB)
-            "traffic": None, "traffic_ncu_r1_constant": 2100550000,
+            # not measured by this run: dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel at this
+            # size (ncu --set full, round 2, profiles/ncu_bandwidth_kernels_r2.csv: 1.073814 + 1.026304 GB)
+            "traffic": None, "traffic_ncu_r2_constant": 2100118000,
             "algorithmic_bytes_per_launch": 2 * n, "avg_launch_ms": round(avg * 1e3, 4), "best_launch_ms": round(min(times) * 1e3, 4),
             "launches_timed": len(times),
             "clear": {"kernel": "vgpu_clear_kernel", "achieved": round(n / cavg / 1e9, 1), "unit": "GB/s",
@@ -440,7 +442,10 @@ def main():
                 # clear figures stay alongside as `utility`
                 roof = {"bound": "hbm", "kernel": mem_path["scrub"]["kernel"], "achieved": mem_path["scrub"]["achieved"],
                         "peak": mem_path["scrub"]["peak"], "peak_source": roof["peak_source"], "unit": "GB/s",
-                        "frac": mem_path["scrub"]["frac"], "traffic": None,
+                        "frac": mem_path["scrub"]["frac"],
+                        # not measured by this run: dram__bytes_read.sum + dram__bytes_write.sum of one 1 GiB launch of this kernel
+                        # (ncu --set full, round 2, profiles/ncu_bandwidth_kernels_r2.csv: 0.000033 + 1.013717 GB)
+                        "traffic": None, "traffic_ncu_r2_constant": 1013750000,
                         "algorithmic_bytes_per_launch": mem_path["scrub"]["algorithmic_bytes"] // max(mem_path["scrub"]["launches"], 1),
                         "launches_timed": mem_path["scrub"]["launches"], "timed_by": "CUDA events recorded by the hook around its own launch",
                         "utility": roof}

@@ -857,7 +857,9 @@ static inline int admit(admit_t *a, unsigned gx, unsigned gy, unsigned gz, CUstr
   if (unlikely((long long)(H->launched[a->slot] + 1 - H->done[a->slot]) >= (long long)VGPU_TICKET_RING - 64)) {
     /* wait for the stream to drain a little; never forever - if completion markers stopped
      * arriving (driver refused the mem-op, context torn down) fall back to marker-less mode */
-    if (sl->marked < H->launched[a->slot] && rt->memops64 > 0 && !stream_capturing(s, ptsz))
+    /* a marker is only added here when none is in flight (the regular one-per-MARK_EVERY markers
+     * normally guarantee progress; every extra one is another operation for the GPU front-end) */
+    if (sl->marked <= H->done[a->slot] && sl->marked < H->launched[a->slot] && rt->memops64 > 0 && !stream_capturing(s, ptsz))
       enqueue_marker(rt, h, a->slot, H->launched[a->slot], s, ptsz);
     struct timespec t0, t1;
     clock_gettime(CLOCK_MONOTONIC, &t0);

@@ -111,6 +111,12 @@ int vgpu_b200_quota_eval(const void *req /* vgpu_quota_req_t */, void *res /* vg
 int vgpu_b200_slab_insert(unsigned long long dptr, unsigned long long bytes);
 int vgpu_b200_slab_remove(unsigned long long dptr, unsigned long long *bytes);
 
+/* One operation on the slab placement table of the VGPU_B200_SLAB mode (vgpu_vslab_req_t ->
+ * vgpu_vslab_res_t, kernel_abi.h): PUT = free-slot scan + insert, TAKE = lookup + remove, SCAN =
+ * coldest slab of a size class in a given placement, its placement bits flipped in the same
+ * launch (the spill / promote decision).  0 / -1. */
+int vgpu_b200_vslab_op(const void *req /* vgpu_vslab_req_t */, void *res /* vgpu_vslab_res_t */);
+
 typedef struct {
   long long granted;   /* cumulative grant (HBM)                                   */
   long long consumed;  /* cumulative consumption (host hook)                       */

@@ -134,6 +134,72 @@ def util_req_from_golden_step(mode, st, seq):
     return u
 
 
+class VslabReq(C.Structure):
+    _fields_ = [("op", C.c_uint32), ("mask", C.c_uint32), ("want", C.c_uint32), ("set_mask", C.c_uint32), ("set_val", C.c_uint32),
+                ("age", C.c_uint32), ("dptr", C.c_uint64), ("bytes", C.c_uint64), ("size", C.c_uint64), ("state", C.c_uint32),
+                ("_pad", C.c_uint32)]
+
+
+class VslabRes(C.Structure):
+    _fields_ = [("dptr", C.c_uint64), ("bytes", C.c_uint64), ("size", C.c_uint64), ("state", C.c_uint32), ("age", C.c_uint32),
+                ("slot", C.c_uint32), ("seq_done", C.c_uint32)]
+
+
+VS_PUT, VS_TAKE, VS_SCAN, VS_UVA, VS_DEV = 0, 1, 2, 1, 2
+
+
+def vslab_model_check(lib, seed=0x5EED, ops=400):
+    """Random PUT / TAKE / SCAN(+flip) against a dictionary model of the placement table; returns the number of
+    operations compared.  Used on the fake driver (plumbing) and on the GPU (the kernel itself)."""
+    import random
+    rng = random.Random(seed)
+    model, age = {}, 0   # dptr -> [bytes, size, state, age]
+    sizes = [2 << 20, 64 << 20, 256 << 20]
+    n = 0
+    for _ in range(ops):
+        kind = rng.random()
+        rq, rs = VslabReq(), VslabRes()
+        if kind < 0.45 or not model:
+            age += 1
+            d = (rng.randrange(1, 1 << 20) << 21)
+            size = rng.choice(sizes)
+            st = rng.choice([VS_DEV, VS_UVA | VS_DEV, VS_UVA, 0])
+            rq.op, rq.dptr, rq.bytes, rq.size, rq.state, rq.age = VS_PUT, d, size - rng.randrange(0, 4096), size, st, age
+            lib.vslab_op(rq, rs)
+            assert rs.slot != 0xFFFFFFFF
+            model[d] = [rq.bytes, size, st, age]
+        elif kind < 0.7:
+            d = rng.choice(list(model)) if rng.random() < 0.8 else 0x123456000
+            rq.op, rq.dptr = VS_TAKE, d
+            lib.vslab_op(rq, rs)
+            if d in model:
+                assert (rs.dptr, rs.bytes, rs.size, rs.state) == (d, model[d][0], model[d][1], model[d][2]), (d, model[d])
+                del model[d]
+            else:
+                assert rs.slot == 0xFFFFFFFF
+        else:
+            size = rng.choice(sizes)
+            want = rng.choice([VS_DEV, VS_UVA | VS_DEV, 0])
+            flip = VS_DEV if not (want & VS_DEV) else 0
+            rq.op, rq.mask, rq.want, rq.set_mask, rq.set_val, rq.size = VS_SCAN, VS_UVA | VS_DEV, want, VS_DEV, flip, size
+            lib.vslab_op(rq, rs)
+            cands = [(v[3], d) for d, v in model.items() if v[1] == size and (v[2] & 3) == want]
+            if not cands:
+                assert rs.slot == 0xFFFFFFFF, (size, want, rs.dptr)
+            else:
+                _, d = min(cands)   # coldest = smallest age
+                assert rs.dptr == d and rs.state == model[d][2], (rs.dptr, d)
+                model[d][2] = (model[d][2] & ~VS_DEV) | flip
+        n += 1
+    # drain: everything that is left must come back exactly once
+    for d in list(model):
+        rq, rs = VslabReq(), VslabRes()
+        rq.op, rq.dptr = VS_TAKE, d
+        lib.vslab_op(rq, rs)
+        assert rs.dptr == d and rs.state == model[d][2]
+    return n
+
+
 class QuotaRes(C.Structure):
     _fields_ = [("used", C.c_uint64), ("vmem", C.c_uint64), ("total", C.c_uint64), ("out_used", C.c_uint64),
                 ("out_free", C.c_uint64), ("path", C.c_uint32), ("seq_done", C.c_uint32)]

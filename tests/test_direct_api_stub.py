@@ -42,6 +42,7 @@ for i, st in enumerate(tr["steps"][:60]):
     rf.append([s.share, s.granted - s.consumed, s.up_limit, s.valid] == st["out"][:4])
     bucket = st["out"][1]
 out["refill_ok"] = all(rf)
+out["vslab_ops"] = H.vslab_model_check(lib, ops=150)
 # memory: quota decision and numbers
 q = H.QuotaReq()
 q.kind, q.mode, q.n_compute, q.total_memory, q.real_memory = 0, 0, 3, 1 << 30, 1 << 30
@@ -83,7 +84,7 @@ def test_direct_api_round_trip_on_the_fake_driver():
     sb.cleanup()
     assert r.returncode == 0, r.stderr[-3000:]
     out = json.loads([l for l in r.stdout.splitlines() if l.startswith("RESULT ")][-1][7:])
-    assert "sm_100a" in out["version"] and out["copy_ok"] and out["clear_ok"] and out["refill_ok"]
+    assert "sm_100a" in out["version"] and out["copy_ok"] and out["clear_ok"] and out["refill_ok"] and out["vslab_ops"] == 150
     assert out["quota"] == [900 << 20, 2]
     # the same trajectory from the oracle (= reference arithmetic, tests/test_oracle_parity.py)
     o = H.oracle()

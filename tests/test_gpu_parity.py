@@ -223,6 +223,13 @@ def test_slab_matches_dictionary_model(gpu):
     assert lib.slab_remove(keys[0])[0] == 1
 
 
+def test_vslab_kernel_matches_dictionary_model(gpu):
+    """vgpu_vslab_kernel (slab placement table of the VGPU_B200_SLAB mode): free-slot scan, lookup, and the
+    coldest-victim scan with the placement flip, 600 random operations against a dictionary model."""
+    lib, torch = gpu
+    assert H.vslab_model_check(lib, ops=600) == 600
+
+
 # ----------------------------------------------------------------------------- controller
 def test_controller_kernel_replays_reference_watcher(gpu):
     """Every golden trajectory was produced by the reference's utilization_watcher thread; the

@@ -729,6 +729,26 @@ VGPU_EXPORT int vgpu_b200_refill(const void *util_req, vgpu_b200_limiter_state_t
   return rc;
 }
 
+/* One operation on the slab placement table (vgpu_vslab_req_t / vgpu_vslab_res_t, kernel_abi.h):
+ * free-slot scan + insert, lookup + remove, or coldest-victim scan with the placement flip. */
+VGPU_EXPORT int vgpu_b200_vslab_op(const void *req, void *res) {
+  vgpu_dev_rt *rt = attached();
+  if (!rt || !req || !res) return -1;
+  pthread_mutex_lock(&rt->q_mu);
+  vgpu_vslab_req_t rq = *(const vgpu_vslab_req_t *)req;
+  uint32_t seq = ++rt->seq;
+  if (!seq) seq = ++rt->seq;
+  void *params[] = {&rt->vslab_d, &rq, &rt->vs_res_d, &seq};
+  int rc = -1;
+  if (vgpu_rt_launch(rt, rt->k_vslab, 1, 1024, 0, rt->q_stream, params) == CUDA_SUCCESS &&
+      R.cuStreamSynchronize(rt->q_stream) == CUDA_SUCCESS && rt->vs_res->seq_done == seq) {
+    *(vgpu_vslab_res_t *)res = *rt->vs_res;
+    rc = 0;
+  }
+  pthread_mutex_unlock(&rt->q_mu);
+  return rc;
+}
+
 VGPU_EXPORT int vgpu_b200_limiter_consume(long long tokens) {
   vgpu_dev_rt *rt = attached();
   if (!rt) return -1;

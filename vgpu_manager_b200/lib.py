@@ -57,6 +57,7 @@ class B200Library:
         h.vgpu_b200_limiter_step.argtypes = [C.c_int] * 4 + [C.POINTER(LimiterState)]
         h.vgpu_b200_limiter_consume.argtypes = [C.c_longlong]
         h.vgpu_b200_refill.argtypes = [C.c_void_p, C.POINTER(LimiterState)]
+        h.vgpu_b200_vslab_op.argtypes = [C.c_void_p, C.c_void_p]
         h.vgpu_b200_limiter_state.argtypes = [C.POINTER(LimiterState)]
         h.vgpu_b200_sampler_run.argtypes = [C.c_uint, C.c_uint, C.c_uint, C.c_int, C.POINTER(LimiterState)]
         h.vgpu_b200_self_bytes.restype = C.c_ulonglong
@@ -112,6 +113,11 @@ class B200Library:
         st = LimiterState()
         self._check(self.h.vgpu_b200_refill(C.byref(util_req), C.byref(st)), "vgpu_b200_refill")
         return st
+
+    def vslab_op(self, req, res):
+        """One slab-placement-table operation (structs mirror kernel_abi.h)."""
+        self._check(self.h.vgpu_b200_vslab_op(C.byref(req), C.byref(res)), "vgpu_b200_vslab_op")
+        return res
 
     def limiter_consume(self, tokens):
         self._check(self.h.vgpu_b200_limiter_consume(tokens), "vgpu_b200_limiter_consume")

@@ -33,4 +33,5 @@ for n in (2, 1024):
     q.request = 1 << 20
     for _ in range(3):
         lib.quota_eval(q, H.QuotaRes())
+print("vslab ops", H.vslab_model_check(lib, ops=int(os.environ.get("VSLAB_OPS", "200"))))
 print("done")

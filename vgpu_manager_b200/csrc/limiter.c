@@ -1128,6 +1128,22 @@ VGPU_EXPORT CUresult cuMemcpyDtoH_v2_ptds(void *dst, CUdeviceptr src, size_t n) 
   return R.cuMemcpyDtoH_v2_ptds(dst, src, n);
 }
 
+/* the synchronous copies order behind everything on the legacy stream (per-thread stream for _ptds) */
+#define BLOCKING_COPY(name, ptsz, T1, T2)                                  \
+  VGPU_EXPORT CUresult name(T1 dst, T2 src, size_t n) {                    \
+    int h;                                                                 \
+    vgpu_dev_rt *rt = current_rt(&h);                                      \
+    if (unlikely(!R.name)) return CUDA_ERROR_NOT_FOUND;                    \
+    wait_until_unparked(rt, h, NULL, ptsz, !(ptsz));                       \
+    return R.name(dst, src, n);                                            \
+  }
+BLOCKING_COPY(cuMemcpyHtoD_v2, 0, CUdeviceptr, const void *)
+BLOCKING_COPY(cuMemcpyHtoD_v2_ptds, 1, CUdeviceptr, const void *)
+BLOCKING_COPY(cuMemcpyDtoD_v2, 0, CUdeviceptr, CUdeviceptr)
+BLOCKING_COPY(cuMemcpyDtoD_v2_ptds, 1, CUdeviceptr, CUdeviceptr)
+BLOCKING_COPY(cuMemcpy, 0, CUdeviceptr, CUdeviceptr)
+BLOCKING_COPY(cuMemcpy_ptds, 1, CUdeviceptr, CUdeviceptr)
+
 /* B200 addition: a device-wide synchronise must not wait for the resident governor, and must not
  * block inside the driver while tenant work is still waiting for tokens */
 VGPU_EXPORT CUresult cuCtxSynchronize(void) {

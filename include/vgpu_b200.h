@@ -71,9 +71,8 @@ typedef int vb_nvmlReturn;               /* nvmlReturn_t  */
  *  cuStreamSynchronize / _ptsz              (none - B200 addition: blocking calls of a throttled tenant first
  *  cuEventSynchronize                         wait in user space while its work is parked behind the gate -
  *  cuMemcpyDtoH_v2 / _ptds                    where the reference's thread would be asleep in rate_limiter)
- *  cuMemcpyHtoD_v2 / _ptds                  (same: the synchronous copies order behind the legacy /
- *  cuMemcpyDtoD_v2 / _ptds                    per-thread stream)
- *  cuMemcpy / _ptds
+ *  cuMemcpyHtoD_v2 / _ptds                  (same: synchronous copies that may involve host memory wait
+ *  cuMemcpy / _ptds                           for the legacy / per-thread stream inside the driver)
  *  cuStreamDestroy_v2                       (none - B200 addition: releases the stream's
  *                                            completion-marker slot)
  *  cuCtxDestroy / _v2                       (none - B200 addition: the token bucket, slab, streams and

@@ -9,6 +9,8 @@
  *   storm [--steps K] [--warmup W] [--per-step L] [--threads T] [--sync-every S] [--device D]
  *         [--no-kernel] [--max-seconds X] [--n N (== --steps 1 --per-step N)]
  *         [--spin-iters I --grid G --block B]   busy kernel instead of the empty one
+ *         [--block-with sync|htod|dtoh|dtod|copy]  which blocking call --sync-every issues (default cuCtxSynchronize;
+ *                                               the others are 256 KiB synchronous copies on a scratch allocation)
  *         [--stream null|created|ptsz]          legacy stream (default), one created stream per thread, or the
  *                                               per-thread default stream through the _ptsz entry point
  */
@@ -46,6 +48,25 @@ static void *g_ctx, *g_func;
 static int g_stream_mode; /* 0 legacy NULL stream, 1 one created stream per thread, 2 per-thread default stream (_ptsz entry) */
 static CUresult (*p_stream_create)(void **, unsigned);
 static long g_per_step = 200000, g_sync_every = 0;
+static int g_block_with; /* 0 cuCtxSynchronize, 1 HtoD, 2 DtoH, 3 DtoD, 4 cuMemcpy */
+static unsigned long long g_scratch;
+static CUresult (*p_htod)(unsigned long long, const void *, size_t);
+static CUresult (*p_dtoh)(void *, unsigned long long, size_t);
+static CUresult (*p_dtod)(unsigned long long, unsigned long long, size_t);
+static CUresult (*p_copy)(unsigned long long, unsigned long long, size_t);
+
+#define BLOCK_BYTES (256u << 10) /* pageable and larger than the driver's inline-copy threshold: the call has to wait for the stream */
+static CUresult block_now(void) {
+  static __thread unsigned char *buf;
+  if (!buf) buf = calloc(1, BLOCK_BYTES);
+  switch (g_scratch ? g_block_with : 0) {
+  case 1: return p_htod(g_scratch, buf, BLOCK_BYTES);
+  case 2: return p_dtoh(buf, g_scratch, BLOCK_BYTES);
+  case 3: return p_dtod(g_scratch + BLOCK_BYTES, g_scratch, BLOCK_BYTES);
+  case 4: return p_copy(g_scratch, (unsigned long long)(uintptr_t)buf, BLOCK_BYTES); /* unified addressing: host -> device */
+  default: return p_sync();
+  }
+}
 static unsigned g_spin_iters = 0, g_grid = 1, g_block = 1;
 static void *g_kparams[1];
 static int g_threads = 1, g_steps = 1, g_warmup = 0;
@@ -73,7 +94,7 @@ static void *worker(void *arg) {
     uint64_t b = now_ns();
     if (w->record) w->lat[i] = (uint32_t)((b - a) > 0xffffffffull ? 0xffffffffull : (b - a));
     w->fails += r != 0;
-    if (g_sync_every && ((i + 1) % g_sync_every) == 0) p_sync();
+    if (g_sync_every && ((i + 1) % g_sync_every) == 0) w->fails += block_now() != 0;
     if (g_deadline_ns && (i & 1023) == 0 && b > g_deadline_ns) g_stop = 1;
   }
   w->done = i;
@@ -101,6 +122,10 @@ int main(int argc, char **argv) {
     else if (!strcmp(argv[i], "--grid") && i + 1 < argc) g_grid = (unsigned)atol(argv[++i]);
     else if (!strcmp(argv[i], "--block") && i + 1 < argc) g_block = (unsigned)atol(argv[++i]);
     else if (!strcmp(argv[i], "--stream") && i + 1 < argc) { i++; g_stream_mode = !strcmp(argv[i], "created") ? 1 : !strcmp(argv[i], "ptsz") ? 2 : 0; }
+    else if (!strcmp(argv[i], "--block-with") && i + 1 < argc) {
+      i++;
+      g_block_with = !strcmp(argv[i], "htod") ? 1 : !strcmp(argv[i], "dtoh") ? 2 : !strcmp(argv[i], "dtod") ? 3 : !strcmp(argv[i], "copy") ? 4 : 0;
+    }
     else if (!strcmp(argv[i], "--no-kernel")) no_kernel = 1;
   }
   if (g_threads < 1) g_threads = 1;
@@ -128,6 +153,15 @@ int main(int argc, char **argv) {
     void *mod = NULL;
     if (p_modload(&mod, k_ptx) || p_getfn(&g_func, mod, g_spin_iters ? "spin_kernel" : "empty_kernel")) { fprintf(stderr, "storm: module load failed\n"); return 4; }
     g_kparams[0] = &g_spin_iters;
+  }
+  if (g_block_with) {
+    CUresult (*p_alloc)(unsigned long long *, size_t) = dlsym(h_cuda, "cuMemAlloc_v2");
+    p_htod = dlsym(h_cuda, "cuMemcpyHtoD_v2");
+    p_dtoh = dlsym(h_cuda, "cuMemcpyDtoH_v2");
+    p_dtod = dlsym(h_cuda, "cuMemcpyDtoD_v2");
+    p_copy = dlsym(h_cuda, "cuMemcpy");
+    int ok = g_block_with == 1 ? !!p_htod : g_block_with == 2 ? !!p_dtoh : g_block_with == 3 ? !!p_dtod : !!p_copy;
+    if (!ok || !p_alloc || p_alloc(&g_scratch, 2 * BLOCK_BYTES)) { fprintf(stderr, "storm: --block-with needs the copy entry point and a scratch allocation\n"); return 5; }
   }
   /* first launches pay lazy loading and, under a preload library, its device bring-up */
   for (int i = 0; i < (g_spin_iters ? 50 : 2000); i++) p_launch(g_func, g_grid, 1, 1, g_block, 1, 1, 0, NULL, g_spin_iters ? g_kparams : NULL, NULL);

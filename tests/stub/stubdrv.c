@@ -384,6 +384,8 @@ EXPORT CUresult cuMemGetAddressRange_v2(CUdeviceptr *base, size_t *size, CUdevic
 EXPORT CUresult cuMemsetD8_v2(CUdeviceptr d, unsigned char v, size_t n) { memset((void *)(uintptr_t)d, v, n); return 0; }
 EXPORT CUresult cuMemcpyDtoH_v2(void *dst, CUdeviceptr src, size_t n) { memcpy(dst, (void *)(uintptr_t)src, n); return 0; }
 EXPORT CUresult cuMemcpyHtoD_v2(CUdeviceptr dst, const void *src, size_t n) { memcpy((void *)(uintptr_t)dst, src, n); return 0; }
+EXPORT CUresult cuMemcpyDtoD_v2(CUdeviceptr dst, CUdeviceptr src, size_t n) { memmove((void *)(uintptr_t)dst, (void *)(uintptr_t)src, n); return 0; }
+EXPORT CUresult cuMemcpy(CUdeviceptr dst, CUdeviceptr src, size_t n) { memmove((void *)(uintptr_t)dst, (void *)(uintptr_t)src, n); return 0; }
 
 /* STUB_CTX_LOCK=1 models the real driver's context lock: a call that blocks on the stream (here
  * the wait itself, on a real GPU e.g. a pageable memcpy behind a parked kernel) keeps every other
@@ -954,6 +956,8 @@ static const struct { const char *name; void *fn; } g_self_table[] = {
   {"cuMemsetD8_v2", (void *)cuMemsetD8_v2},
   {"cuMemcpyDtoH_v2", (void *)cuMemcpyDtoH_v2},
   {"cuMemcpyHtoD_v2", (void *)cuMemcpyHtoD_v2},
+  {"cuMemcpyDtoD_v2", (void *)cuMemcpyDtoD_v2},
+  {"cuMemcpy", (void *)cuMemcpy},
   {"cuStreamCreate", (void *)cuStreamCreate},
   {"cuStreamCreateWithPriority", (void *)cuStreamCreateWithPriority},
   {"cuStreamDestroy_v2", (void *)cuStreamDestroy_v2},

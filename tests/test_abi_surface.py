@@ -33,7 +33,7 @@ def test_exports_the_reference_hook_surface_and_nothing_accidental(built):
     ctx_teardown = {"cuCtxDestroy", "cuCtxDestroy_v2", "cuDevicePrimaryCtxReset", "cuDevicePrimaryCtxReset_v2",
                     "cuDevicePrimaryCtxRelease", "cuDevicePrimaryCtxRelease_v2"}
     blocking = {"cuStreamSynchronize", "cuStreamSynchronize_ptsz", "cuEventSynchronize", "cuMemcpyDtoH_v2", "cuMemcpyDtoH_v2_ptds",
-                "cuMemcpyHtoD_v2", "cuMemcpyHtoD_v2_ptds", "cuMemcpyDtoD_v2", "cuMemcpyDtoD_v2_ptds", "cuMemcpy", "cuMemcpy_ptds"}
+                "cuMemcpyHtoD_v2", "cuMemcpyHtoD_v2_ptds", "cuMemcpy", "cuMemcpy_ptds"}
     assert extra == {"dlsym", "cuCtxSynchronize", "cuStreamDestroy_v2", "nvmlDeviceGetUtilizationRates"} | graph_opt_in | ctx_teardown | blocking, extra
     if H.have_reference():
         ref = exported(H.REF_SO)

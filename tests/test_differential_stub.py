@@ -246,13 +246,13 @@ def test_external_sm_watcher_file_is_mandatory_when_enabled(built):
     assert outs[0] == outs[1] and outs[0][1] == 0
 
 
-def _storm(lib, env, n, threads=1):
+def _storm(lib, env, n, threads=1, extra=()):
     import json
     import subprocess
     sb = H.Sandbox()
     e = H.preload_env(lib, sb, env)
     r = subprocess.run([H.STORM, "--steps", "1", "--warmup", "0", "--per-step", str(n), "--threads", str(threads),
-                        "--no-kernel"], env=e, capture_output=True, text=True, timeout=300)
+                        "--no-kernel"] + list(extra), env=e, capture_output=True, text=True, timeout=300)
     sb.cleanup()
     assert r.returncode == 0, r.stderr[-2000:]
     return json.loads(r.stdout.strip().splitlines()[-1])
@@ -270,6 +270,19 @@ def test_config1_stub_launch_storm_both_libraries(built):
         assert ref["launches"] == new["launches"] == 400000 and ref["fails"] == new["fails"] == 0
         assert new["limiter"]["present"] == 1 and new["sampler_launches"] > 0
         assert new["p50_ns"] < 5000
+
+
+def test_hooked_blocking_calls_forward_under_a_core_cap(built):
+    """cuCtxSynchronize and the synchronous copies are hooked so that a throttled thread waits in user
+    space before it blocks inside the driver (limiter.c wait_until_unparked).  Plumbing check on the stub:
+    a capped storm that issues one of them every 500 launches completes with the copy executed (the
+    call's return code is part of `fails`), for both libraries - the reference forwards them."""
+    env = dict(BASE)
+    env.update({"CUDA_CORE_LIMIT_0": "10", "CUDA_MEM_LIMIT_0": "1g", "STUB_UTIL": "closed:0.02"})
+    for call in ("sync", "htod", "dtoh", "dtod", "copy"):
+        for lib in (H.REF_SO, H.NEW_SO):
+            d = _storm(lib, env, 100000, 2, ("--sync-every", "500", "--block-with", call))
+            assert d["launches"] == 100000 and d["fails"] == 0, (call, lib, d)
 
 
 def test_refill_does_not_need_the_host_to_enter_the_driver(built):

@@ -157,6 +157,28 @@ def test_launch_storm_on_other_stream_kinds(built, mode, threads):
     assert d["sampler_launches"] > 0 and d["p50_ns"] < 20000
 
 
+@pytest.mark.parametrize("call", ["sync", "htod", "dtoh", "copy"])
+def test_blocking_calls_of_a_throttled_tenant_never_need_a_loan(built, call):
+    """A 10 %-capped busy tenant walks into a blocking driver call every 100 launches while its stream is
+    parked behind the gate.  The reference's thread would be asleep inside the launch hook at that point;
+    here the hooked blocking calls (cuCtxSynchronize, the synchronous copies) wait in user space until
+    nothing is parked, so the tick thread is never kept out of the driver: every launch completes, the
+    cap did bite, and the driver-free watchdog never had to lend tokens."""
+    sb = H.Sandbox()
+    env = H.preload_env(H.NEW_SO, sb, {"MANAGER_COMPATIBILITY_MODE": "0", "MANAGER_VISIBLE_DEVICES": gpu0_uuid(),
+                                      "CUDA_CORE_LIMIT_0": "10", "CUDA_MEM_LIMIT_0": "4g", "CUDA_VISIBLE_DEVICES": "0",
+                                      "LOGGER_LEVEL": "1"}, stub=False)
+    r = subprocess.run([H.STORM, "--steps", "1000000", "--warmup", "0", "--per-step", "200", "--max-seconds", "5",
+                        "--spin-iters", "20000", "--grid", "592", "--block", "256", "--sync-every", "100", "--block-with", call],
+                       env=env, capture_output=True, text=True, timeout=300)
+    sb.cleanup()
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads(r.stdout.strip().splitlines()[-1])
+    assert d["fails"] == 0 and d["launches"] > 0 and d["limiter"]["present"] == 1, d
+    assert d["gated_launches"] > 0, d
+    assert d["watchdog_loans"] == 0, d
+
+
 def test_client_mode_registration_and_pids_file_on_real_driver(built):
     """Compatibility mode 200: at start-up the library fork/execs registry/device-client
     (register.c:14-38) and afterwards only pids listed in pids.config count as the container's.  The

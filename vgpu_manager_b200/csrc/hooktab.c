@@ -29,7 +29,7 @@
   X(cuMemFreeAsync_ptsz) X(cuCtxSynchronize) X(cuStreamDestroy_v2)                             \
   X(cuStreamSynchronize) X(cuStreamSynchronize_ptsz) X(cuEventSynchronize)                      \
   X(cuMemcpyDtoH_v2) X(cuMemcpyDtoH_v2_ptds) X(cuMemcpyHtoD_v2) X(cuMemcpyHtoD_v2_ptds)         \
-  X(cuMemcpyDtoD_v2) X(cuMemcpyDtoD_v2_ptds) X(cuMemcpy) X(cuMemcpy_ptds)                       \
+  X(cuMemcpy) X(cuMemcpy_ptds)                                                                  \
   X(cuCtxDestroy_v2) X(cuCtxDestroy) X(cuDevicePrimaryCtxReset_v2) X(cuDevicePrimaryCtxReset)  \
   X(cuDevicePrimaryCtxRelease_v2) X(cuDevicePrimaryCtxRelease)
 /* opt-in (VGPU_B200_GRAPH_LIMIT=1): only then are these names substituted in dlsym /
@@ -67,7 +67,6 @@ void *vgpu_lookup_cuda_hook(const char *name, int want_ptsz) {
   /* the synchronous copies: v2 ABI since CUDA 3.2, per-thread-default-stream suffix is _ptds */
   if (!strcmp(name, "cuMemcpyDtoH")) name = want_ptsz ? "cuMemcpyDtoH_v2_ptds" : "cuMemcpyDtoH_v2";
   else if (!strcmp(name, "cuMemcpyHtoD")) name = want_ptsz ? "cuMemcpyHtoD_v2_ptds" : "cuMemcpyHtoD_v2";
-  else if (!strcmp(name, "cuMemcpyDtoD")) name = want_ptsz ? "cuMemcpyDtoD_v2_ptds" : "cuMemcpyDtoD_v2";
   else if (!strcmp(name, "cuMemcpy")) name = want_ptsz ? "cuMemcpy_ptds" : "cuMemcpy";
   if (!strcmp(name, "cuDevicePrimaryCtxReset")) name = "cuDevicePrimaryCtxReset_v2";     /* since CUDA 11.0 */
   if (!strcmp(name, "cuDevicePrimaryCtxRelease")) name = "cuDevicePrimaryCtxRelease_v2"; /* since CUDA 11.0 */

@@ -1128,7 +1128,8 @@ VGPU_EXPORT CUresult cuMemcpyDtoH_v2_ptds(void *dst, CUdeviceptr src, size_t n) 
   return R.cuMemcpyDtoH_v2_ptds(dst, src, n);
 }
 
-/* the synchronous copies order behind everything on the legacy stream (per-thread stream for _ptds) */
+/* the synchronous copies that involve host memory wait for everything on the legacy stream (per-thread stream
+ * for _ptds) inside the driver; device-to-device copies are only enqueued and stay forwards */
 #define BLOCKING_COPY(name, ptsz, T1, T2)                                  \
   VGPU_EXPORT CUresult name(T1 dst, T2 src, size_t n) {                    \
     int h;                                                                 \
@@ -1139,8 +1140,6 @@ VGPU_EXPORT CUresult cuMemcpyDtoH_v2_ptds(void *dst, CUdeviceptr src, size_t n) 
   }
 BLOCKING_COPY(cuMemcpyHtoD_v2, 0, CUdeviceptr, const void *)
 BLOCKING_COPY(cuMemcpyHtoD_v2_ptds, 1, CUdeviceptr, const void *)
-BLOCKING_COPY(cuMemcpyDtoD_v2, 0, CUdeviceptr, CUdeviceptr)
-BLOCKING_COPY(cuMemcpyDtoD_v2_ptds, 1, CUdeviceptr, CUdeviceptr)
 BLOCKING_COPY(cuMemcpy, 0, CUdeviceptr, CUdeviceptr)
 BLOCKING_COPY(cuMemcpy_ptds, 1, CUdeviceptr, CUdeviceptr)
 

@@ -122,8 +122,6 @@ void vgpu_log_emit(int level, const char *file, int line, const char *fmt, ...)
   X(cuStreamSynchronize_ptsz, CUresult, (CUstream))                                             \
   X(cuMemcpyDtoH_v2_ptds, CUresult, (void *, CUdeviceptr, size_t))                              \
   X(cuMemcpyHtoD_v2_ptds, CUresult, (CUdeviceptr, const void *, size_t))                        \
-  X(cuMemcpyDtoD_v2, CUresult, (CUdeviceptr, CUdeviceptr, size_t))                              \
-  X(cuMemcpyDtoD_v2_ptds, CUresult, (CUdeviceptr, CUdeviceptr, size_t))                         \
   X(cuMemcpy, CUresult, (CUdeviceptr, CUdeviceptr, size_t))                                     \
   X(cuMemcpy_ptds, CUresult, (CUdeviceptr, CUdeviceptr, size_t))                                \
   X(cuStreamDestroy_v2, CUresult, (CUstream))                                                   \

@@ -388,6 +388,25 @@ static void refresh_process_count(vgpu_dev_rt *rt) {
 /* A dense launch train only carries a marker every MARK_EVERY launches, so its tail may stay
  * unmarked.  If a stream has not launched since the previous tick and the driver says it is
  * idle, everything it was given has completed. */
+/* the tick thread is between cuCtxPushCurrent and cuCtxPopCurrent and not in NVML (read by the watchdog) */
+static volatile int g_tick_in_cuda;
+
+/* LOGGER_LEVEL >= 4 only: name any step of the refill path, or any hooked blocking call, that took longer
+ * than a quarter of a control period - the first question when a watchdog loan shows up in a log */
+static int g_trace_slow = -1;
+static inline uint64_t slow_t0(void) {
+  if (unlikely(g_trace_slow < 0)) g_trace_slow = vgpu_log_level() >= VL_VERBOSE;
+  if (likely(!g_trace_slow)) return 0;
+  struct timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return (uint64_t)ts.tv_sec * 1000000000ull + (uint64_t)ts.tv_nsec;
+}
+static inline void slow_end(uint64_t t0, const char *what) {
+  if (likely(!t0)) return;
+  uint64_t dt = slow_t0() - t0;
+  if (dt > 20000000ull) VLOG(VL_VERBOSE, "slow: %s took %llu ms", what, (unsigned long long)(dt / 1000000ull));
+}
+
 static void settle_idle_streams(vgpu_dev_rt *rt, int h) {
   vgpu_lim_host_t *H = rt->lim_h;
   for (uint32_t i = 0; i < VGPU_STREAM_SLOTS - 1; i++) {
@@ -454,12 +473,17 @@ static void *tick_main(void *arg) {
             !vgpu_tunable("VGPU_B200_UTIL_SOURCE")) backlog_push(h);
         continue;
       }
-      if (VGPU_CAPCHK(R.cuCtxPushCurrent_v2(rt->ctx)) != CUDA_SUCCESS) continue;
+      uint64_t ts0 = slow_t0();
+      g_tick_in_cuda = 1;
+      if (VGPU_CAPCHK(R.cuCtxPushCurrent_v2(rt->ctx)) != CUDA_SUCCESS) { g_tick_in_cuda = 0; continue; }
+      slow_end(ts0, "tick: cuCtxPushCurrent");
       if (!relaxed) { /* once, with a context current: this thread never takes part in a tenant's capture */
         vgpu_capture_relax();
         relaxed = 1;
       }
+      ts0 = slow_t0();
       settle_idle_streams(rt, h);
+      slow_end(ts0, "tick: settle_idle_streams");
       if ((epoch % 100) == 1 && rt->lim_h->util_source != VGPU_SRC_NVML) refresh_process_count(rt);
       if ((epoch % 100) == 0 && vgpu_log_level() >= VL_VERBOSE) {
         vgpu_lim_host_t *H = rt->lim_h;
@@ -475,7 +499,11 @@ static void *tick_main(void *arg) {
          * the samples and let one small CTA fold them and refill the bucket */
         if (epoch % g_period_ticks == 0) {
           exchange_with_node_agent(rt, h);
+          ts0 = slow_t0();
+          g_tick_in_cuda = 0; /* NVML and file reads: nothing the tenant's CUDA calls can hold up */
           unsigned block = publish_utilization(h, rt->u_req);
+          g_tick_in_cuda = 1;
+          slow_end(ts0, "tick: publish_utilization (NVML)");
           if (vgpu_log_level() >= VL_VERBOSE) {
             const vgpu_util_req_t *U = rt->u_req;
             const vgpu_lim_host_t *H = rt->lim_h;
@@ -490,7 +518,9 @@ static void *tick_main(void *arg) {
                  (unsigned long long)H->steps);
           }
           void *params[] = {&rt->lim_d, &rt->lim_h_d, &rt->u_req_d};
+          ts0 = slow_t0();
           CUresult r = VGPU_CAPCHK(R.cuLaunchKernel(rt->k_refill, 1, 1, 1, block, 1, 1, 0, rt->s_stream, params, NULL));
+          slow_end(ts0, "tick: refill launch");
           if (r == CUDA_SUCCESS) {
             fails = 0;
             vgpu_metric_add(h, VM_SAMPLER_LAUNCHES, 1);
@@ -539,6 +569,7 @@ static void *tick_main(void *arg) {
       }
       CUcontext dummy;
       R.cuCtxPopCurrent_v2(&dummy);
+      g_tick_in_cuda = 0;
     }
     g_tick_gen++;
     uint64_t after = tick_ns - before;
@@ -549,17 +580,23 @@ static void *tick_main(void *arg) {
 
 /* ------------------------------------------------------------------ watchdog
  * Never calls into the driver, so nothing can lock it out.  Condition for a loan: some stream is
- * parked (its newest launch is not admitted) and the controller's step counter has not moved
- * for g_watchdog_ms.  The loan is the newest parked ticket: everything queued behind the gate
- * (at most GATED_RUNAHEAD launches per stream) is released at once, which is what the blocked
- * driver call is waiting for. */
+ * parked (its newest launch is not admitted), the controller's step counter has not moved, and
+ * the tick thread has spent g_watchdog_ms of that time INSIDE the CUDA driver (g_tick_in_cuda) -
+ * i.e. it is being kept out by a blocking call of the tenant.  Time the tick thread spends asleep
+ * or in NVML does not count: a slow nvmlDeviceGetProcessUtilization (50-110 ms were measured next
+ * to a tenant that issues synchronous copies) delays the reference's watcher by the same amount
+ * while its throttled thread sleeps in the hook, so lending then would hand out tokens the
+ * reference does not.  A tick thread that stopped stepping for any other reason is caught by a
+ * backstop of 12 x g_watchdog_ms (fail open).  The loan is the newest parked ticket: everything
+ * queued behind the gate (at most GATED_RUNAHEAD launches per stream) is released at once, which
+ * is what the blocked driver call is waiting for. */
 static uint32_t g_watchdog_ms = 170;
 static pthread_t g_wd_tid;
 static volatile int g_wd_running;
 static void *watchdog_main(void *arg) {
   (void)arg;
   unsigned long long seen_steps[VGPU_MAX_DEVICES] = {0};
-  uint32_t stalled_ms[VGPU_MAX_DEVICES] = {0};
+  uint32_t stalled_ms[VGPU_MAX_DEVICES] = {0}, parked_ms[VGPU_MAX_DEVICES] = {0};
   const uint32_t step_ms = 10;
   for (;;) {
     struct timespec nap = {0, (long)step_ms * 1000000L};
@@ -584,19 +621,23 @@ static void *watchdog_main(void *arg) {
       unsigned long long st = H->steps;
       if (!parked || st != seen_steps[h]) {
         seen_steps[h] = st;
-        stalled_ms[h] = 0;
+        stalled_ms[h] = parked_ms[h] = 0;
         continue;
       }
-      stalled_ms[h] += step_ms;
-      if (stalled_ms[h] < g_watchdog_ms) continue;
-      stalled_ms[h] = 0;
+      parked_ms[h] += step_ms;
+      if (g_tick_in_cuda) stalled_ms[h] += step_ms;
+      if (stalled_ms[h] < g_watchdog_ms && parked_ms[h] < 12 * g_watchdog_ms) continue;
+      const int locked_out = stalled_ms[h] >= g_watchdog_ms;
+      stalled_ms[h] = parked_ms[h] = 0;
       H->release_floor = newest;
       __sync_synchronize();
       H->release_pending = 1;
       if (newest - H->granted_mirror > 0) H->granted_mirror = newest;
       vgpu_metric_add(h, VM_WATCHDOG_LOANS, 1);
-      VLOG(VL_WARNING, "host device %d: controller has not stepped for %u ms while streams are parked "
-                       "(driver busy?); lent tokens up to ticket %lld", h, g_watchdog_ms, newest);
+      VLOG(VL_WARNING, "host device %d: streams are parked and the controller has not stepped: %s; lent tokens up to ticket %lld", h,
+           locked_out ? "the refill thread has been waiting inside the CUDA driver (a blocking call of the tenant holds it)"
+                      : "the refill thread made no progress for 12 watchdog periods",
+           newest);
     }
     g_wd_gen++;
   }
@@ -909,11 +950,15 @@ static inline int admit(admit_t *a, unsigned gx, unsigned gy, unsigned gz, CUstr
     }
     /* make the controller's view exact at the gate: everything before this launch gets its
      * marker now, so the oldest unfinished launch it will see is this (parked) one */
+    uint64_t tm0 = slow_t0();
     if (likely(rt->memops64 > 0) && sl->marked < seq - 1) enqueue_marker(rt, h, a->slot, seq - 1, s, ptsz);
+    slow_end(tm0, "launch: marker before the gate");
     if (likely(rt->memops64 > 0)) {
       CUresult (*wait)(CUstream, CUdeviceptr, cuuint64_t, unsigned) =
           (ptsz && R.cuStreamWaitValue64_v2_ptsz) ? R.cuStreamWaitValue64_v2_ptsz : R.cuStreamWaitValue64_v2;
+      uint64_t ts0 = slow_t0();
       CUresult wr = VGPU_CAPCHK(wait(s, rt->lim_h_d + offsetof(vgpu_lim_host_t, granted_mirror), (cuuint64_t)ticket, VCU_WAIT_GEQ));
+      slow_end(ts0, "launch: cuStreamWaitValue64 (gate)");
       if (unlikely(wr != CUDA_SUCCESS)) {
         VLOG(VL_ERROR, "cuStreamWaitValue64 failed (%d: %s); falling back to the gate kernel", wr, vgpu_cu_err(wr));
         rt->memops64 = 0;
@@ -956,7 +1001,9 @@ static inline void mark_done(const admit_t *a, CUstream s) {
       while ((d = rt->lim_h->done[a->slot]) < a->seq && !__sync_bool_compare_and_swap(&rt->lim_h->done[a->slot], d, a->seq)) {}
       return;
     }
+    uint64_t tm0 = slow_t0();
     enqueue_marker(rt, h, a->slot, a->seq, s, a->ptsz);
+    slow_end(tm0, "launch: completion marker");
     if (likely(rt->memops64 > 0)) return;
   }
   /* no completion signal available: treat as instantaneous (monotonic: slots can be shared) */
@@ -969,7 +1016,9 @@ static inline void mark_done(const admit_t *a, CUstream s) {
     admit_t a_ = {0};                                           \
     int st_ = admit(&a_, (gx), (gy), (gz), (stream), (ptsz));   \
     if (st_ < 0) return CUDA_ERROR_INVALID_CONTEXT;             \
+    uint64_t ts_ = slow_t0();                                   \
     CUresult r_ = (CALL);                                       \
+    slow_end(ts_, "launch: driver call");                       \
     if (st_ > 0) mark_done(&a_, (stream));                      \
     return r_;                                                  \
   } while (0)
@@ -1064,12 +1113,13 @@ static void wait_until_unparked(vgpu_dev_rt *rt, int h, CUstream s, int ptsz, in
   }
   struct timespec t0, now, nap = {0, 50000};
   clock_gettime(CLOCK_MONOTONIC, &t0);
+  uint64_t ts0 = slow_t0();
   for (int spins = 0;; spins++) {
     int parked = 0;
     if (only < VGPU_STREAM_SLOTS) parked = slot_parked(H, only) || slot_parked(H, VGPU_STREAM_SLOTS - 1);
     else
       for (uint32_t i = 0; i < VGPU_STREAM_SLOTS && !parked; i++) parked = slot_parked(H, i);
-    if (!parked) return;
+    if (!parked) { slow_end(ts0, "blocking call: user-space wait for tokens"); return; }
     if (spins < 32) sched_yield();
     else nanosleep(&nap, NULL);
     if ((spins & 255) == 255) {
@@ -1111,14 +1161,20 @@ VGPU_EXPORT CUresult cuEventSynchronize(CUevent e) {
   vgpu_dev_rt *rt = current_rt(&h);
   if (unlikely(!R.cuEventSynchronize)) return CUDA_ERROR_NOT_FOUND;
   wait_until_unparked(rt, h, NULL, 0, 1); /* the event may sit behind any stream */
-  return R.cuEventSynchronize(e);
+  uint64_t ts0 = slow_t0();
+  CUresult r = R.cuEventSynchronize(e);
+  slow_end(ts0, "cuEventSynchronize: driver call");
+  return r;
 }
 VGPU_EXPORT CUresult cuMemcpyDtoH_v2(void *dst, CUdeviceptr src, size_t n) {
   int h;
   vgpu_dev_rt *rt = current_rt(&h);
   if (unlikely(!R.cuMemcpyDtoH_v2)) return CUDA_ERROR_NOT_FOUND;
   wait_until_unparked(rt, h, NULL, 0, 1);
-  return R.cuMemcpyDtoH_v2(dst, src, n);
+  uint64_t ts0 = slow_t0();
+  CUresult r = R.cuMemcpyDtoH_v2(dst, src, n);
+  slow_end(ts0, "cuMemcpyDtoH: driver call");
+  return r;
 }
 VGPU_EXPORT CUresult cuMemcpyDtoH_v2_ptds(void *dst, CUdeviceptr src, size_t n) {
   int h;
@@ -1136,7 +1192,10 @@ VGPU_EXPORT CUresult cuMemcpyDtoH_v2_ptds(void *dst, CUdeviceptr src, size_t n) 
     vgpu_dev_rt *rt = current_rt(&h);                                      \
     if (unlikely(!R.name)) return CUDA_ERROR_NOT_FOUND;                    \
     wait_until_unparked(rt, h, NULL, ptsz, !(ptsz));                       \
-    return R.name(dst, src, n);                                            \
+    uint64_t ts0 = slow_t0();                                              \
+    CUresult r = R.name(dst, src, n);                                      \
+    slow_end(ts0, #name ": driver call");                                  \
+    return r;                                                              \
   }
 BLOCKING_COPY(cuMemcpyHtoD_v2, 0, CUdeviceptr, const void *)
 BLOCKING_COPY(cuMemcpyHtoD_v2_ptds, 1, CUdeviceptr, const void *)
@@ -1154,7 +1213,9 @@ VGPU_EXPORT CUresult cuCtxSynchronize(void) {
   if (rt) wait_until_unparked(rt, rt->host_index, NULL, 0, 1);
   vgpu_limiter_quiesce(rt);
   __sync_fetch_and_add(&g_sync_waiters, 1);
+  uint64_t ts0 = slow_t0();
   CUresult r = R.cuCtxSynchronize();
+  slow_end(ts0, "cuCtxSynchronize: driver call");
   __sync_fetch_and_sub(&g_sync_waiters, 1);
   vgpu_limiter_resume(rt, r == CUDA_SUCCESS);
   return r;

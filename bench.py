@@ -417,7 +417,10 @@ def main():
             lp = loops[0] if loops else None
             rebalance = {"collective": "all_gather_into_tensor, 4 x f32 per rank, pre-allocated buffers",
                          "collective_us": round(time_collective(dist, torch, torch.device("cuda", local_rank)), 2),
-                         "rounds_during_storm": lp.rounds if lp else 0, "period_ms": 80,
+                         "rounds_during_storm": lp.rounds_run if lp else 0, "period_ms": 80,
+                         "schedule": "one round per 80 ms while any tenant is under pressure, backing off to 640 ms after 4 calm tables "
+                                     "(same decision on every rank from the same gathered table)",
+                         "longest_period_ms": round(1e3 * max(lp.periods), 1) if lp and lp.periods else None,
                          "applied_rank0": lp.applied if lp else 0,
                          "targets_rank0_pct": sorted(set(lp.plans)) if lp else []}
     else:

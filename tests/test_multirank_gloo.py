@@ -64,19 +64,20 @@ sb = H.Sandbox()
 env = H.preload_env(H.NEW_SO, sb, {"MANAGER_COMPATIBILITY_MODE": "0", "MANAGER_VISIBLE_DEVICES": H.STUB_UUID,
                                   "CUDA_CORE_LIMIT_0": "50", "CUDA_MEM_LIMIT_0": "1g", "LOGGER_LEVEL": "3",
                                   "STUB_UTIL": "closed:0.02" if rank == 0 else "fixed:5"})
-loop = RebalanceLoop(dist, torch, "cpu", rank, 50, sb.path("etc/vgpu-manager/config"), sb.path("lock"), rounds=40, period_s=0.08,
+loop = RebalanceLoop(dist, torch, "cpu", rank, 50, sb.path("etc/vgpu-manager/config"), sb.path("lock"), rounds=80, period_s=0.08,
                      host_index=0)
 dist.barrier()
 loop.start()
 if rank == 0:   # saturates its cap: gated
-    cmd = [H.STORM, "--steps", "100000", "--warmup", "0", "--per-step", "40000", "--no-kernel", "--max-seconds", "3"]
+    cmd = [H.STORM, "--steps", "100000", "--warmup", "0", "--per-step", "40000", "--no-kernel", "--max-seconds", "5"]
 else:           # a trickle of launches: never gated
     cmd = [H.SCENARIO]
 r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=120,
-                   input=None if rank == 0 else "init 0\n" + "launch 20 1 1 1\nsleepms 300\n" * 10)
+                   input=None if rank == 0 else "init 0\n" + "launch 20 1 1 1\nsleepms 300\n" * 16)
 loop.join(timeout=60)
 out = {"rank": rank, "rc": r.returncode, "applied": loop.applied, "plans": sorted(set(loop.plans)),
-       "tenant_up_limits": sorted(loop.tenant_up_limits), "assigned_log": r.stderr.count("node agent assigned")}
+       "tenant_up_limits": sorted(loop.tenant_up_limits), "assigned_log": r.stderr.count("node agent assigned"),
+       "rounds_run": loop.rounds_run, "periods": [round(p, 3) for p in loop.periods]}
 rows = [None] * world
 dist.all_gather_object(rows, out)
 if rank == 0:
@@ -106,6 +107,48 @@ def test_rebalance_is_applied_to_the_gated_tenant_only(built, tmp_path):
     assert gated["assigned_log"] >= 1, gated
     assert calm["plans"] == [50] and calm["applied"] == 1, calm
     assert all(u <= 50 for u in calm["tenant_up_limits"]), calm
+    # the schedule is a function of the gathered table only: both ranks ran the same rounds at the same periods
+    assert gated["rounds_run"] == calm["rounds_run"] and gated["periods"] == calm["periods"], rows
+    assert min(gated["periods"]) == 0.08
+
+
+CALM_WORKER = r'''
+import json, os, sys
+sys.path.insert(0, os.environ["REPO_ROOT"]); sys.path.insert(0, os.path.join(os.environ["REPO_ROOT"], "tests"))
+import torch, torch.distributed as dist
+import helpers as H
+from vgpu_manager_b200.multi import RebalanceLoop
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+sb = H.Sandbox()
+os.makedirs(sb.path("etc/vgpu-manager/config"), exist_ok=True)
+loop = RebalanceLoop(dist, torch, "cpu", rank, 50, sb.path("etc/vgpu-manager/config"), sb.path("lock"), rounds=50, period_s=0.02, host_index=0)
+dist.barrier()
+loop.start()
+loop.join(timeout=60)
+rows = [None] * world
+dist.all_gather_object(rows, {"rounds_run": loop.rounds_run, "periods": [round(p, 3) for p in loop.periods], "plans": sorted(set(loop.plans))})
+if rank == 0:
+    print(json.dumps(rows))
+sb.cleanup()
+dist.destroy_process_group()
+'''
+
+
+def test_rebalance_loop_backs_off_identically_on_every_rank_when_nobody_is_gated(built, tmp_path):
+    """No tenant under pressure: after four calm tables the period doubles up to 8 control periods, every
+    rank taking the same decision from the same gathered table - so the collective count stays matched
+    (the loops end together) while an un-throttled job pays for far fewer collectives."""
+    script = tmp_path / "calm.py"
+    script.write_text(CALM_WORKER)
+    env = dict(os.environ, REPO_ROOT=H.ROOT)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29734", str(script)],
+                       capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0, r.stderr[-3000:]
+    rows = json.loads([l for l in r.stdout.splitlines() if l.startswith("[")][-1])
+    assert rows[0] == rows[1], rows
+    assert rows[0]["rounds_run"] < 20 and max(rows[0]["periods"]) == 0.16 and rows[0]["plans"] == [50], rows
 
 
 def test_rebalance_policy_shapes():

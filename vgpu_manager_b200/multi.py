@@ -118,14 +118,20 @@ def all_gather_reports(dist, torch, report: TenantReport, device):
 
 
 class RebalanceLoop(threading.Thread):
-    """The node agent of one GPU while its tenant runs: every `period_s` read the tenant's status,
-    gather, plan, apply the own row.  All ranks must run it for the same number of rounds (the
-    collective is the synchronisation), so the round count is fixed up front."""
+    """The node agent of one GPU while its tenant runs: read the tenant's status, gather, plan, apply
+    the own row, sleep one period.  The collective is the synchronisation, so all ranks must run the
+    same number of rounds; the schedule is therefore a pure function of the gathered tables (which
+    are bit-identical on every rank): the loop covers `rounds * period_s` of *scheduled* time, one
+    control period per round while any tenant of the job is under pressure, and - every rank taking
+    the same decision from the same table - twice the previous period, up to `max_backoff` periods,
+    once `calm_rounds` consecutive tables showed none.  A collective's kernel is another process's
+    work on the tenant's time-sliced GPU; an un-throttled job should not pay for 12 of them a second."""
 
     def __init__(self, dist, torch, device, gpu, quota_pct, cfg_dir, lock_dir, rounds, period_s=0.08, ceiling=100,
-                 host_index=None):
+                 host_index=None, max_backoff=8, calm_rounds=4):
         """`gpu` is this agent's key in the gathered table (the physical GPU on a real node, the rank in the
-        CPU tests); `host_index` the tenant's index of that GPU inside its own config (defaults to `gpu`)."""
+        CPU tests); `host_index` the tenant's index of that GPU inside its own config (defaults to `gpu`).
+        `max_backoff=1` keeps the fixed cadence."""
         super().__init__(daemon=True)
         self.gather = AllGather(dist, torch, device)
         self.torch, self.device = torch, device
@@ -133,6 +139,8 @@ class RebalanceLoop(threading.Thread):
         self.host_index = gpu if host_index is None else host_index
         self.pressure = 0.0
         self.rounds, self.period_s, self.ceiling = rounds, period_s, ceiling
+        self.max_backoff, self.calm_rounds = max(1, int(max_backoff)), max(1, int(calm_rounds))
+        self.rounds_run, self.periods = 0, []
         self.applied, self.plans, self.seq = 0, [], 0
         self.tenant_up_limits = set()  # what the tenant's controller reported back (status file)
         self.last = None
@@ -143,7 +151,9 @@ class RebalanceLoop(threading.Thread):
         prev = None
         if str(self.device).startswith("cuda"):
             self.torch.cuda.set_device(self.device)  # the current device is per thread
-        for _ in range(self.rounds):
+        scheduled, total = 0.0, self.rounds * self.period_s
+        period, calm = self.period_s, 0
+        while scheduled < total - 1e-9:
             t0 = time.perf_counter()
             st = read_status(self.lock_dir, self.host_index)
             util = 0.0
@@ -167,7 +177,17 @@ class RebalanceLoop(threading.Thread):
                 self.last = mine
                 self.applied += 1
             self.plans.append(mine)
-            rest = self.period_s - (time.perf_counter() - t0)
+            # next period: from the gathered table only, so that every rank schedules the same rounds
+            if any(r.gated_frac > 0.01 for r in table):
+                period, calm = self.period_s, 0
+            else:
+                calm += 1
+                if calm >= self.calm_rounds:
+                    period = min(period * 2.0, self.period_s * self.max_backoff)
+            self.rounds_run += 1
+            self.periods.append(period)
+            scheduled += period
+            rest = period - (time.perf_counter() - t0)
             if rest > 0:
                 time.sleep(rest)
 

@@ -30,13 +30,18 @@
  *              10 ms for a 0.5 ms window at a random offset instead (one CTA for `queue`, one per
  *              SM for the probe); the last CTA of every 8th launch runs the controller.  It
  *              also settles unmarked launch-train tails.
- *   watchdog = a second thread that never enters the driver.  Some driver calls block while
- *              holding the context lock (a pageable cuMemcpyDtoH behind a parked kernel is the
- *              common one); the tick thread can then not launch the refill and the stream
- *              would stay parked for ever.  The gate therefore waits on the *host-visible mirror*
- *              of `granted`; when streams are parked and the controller has not stepped for two
- *              periods the watchdog advances the mirror to the newest parked ticket (a loan:
- *              the controller folds it into `granted` at its next step, so it is repaid).
+ *   blocking = driver calls that wait for the stream (cuCtxSynchronize, cuStreamSynchronize,
+ *              cuEventSynchronize, the synchronous copies that involve host memory, cuMemFree)
+ *              hold the context lock while they wait; behind a parked kernel they would keep the
+ *              tick thread from launching the refill that ends them.  Their hooks therefore
+ *              wait in user space - where the reference's thread would be asleep inside the launch
+ *              hook - until nothing they depend on is parked (wait_until_unparked).
+ *   watchdog = last resort for blocking calls that are not hooked: a second thread that never
+ *              enters the driver.  The gate waits on the *host-visible mirror* of `granted`; when
+ *              streams are parked, the controller has not stepped and the tick thread has been
+ *              waiting inside the CUDA driver for two periods, the watchdog advances the mirror
+ *              to the newest parked ticket (a loan: the controller folds it into `granted` at
+ *              its next step, so it is repaid).
  *   governor = opt-in (VGPU_B200_GOVERNOR=1) alternative for GPUs that are not time-sliced with
  *              other contexts: vgpu_governor_kernel, one warp that stays resident while the
  *              tenant has work queued or parked, samples the queues every 50 us and runs the

@@ -63,7 +63,7 @@ def gen_rate(co, rng):
     return cases
 
 
-def watcher_traj(name, mode, hard, soft, core_limit, hard_limit, geom, steps, rng, mine_prob=1.0, procs=(1,)):
+def watcher_traj(name, mode, hard, soft, core_limit, hard_limit, geom, steps, rng, mine_prob=1.0, procs=(1,), util=(0, 100), proc_hold=1):
     """One trajectory of the reference watcher thread, one control step at a time."""
     sb = helpers.Sandbox()
     pids = [4000 + i for i in range(6)]
@@ -81,15 +81,16 @@ def watcher_traj(name, mode, hard, soft, core_limit, hard_limit, geom, steps, rn
     total = sm * thr * 32
     traj = []
     bucket = 0
-    phase_util = rng.randint(0, 100)
+    phase_util = rng.randint(*util)
     for t in range(steps):
         # host consumption between control steps (what rate_limiter does to the bucket)
         consume = rng.choice([0, 0, rng.randint(0, total // 8), rng.randint(0, total)])
         bucket_in = bucket - consume
         assert co.ask("wset %d" % bucket_in) == "ok"
         if t % 17 == 0:
-            phase_util = rng.randint(0, 100)
-        nproc = rng.choice(procs)
+            phase_util = rng.randint(*util)
+        if t % proc_hold == 0:
+            nproc = rng.choice(procs)
         ns = rng.choice([0, 1, 1, 2, 3]) if t % 11 else 0
         samples = []
         for k in range(ns):
@@ -117,6 +118,22 @@ def gen_watcher(rng):
     out.append(watcher_traj("balance50_100_host", 0, 50, 100, 1, 0, B200, 160, rng, procs=(1, 1, 2, 4)))
     out.append(watcher_traj("hard25_cgv2_multi", 2, 25, 0, 1, 1, B200, 120, rng, mine_prob=0.4, procs=(1, 2, 3)))
     out.append(watcher_traj("nolimit", 0, 0, 0, 0, 0, B200, 20, rng))
+    # round 2 (appended, so that the vectors above keep their random stream): the ends of the limit range, a
+    # GPU whose whole bucket is 1024 tokens, a nearly idle single process (the "write the bucket directly"
+    # guard, cuda_hook.c:424-427), long balance-mode runs through several up_limit ramps and process changes
+    out.append(watcher_traj("hard100_host", 0, 100, 0, 1, 1, B200, 100, rng))
+    out.append(watcher_traj("hard1_host", 0, 1, 0, 1, 1, B200, 100, rng, util=(0, 12)))
+    out.append(watcher_traj("hard5_one_sm", 0, 5, 0, 1, 1, (1, 32), 100, rng))
+    out.append(watcher_traj("hard25_idle_single", 0, 25, 0, 1, 1, B200, 160, rng, util=(0, 4)))
+    out.append(watcher_traj("hard40_h100_saturated", 0, 40, 0, 1, 1, (132, 2048), 120, rng, util=(90, 130)))
+    out.append(watcher_traj("balance10_30_host_long", 0, 10, 30, 1, 0, B200, 320, rng, procs=(1, 1, 1, 2, 3), util=(0, 40)))
+    out.append(watcher_traj("balance75_100_cgv2", 2, 75, 100, 1, 0, B200, 240, rng, mine_prob=0.6, procs=(1, 2), util=(20, 100)))
+    out.append(watcher_traj("balance30_90_small_gpu_idle_system", 0, 30, 90, 1, 0, (68, 1536), 320, rng, util=(0, 15)))
+    # the multi-process up_limit ramp (cuda_hook.c:451-462) needs a process count that stays >= 2 for 30 ticks
+    out.append(watcher_traj("balance50_80_two_procs_ramp", 0, 50, 80, 1, 0, B200, 280, rng, procs=(2,), util=(0, 20)))
+    out.append(watcher_traj("balance20_100_procs_come_and_go", 0, 20, 100, 1, 0, B200, 420, rng, procs=(2, 3, 4), util=(0, 30), proc_hold=97))
+    out.append(watcher_traj("balance20_60_three_procs_busy_system", 2, 20, 60, 1, 0, B200, 200, rng, mine_prob=0.5, procs=(3,), util=(80, 120)))
+    out.append(watcher_traj("balance5_50_two_procs_zero_step", 0, 5, 50, 1, 0, B200, 100, rng, procs=(2,), util=(0, 10)))
     return out
 
 

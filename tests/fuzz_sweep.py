@@ -1,0 +1,41 @@
+"""Offline sweep: the two generators of test_differential_fuzz.py under fresh seeds, many cases, mismatches written to a
+file (python tests/fuzz_sweep.py SEED CASES OUT.json).  Not collected by pytest; used to hunt for transcript differences
+against the compiled reference on the stub driver before they reach the seeded tests."""
+import json
+import random
+import sys
+
+sys.path.insert(0, __import__("os").path.dirname(__import__("os").path.abspath(__file__)))
+import helpers as H  # noqa: E402
+import test_differential_fuzz as F  # noqa: E402
+
+
+def main():
+    seed, cases, out = int(sys.argv[1], 0), int(sys.argv[2]), sys.argv[3]
+    H.build_all()
+    rng = random.Random(seed)
+    bad = []
+    for case in range(cases):
+        script = F.random_script(rng, rng.randrange(8, 60))
+        env = F.random_env(rng)
+        prep, args = None, ()
+        if rng.random() < 0.4:
+            env, prep = F.random_membership(rng, env)
+        elif rng.random() < 0.3:
+            args = ("--gpa",)
+        if rng.random() < 0.15:
+            env["VGPU_B200_SLAB"] = "1"  # ignored by the reference; accounting must not change
+        ref = F.run(H.REF_SO, script, env, args, prep)
+        new = F.run(H.NEW_SO, script, env, args, prep)
+        if ref[:3] != new[:3]:
+            bad.append({"case": case, "env": env, "args": list(args), "script": script, "ref": ref[0], "ref_rc": ref[1], "new": new[0],
+                        "new_rc": new[1], "cfg_equal": ref[2] == new[2], "stderr": new[3][-1500:]})
+            with open(out, "w") as f:
+                json.dump(bad, f, indent=1)
+        if case % 100 == 99:
+            print("case", case + 1, "mismatches", len(bad), flush=True)
+    print("done: %d cases, %d mismatches" % (cases, len(bad)))
+
+
+if __name__ == "__main__":
+    main()

@@ -152,3 +152,19 @@ def test_random_scripts_in_every_compatibility_mode(built):
         new = run(H.NEW_SO, script, env, (), prep)
         assert ref[:3] == new[:3], "case %d env %r\nscript:\n%s\n--- reference (rc %d)\n%s\n--- b200 (rc %d)\n%s\n%s" % (
             case, env, script, ref[1], ref[0], new[1], new[0], new[3][-1500:])
+
+
+def test_random_scripts_in_slab_mode_keep_the_reference_accounting(built):
+    """VGPU_B200_SLAB=1 (ignored by the reference) on oversold devices: whatever mix of sizes the tenant asks for - slabs
+    are only made of whole multiples of the 2 MiB mapping granularity, everything else stays on the plain path - every
+    GPU / UVA / OOM decision, every reported number and the ledger stay the reference's (an offline sweep of
+    tests/fuzz_sweep.py found the drift that sub-granularity slabs caused)."""
+    rng = random.Random(0x51AB)
+    for case in range(25):
+        script = random_script(rng, rng.randrange(10, 50))
+        env = random_env(rng)
+        env.update({"VGPU_B200_SLAB": "1", "VMEMORY_NODE_ENABLED": "true", "CUDA_MEM_RATIO_0": rng.choice(("2", "4", "1.5"))})
+        ref = run(H.REF_SO, script, env, ())
+        new = run(H.NEW_SO, script, env, ())
+        assert ref[:3] == new[:3], "case %d env %r\nscript:\n%s\n--- reference (rc %d)\n%s\n--- b200 (rc %d)\n%s\n%s" % (
+            case, env, script, ref[1], ref[0], new[1], new[0], new[3][-1500:])

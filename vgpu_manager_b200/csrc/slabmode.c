@@ -22,8 +22,10 @@
  * Bookkeeping lives in HBM (vgpu_vslab_kernel: free-slot scan, lookup, coldest-victim scan with
  * the placement flip in the same launch); the host half only holds what the driver needs, the
  * allocation handles.  Without a same-size victim the newcomer itself is host-backed (the
- * reference's placement).  Anything VMM cannot do here (no host-NUMA mappings, handles
- * exhausted) falls back to the plain path, loudly, once.
+ * reference's placement).  Requests that are not whole multiples of the 2 MiB mapping granularity
+ * stay on the plain path (their physical footprint would otherwise differ from the reference's).
+ * Anything VMM cannot do here (no host-NUMA mappings, handles exhausted) falls back to the plain
+ * path, loudly, once.
  */
 #include "vgpu_internal.h"
 
@@ -218,7 +220,12 @@ CUresult vgpu_slab_alloc(vgpu_dev_rt *rt, CUdevice dev, int path, CUdeviceptr *d
     if (!rt->ev0 || R.cuEventCreate(&rt->ev1, 0) != CUDA_SUCCESS) rt->ev0 = rt->ev1 = NULL;
   }
   const size_t gran = granularity(dev);
-  const size_t size = (bytes + gran - 1) / gran * gran;
+  /* Only requests that are whole multiples of the mapping granularity (2 MiB) become slabs: a VMM mapping cannot be
+   * smaller, so anything else would occupy more physical memory than the reference's cuMemAlloc of the same bytes and the
+   * NVML-visible `used` - hence every later GPU / UVA / OOM decision - would drift from the reference's (found by the
+   * offline fuzz sweep: 1-byte .. 3 MiB+17 requests).  Those take the plain path: the reference's placement, exactly. */
+  if (bytes % gran) { r = CUDA_ERROR_NOT_SUPPORTED; goto out; }
+  const size_t size = bytes;
   vcu_mem_alloc_prop_t dp, hp;
   dev_prop(&dp, dev);
   host_prop(&hp, dev);

@@ -262,6 +262,37 @@ int main(int argc, char **argv) {
       double sec = (t1.tv_sec - t0.tv_sec) + (t1.tv_nsec - t0.tv_nsec) * 1e-9;
       printf("launch %llu -> ok %llu\n", a, okc);
       fprintf(stderr, "launch_rate %.0f per_s\n", sec > 0 ? a / sec : 0.0);
+    } else if (!strcmp(cmd, "launchvia")) {
+      /* launchvia <kind> <n> <gx> <gy>: the same launch through each of the entry points the reference hooks
+       * (cuda_hook.c:1810-2002).  0 cuLaunchKernel, 1 _ptsz, 2 cuLaunchKernelEx, 3 _ptsz, 4 cuLaunchCooperativeKernel,
+       * 5 _ptsz, 6 cuLaunchGrid, 7 cuLaunchGridAsync, 8 cuFuncSetBlockShape + cuLaunch */
+      typedef CUresult (*k_fn)(void *, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, void *, void **, void **);
+      typedef CUresult (*c_fn)(void *, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, void *, void **);
+      struct { unsigned gx, gy, gz, bx, by, bz, smem; void *stream; void *attrs; unsigned nattrs; } cfg =
+          {(unsigned)c, (unsigned)d, 1, 1, 1, 1, 0, NULL, NULL, 0};
+      static const char *names[] = {"cuLaunchKernel", "cuLaunchKernel_ptsz", "cuLaunchKernelEx", "cuLaunchKernelEx_ptsz",
+                                    "cuLaunchCooperativeKernel", "cuLaunchCooperativeKernel_ptsz", "cuLaunchGrid",
+                                    "cuLaunchGridAsync", "cuLaunch"};
+      unsigned long long okc = 0;
+      if (a > 8) { printf("launchvia %llu -> unknown kind\n", a); continue; }
+      void *fn = sym(names[a]);
+      if (a == 8) {
+        CUresult (*shape)(void *, int, int, int) = sym("cuFuncSetBlockShape");
+        printf("blockshape -> %d\n", shape ? shape(NULL, 4, 2, 1) : -1);
+      }
+      for (unsigned long long i = 0; fn && i < b; i++) {
+        CUresult r;
+        switch (a) {
+        case 0: case 1: r = ((k_fn)fn)(NULL, (unsigned)c, (unsigned)d, 1, 1, 1, 1, 0, NULL, NULL, NULL); break;
+        case 2: case 3: r = ((CUresult(*)(const void *, void *, void **, void **))fn)(&cfg, NULL, NULL, NULL); break;
+        case 4: case 5: r = ((c_fn)fn)(NULL, (unsigned)c, (unsigned)d, 1, 1, 1, 1, 0, NULL, NULL); break;
+        case 6: r = ((CUresult(*)(void *, int, int))fn)(NULL, (int)c, (int)d); break;
+        case 7: r = ((CUresult(*)(void *, int, int, void *))fn)(NULL, (int)c, (int)d, NULL); break;
+        default: r = ((CUresult(*)(void *))fn)(NULL); break;
+        }
+        okc += r == 0;
+      }
+      printf("launchvia %s %llu -> ok %llu\n", names[a], b, okc);
     } else if (!strcmp(cmd, "ledger")) {
       /* raw bytes of this GPU's record in vmem_node.config; pids are normalised to rank order */
       const char *path = getenv("SCENARIO_LEDGER");

@@ -845,7 +845,10 @@ EXPORT CUresult cuLaunchKernel(void *f, unsigned gx, unsigned gy, unsigned gz, u
 }
 EXPORT CUresult cuLaunchKernel_ptsz(void *f, unsigned gx, unsigned gy, unsigned gz, unsigned bx, unsigned by, unsigned bz,
                                     unsigned sm, void *s, void **params, void **extra) {
-  return cuLaunchKernel(f, gx, gy, gz, bx, by, bz, sm, s, params, extra);
+  /* not through the exported cuLaunchKernel: a preloaded library interposes that symbol, the real driver does not
+   * call its own entry points through the PLT */
+  (void)gx; (void)gy; (void)gz; (void)bx; (void)by; (void)bz; (void)sm; (void)s; (void)extra;
+  return launch(f, params);
 }
 EXPORT CUresult cuLaunchKernelEx(const void *cfg, void *f, void **params, void **extra) { (void)cfg; (void)extra; return launch(f, params); }
 EXPORT CUresult cuLaunchKernelEx_ptsz(const void *cfg, void *f, void **params, void **extra) { (void)cfg; (void)extra; return launch(f, params); }
@@ -856,7 +859,8 @@ EXPORT CUresult cuLaunchCooperativeKernel(void *f, unsigned gx, unsigned gy, uns
 }
 EXPORT CUresult cuLaunchCooperativeKernel_ptsz(void *f, unsigned gx, unsigned gy, unsigned gz, unsigned bx, unsigned by,
                                                unsigned bz, unsigned sm, void *s, void **params) {
-  return cuLaunchCooperativeKernel(f, gx, gy, gz, bx, by, bz, sm, s, params);
+  (void)gx; (void)gy; (void)gz; (void)bx; (void)by; (void)bz; (void)sm; (void)s;
+  return launch(f, params);
 }
 EXPORT CUresult cuLaunch(void *f) { return launch(f, NULL); }
 EXPORT CUresult cuLaunchGrid(void *f, int w, int h) { (void)w; (void)h; return launch(f, NULL); }
@@ -995,8 +999,7 @@ static void *self_lookup(const char *name) {
 }
 EXPORT CUresult cuGetProcAddress_v2(const char *sym, void **pfn, int ver, unsigned long long flags, void *status);
 EXPORT CUresult cuGetProcAddress(const char *sym, void **pfn, int ver, unsigned long long flags);
-EXPORT CUresult cuGetProcAddress_v2(const char *sym, void **pfn, int ver, unsigned long long flags, void *status) {
-  (void)ver; (void)status;
+static CUresult get_proc_address(const char *sym, void **pfn, unsigned long long flags) {
   char name[128];
   void *p = NULL;
   if (!strcmp(sym, "cuGetProcAddress")) p = (void *)cuGetProcAddress_v2;
@@ -1006,8 +1009,15 @@ EXPORT CUresult cuGetProcAddress_v2(const char *sym, void **pfn, int ver, unsign
   *pfn = p;
   return p ? 0 : 500;
 }
+/* both entry points use the static helper: an exported one calling the other would go through the PLT and land in a
+ * preloaded library's hook, which the real driver's internal calls never do */
+EXPORT CUresult cuGetProcAddress_v2(const char *sym, void **pfn, int ver, unsigned long long flags, void *status) {
+  (void)ver; (void)status;
+  return get_proc_address(sym, pfn, flags);
+}
 EXPORT CUresult cuGetProcAddress(const char *sym, void **pfn, int ver, unsigned long long flags) {
-  return cuGetProcAddress_v2(sym, pfn, ver, flags, NULL);
+  (void)ver;
+  return get_proc_address(sym, pfn, flags);
 }
 
 /* ------------------------------------------------------------------ NVML */

@@ -272,6 +272,25 @@ def test_config1_stub_launch_storm_both_libraries(built):
         assert new["p50_ns"] < 5000
 
 
+def test_every_launch_entry_point_is_forwarded_and_pays_the_reference_cost(built):
+    """The 11 launch hooks (cuda_hook.c:1810-2002): kernel launches pay gridX*gridY*gridZ tokens, cuLaunchGrid[Async]
+    width*height, the pre-CUDA-4 cuLaunch one token.  Same transcript as the reference through every entry point, and
+    the B200 library's `consumed` counter moves by exactly that cost."""
+    env = dict(BASE)
+    env.update({"CUDA_CORE_LIMIT_0": "50", "CUDA_MEM_LIMIT_0": "1g", "STUB_UTIL": "fixed:5"})
+    n, gx, gy = 20, 7, 3
+    script = "init 0\nlimstate\n" + "".join("launchvia %d %d %d %d\nlimstate\n" % (k, n, gx, gy) for k in range(9))
+    ref, _, _ = H.run_scenario(H.REF_SO, script, env)
+    new, _, _ = H.run_scenario(H.NEW_SO, script, env)
+    strip = lambda t: [l for l in t.splitlines() if not l.startswith("limstate")]
+    assert strip(ref) == strip(new), (ref, new)
+    assert sum("-> ok %d" % n in l for l in strip(new)) == 9, new
+    consumed = [int(l.split()[2]) for l in new.splitlines() if l.startswith("limstate consumed")]
+    assert len(consumed) == 10, new
+    deltas = [b - a for a, b in zip(consumed, consumed[1:])]
+    assert deltas == [n * gx * gy] * 8 + [n * 1], deltas
+
+
 def test_hooked_blocking_calls_forward_under_a_core_cap(built):
     """cuCtxSynchronize and the synchronous copies are hooked so that a throttled thread waits in user
     space before it blocks inside the driver (limiter.c wait_until_unparked).  Plumbing check on the stub:

@@ -457,6 +457,7 @@ static void *tick_main(void *arg) {
   int fails = 0;
   uint64_t rng = 0x9E3779B97F4A7C15ull ^ (uint64_t)getpid();
   int relaxed = 0;
+  g_tick_in_cuda = 0; /* a forked child inherits the flag as the parent's tick thread left it */
   for (;;) {
     /* One short sampler window per tick, at a uniformly random offset inside the tick: the
      * sampler stays resident ~5 % of the time (it would otherwise show up as GPU utilisation in

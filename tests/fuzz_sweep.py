@@ -25,6 +25,27 @@ def main():
             args = ("--gpa",)
         if rng.random() < 0.15:
             env["VGPU_B200_SLAB"] = "1"  # ignored by the reference; accounting must not change
+        if prep is None and rng.random() < 0.25:
+            # two fake GPUs, listed in either order with an optional hole, each with its own limits; the tenant hops
+            # between them (allocations, frees and reports follow the *current* device's host index)
+            u0, u1, hole = H.STUB_UUID, "GPU-22222222-2222-2222-2222-222222222222", "GPU-00000000-0000-0000-0000-000000000000"
+            order = [u0, u1] if rng.random() < 0.5 else [u1, u0]
+            if rng.random() < 0.5:
+                order.insert(rng.randrange(3), hole)
+            env["MANAGER_VISIBLE_DEVICES"] = ",".join(order)
+            env["STUB_GPU_COUNT"] = "2"
+            for i in range(len(order)):
+                if rng.random() < 0.7:
+                    env["CUDA_MEM_LIMIT_%d" % i] = rng.choice(("256m", "1g", "3g"))
+                if rng.random() < 0.3:
+                    env["CUDA_MEM_RATIO_%d" % i] = rng.choice(("2", "4"))
+                if rng.random() < 0.3:
+                    env["CUDA_CORE_LIMIT_%d" % i] = rng.choice(("10", "60"))
+            env.setdefault("STUB_UTIL", "fixed:5")
+            lines = script.splitlines()
+            for _ in range(rng.randrange(1, 6)):
+                lines.insert(rng.randrange(3, len(lines)), "dev %d" % rng.randrange(2))
+            script = "\n".join(lines) + "\n"
         ref = F.run(H.REF_SO, script, env, args, prep)
         new = F.run(H.NEW_SO, script, env, args, prep)
         if ref[:3] != new[:3]:

@@ -421,6 +421,35 @@ def test_one_process_on_two_gpus_with_a_hole_in_the_visible_list(built):
     assert t.count("-> 2") == 2  # one refusal per device, each against its own cap
 
 
+def test_two_gpus_frees_and_reports_across_devices(built):
+    """Three behaviours an offline two-GPU fuzz sweep (tests/fuzz_sweep.py) found differing, pinned here:
+    (1) the reference keeps ONE list of UVA allocations per process and, on free, subtracts the node from the ledger
+        record of whatever device is *current* (loader.c:1869-1907) - an allocation ledgered under GPU A and freed while
+        GPU B is current leaves A's record untouched and shrinks B's;
+    (2) in slab mode a slab may likewise be freed while another device is current;
+    (3) a device without a memory cap reports the driver's own numbers - the library's device-resident state (brought up
+        there by a core limit or by a ledgered managed allocation) must not show in them."""
+    u0, u1 = H.STUB_UUID, "GPU-22222222-2222-2222-2222-222222222222"
+    stub = {"STUB_GPU_COUNT": "2", "STUB_UTIL": "fixed:5"}
+    # (1) both GPUs oversold with a ledger; h1 spills on GPU 0, is freed on GPU 1, which has a spilled allocation of its own
+    env = {"MANAGER_VISIBLE_DEVICES": u0 + "," + u1, "CUDA_MEM_LIMIT_0": "1g", "CUDA_MEM_RATIO_0": "4", "CUDA_MEM_LIMIT_1": "1g",
+           "CUDA_MEM_RATIO_1": "4", "VMEMORY_NODE_ENABLED": "true"}
+    script = ("init 0\nalloc %d\nalloc %d\nledger 0\ndev 1\nalloc %d\nalloc %d\nledger 1\nfree 1\nledger 0\nledger 1\nnvmlinfo\n"
+              "dev 0\nnvmlinfo\nfree 3\nledger 0\nledger 1\nmeminfo\n") % (200 * MiB, 128 * MiB, 200 * MiB, 96 * MiB)
+    t = assert_same(both(script, env, stub))
+    led = [l for l in t.splitlines() if l.startswith("ledger")]
+    assert led[0].endswith("[self %d]" % (128 * MiB)) and led[1].endswith("[self %d]" % (96 * MiB)), t
+    assert led[2] == led[0] and led[3].endswith("[self 0]"), t          # GPU 0 keeps its record, GPU 1 paid for the free
+    # (2) the same hop in slab mode (ignored by the reference)
+    t2 = assert_same(both(script, dict(env, VGPU_B200_SLAB="1"), stub))
+    assert t2 == t
+    # (3) GPU 1 has only a core limit; GPU 0 nothing at all but sees a GLOBAL-attached managed allocation
+    env3 = {"MANAGER_VISIBLE_DEVICES": u0 + "," + u1, "CUDA_CORE_LIMIT_1": "10", "VMEMORY_NODE_ENABLED": "true"}
+    script3 = ("init 0\nmeminfo\nmanaged 4096 1\nmeminfo\nnvmlinfo\nnvmlinfo2\ndev 1\nmeminfo\nlaunch 20 1 1 1\nalloc %d\nmeminfo\nnvmlinfo\n"
+               "nvmlinfo2\n") % (64 * MiB)
+    assert_same(both(script3, env3, stub))
+
+
 def test_closed_loop_share_is_in_the_references_ballpark(built):
     """The reference defines no core-% tolerance (SURVEY.md 8a L-tol); what can be compared is the rate each
     limiter settles at when the fake GPU's utilisation follows the tenant's own launch rate (closed loop,

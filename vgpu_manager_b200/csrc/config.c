@@ -441,7 +441,7 @@ uint64_t vgpu_self_registry(int h, uint64_t publish_bytes, int publish) {
    * recent - one 8-byte pread */
   uint64_t gen = 0;
   time_t now = time(NULL);
-  if (!publish && pread(fd, &gen, sizeof gen, 0) == (ssize_t)sizeof gen && gen == g_self_gen[h] && gen != 0 &&
+  if (publish <= 0 && pread(fd, &gen, sizeof gen, 0) == (ssize_t)sizeof gen && gen == g_self_gen[h] && gen != 0 &&
       now - g_self_checked[h] < 2)
     return g_self_total[h];
 
@@ -460,12 +460,12 @@ uint64_t vgpu_self_registry(int h, uint64_t publish_bytes, int publish) {
     if (kill(tab[i].pid, 0) != 0 && errno == ESRCH) { memset(&tab[i], 0, sizeof tab[i]); dirty = 1; if (free_slot < 0) free_slot = i; continue; }
     total += tab[i].bytes;
   }
-  if (publish) {
+  if (publish > 0) {
     int slot = mine >= 0 ? mine : free_slot;
     if (slot >= 0) { tab[slot].pid = me; tab[slot].key = key; tab[slot].bytes = publish_bytes; dirty = 1; mine = slot; }
   }
   total += mine >= 0 ? tab[mine].bytes : publish_bytes;
-  if (dirty || gen == 0) {
+  if ((dirty || gen == 0) && publish >= 0) { /* publish < 0: a reader that does not hold the GPU lock never writes */
     gen++;
     memcpy(&tab[0], &gen, sizeof gen);
     ssize_t w = pwrite(fd, tab, sizeof tab, 0);

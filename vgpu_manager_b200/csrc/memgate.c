@@ -333,10 +333,20 @@ static void ledger_add(vgpu_dev_rt *rt, CUdeviceptr dptr, uint64_t bytes, int ho
 static void ledger_sub(CUdevice dev, CUdeviceptr dptr) {
   int host_index = vgpu_host_index_of_cuda(dev);
   int slot = host_index >= 0 ? host_index : dev;
-  vgpu_dev_rt *rt = vgpu_rt_peek(slot);
-  if (!rt) return; /* nothing was ever recorded by this process on this device */
   uint64_t bytes = 0;
-  if (vgpu_rt_slab_remove(rt, dptr, &bytes) != 0) return;
+  int found = 0;
+  vgpu_dev_rt *rt = vgpu_rt_peek(slot);
+  if (rt && vgpu_rt_slab_remove(rt, dptr, &bytes) == 0) found = 1;
+  /* The reference keeps ONE list of UVA allocations per process and subtracts a freed node from the ledger record of
+   * whatever device is current at the free (loader.c:1869-1907) - also when the allocation was recorded under another
+   * device.  The records live in per-device tables here, so a miss on the current device's table is followed by the
+   * other runtimes' (skipped without a launch while they hold no record). */
+  for (int h = 0; !found && h < VGPU_MAX_DEVICES; h++) {
+    vgpu_dev_rt *other = vgpu_rt_peek(h);
+    if (!other || other == rt) continue;
+    if (vgpu_rt_slab_remove(other, dptr, &bytes) == 0) found = 1;
+  }
+  if (!found) return;
   if (host_index < 0 || host_index >= VGPU_MAX_DEVICES || !G_vmem) return;
   int fd = vgpu_vmem_lock(host_index, 1);
   if (fd < 0) return;
@@ -622,12 +632,24 @@ static CUresult free_sync(CUdeviceptr dptr) {
   if (r != CUDA_SUCCESS) return r;
   /* cuMemFree synchronises the device: it must not wait for the resident governor */
   vgpu_dev_rt *rt = vgpu_rt_peek(vgpu_host_index_of_cuda(dev));
-  if (rt && rt->vs_host) { /* a slab of the VGPU_B200_SLAB mode is not the driver's to free */
+  if (vgpu_slab_mode()) { /* a slab of the VGPU_B200_SLAB mode is not the driver's to free */
     int was_uva = 0;
     uint64_t sbytes = 0;
-    if (vgpu_slab_free(rt, dptr, &r, &was_uva, &sbytes)) {
+    /* the current device's table first; a pointer may also be freed while another device is current (it is
+     * a unified address, the driver does not care) - then the slab belongs to one of the other runtimes.  The
+     * ledger is only touched for the current device, like the reference (loader.c:1875-1907 searches the
+     * list of the host index it is given) */
+    if (rt && rt->vs_host && vgpu_slab_free(rt, dptr, &r, &was_uva, &sbytes)) {
       if (r == CUDA_SUCCESS) ledger_sub(dev, dptr);
       return r;
+    }
+    for (int h = 0; h < VGPU_MAX_DEVICES; h++) {
+      vgpu_dev_rt *other = vgpu_rt_peek(h);
+      if (!other || other == rt || !other->vs_host) continue;
+      if (vgpu_slab_free(other, dptr, &r, &was_uva, &sbytes)) {
+        if (r == CUDA_SUCCESS) ledger_sub(dev, dptr);
+        return r;
+      }
     }
   }
   PROF_T0();
@@ -650,10 +672,11 @@ static CUresult free_async(CUdeviceptr dptr, CUstream s, int ptsz) {
   if (unlikely(!G_cfg)) vgpu_boot();
   CUresult r = R.cuCtxGetDevice ? R.cuCtxGetDevice(&dev) : CUDA_ERROR_NOT_FOUND;
   if (r != CUDA_SUCCESS) return r;
-  {
-    vgpu_dev_rt *rt = vgpu_rt_peek(vgpu_host_index_of_cuda(dev));
-    if (rt && rt->vs_host) return free_sync(dptr); /* slabs are remapped, not pooled: freed synchronously */
-  }
+  if (vgpu_slab_mode()) /* slabs are remapped, not pooled: freed synchronously (whichever device owns them) */
+    for (int h = 0; h < VGPU_MAX_DEVICES; h++) {
+      vgpu_dev_rt *rt = vgpu_rt_peek(h);
+      if (rt && rt->vs_host) return free_sync(dptr);
+    }
   CUresult (*fn)(CUdeviceptr, CUstream) = ptsz ? R.cuMemFreeAsync_ptsz : R.cuMemFreeAsync;
   r = fn ? fn(dptr, s) : CUDA_ERROR_NOT_FOUND;
   if (r == CUDA_SUCCESS) ledger_sub(dev, dptr);
@@ -681,13 +704,30 @@ static CUresult real_meminfo(size_t *fr, size_t *tot) {
   return R.cuMemGetInfo_v2 ? R.cuMemGetInfo_v2(fr, tot) : R.cuMemGetInfo ? R.cuMemGetInfo(fr, tot) : CUDA_ERROR_NOT_FOUND;
 }
 
+/* A device without a memory cap is reported as the driver reports it (the reference forwards: cuda_hook.c:1745-1750,
+ * nvml_hook.c:57-60) - less what the library instances of this container keep on that device themselves when a core
+ * limit made them bring their runtime up there: under the reference that memory would not exist.  Read-only look at the
+ * footprint registry (no GPU lock is taken on this path, like the reference). */
+static uint64_t own_bytes_on_uncapped(int h) {
+  if (h < 0) return 0; /* not one of the container's devices: no runtime is ever brought up there */
+  /* a core limit or a ledgered managed allocation (cuMemAllocManaged with GLOBAL attach) brings it up */
+  return vgpu_self_registry(h, 0, -1);
+}
+
 static CUresult mem_info(size_t *free_out, size_t *total_out) {
   CUdevice dev;
   if (unlikely(!G_cfg)) vgpu_boot();
   CUresult r = R.cuCtxGetDevice ? R.cuCtxGetDevice(&dev) : CUDA_ERROR_NOT_FOUND;
   if (r != CUDA_SUCCESS) return r;
   int h = vgpu_host_index_of_cuda(dev);
-  if (h < 0 || !G_cfg->devices[h].memory_limit) return real_meminfo(free_out, total_out);
+  if (h < 0 || !G_cfg->devices[h].memory_limit) {
+    r = real_meminfo(free_out, total_out);
+    if (r == CUDA_SUCCESS && free_out && total_out) {
+      uint64_t own = own_bytes_on_uncapped(h);
+      *free_out = (*free_out + own > *total_out) ? *total_out : *free_out + own;
+    }
+    return r;
+  }
   memview_t mv;
   /* the reference takes the lock and measures first, then (not oversold) asks the driver for
    * its real total to clamp against (:1739-1782); the clamp itself happens in the kernel, so
@@ -778,7 +818,14 @@ VGPU_EXPORT nvmlReturn_t nvmlDeviceGetMemoryInfo(nvmlDevice_t device, vnv_memory
     memory->free = res.out_free;
     return NVML_SUCCESS;
   }
-  return R.nvmlDeviceGetMemoryInfo ? R.nvmlDeviceGetMemoryInfo(device, memory) : NVML_ERROR_FUNCTION_NOT_FOUND;
+  nvmlReturn_t r = R.nvmlDeviceGetMemoryInfo ? R.nvmlDeviceGetMemoryInfo(device, memory) : NVML_ERROR_FUNCTION_NOT_FOUND;
+  if (r == NVML_SUCCESS && memory) {
+    uint64_t own = own_bytes_on_uncapped(h);
+    if (own > memory->used) own = memory->used;
+    memory->used -= own;
+    memory->free += own;
+  }
+  return r;
 }
 
 VGPU_EXPORT nvmlReturn_t nvmlDeviceGetMemoryInfo_v2(nvmlDevice_t device, vnv_memory_v2_t *memory) {
@@ -794,6 +841,11 @@ VGPU_EXPORT nvmlReturn_t nvmlDeviceGetMemoryInfo_v2(nvmlDevice_t device, vnv_mem
     memory->total = res.total; /* version / reserved stay the driver's (nvml_hook.c:89-98) */
     memory->used = res.out_used;
     memory->free = res.out_free;
+  } else {
+    uint64_t own = own_bytes_on_uncapped(h);
+    if (own > memory->used) own = memory->used;
+    memory->used -= own;
+    memory->free += own;
   }
   return NVML_SUCCESS;
 }

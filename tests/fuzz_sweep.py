@@ -46,6 +46,10 @@ def main():
             for _ in range(rng.randrange(1, 6)):
                 lines.insert(rng.randrange(3, len(lines)), "dev %d" % rng.randrange(2))
             script = "\n".join(lines) + "\n"
+        if rng.random() < 0.15:  # a device reset in the middle of the tenant's life (handles above it go stale in both)
+            lines = script.splitlines()
+            lines.insert(rng.randrange(3, len(lines)), "reset")
+            script = "\n".join(lines) + "\n"
         ref = F.run(H.REF_SO, script, env, args, prep)
         new = F.run(H.NEW_SO, script, env, args, prep)
         if ref[:3] != new[:3]:

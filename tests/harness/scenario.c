@@ -17,6 +17,8 @@
 #include <time.h>
 #include <unistd.h>
 #include <sys/wait.h>
+#include <execinfo.h>
+#include <signal.h>
 
 typedef int CUresult;
 typedef unsigned long long CUdeviceptr;
@@ -50,7 +52,22 @@ static int g_kind[MAXH]; /* 1 linear, 2 array, 3 mipmap, 4 vmm */
 static int g_np;
 static void *g_exec;
 
+/* a crash inside a preloaded library should leave a trace in the test log: module+offset frames for addr2line */
+static void on_crash(int sig) {
+  void *frames[48];
+  int n = backtrace(frames, 48);
+  static const char msg[] = "scenario: fatal signal, backtrace:\n";
+  if (write(2, msg, sizeof msg - 1) < 0) _exit(128 + sig);
+  backtrace_symbols_fd(frames, n, 2);
+  signal(sig, SIG_DFL);
+  raise(sig);
+}
+
 int main(int argc, char **argv) {
+  signal(SIGSEGV, on_crash);
+  signal(SIGBUS, on_crash);
+  signal(SIGABRT, on_crash);
+  setvbuf(stdout, NULL, _IOLBF, 0); /* keep the transcript up to the crash */
   for (int i = 1; i < argc; i++)
     if (!strcmp(argv[i], "--gpa")) use_gpa = 1;
   h_cuda = dlopen("libcuda.so.1", RTLD_NOW | RTLD_GLOBAL);

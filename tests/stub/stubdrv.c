@@ -52,7 +52,8 @@ static __thread int t_cur_dev = 0;
 static volatile int g_parked; /* callers blocked behind the gate (the fake GPU's "parked streams") */
 static void *volatile g_parked_streams[64]; /* which streams those are (cuStreamQuery answers NOT_READY for them) */
 static __thread int t_has_ctx = 0;
-static int g_any_ctx;
+static int g_any_ctx;            /* this process has (had) a context somewhere: it shows up in NVML's lists */
+static int g_ctx_on[16];         /* ... on this device */
 
 typedef struct { uint32_t pid; uint64_t bytes; int compute, graphics; int sm; } other_t;
 static other_t g_others[64];
@@ -201,23 +202,30 @@ EXPORT CUresult cuGetErrorString(CUresult r, const char **s) {
 EXPORT CUresult cuGetErrorName(CUresult r, const char **s) { return cuGetErrorString(r, s); }
 
 /* contexts: one implicit primary context per device, made current by the harness */
-EXPORT CUresult cuDevicePrimaryCtxRetain(void **ctx, CUdevice d) { stub_init(); *ctx = (void *)(uintptr_t)(0x1000 + d); g_any_ctx = 1; return 0; }
+EXPORT CUresult cuDevicePrimaryCtxRetain(void **ctx, CUdevice d) { stub_init(); *ctx = (void *)(uintptr_t)(0x1000 + d); g_any_ctx = 1; g_ctx_on[d & 15] = 1; return 0; }
 EXPORT CUresult cuDevicePrimaryCtxRelease_v2(CUdevice d) { (void)d; return 0; }
-EXPORT CUresult cuDevicePrimaryCtxGetState(CUdevice d, unsigned *flags, int *active) { (void)d; if (flags) *flags = 0; *active = g_any_ctx; return 0; }
+EXPORT CUresult cuDevicePrimaryCtxGetState(CUdevice d, unsigned *flags, int *active) { if (flags) *flags = 0; *active = g_ctx_on[d & 15]; return 0; }
 /* context death: everything that lived in it is unmapped, so a library that still touches its old
  * device or pinned memory afterwards faults instead of silently reading stale bytes */
 EXPORT CUresult cuDevicePrimaryCtxReset_v2(CUdevice d) {
-  (void)d;
+  /* only this device's context dies: what lives in another GPU's context stays (a two-GPU sweep had the library's
+   * runtime on the other device faulting on memory the stub had wrongly taken away) */
   pthread_mutex_lock(&g_mu);
-  for (size_t i = 0; i < g_nallocs; i++) big_free(g_allocs[i].p, g_allocs[i].n);
-  g_nallocs = 0;
-  memset(g_dev_bytes, 0, sizeof g_dev_bytes);
+  size_t keep = 0;
+  for (size_t i = 0; i < g_nallocs; i++) {
+    if (g_allocs[i].dev == d) big_free(g_allocs[i].p, g_allocs[i].n);
+    else g_allocs[keep++] = g_allocs[i];
+  }
+  g_nallocs = keep;
+  g_dev_bytes[d & 15] = 0;
+  g_ctx_on[d & 15] = 0;
   g_any_ctx = 0;
+  for (int i = 0; i < 16; i++) g_any_ctx |= g_ctx_on[i];
   pthread_mutex_unlock(&g_mu);
-  t_has_ctx = 0;
+  if (t_cur_dev == d) t_has_ctx = 0;
   return 0;
 }
-EXPORT CUresult cuCtxCreate_v2(void **ctx, unsigned f, CUdevice d) { (void)f; stub_init(); *ctx = (void *)(uintptr_t)(0x1000 + d); t_cur_dev = d; t_has_ctx = 1; g_any_ctx = 1; return 0; }
+EXPORT CUresult cuCtxCreate_v2(void **ctx, unsigned f, CUdevice d) { (void)f; stub_init(); *ctx = (void *)(uintptr_t)(0x1000 + d); t_cur_dev = d; t_has_ctx = 1; g_any_ctx = 1; g_ctx_on[d & 15] = 1; return 0; }
 EXPORT CUresult cuCtxDestroy_v2(void *ctx) { (void)ctx; return 0; }
 EXPORT CUresult cuCtxSetCurrent(void *ctx) { if (!ctx) { t_has_ctx = 0; return 0; } t_cur_dev = (int)((uintptr_t)ctx - 0x1000); t_has_ctx = 1; return 0; }
 EXPORT CUresult cuCtxGetCurrent(void **ctx) { *ctx = t_has_ctx ? (void *)(uintptr_t)(0x1000 + t_cur_dev) : NULL; return 0; }
@@ -365,7 +373,7 @@ EXPORT CUresult cuArray3DCreate_v2(void **h, const arr3_t *d) {
 EXPORT CUresult cuMipmappedArrayCreate(void **h, const arr3_t *d, unsigned levels) { (void)levels; return cuArray3DCreate_v2(h, d); }
 EXPORT CUresult cuArrayDestroy(void *h) { return dev_free((CUdeviceptr)(uintptr_t)h); }
 EXPORT CUresult cuMipmappedArrayDestroy(void *h) { return dev_free((CUdeviceptr)(uintptr_t)h); }
-EXPORT CUresult cuMemHostAlloc(void **pp, size_t n, unsigned f) { (void)f; *pp = big_alloc(n); if (!*pp) return 2; track(*pp, n, 2, 0); return 0; }
+EXPORT CUresult cuMemHostAlloc(void **pp, size_t n, unsigned f) { (void)f; *pp = big_alloc(n); if (!*pp) return 2; track(*pp, n, 2, t_has_ctx ? t_cur_dev : 0); return 0; }
 EXPORT CUresult cuMemFreeHost(void *p) { alloc_t a; if (!untrack(p, &a)) return 1; big_free(a.p, a.n); return 0; }
 EXPORT CUresult cuMemHostGetDevicePointer_v2(CUdeviceptr *d, void *p, unsigned f) { (void)f; *d = (CUdeviceptr)(uintptr_t)p; return 0; }
 EXPORT CUresult cuMemGetAddressRange_v2(CUdeviceptr *base, size_t *size, CUdeviceptr d) {

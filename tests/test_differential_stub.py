@@ -450,6 +450,23 @@ def test_two_gpus_frees_and_reports_across_devices(built):
     assert_same(both(script3, env3, stub))
 
 
+def test_reset_of_one_gpu_leaves_the_other_gpus_runtime_alone(built):
+    """Two GPUs, both capped; the tenant resets the primary context of one of them.  Only that device's runtime goes away
+    (and its share of the footprint registry with it); allocations, reports and the ledger on the other device carry on,
+    and the reset device is rebuilt at its next use - transcript identical to the reference."""
+    u0, u1 = H.STUB_UUID, "GPU-22222222-2222-2222-2222-222222222222"
+    env = {"MANAGER_VISIBLE_DEVICES": u1 + "," + u0, "CUDA_MEM_LIMIT_0": "1g", "CUDA_MEM_RATIO_0": "2", "CUDA_MEM_LIMIT_1": "1g",
+           "VMEMORY_NODE_ENABLED": "true"}
+    script = ("init 0\nmanaged %d 1\ndev 1\nalloc %d\nmeminfo\ndev 0\nreset\ndev 1\nalloc 4096\nmeminfo\nnvmlinfo\nledger 0\n"
+              "dev 0\nmeminfo\nalloc %d\nmeminfo\nnvmlinfo\nledger 1\n") % (200 * MiB, 64 * MiB, 32 * MiB)
+    outs = both(script, env, {"STUB_GPU_COUNT": "2", "STUB_UTIL": "fixed:5"})
+    assert_same(outs)
+    # an un-capped GPU that only carried a ledgered managed allocation: after its reset nothing of the library is left there
+    env2 = {"MANAGER_VISIBLE_DEVICES": u0 + "," + u1, "CUDA_MEM_LIMIT_1": "1g", "VMEMORY_NODE_ENABLED": "true"}
+    script2 = "init 0\nmanaged 4096 1\nnvmlinfo\nreset\ndev 0\nnvmlinfo\nmeminfo\ndev 1\nalloc 4096\nnvmlinfo\n"
+    assert_same(both(script2, env2, {"STUB_GPU_COUNT": "2", "STUB_UTIL": "fixed:5"}))
+
+
 def test_closed_loop_share_is_in_the_references_ballpark(built):
     """The reference defines no core-% tolerance (SURVEY.md 8a L-tol); what can be compared is the rate each
     limiter settles at when the fake GPU's utilisation follows the tenant's own launch rate (closed loop,

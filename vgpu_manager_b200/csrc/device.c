@@ -416,6 +416,7 @@ unsigned vgpu_rt_context_before(CUcontext ctx, CUdevice dev, int primary) {
 
 void vgpu_rt_context_after(unsigned mask, int still_alive) {
   if (!mask) return;
+  int gone[VGPU_MAX_DEVICES], n_gone = 0;
   pthread_mutex_lock(&g_rt_mu);
   for (int slot = 0; slot < VGPU_MAX_DEVICES; slot++) {
     if (!(mask & (1u << slot))) continue;
@@ -429,12 +430,22 @@ void vgpu_rt_context_after(unsigned mask, int still_alive) {
        * context brings a fresh one up (token bucket and slab start empty, like a new process) */
       VLOG(VL_INFO, "context of runtime slot %d is gone; device state will be rebuilt on next use", slot);
       if (rt->host_index >= 0) vgpu_limiter_attach(rt->host_index, 1);
+      if (rt->host_index >= 0 && rt->self_bytes) gone[n_gone++] = rt->host_index;
       vgpu_slab_forget(rt);
       pthread_mutex_destroy(&rt->q_mu);
       memset(rt, 0, sizeof *rt);
     }
   }
   pthread_mutex_unlock(&g_rt_mu);
+  /* the device memory went with the context: take this process's share out of the container's footprint registry
+   * (outside g_rt_mu - the allocation path takes the GPU lock first and the runtime table second) */
+  for (int i = 0; i < n_gone; i++) {
+    int fd = vgpu_lock_gpu(gone[i]);
+    if (fd >= 0) {
+      vgpu_self_registry(gone[i], 0, 1);
+      vgpu_unlock_gpu(fd);
+    }
+  }
 }
 
 vgpu_dev_rt *vgpu_rt_peek(int host_index) {

@@ -34,6 +34,8 @@ extern "C" {
 #define VGPU_PIDS_FILE VGPU_CFG_DIR "/pids.config"
 #define VGPU_REBALANCE_FILE VGPU_CFG_DIR "/rebalance.config" /* B200 addition, optional (kernel_abi.h) */
 #define VGPU_STATUS_FMT VGPU_LOCK_DIR "/vgpu_%d.status"       /* B200 addition, written only while the former exists */
+#define VGPU_READINGS_FMT VGPU_LOCK_DIR "/vgpu_%d.readings"   /* B200 addition: on-device utilisation readings (below) */
+#define VGPU_TUNABLES_FILE VGPU_CFG_DIR "/b200.tunables"      /* B200 addition, optional: NAME=value lines from the control plane */
 #define VGPU_SMUTIL_FILE VGPU_ROOT_DIR "/watcher/sm_util.config"
 #define VGPU_SELF_FILE VGPU_ROOT_DIR "/driver/libvgpu-control.so"
 #define VGPU_HOSTPROC_CGROUP_FMT VGPU_ROOT_DIR "/.host_proc/%d/cgroup"
@@ -143,6 +145,28 @@ typedef struct {
 VGPU_STATIC_ASSERT(sizeof(vgpu_cfg_dev_t) == 96, cfg_dev);
 VGPU_STATIC_ASSERT(sizeof(vgpu_cfg_t) == 1848, cfg);
 VGPU_STATIC_ASSERT(offsetof(vgpu_cfg_t, devices) == 248, cfg_devs);
+/* VGPU_LOCK_DIR/vgpu_<host index>.readings (B200 addition): a tenant whose limiter runs on an
+ * on-device utilisation signal (stream queue-busy / per-SM probe) publishes the reading of every control period
+ * here; the node's SM watcher (csrc/smwatcher.c --source device|mixed) turns the fresh ones into the per-process
+ * samples of sm_util.config, so consumers (either interception library in external-watcher mode, the Go
+ * device-monitor) get them without anybody polling nvmlDeviceGetProcessUtilization.  A tenant only knows its pid
+ * inside its own pid namespace: it publishes that together with the namespace's inode and the watcher resolves
+ * NVML's host pids through /proc/<pid>/ns/pid + the NSpid line of /proc/<pid>/status. */
+#define VGPU_READINGS_SLOTS 1024
+typedef struct {
+  uint64_t owner;          /* (pid-namespace inode << 32) | pid inside that namespace; 0 = free slot (claimed by CAS) */
+  uint64_t ts_us;          /* CLOCK_REALTIME of the publication, written last                                         */
+  uint32_t sm_pct;         /* the controller's reading for this period (what NVML calls smUtil), 0..100               */
+  uint32_t queue_busy_pct; /* its two ingredients, for diagnosis                                                      */
+  uint32_t sm_active_pct;
+  uint32_t seq;            /* publications by this owner                                                              */
+} vgpu_reading_t;
+typedef struct {
+  vgpu_reading_t slots[VGPU_READINGS_SLOTS];
+} vgpu_readings_t;
+VGPU_STATIC_ASSERT(sizeof(vgpu_reading_t) == 32, reading);
+VGPU_STATIC_ASSERT(sizeof(vgpu_readings_t) == 32768, readings);
+
 VGPU_STATIC_ASSERT(offsetof(vgpu_cfg_t, compatibility_mode) == 1784, cfg_mode);
 VGPU_STATIC_ASSERT(offsetof(vgpu_cfg_t, reg_uuid) == 1796, cfg_reg);
 VGPU_STATIC_ASSERT(sizeof(vgpu_proc_t) == 16, proc);

@@ -391,6 +391,7 @@ EXPORT CUresult cuMemGetAddressRange_v2(CUdeviceptr *base, size_t *size, CUdevic
 }
 EXPORT CUresult cuMemsetD8_v2(CUdeviceptr d, unsigned char v, size_t n) { memset((void *)(uintptr_t)d, v, n); return 0; }
 EXPORT CUresult cuMemcpyDtoH_v2(void *dst, CUdeviceptr src, size_t n) { memcpy(dst, (void *)(uintptr_t)src, n); return 0; }
+EXPORT CUresult cuMemcpyDtoHAsync_v2(void *dst, CUdeviceptr src, size_t n, void *s) { (void)s; memcpy(dst, (void *)(uintptr_t)src, n); return 0; }
 EXPORT CUresult cuMemcpyHtoD_v2(CUdeviceptr dst, const void *src, size_t n) { memcpy((void *)(uintptr_t)dst, src, n); return 0; }
 EXPORT CUresult cuMemcpyDtoD_v2(CUdeviceptr dst, CUdeviceptr src, size_t n) { memmove((void *)(uintptr_t)dst, (void *)(uintptr_t)src, n); return 0; }
 EXPORT CUresult cuMemcpy(CUdeviceptr dst, CUdeviceptr src, size_t n) { memmove((void *)(uintptr_t)dst, (void *)(uintptr_t)src, n); return 0; }
@@ -967,6 +968,7 @@ static const struct { const char *name; void *fn; } g_self_table[] = {
   {"cuMemHostGetDevicePointer_v2", (void *)cuMemHostGetDevicePointer_v2},
   {"cuMemsetD8_v2", (void *)cuMemsetD8_v2},
   {"cuMemcpyDtoH_v2", (void *)cuMemcpyDtoH_v2},
+  {"cuMemcpyDtoHAsync_v2", (void *)cuMemcpyDtoHAsync_v2},
   {"cuMemcpyHtoD_v2", (void *)cuMemcpyHtoD_v2},
   {"cuMemcpyDtoD_v2", (void *)cuMemcpyDtoD_v2},
   {"cuMemcpy", (void *)cuMemcpy},

@@ -403,6 +403,27 @@ def test_device_reset_rebuilds_the_device_state(built):
     assert "limstate consumed 0" in out  # a fresh bucket after the last reset (nothing launched since)
 
 
+def test_uva_records_outlive_a_device_reset_like_the_reference_list(built):
+    """The reference's list of UVA allocations is host memory: a device reset leaves its nodes in place, and when a
+    later allocation that gets the same address is freed, the stale node is found and the ledger shrinks by ITS size
+    (loader.c:1869-1907) - also when the new allocation was not a UVA one.  The records here live in HBM; they are
+    read back while the context is torn down and searched after the live table (found by the offline sweep: a 1-byte
+    ledger difference in 2 of 2400 random scripts)."""
+    env = {"CUDA_MEM_LIMIT_0": "4g", "CUDA_MEM_RATIO_0": "4", "VMEMORY_NODE_ENABLED": "true", "STUB_PHYS_MEM": str(8 * GiB + 48 * MiB)}
+    # a VMM handle fills the 1 GiB physical share, so the two small allocations are UVA ones (ledger 12288); after the
+    # reset the same two requests get the same addresses on the GPU path (ledger untouched), and freeing them removes
+    # the stale nodes: 12288 -> 8192 -> 0.  Then a second life with live records over stale addresses (newest first).
+    script = ("init 0\ncreate %d\nalloc 4096\nalloc 8192\nledger 0\nreset\nledger 0\n"
+              "alloc 4096\nalloc 8192\nledger 0\nfree 0\nledger 0\nfree 1\nledger 0\n"
+              "create %d\nalloc 4096\nledger 0\nreset\ncreate %d\nalloc 4096\nledger 0\nfree 1\nledger 0\n"
+              "reset\nalloc 4096\nfree 0\nledger 0\nnvmlinfo\n") % (GiB, GiB, GiB)
+    for args in ((), ("--gpa",)):
+        t = assert_same(both(script, env, args=args))
+        led = [int(l.split()[-1].rstrip("]")) for l in t.splitlines() if l.startswith("ledger")]
+        assert led[:5] == [12288, 12288, 12288, 8192, 0], led   # stale nodes matched by address after the reset
+        assert led[5:] == [4096, 8192, 4096, 0], led            # live record first, then the stale one under the same address
+
+
 def test_one_process_on_two_gpus_with_a_hole_in_the_visible_list(built):
     """MANAGER_VISIBLE_DEVICES lists host GPUs by index with all-zero UUIDs as holes (util.c:27-120):
     host 0 = CUDA device 1, host 1 = hole, host 2 = CUDA device 0.  One process uses both devices;
@@ -704,6 +725,27 @@ def test_enforcement_tunables_are_ignored_under_a_mounted_config(built):
     l2, s2 = counts(out2)
     assert l1 >= 60 and l1 >= 5 * s1, (l1, s1)      # queue signal: ~100 windows, a step every 8th
     assert 8 <= l2 <= 16 and l2 == s2, (l2, s2)     # mounted config: the knob is ignored
+
+
+def test_control_plane_sets_tunables_through_a_file_next_to_the_mounted_config(built):
+    """Under a mounted vgpu.config the knobs belong to the control plane: an optional b200.tunables in the same
+    (read-only) config directory, NAME=value per line.  The tenant's environment says `nvml`, the file says `queue`:
+    the file wins; comments, unknown names and a name that is only a prefix of a line are ignored."""
+    env = dict(BASE)
+    env.update({"CUDA_MEM_LIMIT_0": "1g", "CUDA_CORE_LIMIT_0": "30", "STUB_UTIL": "fixed:20", "VGPU_B200_SKIP_IDLE_WINDOWS": "0"})
+    script = "init 0\nlaunch 50 4 1 1\nsleepms 1000\nmetrics 0\n"
+    sb = H.Sandbox()
+    H.run_scenario(H.NEW_SO, "init 0\n", env, sb=sb)  # leaves the env-built vgpu.config behind = "mounted" from now on
+    assert os.path.exists(sb.path("etc/vgpu-manager/config/vgpu.config"))
+    with open(sb.path("etc/vgpu-manager/config/b200.tunables"), "w") as f:
+        f.write("# node defaults\nVGPU_B200_UTIL_SOURCE_X=sm\nSOMETHING=else\nVGPU_B200_UTIL_SOURCE=queue\nVGPU_B200_SKIP_IDLE_WINDOWS=0\n")
+    env["VGPU_B200_UTIL_SOURCE"] = "nvml"
+    out, _, _ = H.run_scenario(H.NEW_SO, script, env, sb=sb)
+    assert os.path.exists(sb.path("lock/vgpu_0.readings"))  # and a tenant on an on-device signal publishes its reading (8f-1)
+    sb.cleanup()
+    m = [l for l in out.splitlines() if l.startswith("metrics")][0].split()
+    launches, steps = int(m[2]), int(m[6])
+    assert launches >= 60 and launches >= 5 * steps, (launches, steps)  # the queue signal's cadence, not the refill's
 
 
 def test_watcher_runs_from_cuinit_and_the_controller_catches_up(built):

@@ -52,10 +52,10 @@ def expected_device(others):
     return comp, graph, samples
 
 
-def run_watcher(path, passes, env_extra=None, period_ms=10):
+def run_watcher(path, passes, env_extra=None, period_ms=10, extra=()):
     env = dict(os.environ, STUB_GPU_COUNT="2", STUB_OTHER_PROCS=OTHERS)
     env.update(env_extra or {})
-    return subprocess.run([WATCHER, "--file", path, "--passes", str(passes), "--period-ms", str(period_ms), "--nvml", NVML_STUB],
+    return subprocess.run([WATCHER, "--file", path, "--passes", str(passes), "--period-ms", str(period_ms), "--nvml", NVML_STUB, *extra],
                           env=env, capture_output=True, text=True, timeout=60)
 
 
@@ -156,3 +156,126 @@ def test_both_libraries_consume_the_produced_file(built):
         sb.cleanup()
     assert all(rc == 0 for _, rc in outs), outs
     assert len(outs) < 2 or outs[0] == outs[1]
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# samples from the tenants' on-device readings (VGPU_LOCK_DIR/vgpu_<i>.readings) instead of
+# nvmlDeviceGetProcessUtilization
+
+
+class Reading(C.Structure):
+    _fields_ = [("owner", C.c_uint64), ("ts_us", C.c_uint64), ("sm_pct", C.c_uint32), ("queue_busy_pct", C.c_uint32),
+                ("sm_active_pct", C.c_uint32), ("seq", C.c_uint32)]
+
+
+assert C.sizeof(Reading) == 32
+READINGS_SIZE = 32 * 1024
+
+
+def owner_key(pid):
+    """What a tenant publishes under: (inode of its pid namespace << 32) | its pid inside that namespace."""
+    inner = pid
+    for line in open("/proc/%d/status" % pid):
+        if line.startswith("NSpid:"):
+            inner = int(line.split()[-1])
+    return (os.stat("/proc/%d/ns/pid" % pid).st_ino << 32) | inner
+
+
+def write_readings(path, entries):
+    raw = bytearray(READINGS_SIZE)
+    for slot, (owner, ts, sm) in entries.items():
+        struct.pack_into("<QQIIII", raw, 32 * slot, owner, ts, sm, sm, 0, 1)
+    with open(path, "wb") as f:
+        f.write(raw)
+
+
+def read_slots(path):
+    raw = open(path, "rb").read()
+    return [r for r in (Reading.from_buffer_copy(raw[32 * i:32 * i + 32]) for i in range(len(raw) // 32)) if r.owner]
+
+
+def test_samples_are_built_from_the_tenants_own_readings(built, tmp_path):
+    """--source device: a compute process with a fresh reading gets a sample carrying that reading (not NVML's figure);
+    processes that publish nothing, stale readings and readings of pids NVML does not list produce none.
+    --source mixed: NVML's samples, with the tenant's own reading replacing NVML's sample of its pid."""
+    me = os.getpid()
+    sleeper = subprocess.Popen(["sleep", "30"])
+    try:
+        now = int(time.time() * 1e6)
+        rd = tmp_path / "lock"
+        rd.mkdir()
+        write_readings(str(rd / "vgpu_0.readings"), {5: (owner_key(me), now, 42),                      # fresh, listed by NVML
+                                                     9: (owner_key(sleeper.pid), now - 5_000_000, 77),  # stale
+                                                     11: ((1 << 32) | 999999, now, 88)})                 # nobody NVML lists
+        write_readings(str(rd / "vgpu_1.readings"), {0: (owner_key(sleeper.pid), now, 13)})
+        procs = "%d:1048576:c:30,%d:2097152:c:10,333:4096:g" % (me, sleeper.pid)
+        path = str(tmp_path / "sm_util.config")
+        r = run_watcher(path, 1, {"STUB_OTHER_PROCS": procs}, extra=["--source", "device", "--readings-dir", str(rd)])
+        assert r.returncode == 0, r.stderr
+        raw = open(path, "rb").read()
+        d0, d1 = (SmDev.from_buffer_copy(raw[i * DEV_SIZE:(i + 1) * DEV_SIZE]) for i in range(2))
+        assert [(p.pid, p.used) for p in d0.compute[:d0.compute_size]] == [(me, 1048576), (sleeper.pid, 2097152)]  # lists: NVML
+        assert [(s.pid, s.sm, s.mem, s.enc, s.dec) for s in d0.samples[:d0.samples_size]] == [(me, 42, 0, 0, 0)]
+        assert d0.samples[0].ts_us == now and d0.samples[0].ts_us > d0.last_seen_us
+        assert [(s.pid, s.sm) for s in d1.samples[:d1.samples_size]] == [(sleeper.pid, 13)]
+        # nothing fresh any more (NVML's NOT_FOUND case): the lists are refreshed, the previous samples stay
+        time.sleep(1.1)
+        r = run_watcher(path, 1, {"STUB_OTHER_PROCS": procs}, extra=["--source", "device", "--readings-dir", str(rd)])
+        assert r.returncode == 0, r.stderr
+        again = SmDev.from_buffer_copy(open(path, "rb").read()[:DEV_SIZE])
+        assert again.samples_size == 1 and again.samples[0].ts_us == now and again.last_seen_us > d0.last_seen_us
+        # mixed
+        now = int(time.time() * 1e6)
+        write_readings(str(rd / "vgpu_0.readings"), {5: (owner_key(me), now, 42)})
+        r = run_watcher(path, 1, {"STUB_OTHER_PROCS": procs}, extra=["--source", "mixed", "--readings-dir", str(rd)])
+        assert r.returncode == 0, r.stderr
+        m0 = SmDev.from_buffer_copy(open(path, "rb").read()[:DEV_SIZE])
+        assert sorted((s.pid, s.sm) for s in m0.samples[:m0.samples_size]) == sorted([(me, 42), (sleeper.pid, 10)])
+    finally:
+        sleeper.kill()
+        sleeper.wait()
+
+
+def test_a_tenant_on_an_on_device_signal_publishes_its_reading_and_the_watcher_serves_it(built):
+    """End to end on the fake driver: a tenant whose limiter steers on the stream queue-busy signal publishes one
+    reading per control period next to the GPU lock file; vgpu-smwatcher --source device turns it into the tenant's
+    sample of sm_util.config without asking NVML for utilisation (the fake NVML would have said 77).  A tenant on the
+    default NVML reading publishes nothing."""
+    base = {"MANAGER_COMPATIBILITY_MODE": "0", "MANAGER_VISIBLE_DEVICES": H.STUB_UUID, "LOGGER_LEVEL": "1",
+            "CUDA_CORE_LIMIT_0": "30", "STUB_UTIL": "fixed:40"}
+    script = "init 0\n" + "launch 500\nsleepms 100\n" * 25
+    for source, expect in (("queue", True), (None, False)):
+        sb = H.Sandbox()
+        env = dict(base)
+        if source:
+            env["VGPU_B200_UTIL_SOURCE"] = source
+        tenant = subprocess.Popen([H.SCENARIO], stdin=subprocess.PIPE, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True,
+                                  env=H.preload_env(H.NEW_SO, sb, env))
+        try:
+            tenant.stdin.write(script)
+            tenant.stdin.close()
+            rfile = sb.path("lock/vgpu_0.readings")
+            t_end = time.time() + 2.0
+            slots = []
+            while time.time() < t_end and not (slots and slots[0].seq >= 3):
+                time.sleep(0.1)
+                slots = read_slots(rfile) if os.path.exists(rfile) else []
+            if not expect:
+                assert not slots, [(s.owner, s.seq) for s in slots]
+                continue
+            assert len(slots) == 1 and slots[0].owner == owner_key(tenant.pid), [(hex(s.owner), s.seq) for s in slots]
+            assert slots[0].seq >= 3 and slots[0].sm_pct <= 100 and abs(slots[0].ts_us - time.time() * 1e6) < 2e6
+            path = sb.path("etc/vgpu-manager/watcher/sm_util.config")
+            r = subprocess.run([WATCHER, "--file", path, "--passes", "1", "--nvml", NVML_STUB, "--source", "device",
+                                "--readings-dir", sb.path("lock")],
+                               env=dict(os.environ, STUB_GPU_COUNT="1", STUB_OTHER_PROCS="%d:1048576:c:77" % tenant.pid),
+                               capture_output=True, text=True, timeout=30)
+            assert r.returncode == 0, r.stderr
+            d = SmDev.from_buffer_copy(open(path, "rb").read()[:DEV_SIZE])
+            fresh = read_slots(rfile)[0]
+            assert d.samples_size == 1 and d.samples[0].pid == tenant.pid and d.samples[0].sm <= 100 and d.samples[0].sm != 77
+            assert abs(int(d.samples[0].sm) - int(fresh.sm_pct)) <= 100 and d.samples[0].ts_us >= d.last_seen_us
+        finally:
+            tenant.kill()
+            tenant.wait()
+            sb.cleanup()

@@ -37,8 +37,36 @@ static vgpu_cfg_t g_env_cfg;
 /* Enforcement-affecting tunables (utilisation source, periods, watchdog ...) are honoured only
  * when the limits themselves came from the tenant's environment, i.e. no control-plane config
  * is mounted; under a mounted vgpu.config the tenant's environment cannot loosen its cap. */
+/* Under a mounted config the control plane can still set them: an optional VGPU_CFG_DIR/b200.tunables next to
+ * vgpu.config (the same read-only mount), NAME=value per line, '#' comments.  Read once. */
+static char g_tunables[4096]; /* [0] stays 0; lines, each 0-terminated, follow */
+static int g_tunables_end;    /* index one past the last byte read; 0 = no file */
+static void tunables_load(void) {
+  int fd = open(VP(VGPU_TUNABLES_FILE), O_RDONLY | O_CLOEXEC);
+  if (fd < 0) return;
+  ssize_t n = read(fd, g_tunables + 1, sizeof g_tunables - 2);
+  close(fd);
+  if (n <= 0) return;
+  g_tunables[1 + n] = 0;
+  for (ssize_t i = 1; i <= n; i++)
+    if (g_tunables[i] == '\n' || g_tunables[i] == '\r') g_tunables[i] = 0;
+  g_tunables_end = 1 + (int)n;
+}
+static const char *tunable_from_file(const char *name) {
+  static pthread_once_t once = PTHREAD_ONCE_INIT;
+  pthread_once(&once, tunables_load);
+  const size_t len = strlen(name);
+  for (int i = 1; i < g_tunables_end;) {
+    const char *line = g_tunables + i;
+    size_t ll = strlen(line);
+    if (ll > len && line[len] == '=' && !strncmp(line, name, len)) return line[len + 1] ? line + len + 1 : NULL;
+    i += (int)ll + 1;
+  }
+  return NULL;
+}
+
 const char *vgpu_tunable(const char *name) {
-  if (G_cfg && G_cfg != &g_env_cfg) return NULL;
+  if (G_cfg && G_cfg != &g_env_cfg) return tunable_from_file(name);
   const char *s = getenv(name);
   return (s && *s) ? s : NULL;
 }

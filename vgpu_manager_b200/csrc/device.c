@@ -397,6 +397,77 @@ vgpu_dev_rt *vgpu_rt_get(int host_index, CUdevice dev) {
   return out;
 }
 
+/* ------------------------------------------------------------------ UVA records that outlive their context
+ * The reference keeps its UVA allocation nodes in a host list (loader.c:1824-1907) which a device reset does not
+ * touch: a node whose memory went with the context stays listed, and when a later allocation that happens to get
+ * the same address is freed, free_gpu_virt_memory finds the stale node and shrinks the ledger by its size.  The
+ * records here live in HBM and would vanish with the context, so they are read back once, while the context is
+ * being torn down (one 256 KiB copy on the library's own stream), and kept as the "stale" list a free falls back
+ * to after the live tables.  Newest first, like list_add: live records are always newer than stale ones, a later
+ * reset's records newer than an earlier one's. */
+static vgpu_slab_slot_t *g_stale;
+static uint32_t g_stale_n, g_stale_cap;
+static pthread_mutex_t g_stale_mu = PTHREAD_MUTEX_INITIALIZER;
+
+int vgpu_stale_uva_remove(CUdeviceptr dptr, uint64_t *bytes) {
+  if (!g_stale_n) return 1;
+  int rc = 1;
+  pthread_mutex_lock(&g_stale_mu);
+  for (uint32_t i = g_stale_n; i-- > 0;)
+    if (g_stale[i].dptr == (uint64_t)dptr) {
+      *bytes = g_stale[i].bytes;
+      memmove(&g_stale[i], &g_stale[i + 1], (size_t)(g_stale_n - i - 1) * sizeof g_stale[0]);
+      g_stale_n--;
+      rc = 0;
+      break;
+    }
+  pthread_mutex_unlock(&g_stale_mu);
+  return rc;
+}
+
+static void stale_keep(vgpu_slab_slot_t *recs, uint32_t n) {
+  pthread_mutex_lock(&g_stale_mu);
+  if (g_stale_n + n > g_stale_cap) {
+    uint32_t cap = (g_stale_n + n + 63u) & ~63u;
+    vgpu_slab_slot_t *p = (vgpu_slab_slot_t *)realloc(g_stale, (size_t)cap * sizeof *p);
+    if (p) { g_stale = p; g_stale_cap = cap; }
+  }
+  if (g_stale_n + n <= g_stale_cap) {
+    memcpy(&g_stale[g_stale_n], recs, (size_t)n * sizeof recs[0]);
+    g_stale_n += n;
+  }
+  pthread_mutex_unlock(&g_stale_mu);
+}
+
+static int ctx_enter(vgpu_dev_rt *rt);
+static void ctx_leave(int pushed);
+
+/* caller holds g_rt_mu; the runtime is still whole */
+static void uva_snapshot(vgpu_dev_rt *rt) {
+  rt->uva_snap = NULL;
+  rt->uva_snap_n = 0;
+  if (rt->uva_live <= 0 || !R.cuMemcpyDtoHAsync_v2 || !R.cuStreamSynchronize) return;
+  vgpu_slab_slot_t *tab = (vgpu_slab_slot_t *)malloc(sizeof(vgpu_slab_slot_t) * VGPU_SLAB_SLOTS);
+  if (!tab) return;
+  pthread_mutex_lock(&rt->q_mu);
+  int pushed = ctx_enter(rt);
+  /* the library's own non-blocking stream: not ordered behind anything of the tenant's */
+  CUresult r = R.cuMemcpyDtoHAsync_v2(tab, rt->slab_d, sizeof(vgpu_slab_slot_t) * VGPU_SLAB_SLOTS, rt->q_stream);
+  if (r == CUDA_SUCCESS) r = R.cuStreamSynchronize(rt->q_stream);
+  ctx_leave(pushed);
+  pthread_mutex_unlock(&rt->q_mu);
+  if (r != CUDA_SUCCESS) {
+    VLOG(VL_WARNING, "could not read the UVA records back before the context goes (%d: %s)", r, vgpu_cu_err(r));
+    free(tab);
+    return;
+  }
+  uint32_t n = 0;
+  for (uint32_t i = 0; i < VGPU_SLAB_SLOTS; i++)
+    if (tab[i].dptr > 1) tab[n++] = tab[i]; /* 0 free, 1 tombstone */
+  rt->uva_snap = tab;
+  rt->uva_snap_n = n;
+}
+
 unsigned vgpu_rt_context_before(CUcontext ctx, CUdevice dev, int primary) {
   unsigned mask = 0;
   if (g_rt_epoch != vgpu_fork_epoch + 1) return 0;
@@ -407,6 +478,7 @@ unsigned vgpu_rt_context_before(CUcontext ctx, CUdevice dev, int primary) {
     int hit = primary ? (rt->cuda_dev == dev && rt->ctx_is_primary) : (rt->ctx == ctx);
     if (!hit) continue;
     if (rt->host_index >= 0) vgpu_limiter_detach(rt->host_index);
+    uva_snapshot(rt);
     rt->ready = 2; /* parked: neither usable nor up for a new bring-up until _after() decides */
     mask |= 1u << slot;
   }
@@ -423,9 +495,13 @@ void vgpu_rt_context_after(unsigned mask, int still_alive) {
     vgpu_dev_rt *rt = &g_rt[slot];
     if (rt->ready != 2) continue;
     if (still_alive) {
+      free(rt->uva_snap); /* the table itself is still there */
+      rt->uva_snap = NULL;
       rt->ready = 1;
       if (rt->host_index >= 0) vgpu_limiter_attach(rt->host_index, 0);
     } else {
+      if (rt->uva_snap_n) stale_keep(rt->uva_snap, rt->uva_snap_n);
+      free(rt->uva_snap);
       /* everything the runtime owned went with the context; the next hooked call in a new
        * context brings a fresh one up (token bucket and slab start empty, like a new process) */
       VLOG(VL_INFO, "context of runtime slot %d is gone; device state will be rebuilt on next use", slot);

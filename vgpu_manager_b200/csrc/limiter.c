@@ -53,6 +53,8 @@
 #include <errno.h>
 #include <fcntl.h>
 #include <sched.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
 #include <time.h>
 
 extern vgpu_dev_rt *vgpu_rt_get(int host_index, CUdevice dev);
@@ -262,6 +264,68 @@ static void exchange_with_node_agent(vgpu_dev_rt *rt, int h) {
     ssize_t w = pwrite(fd_st[h] - 1, &st, sizeof st, 0);
     (void)w;
   }
+}
+
+/* ------------------------------------------------------------------ on-device readings for the node's SM watcher (8f-1)
+ * A tenant whose limiter steers on an on-device signal (queue-busy / per-SM probe, or the governor) knows its own SM
+ * utilisation without NVML.  Once per control period the reading goes into VGPU_LOCK_DIR/vgpu_<h>.readings
+ * (include/vgpu_contract.h), from where vgpu-smwatcher --source device|mixed builds the per-process samples of
+ * sm_util.config for every consumer on the node - the counterpart of watcher.go:160-182 without the
+ * nvmlDeviceGetProcessUtilization poll.  Plain stores into a shared mapping: no lock, no driver call, no syscall
+ * after the first publication. */
+static void publish_device_reading(int h, const vgpu_lim_host_t *H) {
+  static vgpu_readings_t *map[VGPU_MAX_DEVICES];
+  static int slot[VGPU_MAX_DEVICES];    /* index + 1 */
+  static unsigned epoch_of[VGPU_MAX_DEVICES];
+  static uint64_t me;
+  if (epoch_of[h] != vgpu_fork_epoch + 1) { /* a forked child is another owner */
+    epoch_of[h] = vgpu_fork_epoch + 1;
+    slot[h] = 0;
+    me = 0;
+  }
+  if (map[h] == (vgpu_readings_t *)MAP_FAILED) return;
+  if (!map[h]) {
+    char raw[64];
+    snprintf(raw, sizeof raw, VGPU_READINGS_FMT, h);
+    int fd = open(VP(raw), O_RDWR | O_CREAT | O_CLOEXEC, 0666);
+    struct stat st;
+    if (fd < 0 || fstat(fd, &st) != 0 || ((size_t)st.st_size < sizeof(vgpu_readings_t) && ftruncate(fd, (off_t)sizeof(vgpu_readings_t)) != 0)) {
+      if (fd >= 0) close(fd);
+      map[h] = (vgpu_readings_t *)MAP_FAILED;
+      return;
+    }
+    void *m = mmap(NULL, sizeof(vgpu_readings_t), PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+    close(fd);
+    map[h] = (vgpu_readings_t *)m; /* MAP_FAILED: never tried again */
+    if (m == MAP_FAILED) return;
+  }
+  if (!me) {
+    struct stat ns;
+    uint64_t ino = stat("/proc/self/ns/pid", &ns) == 0 ? (uint64_t)ns.st_ino : 0;
+    me = (ino << 32) | (uint32_t)getpid();
+  }
+  vgpu_readings_t *F = map[h];
+  const unsigned long long now = wall_us();
+  if (!slot[h] || F->slots[slot[h] - 1].owner != me) { /* claim: my old slot, a free one, or one nobody wrote for 10 s */
+    slot[h] = 0;
+    for (int pass = 0; pass < 2 && !slot[h]; pass++)
+      for (int i = 0; i < VGPU_READINGS_SLOTS; i++) {
+        uint64_t o = F->slots[i].owner;
+        if (o == me) { slot[h] = i + 1; break; }
+        if (pass == 0) continue; /* first pass only looks for a slot that is already mine */
+        if (o != 0 && now - F->slots[i].ts_us < 10000000ull) continue;
+        if (__sync_bool_compare_and_swap(&F->slots[i].owner, o, me)) { F->slots[i].ts_us = now; F->slots[i].seq = 0; slot[h] = i + 1; break; }
+      }
+    if (!slot[h]) return; /* 1024 live publishers on one GPU: give up quietly */
+  }
+  vgpu_reading_t *r = &F->slots[slot[h] - 1];
+  int u = H->user_current;
+  r->sm_pct = (uint32_t)(u < 0 ? 0 : u > 100 ? 100 : u);
+  r->queue_busy_pct = (uint32_t)H->queue_busy_pct;
+  r->sm_active_pct = (uint32_t)H->sm_active_pct;
+  r->seq++;
+  __sync_synchronize();
+  r->ts_us = now;
 }
 
 static unsigned refill_block(const vgpu_util_req_t *U) {
@@ -479,6 +543,8 @@ static void *tick_main(void *arg) {
             !vgpu_tunable("VGPU_B200_UTIL_SOURCE")) backlog_push(h);
         continue;
       }
+      if ((rt->lim_h->util_source != VGPU_SRC_NVML || g_governor_mode) && epoch % g_period_ticks == 0)
+        publish_device_reading(h, rt->lim_h); /* for the node's SM watcher; the default NVML reading has nothing to add */
       uint64_t ts0 = slow_t0();
       g_tick_in_cuda = 1;
       if (VGPU_CAPCHK(R.cuCtxPushCurrent_v2(rt->ctx)) != CUDA_SUCCESS) { g_tick_in_cuda = 0; continue; }

@@ -346,6 +346,8 @@ static void ledger_sub(CUdevice dev, CUdeviceptr dptr) {
     if (!other || other == rt) continue;
     if (vgpu_rt_slab_remove(other, dptr, &bytes) == 0) found = 1;
   }
+  /* ... and by the records whose context is gone (the reference's list survives a device reset) */
+  if (!found && vgpu_stale_uva_remove(dptr, &bytes) == 0) found = 1;
   if (!found) return;
   if (host_index < 0 || host_index >= VGPU_MAX_DEVICES || !G_vmem) return;
   int fd = vgpu_vmem_lock(host_index, 1);

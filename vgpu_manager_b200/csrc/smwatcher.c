@@ -27,7 +27,16 @@
  *
  * Plain C, libc only; NVML is dlopen'ed like the library does (libnvidia-ml.so.1).
  *
+ * On-device readings (--source device|mixed): tenants whose limiter runs on an on-device
+ * utilisation signal publish their reading every control period in VGPU_LOCK_DIR/vgpu_<i>.readings
+ * (include/vgpu_contract.h; csrc/limiter.c publish_device_reading).  With --source device the samples of a device
+ * are built from those readings alone - nvmlDeviceGetProcessUtilization is never called; with --source mixed NVML
+ * is asked and a tenant's own reading replaces NVML's sample for its pid.  Readings are keyed by (pid-namespace
+ * inode, pid inside it); NVML's host pids are resolved through /proc/<pid>/ns/pid and the NSpid line of
+ * /proc/<pid>/status.  The process lists (memory accounting) always come from NVML.
+ *
  *   vgpu-smwatcher [--file PATH] [--passes N] [--period-ms 80] [--nvml PATH] [--verbose]
+ *                  [--source nvml|device|mixed] [--readings-dir DIR]
  */
 #ifndef _GNU_SOURCE
 #define _GNU_SOURCE
@@ -62,6 +71,10 @@ typedef struct {
   nvml_ret (*proc_util)(nvml_dev, vgpu_util_sample_t *, unsigned *, unsigned long long);
 } nvml_api;
 
+enum { SRC_NVML = 0, SRC_DEVICE = 1, SRC_MIXED = 2 };
+static int g_source = SRC_NVML;
+static const char *g_readings_dir = VGPU_LOCK_DIR;
+
 static volatile sig_atomic_t g_stop;
 static void on_signal(int s) { (void)s; g_stop = 1; }
 
@@ -89,7 +102,7 @@ static int load_nvml(const char *path, nvml_api *n) {
   n->graphics16 = (nvml_ret(*)(nvml_dev, unsigned *, vgpu_proc_t *))sym(h, "nvmlDeviceGetGraphicsRunningProcesses", NULL, NULL);
   n->proc_util = (nvml_ret(*)(nvml_dev, vgpu_util_sample_t *, unsigned *, unsigned long long))sym(
       h, "nvmlDeviceGetProcessUtilization", NULL, NULL);
-  if (!n->init || !n->count || !n->by_index || !(n->compute24 || n->compute16) || !n->proc_util) {
+  if (!n->init || !n->count || !n->by_index || !(n->compute24 || n->compute16) || (!n->proc_util && g_source != SRC_DEVICE)) {
     fprintf(stderr, "vgpu-smwatcher: NVML library lacks a required entry point\n");
     return -1;
   }
@@ -172,6 +185,67 @@ static unsigned long long now_us(void) {
   return (unsigned long long)ts.tv_sec * 1000000ull + (unsigned long long)ts.tv_nsec / 1000ull;
 }
 
+/* ------------------------------------------------------------------ on-device readings */
+static const vgpu_readings_t *readings_of(int i) {
+  static const vgpu_readings_t *map[VGPU_MAX_DEVICES];
+  if (map[i]) return map[i];
+  char path[4096];
+  snprintf(path, sizeof path, "%s/vgpu_%d.readings", g_readings_dir, i);
+  int fd = open(path, O_RDONLY | O_CLOEXEC);
+  if (fd < 0) return NULL; /* no tenant has published on this GPU yet: looked for again next pass */
+  struct stat st;
+  void *m = (fstat(fd, &st) == 0 && (size_t)st.st_size >= sizeof(vgpu_readings_t))
+                ? mmap(NULL, sizeof(vgpu_readings_t), PROT_READ, MAP_SHARED, fd, 0) : MAP_FAILED;
+  close(fd);
+  if (m == MAP_FAILED) return NULL;
+  return map[i] = (const vgpu_readings_t *)m;
+}
+
+/* the key a tenant publishes under, for one of NVML's (host) pids: its pid namespace and its pid in there */
+static uint64_t owner_key_of(unsigned pid) {
+  char path[64], line[256];
+  struct stat ns;
+  snprintf(path, sizeof path, "/proc/%u/ns/pid", pid);
+  if (stat(path, &ns) != 0) return 0;
+  snprintf(path, sizeof path, "/proc/%u/status", pid);
+  FILE *f = fopen(path, "r");
+  if (!f) return 0;
+  unsigned inner = pid;
+  while (fgets(line, sizeof line, f))
+    if (!strncmp(line, "NSpid:", 6)) { /* outermost ... innermost */
+      for (char *tok = strtok(line + 6, " \t\n"); tok; tok = strtok(NULL, " \t\n")) inner = (unsigned)strtoul(tok, NULL, 10);
+      break;
+    }
+  fclose(f);
+  return ((uint64_t)ns.st_ino << 32) | inner;
+}
+
+/* samples for the compute processes that published a reading since `since_us`; returns their number */
+static unsigned samples_from_readings(int i, const vgpu_proc_v2_t *compute, int nc, unsigned long long since_us, vgpu_util_sample_t *out) {
+  const vgpu_readings_t *R = readings_of(i);
+  if (!R) return 0;
+  unsigned n = 0;
+  for (int p = 0; p < nc && n < VGPU_MAX_PIDS; p++) {
+    uint64_t key = owner_key_of(compute[p].pid);
+    if (!key) continue;
+    for (int k = 0; k < VGPU_READINGS_SLOTS; k++) {
+      if (R->slots[k].owner != key) continue;
+      unsigned long long ts = R->slots[k].ts_us;
+      __sync_synchronize();
+      unsigned sm = R->slots[k].sm_pct;
+      if (ts >= since_us && R->slots[k].owner == key) {
+        memset(&out[n], 0, sizeof out[n]);
+        out[n].pid = compute[p].pid;
+        out[n].ts_us = ts;
+        out[n].sm = sm > 100 ? 100 : sm;
+        n++;
+      }
+      break;
+    }
+  }
+  return n;
+}
+
 /* smWatcherSingleDevice (watcher.go:128-184) */
 static int publish_device(const nvml_api *n, vgpu_smutil_t *file, const char *path, int i, nvml_dev d) {
   static vgpu_proc_v2_t compute[VGPU_MAX_PIDS], graphics[VGPU_MAX_PIDS];
@@ -186,8 +260,29 @@ static int publish_device(const nvml_api *n, vgpu_smutil_t *file, const char *pa
   if (ng < 0) return 0;
   unsigned long long last_ts = now_us() - 1000000ull;
   unsigned ns = VGPU_MAX_PIDS;
-  nvml_ret sr = n->proc_util(d, samples, &ns, last_ts);
-  if (ns > VGPU_MAX_PIDS) ns = VGPU_MAX_PIDS;
+  nvml_ret sr = 0;
+  if (g_source == SRC_DEVICE) {
+    /* the tenants' own readings, nothing else; none fresh = NVML's NOT_FOUND: the previous samples stay */
+    ns = samples_from_readings(i, compute, nc, last_ts, samples);
+    sr = ns ? 0 : 6 /* NVML_ERROR_NOT_FOUND */;
+  } else {
+    sr = n->proc_util(d, samples, &ns, last_ts);
+    if (ns > VGPU_MAX_PIDS) ns = VGPU_MAX_PIDS;
+    if (g_source == SRC_MIXED) {
+      static vgpu_util_sample_t own[VGPU_MAX_PIDS];
+      unsigned no = samples_from_readings(i, compute, nc, last_ts, own);
+      if (sr != 0) ns = 0;
+      for (unsigned a = 0; a < no; a++) { /* a tenant's reading of itself wins over NVML's sample of it */
+        unsigned b = 0;
+        while (b < ns && samples[b].pid != own[a].pid) b++;
+        if (b == ns && ns == VGPU_MAX_PIDS) continue;
+        if (b == ns) ns++;
+        else { own[a].mem = samples[b].mem; own[a].enc = samples[b].enc; own[a].dec = samples[b].dec; } /* NVML's other engines */
+        samples[b] = own[a];
+      }
+      if (no) sr = 0;
+    }
+  }
 
   int fd = wlock(path, i);
   if (fd < 0) return -1;
@@ -216,8 +311,13 @@ int main(int argc, char **argv) {
     else if (!strcmp(argv[a], "--period-ms") && a + 1 < argc) period_ms = (unsigned)atoi(argv[++a]);
     else if (!strcmp(argv[a], "--nvml") && a + 1 < argc) nvml_path = argv[++a];
     else if (!strcmp(argv[a], "--verbose")) verbose = 1;
-    else {
-      fprintf(stderr, "usage: vgpu-smwatcher [--file PATH] [--passes N] [--period-ms 80] [--nvml PATH] [--verbose]\n");
+    else if (!strcmp(argv[a], "--readings-dir") && a + 1 < argc) g_readings_dir = argv[++a];
+    else if (!strcmp(argv[a], "--source") && a + 1 < argc && (!strcmp(argv[a + 1], "nvml") || !strcmp(argv[a + 1], "device") || !strcmp(argv[a + 1], "mixed"))) {
+      a++;
+      g_source = !strcmp(argv[a], "device") ? SRC_DEVICE : !strcmp(argv[a], "mixed") ? SRC_MIXED : SRC_NVML;
+    } else {
+      fprintf(stderr, "usage: vgpu-smwatcher [--file PATH] [--passes N] [--period-ms 80] [--nvml PATH] [--verbose]\n"
+                      "                      [--source nvml|device|mixed] [--readings-dir DIR]\n");
       return 2;
     }
   }

@@ -111,6 +111,7 @@ void vgpu_log_emit(int level, const char *file, int line, const char *fmt, ...)
   X(cuMemsetD8_v2, CUresult, (CUdeviceptr, unsigned char, size_t))                              \
   X(cuMemcpyDtoH_v2, CUresult, (void *, CUdeviceptr, size_t))                                   \
   X(cuMemcpyHtoD_v2, CUresult, (CUdeviceptr, const void *, size_t))                             \
+  X(cuMemcpyDtoHAsync_v2, CUresult, (void *, CUdeviceptr, size_t, CUstream))                    \
   X(cuModuleLoadData, CUresult, (CUmodule *, const void *))                                     \
   X(cuModuleGetFunction, CUresult, (CUfunction *, CUmodule, const char *))                      \
   X(cuModuleUnload, CUresult, (CUmodule))                                                       \
@@ -292,6 +293,8 @@ typedef struct vgpu_dev_rt {
   int quota_armed;     /* allocation hooks launch the quota kernel ahead of the NVML queries */
   int gfx_valid;       /* q_req->graphics / gflags hold the graphics list of the previous evaluation */
   volatile long uva_live; /* records in the slab (host-side count; skip lookups when 0) */
+  vgpu_slab_slot_t *uva_snap; /* records read back while the context is being torn down (vgpu_rt_context_before) */
+  uint32_t uva_snap_n;
   pthread_mutex_t q_mu;
   int sm_num, max_thread_per_sm;
   int64_t total_cores;
@@ -317,6 +320,7 @@ void vgpu_rt_quota_publish(vgpu_dev_rt *rt, uint32_t seq);
 int vgpu_rt_quota_collect(vgpu_dev_rt *rt, uint32_t seq, vgpu_quota_res_t *out);
 int vgpu_rt_slab_insert(vgpu_dev_rt *rt, CUdeviceptr dptr, uint64_t bytes);
 int vgpu_rt_slab_remove(vgpu_dev_rt *rt, CUdeviceptr dptr, uint64_t *bytes);
+int vgpu_stale_uva_remove(CUdeviceptr dptr, uint64_t *bytes); /* records that outlived their context (device.c) */
 CUresult vgpu_rt_clear(vgpu_dev_rt *rt, CUdeviceptr dst, size_t bytes, CUstream s);
 CUresult vgpu_rt_spill(vgpu_dev_rt *rt, CUdeviceptr dst, CUdeviceptr src, size_t bytes, CUstream s);
 

@@ -137,6 +137,29 @@ def gen_watcher(rng):
     return out
 
 
+RANDOM_SEED = 0xB200
+RANDOM_TRAJECTORIES = 16
+
+
+def random_trajectory(rng, steps, name):
+    """Parameters drawn at random (limits, soft limit on either side of the hard one, geometry, process counts, host /
+    cgroup-v2 membership - the two modes watcher_traj can prepare membership files for)."""
+    mode = rng.choice([0, 2])
+    hard = rng.choice([1, 2, 5, 10, 20, 25, 33, 50, 75, 99, 100])
+    balance = rng.random() < 0.45
+    soft = rng.choice([hard + 1, min(100, hard + rng.randint(1, 60)), 100]) if balance else rng.choice([0, hard, max(0, hard - 5)])
+    lo = rng.choice([0, 0, 10, 40, 90])
+    util = (lo, lo + rng.choice([5, 20, 60, 110]))
+    procs = rng.choice([(1,), (1, 2), (2,), (1, 1, 2, 4), (3,), (2, 3, 4)])
+    return watcher_traj(name, mode, hard, soft, 1, 0 if soft > hard else 1, rng.choice(GEOMS + [(160, 2048), (2, 64)]), steps, rng,
+                        mine_prob=rng.choice([1.0, 0.5, 0.3]), procs=procs, util=util, proc_hold=rng.choice([1, 1, 7, 31, 97]))
+
+
+def gen_watcher_random():
+    rng = random.Random(RANDOM_SEED)
+    return [random_trajectory(rng, 100, "random%02d" % i) for i in range(RANDOM_TRAJECTORIES)]
+
+
 ENV_CASES = [
     {"MANAGER_VISIBLE_DEVICES": helpers.STUB_UUID, "CUDA_MEM_LIMIT_0": "1g", "CUDA_CORE_LIMIT_0": "10",
      "MANAGER_COMPATIBILITY_MODE": "0"},
@@ -233,7 +256,9 @@ def main():
         json.dump(gold, f, separators=(",", ":"))
     with open(os.path.join(HERE, "watcher.json"), "w") as f:
         json.dump({"seed": SEED, "trajectories": gen_watcher(rng)}, f, separators=(",", ":"))
-    print("wrote", os.path.join(HERE, "limiter_memory.json"), os.path.join(HERE, "watcher.json"))
+    with open(os.path.join(HERE, "watcher_random.json"), "w") as f:
+        json.dump({"seed": RANDOM_SEED, "trajectories": gen_watcher_random()}, f, separators=(",", ":"))
+    print("wrote", os.path.join(HERE, "limiter_memory.json"), os.path.join(HERE, "watcher.json"), os.path.join(HERE, "watcher_random.json"))
 
 
 if __name__ == "__main__":

@@ -274,6 +274,38 @@ def test_refill_kernel_folds_samples_and_replays_reference_watcher(gpu):
             bucket = bucket_w
 
 
+def test_refill_and_controller_kernels_replay_random_reference_trajectories(gpu):
+    """tests/golden/watcher_random.json (16 trajectories with randomly drawn limits / soft limits / geometries /
+    process counts / membership, produced by the reference's watcher code): the raw samples through
+    vgpu_refill_kernel and the readings through vgpu_controller_kernel, bit-exact at each of the 1600 steps."""
+    lib, torch = gpu
+    with open(os.path.join(GOLD, "watcher_random.json")) as f:
+        trajs = json.load(f)["trajectories"]
+    for tr in trajs:
+        lib.limiter_reset(tr["sm"], tr["thr"], tr["hard"], tr["soft"], tr["core_limit"], tr["hard_limit"])
+        bucket = 0
+        for i, st in enumerate(tr["steps"]):
+            share_w, bucket_w, up_w, valid_w, user_w, sys_w = st["out"]
+            lib.limiter_consume(bucket - st["bucket_in"])
+            s = lib.refill(H.util_req_from_golden_step(tr["mode"], st, i + 1))
+            got = (s.share, s.granted - s.consumed, s.up_limit, s.valid)
+            assert got == (share_w, bucket_w, up_w, valid_w), (tr["name"], i, got, st["out"])
+            if tr["core_limit"] and valid_w:
+                assert (s.user_current, s.sys_current) == (user_w, sys_w), (tr["name"], i, s.user_current, s.sys_current, st["out"])
+            bucket = bucket_w
+        lib.limiter_reset(tr["sm"], tr["thr"], tr["hard"], tr["soft"], tr["core_limit"], tr["hard_limit"])
+        bucket, seen_valid = 0, 0
+        for i, st in enumerate(tr["steps"]):
+            share_w, bucket_w, up_w, valid_w, user_w, sys_w = st["out"]
+            lib.limiter_consume(bucket - st["bucket_in"])
+            valid_now = 1 if (valid_w and not seen_valid) else 0
+            seen_valid |= valid_w
+            s = lib.limiter_step(user_w, sys_w, valid_now, st["nproc"])
+            got = (s.share, s.granted - s.consumed, s.up_limit, s.valid)
+            assert got == (share_w, bucket_w, up_w, valid_w), (tr["name"], i, got, st["out"])
+            bucket = bucket_w
+
+
 def test_refill_kernel_full_width_publication(gpu):
     """1024 samples (the contract's maximum): one thread per sample, block reductions across 32 warps,
     against the oracle's sequential fold in every compatibility mode."""

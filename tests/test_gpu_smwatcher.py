@@ -62,15 +62,15 @@ def test_on_device_readings_reach_sm_util_config(built, tmp_path):
     sb = H.Sandbox()
     env = band.tenant_env(H.NEW_SO, sb, 50)
     env["VGPU_B200_UTIL_SOURCE"] = "queue"
-    tenant = subprocess.Popen([H.STORM, "--steps", "1000000", "--warmup", "0", "--per-step", "200", "--max-seconds", "9", *band.BUSY],
+    tenant = subprocess.Popen([H.STORM, "--steps", "1000000", "--warmup", "0", "--per-step", "200", "--max-seconds", "12", *band.BUSY],
                               env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
     try:
         rfile = sb.path("lock/vgpu_0.readings")
         slots, t_end = [], time.time() + 8
-        while time.time() < t_end and not (slots and slots[0].seq >= 25):  # ~2 s of control periods after bring-up
+        while time.time() < t_end and not (slots and slots[0].seq >= 12):  # ~1 s of control periods after bring-up
             time.sleep(0.2)
             slots = T.read_slots(rfile) if os.path.exists(rfile) else []
-        assert len(slots) == 1 and slots[0].owner == T.owner_key(tenant.pid) and slots[0].seq >= 25, [(hex(s.owner), s.seq) for s in slots]
+        assert len(slots) == 1 and slots[0].owner == T.owner_key(tenant.pid) and slots[0].seq >= 12, [(hex(s.owner), s.seq) for s in slots]
         path = str(tmp_path / "sm_util.config")
         r = subprocess.run([WATCHER, "--file", path, "--passes", "2", "--period-ms", "100", "--source", "device", "--readings-dir",
                             sb.path("lock")], capture_output=True, text=True, timeout=60)

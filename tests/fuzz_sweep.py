@@ -72,6 +72,26 @@ def main():
             lines = script.splitlines()
             lines.insert(rng.randrange(3, len(lines)), "reset")
             script = "\n".join(lines) + "\n"
+        if rng.random() < 0.12:
+            # an NVML-only client (nvidia-smi style, no CUDA context): the report is a host evaluation of the same fold
+            # (memgate.c host_nvml_view vs nvml_hook.c:47-103); other tenants' UVA records already in the ledger count
+            script = "nvmlinit 0\n" + "".join(rng.choice(("nvmlinfo\n", "nvmlinfo2\n", "persistence\n", "setmode 0\n", "ledger 0\n"))
+                                               for _ in range(rng.randrange(2, 7)))
+            args = ()
+            recs = [(rng.choice((1, 4100000 + rng.randrange(60))), rng.choice((4096, 64 << 20, 3 << 30, (1 << 64) - 1))) for _ in range(rng.randrange(0, 4))]
+            inner = prep
+
+            def prep(sb, recs=recs, inner=inner):
+                import struct
+                if inner:
+                    inner(sb)
+                if recs:
+                    raw = bytearray(262272)
+                    for i, (pid, used) in enumerate(recs):
+                        struct.pack_into("<iiQ", raw, 16 * i, pid, 0, used)
+                    struct.pack_into("<I", raw, 16384, len(recs))
+                    with open(sb.ledger(), "wb") as f:
+                        f.write(raw)
         try:
             ref = F.run(H.REF_SO, script, env, args, prep)
         except subprocess.TimeoutExpired:

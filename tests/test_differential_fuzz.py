@@ -168,3 +168,57 @@ def test_random_scripts_in_slab_mode_keep_the_reference_accounting(built):
         new = run(H.NEW_SO, script, env, ())
         assert ref[:3] == new[:3], "case %d env %r\nscript:\n%s\n--- reference (rc %d)\n%s\n--- b200 (rc %d)\n%s\n%s" % (
             case, env, script, ref[1], ref[0], new[1], new[0], new[3][-1500:])
+
+
+def random_slab_script(rng, n_cmds, budget):
+    """Allocations that qualify as slabs (whole multiples of 2 MiB, three size classes) filled with a per-buffer value,
+    frees, re-checks of buffers that may have been demoted to host memory or promoted back in between.  The live total
+    stays under `budget` so that no request is refused by the cap (the harness numbers handles by success)."""
+    lines = ["init 0"]
+    live = {}   # handle -> (bytes, value)
+    handles = 0
+    sizes = [2 * MiB, 32 * MiB, 64 * MiB, 64 * MiB, 64 * MiB]
+    for _ in range(n_cmds):
+        k = rng.random()
+        n = rng.choice(sizes)
+        if k < 0.45 and sum(b for b, _ in live.values()) + n <= budget:
+            lines.append("alloc %d" % n)
+            v = rng.randrange(1, 255)
+            lines.append("fill %d %d %d" % (handles, n, v))
+            live[handles] = (n, v)
+            handles += 1
+        elif k < 0.7 and live:
+            h = rng.choice(sorted(live))
+            lines.append("check %d %d %d" % (h, live[h][0], live[h][1]))
+        elif k < 0.9 and live:
+            h = rng.choice(sorted(live))
+            lines.append("free %d" % h)
+            del live[h]
+        else:
+            lines.append(rng.choice(("meminfo", "nvmlinfo", "ledger 0")))
+    for h in sorted(live):
+        lines.append("check %d %d %d" % (h, live[h][0], live[h][1]))
+    lines += ["meminfo", "nvmlinfo2", "ledger 0"]
+    return "\n".join(lines) + "\n"
+
+
+def test_random_slab_traffic_keeps_contents_and_accounting(built):
+    """VGPU_B200_SLAB=1 under an oversold cap with little physical memory: random allocate / fill / check / free traffic
+    in three slab size classes drives demotions (spill copy), promotions and scrubs; every buffer must read back what
+    was written to it, and the transcript (decisions, reports, ledger) must be the reference's."""
+    rng = random.Random(0x5AB2)
+    moved = 0
+    for case in range(12):
+        cap = rng.choice((1, 2))
+        script = random_slab_script(rng, rng.randrange(25, 70), cap * GiB - 320 * MiB)
+        env = {"MANAGER_COMPATIBILITY_MODE": "0", "MANAGER_VISIBLE_DEVICES": H.STUB_UUID, "LOGGER_LEVEL": "0",
+               "CUDA_MEM_LIMIT_0": "%dg" % cap, "CUDA_MEM_RATIO_0": rng.choice(("4", "8")), "VMEMORY_NODE_ENABLED": "true"}
+        ref = run(H.REF_SO, script, env, ())
+        new = run(H.NEW_SO, script + "slabstats 0\n", dict(env, VGPU_B200_SLAB="1"), ())
+        body, stats = new[0].rsplit("slabstats", 1)
+        assert (ref[0], ref[1]) == (body, new[1]), "case %d env %r\nscript:\n%s\n--- reference (rc %d)\n%s\n--- b200 (rc %d)\n%s\n%s" % (
+            case, env, script, ref[1], ref[0], new[1], new[0], new[3][-1500:])
+        assert "CORRUPT" not in body and "-> 2" not in body and body.count("intact") >= 3
+        st = dict(zip(stats.split()[0::2], map(int, stats.split()[1::2])))
+        moved += st["demotions"]
+    assert moved >= 12, moved  # the traffic really did push slabs out

@@ -408,7 +408,10 @@ def test_uva_records_outlive_a_device_reset_like_the_reference_list(built):
     later allocation that gets the same address is freed, the stale node is found and the ledger shrinks by ITS size
     (loader.c:1869-1907) - also when the new allocation was not a UVA one.  The records here live in HBM; they are
     read back while the context is torn down and searched after the live table (found by the offline sweep: a 1-byte
-    ledger difference in 2 of 2400 random scripts)."""
+    ledger difference in 2 of 2400 random scripts).  What cannot be matched in general is WHICH later allocation gets a
+    stale address: the library's own device allocations perturb the driver's address sequence, so in long random
+    scripts the coincidence sometimes happens under one library only (3 of 3400 scripts in the later sweeps); here
+    both lives bring the runtime up at the same point, so the addresses repeat under both."""
     env = {"CUDA_MEM_LIMIT_0": "4g", "CUDA_MEM_RATIO_0": "4", "VMEMORY_NODE_ENABLED": "true", "STUB_PHYS_MEM": str(8 * GiB + 48 * MiB)}
     # a VMM handle fills the 1 GiB physical share, so the two small allocations are UVA ones (ledger 12288); after the
     # reset the same two requests get the same addresses on the GPU path (ledger untouched), and freeing them removes
@@ -418,7 +421,11 @@ def test_uva_records_outlive_a_device_reset_like_the_reference_list(built):
               "create %d\nalloc 4096\nledger 0\nreset\ncreate %d\nalloc 4096\nledger 0\nfree 1\nledger 0\n"
               "reset\nalloc 4096\nfree 0\nledger 0\nnvmlinfo\n") % (GiB, GiB, GiB)
     for args in ((), ("--gpa",)):
-        t = assert_same(both(script, env, args=args))
+        outs = both(script, env, args=args)
+        ref_led = [int(l.split()[-1].rstrip("]")) for l in outs[0][0].splitlines() if l.startswith("ledger")]
+        if ref_led[:5] != [12288, 12288, 12288, 8192, 0]:
+            pytest.skip("the fake driver (mmap) did not hand the same addresses out again after the reset on this kernel")
+        t = assert_same(outs)
         led = [int(l.split()[-1].rstrip("]")) for l in t.splitlines() if l.startswith("ledger")]
         assert led[:5] == [12288, 12288, 12288, 8192, 0], led   # stale nodes matched by address after the reset
         assert led[5:] == [4096, 8192, 4096, 0], led            # live record first, then the stale one under the same address

@@ -471,7 +471,16 @@ EXPORT CUresult cuStreamWriteValue64_v2_ptsz(void *s, CUdeviceptr a, unsigned lo
 
 /* ------------------------------------------------------------------ CUDA: modules and the fake GPU's kernels */
 typedef struct { char name[64]; } fn_t;
-EXPORT CUresult cuModuleLoadData(void **m, const void *img) { (void)img; *m = (void *)0x7000; return 0; }
+/* STUB_FAIL_MODULE=N: the first N module loads fail like a full GPU (the library's bring-up must free what it built,
+ * back off and try again) */
+EXPORT CUresult cuModuleLoadData(void **m, const void *img) {
+  static int left = -1;
+  (void)img;
+  if (left < 0) { const char *s = getenv("STUB_FAIL_MODULE"); left = s ? atoi(s) : 0; }
+  if (left > 0) { left--; return 2; }
+  *m = (void *)0x7000;
+  return 0;
+}
 EXPORT CUresult cuModuleUnload(void *m) { (void)m; return 0; }
 EXPORT CUresult cuModuleGetFunction(void **f, void *m, const char *name) {
   (void)m;

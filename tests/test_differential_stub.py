@@ -755,6 +755,25 @@ def test_control_plane_sets_tunables_through_a_file_next_to_the_mounted_config(b
     assert launches >= 60 and launches >= 5 * steps, (launches, steps)  # the queue signal's cadence, not the refill's
 
 
+def test_failed_bring_up_is_retried_and_can_fail_closed(built):
+    """A transient bring-up failure (module load on a full GPU): partial state is freed, capped allocations are refused
+    (NOT_SUPPORTED) and the next hooked call after the 1 s back-off brings the runtime up.  There is no CPU enforcement
+    path: by default launches pass un-throttled meanwhile (ERROR log); with VGPU_B200_FAIL_CLOSED=1 they are refused too."""
+    env = dict(BASE)
+    env.update({"CUDA_MEM_LIMIT_0": "1g", "CUDA_CORE_LIMIT_0": "30", "STUB_UTIL": "fixed:5", "STUB_FAIL_MODULE": "1", "LOGGER_LEVEL": "2"})
+    script = "init 0\nlaunch 5 1 1 1\nalloc 4096\nsleepms 1200\nlaunch 5 1 1 1\nalloc 4096\nmeminfo\nmetrics 0\n"
+    for closed, first in ((None, "launch 5 -> ok 5"), ("1", "launch 5 -> ok 0")):
+        e = dict(env)
+        if closed:
+            e["VGPU_B200_FAIL_CLOSED"] = closed
+        out, err, sb = H.run_scenario(H.NEW_SO, script, e)
+        sb.cleanup()
+        lines = out.splitlines()
+        assert lines[1] == first and lines[2] == "alloc 4096 -> 801 h-1", out
+        assert lines[4] == "launch 5 -> ok 5" and lines[5] == "alloc 4096 -> 0 h0", out  # after the back-off: up, metered, capped
+        assert "bring-up failed on cuda device 0 (attempt 1)" in err and err.count("bring-up failed") == 1
+
+
 def test_watcher_runs_from_cuinit_and_the_controller_catches_up(built):
     """The reference's watcher steps from the first successful cuInit (cuda_hook.c:566-577), i.e. while the
     application is still creating its context.  The device-resident controller can only exist once a

@@ -952,7 +952,14 @@ static inline int admit(admit_t *a, unsigned gx, unsigned gy, unsigned gz, CUstr
   int h = vgpu_host_index_of_cuda(dev);
   if (h < 0 || !G_cfg->devices[h].core_limit) return 0;
   vgpu_dev_rt *rt = vgpu_rt_get(h, dev);
-  if (unlikely(!rt)) return 0; /* bring-up failed: logged there, retried after its back-off */
+  if (unlikely(!rt)) { /* bring-up failed: logged there, retried after its back-off */
+    /* There is no CPU enforcement path to fall back to.  Default: the launch passes un-throttled until the retry
+     * (availability first, like a reference whose watcher thread failed to start).  VGPU_B200_FAIL_CLOSED=1 (a †
+     * tunable: control plane's b200.tunables, or the env of an env-configured tenant): refuse it instead. */
+    static int fail_closed = -1;
+    if (fail_closed < 0) fail_closed = env_u32("VGPU_B200_FAIL_CLOSED", 0) != 0;
+    return fail_closed ? -2 : 0;
+  }
   if (unlikely(!g_tick_devices[h])) {
     g_tick_devices[h] = 1;
     pthread_once(&g_tick_once, tick_start);
@@ -1087,7 +1094,7 @@ static inline void mark_done(const admit_t *a, CUstream s) {
   do {                                                          \
     admit_t a_ = {0};                                           \
     int st_ = admit(&a_, (gx), (gy), (gz), (stream), (ptsz));   \
-    if (st_ < 0) return CUDA_ERROR_INVALID_CONTEXT;             \
+    if (st_ < 0) return st_ == -2 ? CUDA_ERROR_NOT_SUPPORTED : CUDA_ERROR_INVALID_CONTEXT; \
     uint64_t ts_ = slow_t0();                                   \
     CUresult r_ = (CALL);                                       \
     slow_end(ts_, "launch: driver call");                       \

@@ -213,6 +213,7 @@ uint64_t orc_used_memory(int mode, const vgpu_proc_t *comp, uint32_t nc, const u
   vgpu_proc_t *uniq = (vgpu_proc_t *)malloc(sizeof(vgpu_proc_t) * (ng ? ng : 1));
   uint8_t *up = (uint8_t *)malloc(ng ? ng : 1), *ul = (uint8_t *)malloc(ng ? ng : 1);
   uint32_t k = 0;
+  if (!uniq || !up || !ul) abort(); /* test infrastructure: no partial answers */
   for (uint32_t i = 0; i < ng; i++) {
     int seen = 0;
     for (uint32_t j = 0; j < nc; j++)

@@ -1,6 +1,6 @@
 """SASS evidence for the device image (no GPU needed): cuobjdump -sass of kernels.fatbin, split per
 kernel; full listings of the two bandwidth kernels, mnemonic counts for all.
-    python profiles/sass_summary.py   -> profiles/sass_r2/{summary.json, vgpu_spill_copy_kernel.sass, vgpu_clear_kernel.sass}
+    python profiles/sass_summary.py   -> profiles/sass_r2/{summary.json, <kernel>.sass for the bandwidth, refill, quota, sampler and slab-placement kernels}
 """
 import collections
 import json
@@ -11,7 +11,7 @@ import subprocess
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 FATBIN = os.path.join(ROOT, "vgpu_manager_b200", "csrc", "kernels.fatbin")
 OUT = os.path.join(ROOT, "profiles", "sass_r2")
-FULL = ("vgpu_spill_copy_kernel", "vgpu_clear_kernel")
+FULL = ("vgpu_spill_copy_kernel", "vgpu_clear_kernel", "vgpu_refill_kernel", "vgpu_quota_kernel", "vgpu_sampler_kernel", "vgpu_vslab_kernel")
 WATCH = ("UBLKCP", "SYNCS", "STG.E.128", "STG.E.EF.128", "LDG.E.128", "LDG.E.CONSTANT.128", "LDG.E.128.CONSTANT", "UTMALDG", "NANOSLEEP",
          "ATOMG", "RED", "BAR.SYNC", "SHFL", "MEMBAR", "CS2R", "S2UR", "LDS", "STS")
 

@@ -7,6 +7,15 @@ import sys
 
 import helpers as H
 
+
+def free_port():
+    """A rendezvous port nobody listens on right now (a fixed one collides with a second suite on the same machine)."""
+    import socket
+    with socket.socket() as so:
+        so.bind(("127.0.0.1", 0))
+        return str(so.getsockname()[1])
+
+
 WORKER = r'''
 import json, os, subprocess, sys
 sys.path.insert(0, os.environ["REPO_ROOT"]); sys.path.insert(0, os.path.join(os.environ["REPO_ROOT"], "tests"))
@@ -42,7 +51,7 @@ def test_two_ranks_independent_tenants_and_rebalance_gather(built, tmp_path):
     script.write_text(WORKER)
     env = dict(os.environ, REPO_ROOT=H.ROOT)
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
-                        "--master-addr", "127.0.0.1", "--master-port", "29731", str(script)],
+                        "--master-addr", "127.0.0.1", "--master-port", free_port(), str(script)],
                        capture_output=True, text=True, env=env, timeout=300)
     assert r.returncode == 0, r.stderr[-3000:]
     line = [l for l in r.stdout.splitlines() if l.startswith("{")][-1]
@@ -96,7 +105,7 @@ def test_rebalance_is_applied_to_the_gated_tenant_only(built, tmp_path):
     script.write_text(REBALANCE_WORKER)
     env = dict(os.environ, REPO_ROOT=H.ROOT)
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
-                        "--master-addr", "127.0.0.1", "--master-port", "29733", str(script)],
+                        "--master-addr", "127.0.0.1", "--master-port", free_port(), str(script)],
                        capture_output=True, text=True, env=env, timeout=300)
     assert r.returncode == 0, r.stderr[-3000:]
     rows = json.loads([l for l in r.stdout.splitlines() if l.startswith("[")][-1])
@@ -143,7 +152,7 @@ def test_rebalance_loop_backs_off_identically_on_every_rank_when_nobody_is_gated
     script.write_text(CALM_WORKER)
     env = dict(os.environ, REPO_ROOT=H.ROOT)
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
-                        "--master-addr", "127.0.0.1", "--master-port", "29734", str(script)],
+                        "--master-addr", "127.0.0.1", "--master-port", free_port(), str(script)],
                        capture_output=True, text=True, env=env, timeout=300)
     assert r.returncode == 0, r.stderr[-3000:]
     rows = json.loads([l for l in r.stdout.splitlines() if l.startswith("[")][-1])

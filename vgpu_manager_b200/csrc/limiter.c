@@ -515,6 +515,12 @@ static int tenant_activity(vgpu_dev_rt *rt, uint32_t *skipped) {
   return 0;
 }
 
+/* same reading of the knob as device.c read_util_tunables: anything but queue | sm | max is the default NVML reading */
+static int source_is_nvml(void) {
+  const char *s = vgpu_tunable("VGPU_B200_UTIL_SOURCE");
+  return !s || (strcmp(s, "queue") && strcmp(s, "sm") && strcmp(s, "max"));
+}
+
 static void *tick_main(void *arg) {
   (void)arg;
   uint32_t epoch = 0;
@@ -540,7 +546,7 @@ static void *tick_main(void *arg) {
       if (!rt) {
         /* no context yet: the watcher's readings are kept for the controller to catch up on */
         if (!g_governor_mode && epoch % g_period_ticks == 0 && G_cfg->devices[h].core_limit &&
-            !vgpu_tunable("VGPU_B200_UTIL_SOURCE")) backlog_push(h);
+            source_is_nvml()) backlog_push(h);
         continue;
       }
       if ((rt->lim_h->util_source != VGPU_SRC_NVML || g_governor_mode) && epoch % g_period_ticks == 0)

@@ -294,6 +294,7 @@ static void publish_device_reading(int h, const vgpu_lim_host_t *H) {
       map[h] = (vgpu_readings_t *)MAP_FAILED;
       return;
     }
+    if (st.st_size == 0 && fchmod(fd, 0666) != 0) { /* created here: tenants of other uids publish into it too */ }
     void *m = mmap(NULL, sizeof(vgpu_readings_t), PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
     close(fd);
     map[h] = (vgpu_readings_t *)m; /* MAP_FAILED: never tried again */
